@@ -1,0 +1,132 @@
+/*
+ * tfpnp_b200 -- C ABI of the B200-native PnP-ADMM inner solver.
+ *
+ * The reference (Vandermode/TFPnP) has no FFI layer: its boundary for this path
+ * is the Python duck-type `PnPSolver` (tfpnp/pnp/solver/base.py:5-84) as driven
+ * by `PnPEnv.step` (tfpnp/env/base.py:157-191).  The Python classes in
+ * tfpnp_b200/solver.py keep that interface and marshal raw device pointers into
+ * the entry points below through ctypes.  No torch types cross this boundary:
+ * plain pointers, sizes and a cudaStream_t (passed as void*).
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative tfpnp_status on error;
+ *    tfpnp_last_error() returns a thread-local message.  Nothing throws.
+ *  - all data pointers are DEVICE pointers, borrowed for the duration of the
+ *    call (the kernels are enqueued on `stream`; the caller keeps the buffers
+ *    alive until the stream has drained, as PyTorch's caching allocator does).
+ *  - a handle is bound to the CUDA device current at creation; it is not
+ *    thread-safe.  DataParallel-style use = one handle per device.
+ *  - fp32 everywhere unless noted; complex tensors are (re,im)-interleaved.
+ */
+#ifndef TFPNP_B200_H
+#define TFPNP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFPNP_B200_VERSION 100
+
+typedef enum {
+  TFPNP_OK = 0,
+  TFPNP_ERR_INVALID = -1,      /* bad argument / unsupported shape            */
+  TFPNP_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed         */
+  TFPNP_ERR_UNSUPPORTED = -3,  /* device is not sm_100 / feature not built    */
+  TFPNP_ERR_NOMEM = -4
+} tfpnp_status;
+
+/* which inner loop (tasks/<task>/solver.py) */
+typedef enum {
+  TFPNP_TASK_CSMRI = 0, /* ADMMSolver_CSMRI.forward  tasks/csmri/solver.py:29-57 */
+  TFPNP_TASK_PR = 1,    /* IADMMSolver_PR.forward    tasks/pr/solver.py:37-76    */
+  TFPNP_TASK_CT = 2,    /* IADMMSolver_CT.forward    tasks/ct/solver.py:17-53    */
+  TFPNP_TASK_SPI = 3    /* ADMMSolver_SPI.forward    tasks/spi/solver.py:17-51   */
+} tfpnp_task;
+
+/* arithmetic of the denoiser convolutions */
+typedef enum {
+  TFPNP_PREC_FP16 = 0,     /* tcgen05 kind::f16, fp16 operands, fp32 accumulate (TMEM)  */
+  TFPNP_PREC_FP16X3 = 1,   /* tcgen05, split-fp16 (hi,lo) 3-product emulation of fp32    */
+  TFPNP_PREC_FP32_SIMT = 2 /* fp32 FFMA on CUDA cores (verification mode, slow)         */
+} tfpnp_precision;
+
+int tfpnp_version(void);
+const char* tfpnp_last_error(void);
+
+/* ---- denoiser: UNetDenoiser2D (tfpnp/pnp/denoiser/base.py:7-32) ------------ */
+
+/* `weights_host`: the 56 tensors of UNet(2,1).state_dict() (tfpnp/pnp/denoiser/
+ * models/unet.py:34-47) flattened and concatenated in state_dict order
+ * (n_floats must be 11,773,857).  Copied and re-laid-out once; replaces the
+ * per-call weight broadcast of DataParallel (tfpnp/policy/sync_batchnorm/
+ * replicate.py:50-75). */
+int tfpnp_denoiser_create(const float* weights_host, size_t n_floats, int precision,
+                          void** out_handle);
+int tfpnp_denoiser_destroy(void* handle);
+
+/* out[b] = clamp(UNet(cat[x[b], sigma[b]]) , 0, 1)   denoiser/base.py:23-32
+ * x, out: [B,1,H,W]; sigma: [B] with element stride `sigma_stride` (floats).
+ * H, W multiples of 16 (four 2x poolings), H,W >= 16. */
+int tfpnp_denoiser_forward(void* handle, const float* x, const float* sigma,
+                           int64_t sigma_stride, float* out, int B, int H, int W, void* stream);
+
+/* ---- solver: PnPSolver.forward (tfpnp/pnp/solver/base.py:21-32) ------------ */
+
+typedef struct {
+  int task;          /* tfpnp_task                                             */
+  int H, W;          /* image size                                             */
+  int n_masks;       /* PR: number of CDP masks (4); else 0                    */
+  int views;         /* CT: number of projection angles; else 0                */
+  float opnorm;      /* CT: sqrt(lambda_max(A^T A)) (transforms.py:447-472)    */
+  const float* ct_cos; /* CT: optional HOST tables cos/sin(angle_v), [views]; NULL = computed */
+  const float* ct_sin; /*     internally from linspace(0, 179pi/180, views)         */
+  int use_graph;     /* capture the iteration loop in a CUDA graph (0/1)       */
+} tfpnp_solver_config;
+
+int tfpnp_solver_create(const tfpnp_solver_config* cfg, void* denoiser, void** out_handle);
+int tfpnp_solver_destroy(void* handle);
+
+/* One `solver(inputs, parameters)` call = `iters` inner iterations.
+ *  state_in/state_out : variables cat((x,z,u),1): [B,3,H,W,2] (CSMRI, PR) or [B,3,H,W]
+ *                       (CT, SPI); contiguous; state_out may not alias state_in.
+ *  aux0, aux1         : CSMRI: y0 [B,1,H,W,2] f32, mask [B,1,H,W] u8 (torch.bool)
+ *                       PR   : y0 [B,M,H,W] f32,   mask [B,M,H,W,2] f32
+ *                       CT   : y0 [B,1,views,det] f32, NULL
+ *                       SPI  : x0 [B,1,H,W] f32,   K [B] f32 with stride aux1_stride
+ *                              (= K tensor[:,0,0,0], still divided by 10)
+ *  sigma_d, mu, tau   : [B,iters] f32, element (b,i) at p[b*row_stride + i*col_stride]
+ *                       (tau NULL for CSMRI/SPI)
+ */
+int tfpnp_solver_forward(void* handle, const float* state_in, const void* aux0,
+                         const void* aux1, int64_t aux1_stride, const float* sigma_d,
+                         const float* mu, const float* tau, int64_t row_stride,
+                         int64_t col_stride, int B, int iters, float* state_out, void* stream);
+
+/* number of kernels the last tfpnp_solver_forward enqueued (graph nodes included) */
+int64_t tfpnp_solver_last_launch_count(void* handle);
+
+/* ---- CT operators (own discretisation of the reference geometry,
+ *      tfpnp/utils/transforms.py:465-491) ------------------------------------- */
+/* img [B,1,N,N] <-> sino [B,1,views,ceil(sqrt(2)N)]; cos/sin: optional HOST tables as above */
+int tfpnp_radon_forward(const float* img, float* sino, int B, int N, int views,
+                        const float* cos_host, const float* sin_host, void* stream);
+int tfpnp_radon_backward(const float* sino, float* img, int B, int N, int views,
+                         const float* cos_host, const float* sin_host, void* stream);
+
+/* ---- reward metric: torch_psnr (tfpnp/env/base.py:237-242) ------------------
+ * psnr[b] = 10 log10(1 / mean((clamp(out[b],0,1) - gt[b])^2)); out, gt: [B,HW] */
+int tfpnp_psnr(const float* out, const float* gt, float* psnr, int B, int64_t HW, void* stream);
+
+/* ---- introspection used by tests / bench ---------------------------------- */
+/* measured device time (ms) of the denoiser part and the data-fidelity part of the last
+ * forward when profiling is enabled with tfpnp_solver_set_profiling(handle, 1) */
+int tfpnp_solver_set_profiling(void* handle, int enable);
+int tfpnp_solver_get_profile(void* handle, float* denoiser_ms, float* update_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFPNP_B200_H */

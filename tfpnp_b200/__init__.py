@@ -1,0 +1,14 @@
+"""tfpnp_b200 -- B200-native PnP-ADMM inner solver behind the TFPnP solver API.
+
+Host-side mirror of the reference interface for ONE hot path:
+``PnPSolver.forward(inputs, parameters)`` for CS-MRI / phase retrieval / sparse-view CT /
+single-photon imaging, with the UNet prox_sigma denoiser, implemented as hand-written
+sm_100a CUDA in ``libtfpnp_b200.so`` (C ABI: include/tfpnp_b200.h).  No fallback paths.
+"""
+from ._lib import build, lib, LIB_PATH  # noqa: F401
+from .denoiser import UNetDenoiser2D, create_denoiser  # noqa: F401
+from .solver import (PnPSolver, ADMMSolver, IADMMSolver, ADMMSolver_CSMRI, IADMMSolver_PR,  # noqa: F401
+                     IADMMSolver_CT, ADMMSolver_SPI, RadonGenerator, create_solver_csmri,
+                     create_solver_pr, create_solver_ct, create_solver_spi)
+from .ops import radon_forward, radon_backward, torch_psnr  # noqa: F401
+from .dist import shard_batch, shard_bounds, all_gather_psnr  # noqa: F401

@@ -1,0 +1,84 @@
+"""ctypes binding of libtfpnp_b200.so (the C ABI declared in include/tfpnp_b200.h).
+
+The library is built in-tree by ``tfpnp_b200/csrc/Makefile`` (see ``__graft_entry__.build``).
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised -- the product path never silently degrades to PyTorch/CPU code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtfpnp_b200.so")
+
+TASK_CSMRI, TASK_PR, TASK_CT, TASK_SPI = 0, 1, 2, 3
+PREC_FP16, PREC_FP16X3, PREC_FP32_SIMT = 0, 1, 2
+PRECISIONS = {"fp16": PREC_FP16, "fp16x3": PREC_FP16X3, "fp32_simt": PREC_FP32_SIMT}
+
+
+class SolverConfig(C.Structure):
+    _fields_ = [("task", C.c_int), ("H", C.c_int), ("W", C.c_int), ("n_masks", C.c_int),
+                ("views", C.c_int), ("opnorm", C.c_float), ("ct_cos", C.POINTER(C.c_float)),
+                ("ct_sin", C.POINTER(C.c_float)), ("use_graph", C.c_int)]
+
+
+# every symbol include/tfpnp_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "tfpnp_version": (C.c_int, []),
+    "tfpnp_last_error": (C.c_char_p, []),
+    "tfpnp_denoiser_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "tfpnp_denoiser_destroy": (C.c_int, [C.c_void_p]),
+    "tfpnp_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tfpnp_solver_create": (C.c_int, [C.POINTER(SolverConfig), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tfpnp_solver_destroy": (C.c_int, [C.c_void_p]),
+    "tfpnp_solver_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "tfpnp_solver_last_launch_count": (C.c_int64, [C.c_void_p]),
+    "tfpnp_radon_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "tfpnp_radon_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "tfpnp_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "tfpnp_solver_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "tfpnp_solver_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libtfpnp_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libtfpnp_b200.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    if verbose:
+        print(res.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA library has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C tfpnp_b200/csrc`). "
+                "tfpnp_b200 has no CPU/PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = lib().tfpnp_last_error()
+        raise RuntimeError(f"{what} failed (status {status}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,114 @@
+// Shared host/device helpers for libtfpnp_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+
+#include "../../include/tfpnp_b200.h"
+
+namespace tfpnp {
+
+// ---- error plumbing (never throw across the C ABI) --------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define TFPNP_CUDA_OK(expr)                                                         \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ::tfpnp::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,         \
+                         cudaGetErrorString(_e));                                   \
+      return TFPNP_ERR_CUDA;                                                        \
+    }                                                                               \
+  } while (0)
+
+#define TFPNP_CHECK(cond, ...)                                                      \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      ::tfpnp::set_error(__VA_ARGS__);                                              \
+      return TFPNP_ERR_INVALID;                                                     \
+    }                                                                               \
+  } while (0)
+
+#define TFPNP_TRY(expr)                                                             \
+  do {                                                                              \
+    int _s = (expr);                                                                \
+    if (_s != 0) return _s;                                                         \
+  } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// launch counter: every kernel launch in the library goes through LAUNCH_COUNT()
+// so tfpnp_solver_last_launch_count() reports what was really enqueued.
+extern thread_local int64_t g_launch_count;
+#define TFPNP_COUNT_LAUNCH() (++::tfpnp::g_launch_count)
+
+// simple owned device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t n) {
+    if (n <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+      return TFPNP_ERR_NOMEM;
+    }
+    bytes = n;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int kNumUnetConv3 = 27;
+constexpr size_t kUnetParamCount = 11773857;
+
+// UNet(2,1) 3x3 conv layer table in state_dict order (unet.py:37-46):
+// {cin, cout, level} with level = log2 downsampling of the layer's resolution.
+struct ConvSpec { int cin, cout, level; };
+inline const ConvSpec* unet_conv_specs() {
+  static const ConvSpec s[kNumUnetConv3] = {
+      {2, 32, 0},    {32, 32, 0},   {32, 32, 0},     // inc
+      {32, 64, 1},   {64, 64, 1},   {64, 64, 1},     // down1
+      {64, 128, 2},  {128, 128, 2}, {128, 128, 2},   // down2
+      {128, 256, 3}, {256, 256, 3}, {256, 256, 3},   // down3
+      {256, 512, 4}, {512, 512, 4}, {512, 512, 4},   // down4
+      {768, 256, 3}, {256, 256, 3}, {256, 256, 3},   // up1  (cat[skip 256, up 512])
+      {384, 128, 2}, {128, 128, 2}, {128, 128, 2},   // up2  (cat[skip 128, up 256])
+      {192, 64, 1},  {64, 64, 1},   {64, 64, 1},     // up3  (cat[skip 64,  up 128])
+      {96, 32, 0},   {32, 32, 0},   {32, 32, 0},     // up4  (cat[skip 32,  up 64])
+  };
+  return s;
+}
+
+// abstract denoiser: d -> clamp(UNet(cat[d, sigma]), 0, 1)
+struct Denoiser {
+  int precision = 0;
+  // bumped whenever prepare() moves the workspaces: CUDA graphs that captured the old
+  // addresses must be dropped by their owners
+  int generation = 0;
+  virtual ~Denoiser() {}
+  // allocate workspaces / descriptors for this shape (never called during graph capture)
+  virtual int prepare(int B, int H, int W) = 0;
+  // x, out: [B,H,W] fp32 (C=1); sigma[b] at sigma[b*sigma_stride]
+  virtual int forward(const float* x, const float* sigma, int64_t sigma_stride, float* out, int B,
+                      int H, int W, cudaStream_t st) = 0;
+};
+
+Denoiser* make_unet_simt(const float* weights_host);                 // unet_simt.cu
+Denoiser* make_unet_tc(const float* weights_host, int precision);    // unet_tc.cu
+
+}  // namespace tfpnp

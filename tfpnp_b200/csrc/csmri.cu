@@ -1,0 +1,173 @@
+// CS-MRI data-fidelity step fused with the ADMM primal/dual update
+// (tasks/csmri/solver.py:47-55):
+//     Z = fft2c(x + u);  Z[mask] = (mu Z + y0)[mask] / (1 + mu);  z = ifft2c(Z);  u += x - z
+// plus the next denoiser input d = Re(z - u).
+//
+// The centred transforms (transforms.py:68-103) are computed as plain FFTs: for even N,
+// fft2c(x)[k + N/2] = (-1)^(k1+k2) FFT(x)[k] and the two sign/roll pairs cancel around the
+// pointwise step once y0 is pre-multiplied by (-1)^(k1+k2) and y0/mask are pre-rolled
+// (csmri_prep, once per solver call).  Sign flips and the 1/N scale (a power of two) are
+// exact, so the masked update is the reference's arithmetic on the same operands.
+//
+// Three launches per iteration, all HBM/L2-streaming with coalesced float2 access:
+//   rows_fwd : warp per image row   (x+u) -> row FFT -> T
+//   cols     : 16 columns per CTA through a padded smem tile: col FFT -> DC -> inverse col FFT
+//   rows_inv : warp per image row   inverse row FFT -> z, u, d
+#include "tasks.cuh"
+#include "fft.cuh"
+
+namespace tfpnp {
+namespace {
+
+constexpr int ROWS_PER_CTA = 8;   // warps per CTA in the row kernels
+constexpr int COLS_PER_CTA = 16;  // columns (= warps) per CTA in the column kernel
+
+__global__ void csmri_prep_kernel(const float2* __restrict__ y0, const uint8_t* __restrict__ mask,
+                                  float2* __restrict__ y0p, uint8_t* __restrict__ maskp, int N, int R) {
+  // one thread per (b, c, r); r fastest so the transposed write is coalesced
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int r = i % N, c = (i / N) % N;
+  size_t b = i / ((size_t)N * N);
+  int kx = fft_pos_to_freq(c, R), ky = fft_pos_to_freq(r, R);
+  int sx = (kx + N / 2) % N, sy = (ky + N / 2) % N;      // position in the centred spectrum
+  size_t src = (b * N + sy) * N + sx;
+  float2 v = y0[src];
+  if ((kx + ky) & 1) { v.x = -v.x; v.y = -v.y; }
+  y0p[i] = v;
+  maskp[i] = mask[src];
+}
+
+template <int R>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
+csmri_rows_fwd(const float* __restrict__ x, const float2* __restrict__ u, float2* __restrict__ T) {
+  constexpr int N = 32 * R;
+  WarpFFT<R> f;
+  f.init();
+  size_t row = (size_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+  const float* xr = x + row * N;
+  const float2* ur = u + row * N;
+  float2 v[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    float2 uu = ur[32 * j + f.lane];
+    v[j] = make_float2(xr[32 * j + f.lane] + uu.x, uu.y);
+  }
+  f.forward(v);
+  float2* tr = T + row * N;
+#pragma unroll
+  for (int j = 0; j < R; ++j) tr[32 * j + f.lane] = v[j];
+}
+
+template <int R>
+__global__ void __launch_bounds__(COLS_PER_CTA * 32)
+csmri_cols(float2* __restrict__ T, const float2* __restrict__ y0p, const uint8_t* __restrict__ maskp,
+           const float* __restrict__ mu) {
+  constexpr int N = 32 * R;
+  constexpr int PITCH = COLS_PER_CTA + 1;  // float2 pitch 17 -> conflict-free column walks
+  __shared__ float2 tile[N * PITCH];
+  const int b = blockIdx.y, c0 = blockIdx.x * COLS_PER_CTA;
+  float2* Tb = T + (size_t)b * N * N;
+  for (int i = threadIdx.x; i < N * COLS_PER_CTA; i += COLS_PER_CTA * 32) {
+    int r = i / COLS_PER_CTA, cc = i % COLS_PER_CTA;
+    tile[r * PITCH + cc] = Tb[(size_t)r * N + c0 + cc];
+  }
+  __syncthreads();
+  WarpFFT<R> f;
+  f.init();
+  const int w = threadIdx.x >> 5;
+  float2 v[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) v[j] = tile[(32 * j + f.lane) * PITCH + w];
+  f.forward(v);
+  const float m = mu[b];
+  const float inv_n = 1.0f / (float)N;  // ortho 2-D scale, exact power of two
+  const size_t col = ((size_t)b * N + c0 + w) * N;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    float2 zf = make_float2(v[j].x * inv_n, v[j].y * inv_n);
+    if (maskp[col + 32 * j + f.lane]) {        // z[mask] = ((mu z + y0)/(1+mu))[mask], solver.py:50-51
+      float2 y = y0p[col + 32 * j + f.lane];
+      zf.x = (m * zf.x + y.x) / (1.0f + m);
+      zf.y = (m * zf.y + y.y) / (1.0f + m);
+    }
+    v[j] = zf;
+  }
+  f.inverse(v);
+#pragma unroll
+  for (int j = 0; j < R; ++j) tile[(32 * j + f.lane) * PITCH + w] = v[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < N * COLS_PER_CTA; i += COLS_PER_CTA * 32) {
+    int r = i / COLS_PER_CTA, cc = i % COLS_PER_CTA;
+    Tb[(size_t)r * N + c0 + cc] = tile[r * PITCH + cc];
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
+csmri_rows_inv(const float2* __restrict__ T, const float* __restrict__ x, float2* __restrict__ z,
+               float2* __restrict__ u, float* __restrict__ d) {
+  constexpr int N = 32 * R;
+  WarpFFT<R> f;
+  f.init();
+  size_t row = (size_t)blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+  const float2* tr = T + row * N;
+  float2 v[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) v[j] = tr[32 * j + f.lane];
+  f.inverse(v);
+  const float inv_n = 1.0f / (float)N;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    size_t i = row * N + 32 * j + f.lane;
+    float2 zz = make_float2(v[j].x * inv_n, v[j].y * inv_n);
+    float2 uu = u[i];
+    float xx = x[i];
+    uu.x = uu.x + xx - zz.x;   // u = u + x - z (solver.py:55), Im(x) = 0
+    uu.y = uu.y - zz.y;
+    z[i] = zz;
+    u[i] = uu;
+    d[i] = zz.x - uu.x;        // complex2real(z - u) (solver.py:45)
+  }
+}
+
+template <int R>
+int launch_update(const float* x, float2* z, float2* u, float* d, float2* T, const float2* y0p,
+                  const uint8_t* maskp, const float* mu, int B, cudaStream_t st) {
+  constexpr int N = 32 * R;
+  const int row_blocks = B * N / ROWS_PER_CTA;
+  csmri_rows_fwd<R><<<row_blocks, ROWS_PER_CTA * 32, 0, st>>>(x, u, T);
+  TFPNP_COUNT_LAUNCH();
+  csmri_cols<R><<<dim3(N / COLS_PER_CTA, B), COLS_PER_CTA * 32, 0, st>>>(T, y0p, maskp, mu);
+  TFPNP_COUNT_LAUNCH();
+  csmri_rows_inv<R><<<row_blocks, ROWS_PER_CTA * 32, 0, st>>>(T, x, z, u, d);
+  TFPNP_COUNT_LAUNCH();
+  TFPNP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int csmri_prep(const float* y0, const uint8_t* mask, float2* y0p, uint8_t* maskp, int B, int N,
+               cudaStream_t st) {
+  TFPNP_CHECK(N == 32 || N == 64 || N == 128 || N == 256, "csmri: N must be 32/64/128/256, got %d", N);
+  size_t n = (size_t)B * N * N;
+  csmri_prep_kernel<<<(unsigned)(n / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(y0), mask, y0p,
+                                                         maskp, N, N / 32);
+  TFPNP_COUNT_LAUNCH();
+  TFPNP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int csmri_update(const float* x, float2* z, float2* u, float* d, float2* T, const float2* y0p,
+                 const uint8_t* maskp, const float* mu, int B, int N, cudaStream_t st) {
+  switch (N) {
+    case 32: return launch_update<1>(x, z, u, d, T, y0p, maskp, mu, B, st);
+    case 64: return launch_update<2>(x, z, u, d, T, y0p, maskp, mu, B, st);
+    case 128: return launch_update<4>(x, z, u, d, T, y0p, maskp, mu, B, st);
+    case 256: return launch_update<8>(x, z, u, d, T, y0p, maskp, mu, B, st);
+  }
+  set_error("csmri: unsupported size %d", N);
+  return TFPNP_ERR_INVALID;
+}
+
+}  // namespace tfpnp

@@ -1,0 +1,245 @@
+// UNet(2,1) denoiser on CUDA cores in fp32 (TFPNP_PREC_FP32_SIMT).
+//
+// Verification mode: the same network as tfpnp/pnp/denoiser/models/unet.py:34-131
+// evaluated with plain FFMA so the tensor-core path (unet_tc.cu) can be checked
+// on the GPU against an fp32 result that shares nothing with it but the weights.
+// NCHW fp32 activations, direct 3x3 convolution with shared-memory halo tiles.
+#include "common.cuh"
+
+namespace tfpnp {
+namespace {
+
+constexpr int TS = 16;    // output tile edge
+constexpr int CI_T = 8;   // input channels staged per step
+constexpr int CO_T = 16;  // output channels per block
+
+// out[b,co,y,x] = act(bias[co] + sum_{ci,ky,kx} w[co,ci,ky,kx] * in[b,ci,y+ky-1,x+kx-1])
+// the input is the channel-concatenation of src0 (C0 ch) and src1 (C1 ch)  (unet.py:119)
+__global__ void __launch_bounds__(TS* TS)
+conv3x3_simt(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
+             const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+             int Cout, int H, int W, int leaky) {
+  __shared__ float s_in[CI_T][TS + 2][TS + 2];
+  __shared__ float s_w[CI_T][9][CO_T];
+  const int tiles_x = (W + TS - 1) / TS;
+  const int tx0 = (blockIdx.x % tiles_x) * TS, ty0 = (blockIdx.x / tiles_x) * TS;
+  const int co0 = blockIdx.y * CO_T;
+  const int b = blockIdx.z;
+  const int tx = threadIdx.x % TS, ty = threadIdx.x / TS;
+  const int Cin = C0 + C1;
+  float acc[CO_T];
+#pragma unroll
+  for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
+
+  for (int c0 = 0; c0 < Cin; c0 += CI_T) {
+    for (int i = threadIdx.x; i < CI_T * (TS + 2) * (TS + 2); i += TS * TS) {
+      int ci = i / ((TS + 2) * (TS + 2));
+      int r = i % ((TS + 2) * (TS + 2));
+      int yy = ty0 + r / (TS + 2) - 1, xx = tx0 + r % (TS + 2) - 1;
+      int c = c0 + ci;
+      float v = 0.f;
+      if (c < Cin && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        v = (c < C0) ? src0[((size_t)(b * C0 + c) * H + yy) * W + xx]
+                     : src1[((size_t)(b * C1 + (c - C0)) * H + yy) * W + xx];
+      }
+      s_in[ci][r / (TS + 2)][r % (TS + 2)] = v;
+    }
+    for (int i = threadIdx.x; i < CI_T * 9 * CO_T; i += TS * TS) {
+      int co = i % CO_T, k = (i / CO_T) % 9, ci = i / (CO_T * 9);
+      int c = c0 + ci;
+      float v = 0.f;
+      if (c < Cin && co0 + co < Cout) v = w[((size_t)(co0 + co) * Cin + c) * 9 + k];
+      s_w[ci][k][co] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI_T; ++ci) {
+      float v[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[k] = s_in[ci][ty + k / 3][tx + k % 3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(s_w[ci][k][co], v[k], acc[co]);
+      }
+    }
+    __syncthreads();
+  }
+  const int y = ty0 + ty, x = tx0 + tx;
+  if (y < H && x < W) {
+#pragma unroll
+    for (int co = 0; co < CO_T; ++co) {
+      if (co0 + co < Cout) {
+        float r = acc[co] + bias[co0 + co];
+        if (leaky) r = r > 0.f ? r : 0.2f * r;
+        out[((size_t)(b * Cout + co0 + co) * H + y) * W + x] = r;
+      }
+    }
+  }
+}
+
+// cat[x, ones * sigma]  (denoiser/base.py:29-30)
+__global__ void make_input_simt(const float* __restrict__ x, const float* __restrict__ sigma,
+                                int64_t sstride, float* __restrict__ out, int HW, int B) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * HW) return;
+  int b = i / HW, p = i % HW;
+  out[((size_t)b * 2) * HW + p] = x[i];
+  out[((size_t)b * 2 + 1) * HW + p] = sigma[b * sstride];
+}
+
+__global__ void maxpool2_simt(const float* __restrict__ in, float* __restrict__ out, int BC, int H,
+                              int W) {  // nn.MaxPool2d(2), unet.py:83
+  int Ho = H / 2, Wo = W / 2;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)BC * Ho * Wo) return;
+  int x = i % Wo, y = (i / Wo) % Ho;
+  size_t bc = i / ((size_t)Wo * Ho);
+  const float* p = in + (bc * H + 2 * y) * W + 2 * x;
+  out[i] = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[W], p[W + 1]));
+}
+
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True), unet.py:99
+__global__ void upsample2_simt(const float* __restrict__ in, float* __restrict__ out, int BC, int H,
+                               int W) {
+  int Ho = 2 * H, Wo = 2 * W;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)BC * Ho * Wo) return;
+  int x = i % Wo, y = (i / Wo) % Ho;
+  size_t bc = i / ((size_t)Wo * Ho);
+  float sy = (float)(H - 1) / (float)(Ho - 1), sx = (float)(W - 1) / (float)(Wo - 1);
+  float fy = sy * y, fx = sx * x;
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  float ly = fy - y0, lx = fx - x0;
+  const float* p = in + bc * H * W;
+  float top = (1.f - lx) * p[y0 * W + x0] + lx * p[y0 * W + x1];
+  float bot = (1.f - lx) * p[y1 * W + x0] + lx * p[y1 * W + x1];
+  out[i] = (1.f - ly) * top + ly * bot;
+}
+
+// outconv 1x1 (unet.py:124-131) + residual (unet.py:65-66) + clamp (denoiser/base.py:32)
+__global__ void outc_simt(const float* __restrict__ feat, const float* __restrict__ w,
+                          const float* __restrict__ bias, const float* __restrict__ x,
+                          float* __restrict__ out, int C, int HW, int B) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * HW) return;
+  int b = i / HW, p = i % HW;
+  float acc = bias[0];
+  for (int c = 0; c < C; ++c) acc = fmaf(w[c], feat[((size_t)b * C + c) * HW + p], acc);
+  float r = x[i] + acc;
+  out[i] = fminf(fmaxf(r, 0.f), 1.f);
+}
+
+struct UNetSimt : Denoiser {
+  DevBuf weights;   // raw state_dict floats
+  size_t w_off[kNumUnetConv3], b_off[kNumUnetConv3], outc_w, outc_b;
+  DevBuf ws;        // activation workspace
+  size_t ws_B = 0, ws_HW = 0;
+
+  int init(const float* host) {
+    TFPNP_TRY(weights.alloc(kUnetParamCount * sizeof(float)));
+    TFPNP_CUDA_OK(cudaMemcpy(weights.p, host, kUnetParamCount * sizeof(float), cudaMemcpyHostToDevice));
+    size_t off = 0;
+    const ConvSpec* sp = unet_conv_specs();
+    for (int l = 0; l < kNumUnetConv3; ++l) {
+      w_off[l] = off; off += (size_t)sp[l].cout * sp[l].cin * 9;
+      b_off[l] = off; off += sp[l].cout;
+    }
+    outc_w = off; off += 32;
+    outc_b = off; off += 1;
+    if (off != kUnetParamCount) { set_error("unet param table mismatch"); return TFPNP_ERR_INVALID; }
+    return 0;
+  }
+
+  int conv(int l, const float* s0, int C0, const float* s1, int C1, float* out, int B, int H, int W,
+           cudaStream_t st) {
+    const ConvSpec& sp = unet_conv_specs()[l];
+    if (C0 + C1 != sp.cin) { set_error("simt conv %d channel mismatch", l); return TFPNP_ERR_INVALID; }
+    dim3 grid(cdiv(W, TS) * cdiv(H, TS), cdiv(sp.cout, CO_T), B);
+    const float* wp = weights.as<float>();
+    conv3x3_simt<<<grid, TS * TS, 0, st>>>(s0, C0, s1, C1, wp + w_off[l], wp + b_off[l], out, sp.cout, H, W, 1);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+
+  // workspace (floats per image, in units of HW): in 2 | x1 32 | x2 16 | x3 8 | x4 4 | x5 2 |
+  // tmpA 64 | tmpB 64 (ping-pong for block-internal activations, pooled and upsampled tensors)
+  int prepare(int B, int H, int W) override {
+    TFPNP_CHECK(H % 16 == 0 && W % 16 == 0 && H >= 16 && W >= 16, "UNet needs H,W multiples of 16, got %dx%d", H, W);
+    const size_t per_img = (size_t)(2 + 32 + 16 + 8 + 4 + 2 + 64 + 64) * H * W;
+    const void* before = ws.p;
+    TFPNP_TRY(ws.alloc(per_img * B * sizeof(float)));
+    if (ws.p != before) ++generation;
+    return 0;
+  }
+
+  int forward(const float* x, const float* sigma, int64_t sstride, float* out, int B, int H, int W,
+              cudaStream_t st) override {
+    const size_t HW = (size_t)H * W;
+    TFPNP_CHECK(ws.bytes >= (size_t)(2 + 32 + 16 + 8 + 4 + 2 + 64 + 64) * HW * B * sizeof(float), "prepare() not called");
+    float* base = ws.as<float>();
+    float* in2 = base;
+    float* x1 = in2 + 2 * HW * B;
+    float* x2 = x1 + 32 * HW * B;
+    float* x3 = x2 + 16 * HW * B;
+    float* x4 = x3 + 8 * HW * B;
+    float* x5 = x4 + 4 * HW * B;
+    float* tA = x5 + 2 * HW * B;
+    float* tB = tA + 64 * HW * B;
+    const int T = 256;
+    make_input_simt<<<cdiv((int)(B * HW), T), T, 0, st>>>(x, sigma, sstride, in2, (int)HW, B);
+    TFPNP_COUNT_LAUNCH();
+    // encoder
+    TFPNP_TRY(conv(0, in2, 2, nullptr, 0, tA, B, H, W, st));
+    TFPNP_TRY(conv(1, tA, 32, nullptr, 0, tB, B, H, W, st));
+    TFPNP_TRY(conv(2, tB, 32, nullptr, 0, x1, B, H, W, st));
+    float* skips[5] = {x1, x2, x3, x4, x5};
+    int ch[5] = {32, 64, 128, 256, 512};
+    for (int lv = 1; lv <= 4; ++lv) {
+      int h = H >> lv, w = W >> lv;
+      size_t n = (size_t)B * ch[lv - 1] * h * w;
+      maxpool2_simt<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(skips[lv - 1], tA, B * ch[lv - 1], h * 2, w * 2);
+      TFPNP_COUNT_LAUNCH();
+      int l0 = 3 * lv;
+      TFPNP_TRY(conv(l0, tA, ch[lv - 1], nullptr, 0, tB, B, h, w, st));
+      TFPNP_TRY(conv(l0 + 1, tB, ch[lv], nullptr, 0, tA, B, h, w, st));
+      TFPNP_TRY(conv(l0 + 2, tA, ch[lv], nullptr, 0, skips[lv], B, h, w, st));
+    }
+    // decoder
+    const float* cur = x5;
+    int cur_c = 512;
+    for (int k = 0; k < 4; ++k) {
+      int lv = 3 - k;  // output level
+      int h = H >> lv, w = W >> lv;
+      size_t n = (size_t)B * cur_c * h * w;
+      upsample2_simt<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(cur, tA, B * cur_c, h / 2, w / 2);
+      TFPNP_COUNT_LAUNCH();
+      int l0 = 15 + 3 * k;
+      float* o0 = tB;
+      float* o1 = tA;  // tA (upsampled) is dead after conv-0
+      TFPNP_TRY(conv(l0, skips[lv], ch[lv], tA, cur_c, o0, B, h, w, st));
+      TFPNP_TRY(conv(l0 + 1, o0, ch[lv], nullptr, 0, o1, B, h, w, st));
+      TFPNP_TRY(conv(l0 + 2, o1, ch[lv], nullptr, 0, o0, B, h, w, st));
+      cur = o0;
+      cur_c = ch[lv];
+    }
+    const float* wp = weights.as<float>();
+    outc_simt<<<cdiv((int)(B * HW), T), T, 0, st>>>(cur, wp + outc_w, wp + outc_b, x, out, 32, (int)HW, B);
+    TFPNP_COUNT_LAUNCH();
+    TFPNP_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  ~UNetSimt() override { weights.release(); ws.release(); }
+};
+
+}  // namespace
+
+Denoiser* make_unet_simt(const float* weights_host) {
+  UNetSimt* u = new UNetSimt();
+  u->precision = TFPNP_PREC_FP32_SIMT;
+  if (u->init(weights_host) != 0) { delete u; return nullptr; }
+  return u;
+}
+
+}  // namespace tfpnp

@@ -1,0 +1,608 @@
+// UNet(2,1) denoiser (tfpnp/pnp/denoiser/models/unet.py:34-131, denoiser/base.py:23-32) on the
+// 5th-generation tensor cores: every 3x3 convolution except the 2-channel input layer is an
+// implicit GEMM   D[128 pixels, BN couts] += A[128 pixels, kc cin] * W[BN couts, kc cin]^T
+// issued as tcgen05.mma (kind::f16, fp32 accumulators in TMEM), with
+//   * activations NHWC fp16 in HBM; the A tile of tap (dy,dx) is ONE 4-D TMA box
+//     {kc channels, TW, TH, TB} at (w0+dx, h0+dy): the conv's zero padding is TMA's
+//     out-of-bounds fill, and the decoder's torch.cat([skip, up]) (unet.py:119) is a K-loop over
+//     two tensor maps -- neither padding nor concat is ever materialised;
+//   * weights re-laid-out once to [tap][Cout][Cin] fp16 (K-major B operand), 3-D TMA boxes;
+//   * 128B/64B-swizzled K-major smem tiles feeding UMMA descriptors directly;
+//   * a warp-specialised CTA: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue
+//     (tcgen05.ld -> +bias -> LeakyReLU(0.2) -> fp16 -> NHWC store), mbarrier full/empty ring.
+// Precision modes: FP16 (one product) and FP16X3 (activations and weights split into fp16
+// hi+lo; hi*hi + lo*hi + hi*lo accumulate in the same fp32 TMEM tile: ~22-bit operands).
+#include "common.cuh"
+#include "sm100.cuh"
+#include <cuda.h>
+#include <vector>
+#include <map>
+#include <cstring>
+
+namespace tfpnp {
+namespace {
+
+using namespace sm100;
+
+constexpr int kTileM = 128;          // pixels per CTA tile (UMMA M)
+constexpr int kConvThreads = 192;    // 6 warps
+
+struct ConvParams {
+  CUtensorMap a_map[2][2];  // [source][plane]  activations {C, W, H, B}
+  CUtensorMap w_map[2];     // [plane]          weights     {Cin, Cout, 9}
+  int nchunk0, nchunk1;     // channel chunks of source 0 / 1
+  int kc;                   // channels per chunk (32 -> 64B rows, 64 -> 128B rows)
+  int nprod;                // 1 (FP16) or 3 (FP16X3)
+  int TW, TH, TB;           // tile geometry, TW*TH*TB == 128
+  int box_rows;             // pixel rows one A box really carries (TB clamped to B)
+  int tiles_w, tiles_h;
+  int B, H, W, Cout;
+  const float* bias;
+  __half* out_hi;
+  __half* out_lo;           // nullptr unless FP16X3
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kStages = BN >= 128 ? 3 : 4;
+  static constexpr int kABytes = kTileM * 128;   // room for kc = 64
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, BN <= 128 ? 2 : 1)
+conv3x3_tc(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* empty = full + S;
+  uint64_t* accum = empty + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int w0 = (mt % p.tiles_w) * p.TW;
+  const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+  const int b0 = (mt / (p.tiles_w * p.tiles_h)) * p.TB;
+  const int n0 = blockIdx.y * BN;
+  const int nchunks = p.nchunk0 + p.nchunk1;
+  const int kiters = 9 * nchunks * p.nprod;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.a_map[0][0]);
+    prefetch_tensormap(&p.w_map[0]);
+    if (p.nchunk1) prefetch_tensormap(&p.a_map[1][0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      const uint32_t stage_tx = (uint32_t)(p.box_rows + BN) * p.kc * 2;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int prod = it % p.nprod;
+        const int t = it / p.nprod;
+        const int chunk = t % nchunks, tap = t / nchunks;
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int src = chunk < p.nchunk0 ? 0 : 1;
+        const int cc = (src == 0 ? chunk : chunk - p.nchunk0) * p.kc;
+        uint8_t* sA = smem + s * Cfg::kStageBytes;
+        uint8_t* sB = sA + Cfg::kABytes;
+        mbar_arrive_expect_tx(&full[s], stage_tx);
+        tma_load_4d(sA, &p.a_map[src][prod == 1 ? 1 : 0], &full[s], cc, w0 + dx, h0 + dy, b0);
+        tma_load_3d(sB, &p.w_map[prod == 2 ? 1 : 0], &full[s], chunk * p.kc, n0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = make_idesc_f16(kTileM, BN);
+      const uint32_t row_bytes = p.kc * 2;
+      const int ksteps = p.kc / 16;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t b_addr = a_addr + Cfg::kABytes;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          umma_f16(tmem_base, make_smem_desc(a_addr + kk * 32, row_bytes),
+                   make_smem_desc(b_addr + kk * 32, row_bytes), idesc, (it | kk) != 0);
+        }
+        umma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(accum);          // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> bias -> LeakyReLU -> fp16 NHWC ----------------
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;            // tile row = pixel
+    const int tw = m % p.TW, th = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
+    const int b = b0 + tb, h = h0 + th, w = w0 + tw;
+    const bool valid = b < p.B && h < p.H && w < p.W;
+    const size_t pix = ((size_t)b * p.H + h) * p.W + w;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+      tmem_ld_wait();
+      if (valid) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float v0 = __uint_as_float(r[j]) + __ldg(p.bias + n0 + c0 + j);
+          float v1 = __uint_as_float(r[j + 1]) + __ldg(p.bias + n0 + c0 + j + 1);
+          v0 = v0 > 0.f ? v0 : 0.2f * v0;   // LeakyReLU(0.2), unet.py:22
+          v1 = v1 > 0.f ? v1 : 0.2f * v1;
+          __half2 hh = __floats2half2_rn(v0, v1);
+          hi[j / 2] = *reinterpret_cast<uint32_t*>(&hh);
+          if (p.out_lo) {
+            float2 back = __half22float2(hh);
+            __half2 ll = __floats2half2_rn(v0 - back.x, v1 - back.y);
+            lo[j / 2] = *reinterpret_cast<uint32_t*>(&ll);
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + n0 + c0);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dst[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+        if (p.out_lo) {
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + n0 + c0);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) dl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---- CUDA-core layers around the tensor-core convs ---------------------------------------
+
+// inc.conv-0: 3x3 conv over cat[d, sigma*ones] (2 ch, denoiser/base.py:29-30) -> 32 ch, fp32 FFMA
+// (K = 18: 0.2 % of the FLOPs), bias + LeakyReLU, NHWC fp16 out.
+__global__ void __launch_bounds__(128)
+conv_first_kernel(const float* __restrict__ d, const float* __restrict__ sigma, int64_t sstride,
+                  const float* __restrict__ w /*[32][2][9]*/, const float* __restrict__ bias,
+                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W) {
+  __shared__ float sw[18][32];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < 576; i += blockDim.x) {
+    int co = i / 18, k = i % 18;
+    sw[k][co] = w[i];
+  }
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const int y = p / W, x = p % W;
+  const float sg = sigma[b * sstride];
+  float in[18];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+    bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    in[k] = ok ? d[((size_t)b * H + yy) * W + xx] : 0.f;
+    in[9 + k] = ok ? sg : 0.f;
+  }
+  const size_t o = (((size_t)b * H + y) * W + x) * 32;
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 8) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float a0 = sb[c0 + j], a1 = sb[c0 + j + 1];
+#pragma unroll
+      for (int k = 0; k < 18; ++k) {
+        a0 = fmaf(sw[k][c0 + j], in[k], a0);
+        a1 = fmaf(sw[k][c0 + j + 1], in[k], a1);
+      }
+      a0 = a0 > 0.f ? a0 : 0.2f * a0;
+      a1 = a1 > 0.f ? a1 : 0.2f * a1;
+      __half2 hh = __floats2half2_rn(a0, a1);
+      hi[j / 2] = *reinterpret_cast<uint32_t*>(&hh);
+      float2 back = __half22float2(hh);
+      __half2 ll = __floats2half2_rn(a0 - back.x, a1 - back.y);
+      lo[j / 2] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(out_hi + o + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + o + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+struct H8 { __half2 v[4]; };  // 8 channels = 16 bytes
+
+__device__ __forceinline__ void load8(const __half* hi, const __half* lo, size_t off, float (&f)[8]) {
+  H8 a = *reinterpret_cast<const H8*>(hi + off);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __half22float2(a.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  if (lo) {
+    H8 l = *reinterpret_cast<const H8*>(lo + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(l.v[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
+  }
+}
+__device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const float (&f)[8]) {
+  H8 a, l;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a.v[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    float2 back = __half22float2(a.v[i]);
+    l.v[i] = __floats2half2_rn(f[2 * i] - back.x, f[2 * i + 1] - back.y);
+  }
+  *reinterpret_cast<H8*>(hi + off) = a;
+  if (lo) *reinterpret_cast<H8*>(lo + off) = l;
+}
+
+// nn.MaxPool2d(2) (unet.py:83), NHWC, 8 channels per thread
+__global__ void maxpool2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                              __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B, int H, int W,
+                              int C) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * Ho * Wo * C8) return;
+  int c8 = i % C8;
+  size_t pix = i / C8;
+  int x = pix % Wo, y = (pix / Wo) % Ho;
+  size_t b = pix / ((size_t)Wo * Ho);
+  float m[8], t[8];
+  size_t base = ((b * H + 2 * y) * W + 2 * x) * C + c8 * 8;
+  load8(in_hi, in_lo, base, m);
+  load8(in_hi, in_lo, base + C, t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], t[k]);
+  load8(in_hi, in_lo, base + (size_t)W * C, t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], t[k]);
+  load8(in_hi, in_lo, base + (size_t)W * C + C, t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], t[k]);
+  store8(out_hi, out_lo, pix * C + c8 * 8, m);
+}
+
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet.py:99), NHWC
+__global__ void upsample2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                               __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B, int H, int W,
+                               int C) {
+  const int Ho = 2 * H, Wo = 2 * W, C8 = C / 8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * Ho * Wo * C8) return;
+  int c8 = i % C8;
+  size_t pix = i / C8;
+  int x = pix % Wo, y = (pix / Wo) % Ho;
+  size_t b = pix / ((size_t)Wo * Ho);
+  float sy = (float)(H - 1) / (float)(Ho - 1), sx = (float)(W - 1) / (float)(Wo - 1);
+  float fy = sy * y, fx = sx * x;
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  float ly = fy - y0, lx = fx - x0;
+  float v00[8], v01[8], v10[8], v11[8], r[8];
+  size_t ib = b * H * W;
+  load8(in_hi, in_lo, ((ib + (size_t)y0 * W + x0) * C) + c8 * 8, v00);
+  load8(in_hi, in_lo, ((ib + (size_t)y0 * W + x1) * C) + c8 * 8, v01);
+  load8(in_hi, in_lo, ((ib + (size_t)y1 * W + x0) * C) + c8 * 8, v10);
+  load8(in_hi, in_lo, ((ib + (size_t)y1 * W + x1) * C) + c8 * 8, v11);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float top = (1.f - lx) * v00[k] + lx * v01[k];
+    float bot = (1.f - lx) * v10[k] + lx * v11[k];
+    r[k] = (1.f - ly) * top + ly * bot;
+  }
+  store8(out_hi, out_lo, pix * C + c8 * 8, r);
+}
+
+// outconv 1x1 32->1 (unet.py:124-131) + residual (unet.py:65-66) + clamp (denoiser/base.py:32)
+__global__ void outc_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                          const float* __restrict__ w, const float* __restrict__ bias,
+                          const float* __restrict__ d, float* __restrict__ out, size_t npix) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  float acc = bias[0];
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {
+    float f[8];
+    load8(in_hi, in_lo, i * 32 + c8 * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(w + c8 * 8 + k), f[k], acc);
+  }
+  float r = d[i] + acc;
+  out[i] = fminf(fmaxf(r, 0.f), 1.f);
+}
+
+// ---- host side ---------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+               const cuuint32_t* box, int inner_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return TFPNP_ERR_CUDA;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0],
+              box[1], box[2]);
+    return TFPNP_ERR_CUDA;
+  }
+  return 0;
+}
+
+struct Act {            // NHWC fp16 activation tensor (hi plane, optional lo plane)
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  int C = 0, H = 0, W = 0;
+};
+
+struct UNetTc : Denoiser {
+  bool x3 = false;
+  // weights
+  DevBuf w_first, w_hi, w_lo, biases, w_out;
+  size_t w_off[kNumUnetConv3];   // element offset of layer l in w_hi / w_lo ([9][Cout][Cin])
+  size_t b_off[kNumUnetConv3];
+  // plan for one (B,H,W)
+  int pB = 0, pH = 0, pW = 0;
+  DevBuf act;                    // all activation planes
+  Act S0, S1, S2, skip[5];
+  std::vector<ConvParams> convs; // layers 1..26 -> convs[l]
+  std::vector<int> conv_bn;
+
+  int init(const float* host) {
+    const ConvSpec* sp = unet_conv_specs();
+    // first layer + biases + outc stay fp32
+    size_t off = 0, woff = 0, boff = 0, total_b = 0, total_w = 0;
+    for (int l = 0; l < kNumUnetConv3; ++l) { total_b += sp[l].cout; if (l) total_w += (size_t)9 * sp[l].cout * sp[l].cin; }
+    std::vector<float> hb(total_b);
+    std::vector<__half> hhi(total_w), hlo(total_w);
+    std::vector<float> hfirst(576);
+    for (int l = 0; l < kNumUnetConv3; ++l) {
+      const int ci = sp[l].cin, co = sp[l].cout;
+      const float* w = host + off;
+      off += (size_t)co * ci * 9;
+      const float* b = host + off;
+      off += co;
+      b_off[l] = boff;
+      for (int i = 0; i < co; ++i) hb[boff + i] = b[i];
+      boff += co;
+      if (l == 0) {
+        for (int i = 0; i < 576; ++i) hfirst[i] = w[i];   // [32][2][9]
+        w_off[l] = 0;
+        continue;
+      }
+      w_off[l] = woff;
+      // [Cout][Cin][3][3] fp32 -> [tap][Cout][Cin] fp16 (+ residual plane)
+      for (int t = 0; t < 9; ++t)
+        for (int o = 0; o < co; ++o)
+          for (int c = 0; c < ci; ++c) {
+            float v = w[((size_t)o * ci + c) * 9 + t];
+            __half h = __float2half_rn(v);
+            size_t idx = woff + ((size_t)t * co + o) * ci + c;
+            hhi[idx] = h;
+            hlo[idx] = __float2half_rn(v - __half2float(h));
+          }
+      woff += (size_t)9 * co * ci;
+    }
+    std::vector<float> hout(33);
+    for (int i = 0; i < 33; ++i) hout[i] = host[off + i];
+    off += 33;
+    if (off != kUnetParamCount) { set_error("unet param table mismatch"); return TFPNP_ERR_INVALID; }
+    TFPNP_TRY(w_first.alloc(576 * sizeof(float)));
+    TFPNP_TRY(biases.alloc(total_b * sizeof(float)));
+    TFPNP_TRY(w_out.alloc(33 * sizeof(float)));
+    TFPNP_TRY(w_hi.alloc(total_w * sizeof(__half)));
+    TFPNP_CUDA_OK(cudaMemcpy(w_first.p, hfirst.data(), 576 * sizeof(float), cudaMemcpyHostToDevice));
+    TFPNP_CUDA_OK(cudaMemcpy(biases.p, hb.data(), total_b * sizeof(float), cudaMemcpyHostToDevice));
+    TFPNP_CUDA_OK(cudaMemcpy(w_out.p, hout.data(), 33 * sizeof(float), cudaMemcpyHostToDevice));
+    TFPNP_CUDA_OK(cudaMemcpy(w_hi.p, hhi.data(), total_w * sizeof(__half), cudaMemcpyHostToDevice));
+    if (x3) {
+      TFPNP_TRY(w_lo.alloc(total_w * sizeof(__half)));
+      TFPNP_CUDA_OK(cudaMemcpy(w_lo.p, hlo.data(), total_w * sizeof(__half), cudaMemcpyHostToDevice));
+    }
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<32>::kSmemBytes));
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
+    return 0;
+  }
+
+  static void tile_geom(int H, int W, int& TW, int& TH, int& TB) {
+    TW = W < 8 ? W : 8;
+    TH = H < kTileM / TW ? H : kTileM / TW;
+    TB = kTileM / (TW * TH);
+  }
+
+  int make_act_maps(CUtensorMap (&maps)[2], const Act& a, int B, int kc, int TW, int TH, int TB) {
+    cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)(TB < B ? TB : B)};
+    TFPNP_TRY(encode_map(&maps[0], a.hi, 4, dims, strides, box, kc * 2));
+    if (x3) TFPNP_TRY(encode_map(&maps[1], a.lo, 4, dims, strides, box, kc * 2));
+    else maps[1] = maps[0];
+    return 0;
+  }
+
+  // build ConvParams for layer l reading (src0 [, src1]) and writing dst
+  int plan_conv(int l, const Act& s0, const Act* s1, const Act& dst, int B) {
+    const ConvSpec& sp = unet_conv_specs()[l];
+    ConvParams& p = convs[l];
+    memset(&p, 0, sizeof(p));
+    const int c1 = s1 ? s1->C : 0;
+    TFPNP_CHECK(s0.C + c1 == sp.cin && dst.C == sp.cout, "plan_conv %d: channel mismatch", l);
+    const int kc = (s0.C % 64 == 0 && c1 % 64 == 0) ? 64 : 32;
+    const int BN = sp.cout >= 128 ? 128 : sp.cout;
+    conv_bn[l] = BN;
+    p.kc = kc;
+    p.nchunk0 = s0.C / kc;
+    p.nchunk1 = c1 / kc;
+    p.nprod = x3 ? 3 : 1;
+    tile_geom(dst.H, dst.W, p.TW, p.TH, p.TB);
+    p.box_rows = p.TW * p.TH * (p.TB < B ? p.TB : B);
+    p.tiles_w = dst.W / p.TW;
+    p.tiles_h = dst.H / p.TH;
+    p.B = B; p.H = dst.H; p.W = dst.W; p.Cout = sp.cout;
+    p.bias = biases.as<float>() + b_off[l];
+    p.out_hi = dst.hi;
+    p.out_lo = x3 ? dst.lo : nullptr;
+    TFPNP_TRY(make_act_maps(p.a_map[0], s0, B, kc, p.TW, p.TH, p.TB));
+    if (s1) TFPNP_TRY(make_act_maps(p.a_map[1], *s1, B, kc, p.TW, p.TH, p.TB));
+    else { p.a_map[1][0] = p.a_map[0][0]; p.a_map[1][1] = p.a_map[0][1]; }
+    cuuint64_t wd[3] = {(cuuint64_t)sp.cin, (cuuint64_t)sp.cout, 9};
+    cuuint64_t ws[2] = {(cuuint64_t)sp.cin * 2, (cuuint64_t)sp.cin * sp.cout * 2};
+    cuuint32_t wb[3] = {(cuuint32_t)kc, (cuuint32_t)BN, 1};
+    TFPNP_TRY(encode_map(&p.w_map[0], w_hi.as<__half>() + w_off[l], 3, wd, ws, wb, kc * 2));
+    if (x3) TFPNP_TRY(encode_map(&p.w_map[1], w_lo.as<__half>() + w_off[l], 3, wd, ws, wb, kc * 2));
+    else p.w_map[1] = p.w_map[0];
+    return 0;
+  }
+
+  int prepare(int B, int H, int W) override {
+    TFPNP_CHECK(H % 16 == 0 && W % 16 == 0 && H >= 16 && W >= 16, "UNet needs H,W multiples of 16, got %dx%d", H, W);
+    if (B == pB && H == pH && W == pW) return 0;
+    const size_t HW = (size_t)H * W;
+    const int planes = x3 ? 2 : 1;
+    // elements per image: S0 64 | S1 32 | S2 32 | x1 32 | x2 16 | x3 8 | x4 4 | x5 2  (units of HW)
+    const size_t per_plane = (size_t)(64 + 32 + 32 + 32 + 16 + 8 + 4 + 2) * HW * B;
+    const void* before = act.p;
+    TFPNP_TRY(act.alloc(per_plane * planes * sizeof(__half)));
+    if (act.p != before) ++generation;
+    __half* base = act.as<__half>();
+    size_t cur = 0;
+    auto carve = [&](Act& a, size_t units) {
+      a.hi = base + cur;
+      a.lo = x3 ? base + per_plane + cur : nullptr;
+      cur += units * HW * B;
+    };
+    carve(S0, 64); carve(S1, 32); carve(S2, 32);
+    const int ch[5] = {32, 64, 128, 256, 512};
+    const size_t units[5] = {32, 16, 8, 4, 2};
+    for (int i = 0; i < 5; ++i) { carve(skip[i], units[i]); skip[i].C = ch[i]; skip[i].H = H >> i; skip[i].W = W >> i; }
+    convs.assign(kNumUnetConv3, ConvParams{});
+    conv_bn.assign(kNumUnetConv3, 0);
+    auto view = [](const Act& buf, int C, int h, int w) { Act a = buf; a.C = C; a.H = h; a.W = w; return a; };
+    // encoder level 0: first -> S0 ; conv1: S0 -> S1 ; conv2: S1 -> x1
+    TFPNP_TRY(plan_conv(1, view(S0, 32, H, W), nullptr, view(S1, 32, H, W), B));
+    TFPNP_TRY(plan_conv(2, view(S1, 32, H, W), nullptr, skip[0], B));
+    for (int lv = 1; lv <= 4; ++lv) {
+      int h = H >> lv, w = W >> lv, l0 = 3 * lv;
+      TFPNP_TRY(plan_conv(l0, view(S0, ch[lv - 1], h, w), nullptr, view(S1, ch[lv], h, w), B));
+      TFPNP_TRY(plan_conv(l0 + 1, view(S1, ch[lv], h, w), nullptr, view(S0, ch[lv], h, w), B));
+      TFPNP_TRY(plan_conv(l0 + 2, view(S0, ch[lv], h, w), nullptr, skip[lv], B));
+    }
+    for (int k = 0; k < 4; ++k) {
+      int lv = 3 - k, h = H >> lv, w = W >> lv, l0 = 15 + 3 * k;
+      Act up = view(S0, ch[lv + 1], h, w);
+      TFPNP_TRY(plan_conv(l0, skip[lv], &up, view(S1, ch[lv], h, w), B));
+      TFPNP_TRY(plan_conv(l0 + 1, view(S1, ch[lv], h, w), nullptr, view(S0, ch[lv], h, w), B));
+      TFPNP_TRY(plan_conv(l0 + 2, view(S0, ch[lv], h, w), nullptr, view(S2, ch[lv], h, w), B));
+    }
+    pB = B; pH = H; pW = W;
+    return 0;
+  }
+
+  int launch_conv(int l, cudaStream_t st) {
+    const ConvParams& p = convs[l];
+    const int BN = conv_bn[l];
+    dim3 grid(p.tiles_w * p.tiles_h * cdiv(p.B, p.TB), p.Cout / BN);
+    switch (BN) {
+      case 32: conv3x3_tc<32><<<grid, kConvThreads, ConvCfg<32>::kSmemBytes, st>>>(p); break;
+      case 64: conv3x3_tc<64><<<grid, kConvThreads, ConvCfg<64>::kSmemBytes, st>>>(p); break;
+      case 128: conv3x3_tc<128><<<grid, kConvThreads, ConvCfg<128>::kSmemBytes, st>>>(p); break;
+      default: set_error("unsupported BN %d", BN); return TFPNP_ERR_INVALID;
+    }
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+
+  int forward(const float* x, const float* sigma, int64_t sstride, float* out, int B, int H, int W,
+              cudaStream_t st) override {
+    TFPNP_CHECK(B == pB && H == pH && W == pW, "prepare(%d,%d,%d) not called (plan is %d,%d,%d)", B, H, W, pB, pH, pW);
+    const int ch[5] = {32, 64, 128, 256, 512};
+    const int T = 256;
+    conv_first_kernel<<<dim3(cdiv(H * W, 128), B), 128, 0, st>>>(x, sigma, sstride, w_first.as<float>(),
+                                                                biases.as<float>() + b_off[0], S0.hi,
+                                                                x3 ? S0.lo : nullptr, H, W);
+    TFPNP_COUNT_LAUNCH();
+    TFPNP_TRY(launch_conv(1, st));
+    TFPNP_TRY(launch_conv(2, st));
+    for (int lv = 1; lv <= 4; ++lv) {
+      int h = H >> lv, w = W >> lv;
+      size_t n = (size_t)B * h * w * (ch[lv - 1] / 8);
+      maxpool2_nhwc<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(skip[lv - 1].hi, skip[lv - 1].lo, S0.hi, S0.lo, B,
+                                                                2 * h, 2 * w, ch[lv - 1]);
+      TFPNP_COUNT_LAUNCH();
+      for (int k = 0; k < 3; ++k) TFPNP_TRY(launch_conv(3 * lv + k, st));
+    }
+    for (int k = 0; k < 4; ++k) {
+      int lv = 3 - k, h = H >> lv, w = W >> lv;
+      const Act& src = k == 0 ? skip[4] : S2;
+      size_t n = (size_t)B * h * w * (ch[lv + 1] / 8);
+      upsample2_nhwc<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(src.hi, src.lo, S0.hi, S0.lo, B, h / 2, w / 2,
+                                                                 ch[lv + 1]);
+      TFPNP_COUNT_LAUNCH();
+      for (int j = 0; j < 3; ++j) TFPNP_TRY(launch_conv(15 + 3 * k + j, st));
+    }
+    size_t npix = (size_t)B * H * W;
+    outc_nhwc<<<(unsigned)((npix + T - 1) / T), T, 0, st>>>(S2.hi, S2.lo, w_out.as<float>(), w_out.as<float>() + 32,
+                                                            x, out, npix);
+    TFPNP_COUNT_LAUNCH();
+    TFPNP_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  ~UNetTc() override {
+    w_first.release(); w_hi.release(); w_lo.release(); biases.release(); w_out.release(); act.release();
+  }
+};
+
+}  // namespace
+
+Denoiser* make_unet_tc(const float* weights_host, int precision) {
+  UNetTc* u = new UNetTc();
+  u->precision = precision;
+  u->x3 = precision == TFPNP_PREC_FP16X3;
+  if (u->init(weights_host) != 0) { delete u; return nullptr; }
+  return u;
+}
+
+}  // namespace tfpnp

@@ -1,0 +1,108 @@
+"""B200-native stand-in for ``tfpnp.pnp.denoiser.UNetDenoiser2D``
+(reference: tfpnp/pnp/denoiser/base.py:7-32, models/unet.py:34-131).
+
+Same constructor / call signature: ``UNetDenoiser2D(ckpt_path)`` loads a
+``UNet(2,1).state_dict()`` checkpoint, ``forward(x, sigma)`` maps ``x [B,1,H,W]``,
+``sigma [B]`` to ``clamp(UNet(cat[x, sigma map]), 0, 1)``.  The network itself runs
+in libtfpnp_b200 (tcgen05 implicit-GEMM convolutions); the weights are uploaded and
+re-laid-out once per device, not broadcast per call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+
+#: state_dict order of UNet(2,1) (unet.py:37-46): (block, cin, cout)
+_BLOCKS = (("inc.conv", 2, 32), ("down1.mpconv.1", 32, 64), ("down2.mpconv.1", 64, 128),
+           ("down3.mpconv.1", 128, 256), ("down4.mpconv.1", 256, 512), ("up1.conv", 768, 256),
+           ("up2.conv", 384, 128), ("up3.conv", 192, 64), ("up4.conv", 96, 32))
+
+
+def unet_state_dict_layout():
+    out = []
+    for name, cin, cout in _BLOCKS:
+        for k in range(3):
+            ci = cin if k == 0 else cout
+            out.append((f"{name}.conv-{k}.conv2d.weight", (cout, ci, 3, 3)))
+            out.append((f"{name}.conv-{k}.conv2d.bias", (cout,)))
+    out.append(("outc.conv.weight", (1, 32, 1, 1)))
+    out.append(("outc.conv.bias", (1,)))
+    return out
+
+
+def flatten_state_dict(sd) -> torch.Tensor:
+    """Concatenate the 56 tensors in state_dict order; validates names and shapes."""
+    parts = []
+    for key, shape in unet_state_dict_layout():
+        if key not in sd:
+            raise KeyError(f"UNet(2,1) checkpoint is missing '{key}'")
+        t = sd[key]
+        if tuple(t.shape) != shape:
+            raise ValueError(f"'{key}' has shape {tuple(t.shape)}, expected {shape}")
+        parts.append(t.detach().to(torch.float32).cpu().contiguous().reshape(-1))
+    return torch.cat(parts).contiguous()
+
+
+class UNetDenoiser2D(torch.nn.Module):
+    def __init__(self, ckpt_path=None, state_dict=None, precision="fp16"):
+        super().__init__()
+        if state_dict is None:
+            if ckpt_path is None:
+                # the reference falls back to its bundled pretrained file and raises if absent
+                # (denoiser/base.py:10-13); this build ships no weights
+                raise ValueError('Default ckpt not found, you have to provide a ckpt path')
+            state_dict = torch.load(ckpt_path, map_location="cpu")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(_lib.PRECISIONS)}")
+        self.precision = precision
+        self._flat = flatten_state_dict(state_dict)
+        self._handles = {}   # device index -> c_void_p
+
+    def _handle(self, device: torch.device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            with torch.cuda.device(idx):
+                out = C.c_void_p()
+                _lib.check(_lib.lib().tfpnp_denoiser_create(self._flat.data_ptr(), self._flat.numel(),
+                                                            _lib.PRECISIONS[self.precision], C.byref(out)),
+                           "tfpnp_denoiser_create")
+            self._handles[idx] = h = out
+        return h
+
+    def forward(self, x, sigma):
+        if not x.is_cuda:
+            raise RuntimeError("tfpnp_b200.UNetDenoiser2D runs on CUDA (sm_100) tensors only; no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or sigma.requires_grad):
+            raise NotImplementedError("differentiable denoiser is out of scope (SURVEY 8f, N4)")
+        N, Cc, H, W = x.shape
+        assert Cc == 1
+        x = x.contiguous().float()
+        sigma = sigma.reshape(N).float()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().tfpnp_denoiser_forward(self._handle(x.device), x.data_ptr(), sigma.data_ptr(),
+                                                         sigma.stride(0), out.data_ptr(), N, H, W, st),
+                       "tfpnp_denoiser_forward")
+        return out
+
+    def __del__(self):
+        try:
+            for h in self._handles.values():
+                _lib.lib().tfpnp_denoiser_destroy(h)
+        except Exception:
+            pass
+
+
+def create_denoiser(opt, ckpt_path=None, state_dict=None, precision="fp16"):
+    """Mirror of tfpnp.pnp.create_denoiser (tfpnp/pnp/__init__.py:5-13)."""
+    print(f'[i] use denoiser: {opt.denoiser}')
+    if opt.denoiser == 'unet':
+        return UNetDenoiser2D(ckpt_path, state_dict, precision)
+    raise NotImplementedError

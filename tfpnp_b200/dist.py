@@ -1,0 +1,46 @@
+"""Multi-GPU: env_batch shards on dim 0, one process per GPU, state resident per rank.
+
+Replaces ``DataParallelWithCallback(solver)`` (tfpnp/policy/sync_batchnorm/replicate.py:50-75;
+tasks/csmri/main.py:79-80), which scatters the state, re-broadcasts all 11.8 M UNet parameters and
+gathers the result on EVERY solver call.  The images are independent, so the data path needs no
+collective; the only exchange is one all-gather of the per-image PSNR vector (tfpnp/env/base.py:
+237-242) after the last iteration.  Works with any torch.distributed backend (NCCL on GPUs, gloo
+in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous split of ``n`` items: the first ``n % world`` ranks get one extra."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(obj, rank: int, world: int):
+    """Slice dim 0 of every tensor in a (nested) dict / list / tuple."""
+    if isinstance(obj, torch.Tensor):
+        lo, hi = shard_bounds(obj.shape[0], rank, world)
+        return obj[lo:hi]
+    if isinstance(obj, dict):
+        return {k: shard_batch(v, rank, world) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(shard_batch(v, rank, world) for v in obj)
+    return obj
+
+
+def all_gather_psnr(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Gather the [B_local,1] PSNR vectors of all ranks into [n_total,1] (rank order = batch order)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    sizes = [shard_bounds(n_total, r, world) for r in range(world)]
+    pad = max(hi - lo for lo, hi in sizes)
+    buf = torch.zeros(pad, 1, dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)

@@ -1,0 +1,59 @@
+"""Stand-alone native operators: the CT Radon pair and the PSNR reward metric."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+
+
+def _tables(views):
+    angles = torch.linspace(0, 179 / 180 * math.pi, views, dtype=torch.float32)   # transforms.py:488
+    return torch.cos(angles.double()).float().contiguous(), torch.sin(angles.double()).float().contiguous()
+
+
+def det_count(resolution: int) -> int:
+    return int(math.ceil(math.sqrt(2) * resolution))                              # transforms.py:489
+
+
+def radon_forward(img: torch.Tensor, views: int) -> torch.Tensor:
+    """A: [B,1,N,N] -> [B,1,views,det]  (role of torch_radon's Radon.forward, transforms.py:465-491)."""
+    assert img.is_cuda and img.dim() == 4 and img.shape[1] == 1 and img.shape[2] == img.shape[3]
+    B, _, N, _ = img.shape
+    img = img.contiguous().float()
+    out = torch.empty(B, 1, views, det_count(N), device=img.device, dtype=torch.float32)
+    cos, sin = _tables(views)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().tfpnp_radon_forward(img.data_ptr(), out.data_ptr(), B, N, views, cos.data_ptr(),
+                                                  sin.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "tfpnp_radon_forward")
+    return out
+
+
+def radon_backward(sino: torch.Tensor, resolution: int, views: int) -> torch.Tensor:
+    """A^T: [B,1,views,det] -> [B,1,N,N]  (role of Radon.backprojection)."""
+    assert sino.is_cuda and sino.dim() == 4 and sino.shape[2] == views and sino.shape[3] == det_count(resolution)
+    B = sino.shape[0]
+    sino = sino.contiguous().float()
+    out = torch.empty(B, 1, resolution, resolution, device=sino.device, dtype=torch.float32)
+    cos, sin = _tables(views)
+    with torch.cuda.device(sino.device):
+        _lib.check(_lib.lib().tfpnp_radon_backward(sino.data_ptr(), out.data_ptr(), B, resolution, views,
+                                                   cos.data_ptr(), sin.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream),
+                   "tfpnp_radon_backward")
+    return out
+
+
+def torch_psnr(output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """Per-image PSNR [B,1], tfpnp/env/base.py:237-242, one fused kernel."""
+    assert output.is_cuda and gt.is_cuda
+    N = output.shape[0]
+    o = output.contiguous().float().reshape(N, -1)
+    g = gt.contiguous().float().reshape(N, -1)
+    res = torch.empty(N, device=o.device, dtype=torch.float32)
+    with torch.cuda.device(o.device):
+        _lib.check(_lib.lib().tfpnp_psnr(o.data_ptr(), g.data_ptr(), res.data_ptr(), N, o.shape[1],
+                                         torch.cuda.current_stream().cuda_stream), "tfpnp_psnr")
+    return res.unsqueeze(1)

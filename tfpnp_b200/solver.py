@@ -1,0 +1,305 @@
+"""B200-native PnP solvers behind the reference's ``PnPSolver`` interface.
+
+Mirrors tfpnp/pnp/solver/base.py:5-116 and the four task solvers
+(tasks/csmri/solver.py:9-57, tasks/pr/solver.py:15-76, tasks/ct/solver.py:7-53,
+tasks/spi/solver.py:8-51): same class names, ``reset / forward(inputs, parameters,
+iter_num=None) / get_output / prox_mapping / num_var / filter_aux_inputs /
+filter_hyperparameter``, so ``PnPEnv.step`` (tfpnp/env/base.py:157-191) drives them
+unchanged.  ``forward`` marshals raw device pointers into ``tfpnp_solver_forward``
+(include/tfpnp_b200.h); the iterated proximal loop itself is hand-written sm_100a CUDA.
+
+There is no PyTorch/CPU fallback.  The differentiable use (``PnPEnv.forward`` under
+autograd, tfpnp/env/base.py:193-206) is out of scope for this build and
+raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .denoiser import UNetDenoiser2D
+
+
+class PnPSolver(nn.Module):
+    """tfpnp/pnp/solver/base.py:5-84."""
+
+    def __init__(self, denoiser):
+        super().__init__()
+        self.denoiser = denoiser
+
+    def reset(self, data):
+        raise NotImplementedError
+
+    def forward(self, inputs, parameters, iter_num):
+        raise NotImplementedError
+
+    def get_output(self, state):
+        raise NotImplementedError
+
+    def prox_mapping(self, x, sigma):
+        return self.denoiser(x, sigma)
+
+    @property
+    def num_var(self):
+        raise NotImplementedError
+
+    def filter_aux_inputs(self, state):
+        raise NotImplementedError
+
+    def filter_hyperparameter(self, action):
+        raise NotImplementedError
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+class _NativeADMM(PnPSolver):
+    """Shared host logic: handle cache + pointer marshalling for one task."""
+    _task = None
+    _complex_state = False
+    use_graph = True
+
+    def __init__(self, denoiser):
+        if not isinstance(denoiser, UNetDenoiser2D):
+            raise TypeError("tfpnp_b200 solvers need a tfpnp_b200.UNetDenoiser2D (the denoiser runs inside "
+                            "the fused CUDA path)")
+        super().__init__(denoiser)
+        self._solvers = {}      # (device idx, H, W, extra) -> handle
+        self.last_launch_count = 0
+
+    @property
+    def num_var(self):                      # base.py:91-93
+        return 3
+
+    def reset(self, data):                  # base.py:95-99
+        x = data['x0'].clone().detach()
+        z = x.clone().detach()
+        u = torch.zeros_like(x)
+        return torch.cat((x, z, u), dim=1)
+
+    def get_output(self, state):            # base.py:101-104
+        x, _, _ = torch.split(state, state.shape[1] // 3, dim=1)
+        return x[..., 0] if self._complex_state else x
+
+    def filter_hyperparameter(self, action):  # base.py:106-107
+        return action['sigma_d'], action['mu']
+
+    # -- native plumbing -------------------------------------------------------
+    def _solver_handle(self, device, H, W, n_masks=0, views=0, opnorm=0.0, cos=None, sin=None):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, H, W, n_masks, views, float(opnorm))
+        h = self._solvers.get(key)
+        if h is None:
+            cfg = _lib.SolverConfig(self._task, H, W, n_masks, views, float(opnorm), None, None,
+                                    1 if self.use_graph else 0)
+            if cos is not None:
+                cfg.ct_cos = C.cast(cos.data_ptr(), C.POINTER(C.c_float))
+                cfg.ct_sin = C.cast(sin.data_ptr(), C.POINTER(C.c_float))
+            out = C.c_void_p()
+            with torch.cuda.device(idx):
+                _lib.check(_lib.lib().tfpnp_solver_create(C.byref(cfg), self.denoiser._handle(device), C.byref(out)),
+                           "tfpnp_solver_create")
+            self._solvers[key] = h = out
+        return h
+
+    def _check_inputs(self, variables, parameters):
+        if not variables.is_cuda:
+            raise RuntimeError("tfpnp_b200 solvers run on CUDA (sm_100) tensors only; there is no CPU fallback")
+        if torch.is_grad_enabled() and (variables.requires_grad or any(p.requires_grad for p in parameters)):
+            raise NotImplementedError(
+                "the differentiable solver path (PnPEnv.forward under autograd) is out of scope (SURVEY 8f N4)")
+
+    def _run(self, handle, variables, aux0, aux1, aux1_stride, params, iter_num):
+        B = variables.shape[0]
+        sigma_d = params[0]
+        if iter_num is None:                # infer from the hyper-parameters (tasks/csmri/solver.py:40-41)
+            iter_num = sigma_d.shape[-1]
+        state_in = _f32c(variables)
+        out = torch.empty_like(state_in)
+        # all parameter tensors must share strides; slices of one action tensor do, else copy
+        ps = [p if p.dtype == torch.float32 else p.float() for p in params]
+        ps = [p.reshape(B, -1) for p in ps]
+        if any(p.stride() != ps[0].stride() for p in ps):
+            ps = [p.contiguous() for p in ps]
+        if any(p.shape[1] < iter_num for p in ps):
+            raise IndexError(f"iter_num={iter_num} exceeds the hyper-parameter width {ps[0].shape[1]}")
+        rs, cs = ps[0].stride()
+        tau_ptr = ps[2].data_ptr() if len(ps) > 2 else None
+        with torch.cuda.device(variables.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().tfpnp_solver_forward(
+                handle, state_in.data_ptr(), aux0.data_ptr(), aux1.data_ptr() if aux1 is not None else None,
+                aux1_stride, ps[0].data_ptr(), ps[1].data_ptr(), tau_ptr, rs, cs, B, int(iter_num),
+                out.data_ptr(), st), "tfpnp_solver_forward")
+            self.last_launch_count = int(_lib.lib().tfpnp_solver_last_launch_count(handle))
+        return out
+
+    def __del__(self):
+        try:
+            for h in self._solvers.values():
+                _lib.lib().tfpnp_solver_destroy(h)
+        except Exception:
+            pass
+
+
+class ADMMSolver(_NativeADMM):
+    """tfpnp/pnp/solver/base.py:87-107."""
+
+
+class IADMMSolver(ADMMSolver):
+    """tfpnp/pnp/solver/base.py:110-116 (inexact ADMM: adds tau)."""
+
+    def filter_hyperparameter(self, action):
+        return action['sigma_d'], action['mu'], action['tau']
+
+
+class ADMMSolver_CSMRI(ADMMSolver):
+    """tasks/csmri/solver.py:9-57."""
+    _task = _lib.TASK_CSMRI
+    _complex_state = True
+
+    def filter_aux_inputs(self, state):     # solver.py:20-21
+        return (state['y0'], state['mask'])
+
+    def forward(self, inputs, parameters, iter_num=None):
+        variables, aux = inputs
+        y0, mask = tuple(aux)               # may be a one-shot generator (tfpnp/utils/misc.py:138-139)
+        sigma_d, mu = parameters
+        self._check_inputs(variables, (sigma_d, mu))
+        B, _, H, W, _ = variables.shape
+        m8 = mask.contiguous()
+        m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else (m8 != 0).view(torch.uint8)
+        h = self._solver_handle(variables.device, H, W)
+        return self._run(h, variables, _f32c(y0), m8, 0, (sigma_d, mu), iter_num)
+
+
+class IADMMSolver_PR(IADMMSolver):
+    """tasks/pr/solver.py:15-76."""
+    _task = _lib.TASK_PR
+    _complex_state = True
+
+    def filter_aux_inputs(self, state):     # solver.py:20-21
+        return (state['y0'], state['mask'])
+
+    def reset(self, data):                  # solver.py:29-35
+        x0 = data['x0'].clone().detach()
+        x = torch.stack([x0, torch.zeros_like(x0)], dim=4)
+        return torch.cat([x, x.clone(), torch.zeros_like(x)], dim=1)
+
+    def forward(self, inputs, parameters, iter_num=None):
+        variables, aux = inputs
+        y0, mask = tuple(aux)
+        sigma_d, mu, tau = parameters
+        self._check_inputs(variables, (sigma_d, mu, tau))
+        B, _, H, W, _ = variables.shape
+        h = self._solver_handle(variables.device, H, W, n_masks=mask.shape[1])
+        return self._run(h, variables, _f32c(y0), _f32c(mask), 0, (sigma_d, mu, tau), iter_num)
+
+
+class RadonGenerator:
+    """Per-(resolution, views) operator-norm cache, as tfpnp/utils/transforms.py:494-508.
+    The power method (transforms.py:447-462) runs on the GPU operators of libtfpnp_b200 from a
+    SEEDED start vector (the reference starts from an unseeded torch.randn)."""
+
+    def __init__(self):
+        self.opnorms = {}
+
+    @staticmethod
+    def tables(views):
+        angles = torch.linspace(0, 179 / 180 * math.pi, views, dtype=torch.float32)   # transforms.py:488
+        return torch.cos(angles.double()).float().contiguous(), torch.sin(angles.double()).float().contiguous()
+
+    def __call__(self, resolution, views, device):
+        key = (resolution, views)
+        if key not in self.opnorms:
+            from .ops import radon_forward, radon_backward
+            g = torch.Generator().manual_seed(0)
+            x = torch.randn(1, 1, resolution, resolution, generator=g).to(device)
+            x = x / x.norm()
+            v = 0.0
+            for _ in range(10):
+                x = radon_backward(radon_forward(x, views), resolution, views)
+                v = float(x.norm())
+                x = x / v
+            self.opnorms[key] = v ** 0.5
+        return self.opnorms[key]
+
+
+class IADMMSolver_CT(IADMMSolver):
+    """tasks/ct/solver.py:7-53 (Radon pair: this build's own discretisation, parity unpinned
+    w.r.t. the absent torch_radon)."""
+    _task = _lib.TASK_CT
+
+    def __init__(self, denoiser):
+        super().__init__(denoiser)
+        self.radon_generator = RadonGenerator()
+        self.opnorm_override = None         # tests pass the CPU checker's opnorm explicitly
+
+    def filter_aux_inputs(self, state):     # solver.py:8-9
+        return (state['y0'], state['view'])
+
+    def forward(self, inputs, parameters, iter_num=None):
+        variables, aux = inputs
+        y0, view = tuple(aux)
+        sigma_d, mu, tau = parameters
+        self._check_inputs(variables, (sigma_d, mu, tau))
+        B, _, H, W = variables.shape
+        views = int(view[0, 0, 0, 0].item() * 120)          # solver.py:26 (one host sync per call)
+        opnorm = self.opnorm_override or self.radon_generator(W, views, variables.device)
+        cos, sin = RadonGenerator.tables(views)
+        h = self._solver_handle(variables.device, H, W, views=views, opnorm=opnorm, cos=cos, sin=sin)
+        return self._run(h, variables, _f32c(y0), None, 0, (sigma_d, mu, tau), iter_num)
+
+
+class ADMMSolver_SPI(ADMMSolver):
+    """tasks/spi/solver.py:8-51."""
+    _task = _lib.TASK_SPI
+
+    def filter_aux_inputs(self, state):     # solver.py:9-10
+        return (state['x0'], state['K'])
+
+    def forward(self, inputs, parameters, iter_num=None):
+        variables, aux = inputs
+        x0, K = tuple(aux)
+        sigma_d, mu = parameters
+        self._check_inputs(variables, (sigma_d, mu))
+        B, _, H, W = variables.shape
+        Kf = K if K.dtype == torch.float32 else K.float()
+        Kv = Kf[:, 0, 0, 0]                                   # solver.py:32 (the *10 happens on device)
+        h = self._solver_handle(variables.device, H, W)
+        return self._run(h, variables, _f32c(x0), Kv, Kv.stride(0), (sigma_d, mu), iter_num)
+
+
+# ---- factories, same names / error behaviour as the reference ---------------------------------
+_csmri_map = {'admm': ADMMSolver_CSMRI}      # tasks/csmri/solver.py:253-270 (hqs/pg/apg/redadmm/amp: out of scope)
+_pr_map = {'iadmm': IADMMSolver_PR}          # tasks/pr/solver.py:115-128
+_ct_map = {'iadmm': IADMMSolver_CT}          # tasks/ct/solver.py:90-103
+_spi_map = {'admm_spi': ADMMSolver_SPI}      # tasks/spi/solver.py:54-66
+
+
+def _create(opt, denoiser, table):
+    print(f'[i] use solver: {opt.solver}')
+    if opt.solver in table:
+        return table[opt.solver](denoiser)
+    raise NotImplementedError
+
+
+def create_solver_csmri(opt, denoiser):
+    return _create(opt, denoiser, _csmri_map)
+
+
+def create_solver_pr(opt, denoiser):
+    return _create(opt, denoiser, _pr_map)
+
+
+def create_solver_ct(opt, denoiser):
+    return _create(opt, denoiser, _ct_map)
+
+
+def create_solver_spi(opt, denoiser):
+    return _create(opt, denoiser, _spi_map)
