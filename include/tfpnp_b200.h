@@ -73,6 +73,14 @@ int tfpnp_denoiser_destroy(void* handle);
 int tfpnp_denoiser_forward(void* handle, const float* x, const float* sigma,
                            int64_t sigma_stride, float* out, int B, int H, int W, void* stream);
 
+/* One denoiser layer on its own (kernel-level parity tests): ConvLayer = nn.Conv2d(3x3, pad 1,
+ * bias) + LeakyReLU(0.2) (unet.py:8-22) over the channel concatenation of x0 [B,H,W,C0] and the
+ * optional x1 [B,H,W,C1] (torch.cat, unet.py:119), NHWC fp16 in/out, tcgen05 implicit GEMM.
+ * w_taps: fp16 [9][Cout][C0+C1] (tap = ky*3+kx); bias fp32 [Cout].  C0, C1 multiples of 32;
+ * Cout 32, 64 or a multiple of 128. */
+int tfpnp_conv3x3_nhwc(const void* x0, int C0, const void* x1, int C1, const void* w_taps,
+                       const float* bias, void* out, int B, int H, int W, int Cout, void* stream);
+
 /* ---- solver: PnPSolver.forward (tfpnp/pnp/solver/base.py:21-32) ------------ */
 
 typedef struct {

@@ -10,5 +10,5 @@ from .denoiser import UNetDenoiser2D, create_denoiser  # noqa: F401
 from .solver import (PnPSolver, ADMMSolver, IADMMSolver, ADMMSolver_CSMRI, IADMMSolver_PR,  # noqa: F401
                      IADMMSolver_CT, ADMMSolver_SPI, RadonGenerator, create_solver_csmri,
                      create_solver_pr, create_solver_ct, create_solver_spi)
-from .ops import radon_forward, radon_backward, torch_psnr  # noqa: F401
+from .ops import radon_forward, radon_backward, torch_psnr, conv3x3_lrelu_nhwc  # noqa: F401
 from .dist import shard_batch, shard_bounds, all_gather_psnr  # noqa: F401

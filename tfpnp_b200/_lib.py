@@ -32,6 +32,8 @@ SIGNATURES = {
     "tfpnp_denoiser_destroy": (C.c_int, [C.c_void_p]),
     "tfpnp_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tfpnp_conv3x3_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tfpnp_solver_create": (C.c_int, [C.POINTER(SolverConfig), C.c_void_p, C.POINTER(C.c_void_p)]),
     "tfpnp_solver_destroy": (C.c_int, [C.c_void_p]),
     "tfpnp_solver_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

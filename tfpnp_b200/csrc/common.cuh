@@ -110,5 +110,7 @@ struct Denoiser {
 
 Denoiser* make_unet_simt(const float* weights_host);                 // unet_simt.cu
 Denoiser* make_unet_tc(const float* weights_host, int precision);    // unet_tc.cu
+int conv3x3_nhwc(const void* x0, int C0, const void* x1, int C1, const void* w_taps, const float* bias,
+                 void* out, int B, int H, int W, int Cout, cudaStream_t st);   // unet_tc.cu
 
 }  // namespace tfpnp

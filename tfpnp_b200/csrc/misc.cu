@@ -61,6 +61,12 @@ int tfpnp_psnr(const float* out, const float* gt, float* psnr, int B, int64_t HW
   return 0;
 }
 
+int tfpnp_conv3x3_nhwc(const void* x0, int C0, const void* x1, int C1, const void* w_taps, const float* bias,
+                       void* out, int B, int H, int W, int Cout, void* stream) {
+  TFPNP_CHECK(x0 && w_taps && bias && out && B > 0, "bad argument");
+  return conv3x3_nhwc(x0, C0, x1, C1, w_taps, bias, out, B, H, W, Cout, static_cast<cudaStream_t>(stream));
+}
+
 int tfpnp_radon_forward(const float* img, float* sino, int B, int N, int views, const float* cos_host,
                         const float* sin_host, void* stream) {
   TFPNP_CHECK(img && sino && B > 0 && N > 0 && views > 0, "bad argument");

@@ -370,6 +370,34 @@ int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, con
   return 0;
 }
 
+int set_conv_attrs() {
+  static bool done = false;
+  if (done) return 0;
+  TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<32>::kSmemBytes));
+  TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
+  TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
+  done = true;
+  return 0;
+}
+
+int launch_conv_params(const ConvParams& p, int BN, cudaStream_t st) {
+  dim3 grid(p.tiles_w * p.tiles_h * cdiv(p.B, p.TB), p.Cout / BN);
+  switch (BN) {
+    case 32: conv3x3_tc<32><<<grid, kConvThreads, ConvCfg<32>::kSmemBytes, st>>>(p); break;
+    case 64: conv3x3_tc<64><<<grid, kConvThreads, ConvCfg<64>::kSmemBytes, st>>>(p); break;
+    case 128: conv3x3_tc<128><<<grid, kConvThreads, ConvCfg<128>::kSmemBytes, st>>>(p); break;
+    default: set_error("unsupported BN %d", BN); return TFPNP_ERR_INVALID;
+  }
+  TFPNP_COUNT_LAUNCH();
+  return 0;
+}
+
+void tile_geom(int H, int W, int& TW, int& TH, int& TB) {
+  TW = W < 8 ? W : 8;
+  TH = H < kTileM / TW ? H : kTileM / TW;
+  TB = kTileM / (TW * TH);
+}
+
 struct Act {            // NHWC fp16 activation tensor (hi plane, optional lo plane)
   __half* hi = nullptr;
   __half* lo = nullptr;
@@ -440,16 +468,7 @@ struct UNetTc : Denoiser {
       TFPNP_TRY(w_lo.alloc(total_w * sizeof(__half)));
       TFPNP_CUDA_OK(cudaMemcpy(w_lo.p, hlo.data(), total_w * sizeof(__half), cudaMemcpyHostToDevice));
     }
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<32>::kSmemBytes));
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
-    return 0;
-  }
-
-  static void tile_geom(int H, int W, int& TW, int& TH, int& TB) {
-    TW = W < 8 ? W : 8;
-    TH = H < kTileM / TW ? H : kTileM / TW;
-    TB = kTileM / (TW * TH);
+    return set_conv_attrs();
   }
 
   int make_act_maps(CUtensorMap (&maps)[2], const Act& a, int B, int kc, int TW, int TH, int TB) {
@@ -540,19 +559,7 @@ struct UNetTc : Denoiser {
     return 0;
   }
 
-  int launch_conv(int l, cudaStream_t st) {
-    const ConvParams& p = convs[l];
-    const int BN = conv_bn[l];
-    dim3 grid(p.tiles_w * p.tiles_h * cdiv(p.B, p.TB), p.Cout / BN);
-    switch (BN) {
-      case 32: conv3x3_tc<32><<<grid, kConvThreads, ConvCfg<32>::kSmemBytes, st>>>(p); break;
-      case 64: conv3x3_tc<64><<<grid, kConvThreads, ConvCfg<64>::kSmemBytes, st>>>(p); break;
-      case 128: conv3x3_tc<128><<<grid, kConvThreads, ConvCfg<128>::kSmemBytes, st>>>(p); break;
-      default: set_error("unsupported BN %d", BN); return TFPNP_ERR_INVALID;
-    }
-    TFPNP_COUNT_LAUNCH();
-    return 0;
-  }
+  int launch_conv(int l, cudaStream_t st) { return launch_conv_params(convs[l], conv_bn[l], st); }
 
   int forward(const float* x, const float* sigma, int64_t sstride, float* out, int B, int H, int W,
               cudaStream_t st) override {
@@ -595,7 +602,53 @@ struct UNetTc : Denoiser {
   }
 };
 
+// One 3x3 conv (pad 1) + bias + LeakyReLU(0.2) on NHWC fp16 tensors, FP16 mode: the kernel-level
+// entry point behind tfpnp_conv3x3_nhwc (per-kernel parity tests).
+int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, const __half* w_taps,
+                            const float* bias, __half* out, int B, int H, int W, int Cout, cudaStream_t st) {
+  TFPNP_CHECK(C0 > 0 && C0 % 32 == 0 && C1 % 32 == 0, "channel counts must be multiples of 32");
+  TFPNP_CHECK(Cout == 32 || Cout == 64 || Cout % 128 == 0, "Cout must be 32, 64 or a multiple of 128");
+  TFPNP_TRY(set_conv_attrs());
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  const int Cin = C0 + C1;
+  const int kc = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  const int BN = Cout >= 128 ? 128 : Cout;
+  p.kc = kc; p.nchunk0 = C0 / kc; p.nchunk1 = C1 / kc; p.nprod = 1;
+  tile_geom(H, W, p.TW, p.TH, p.TB);
+  TFPNP_CHECK(W % p.TW == 0 && H % p.TH == 0, "H, W must tile by %dx%d", p.TH, p.TW);
+  p.box_rows = p.TW * p.TH * (p.TB < B ? p.TB : B);
+  p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.bias = bias; p.out_hi = out; p.out_lo = nullptr;
+  const __half* srcs[2] = {x0, x1};
+  const int cs[2] = {C0, C1};
+  for (int s = 0; s < 2; ++s) {
+    if (!srcs[s]) { p.a_map[s][0] = p.a_map[0][0]; p.a_map[s][1] = p.a_map[0][0]; continue; }
+    cuuint64_t dims[4] = {(cuuint64_t)cs[s], (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)cs[s] * 2, (cuuint64_t)W * cs[s] * 2, (cuuint64_t)H * W * cs[s] * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)(p.TB < B ? p.TB : B)};
+    TFPNP_TRY(encode_map(&p.a_map[s][0], const_cast<__half*>(srcs[s]), 4, dims, strides, box, kc * 2));
+    p.a_map[s][1] = p.a_map[s][0];
+  }
+  cuuint64_t wd[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+  cuuint64_t ws[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
+  cuuint32_t wb[3] = {(cuuint32_t)kc, (cuuint32_t)BN, 1};
+  TFPNP_TRY(encode_map(&p.w_map[0], const_cast<__half*>(w_taps), 3, wd, ws, wb, kc * 2));
+  p.w_map[1] = p.w_map[0];
+  TFPNP_TRY(launch_conv_params(p, BN, st));
+  TFPNP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
+
+int conv3x3_nhwc(const void* x0, int C0, const void* x1, int C1, const void* w_taps, const float* bias,
+                 void* out, int B, int H, int W, int Cout, cudaStream_t st) {
+  return conv3x3_nhwc_standalone(static_cast<const __half*>(x0), C0, static_cast<const __half*>(x1), C1,
+                                 static_cast<const __half*>(w_taps), bias, static_cast<__half*>(out), B, H, W,
+                                 Cout, st);
+}
 
 Denoiser* make_unet_tc(const float* weights_host, int precision) {
   UNetTc* u = new UNetTc();

@@ -57,3 +57,21 @@ def torch_psnr(output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
         _lib.check(_lib.lib().tfpnp_psnr(o.data_ptr(), g.data_ptr(), res.data_ptr(), N, o.shape[1],
                                          torch.cuda.current_stream().cuda_stream), "tfpnp_psnr")
     return res.unsqueeze(1)
+
+
+def conv3x3_lrelu_nhwc(x0: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, x1: torch.Tensor = None):
+    """One UNet ConvLayer (unet.py:8-22) on the tensor cores: x0 [B,H,W,C0] (+ x1 [B,H,W,C1]) fp16 NHWC,
+    ``weight`` [Cout, C0+C1, 3, 3] fp32 (re-laid-out to [tap][Cout][Cin] fp16 here) -> [B,H,W,Cout] fp16."""
+    assert x0.is_cuda and x0.dtype == torch.float16 and x0.is_contiguous()
+    B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[-1]
+    Cout = weight.shape[0]
+    assert weight.shape[1] == C0 + C1
+    wt = weight.permute(2, 3, 0, 1).reshape(9, Cout, C0 + C1).to(torch.float16).contiguous().to(x0.device)
+    b = bias.float().contiguous().to(x0.device)
+    out = torch.empty(B, H, W, Cout, device=x0.device, dtype=torch.float16)
+    with torch.cuda.device(x0.device):
+        _lib.check(_lib.lib().tfpnp_conv3x3_nhwc(x0.data_ptr(), C0, x1.data_ptr() if x1 is not None else None, C1,
+                                                 wt.data_ptr(), b.data_ptr(), out.data_ptr(), B, H, W, Cout,
+                                                 torch.cuda.current_stream().cuda_stream), "tfpnp_conv3x3_nhwc")
+    return out
