@@ -129,6 +129,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= layout << 61;                                  // swizzle mode         bits [61,64)
   return d;
 }
+// general form: explicit 8-row-group stride (SBO) and swizzle-pattern phase (base offset).
+// Used by the halo-tile convolution, whose A descriptors start at arbitrary pixel rows of a
+// TMA-written (address-swizzled) halo tile and whose row groups are one halo row apart.
+__device__ __forceinline__ uint64_t make_smem_desc_ex(uint32_t smem_addr, uint32_t row_bytes, uint32_t sbo_bytes,
+                                                      uint32_t base_offset) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7) << 49;
+  d |= layout << 61;
+  return d;
+}
 // kind::f16, A/B = fp16 K-major, D = fp32, M = 128  (cute::UMMA::InstrDescriptor bit layout)
 __host__ __device__ inline uint32_t make_idesc_f16(int M, int N) {
   uint32_t d = 0;
