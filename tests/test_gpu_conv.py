@@ -26,6 +26,7 @@ CASES = [
     (64, 0, 64, 4, 4, 3),         # 4x4 level of a 64x64 image: 8 images per tile
     (512, 0, 512, 2, 2, 5),       # 2x2 level of a 32x32 image: 32 images per tile
     (512, 0, 512, 1, 1, 5),       # 1x1 level of a 16x16 image
+    (96, 0, 32, 32, 32, 2),       # three 32-channel chunks from one source
     (32, 0, 32, 128, 128, 4),     # 512 tiles > resident CTAs: persistent multi-tile loop, TMEM double buffer
     (64, 0, 64, 64, 64, 8),       # resident 72 KB weights, 1 CTA/SM
     (128, 0, 128, 32, 32, 6),     # streamed weights, multi-tile

@@ -180,58 +180,69 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
 }
 
 // ==========================================================================================
-// v2: persistent halo-tile convolution (used wherever the image tiles by 16 rows x 8 columns)
+// v2: persistent halo-tile convolution (used wherever the image tiles by 16 x 16 pixels)
 // ==========================================================================================
-// One CTA loops over output tiles of 16x8 pixels.  Per channel chunk it loads ONE halo box
-// {kc, 10, 18, 1} at (w0-1, h0-1) -- 180 pixel rows of kc*2 bytes, TMA-swizzled -- and all
-// nine taps read it through shifted UMMA descriptors: tap (ky,kx) starts at pixel row
-// ky*10 + kx and its sixteen 8-row groups are one halo row (10 pixels) apart (SBO).  The
-// activation traffic from L2 drops 9x -> 1.4x of the tile.  Weights are either RESIDENT in smem for
-// the whole kernel (small layers: 9*Cin*BN*2 bytes) or streamed per (chunk, tap) through a second
-// ring.  Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of
-// tile i+1; TMA runs ahead across tile boundaries.
-constexpr int kHaloW = 10, kHaloH = 18, kHaloRows = kHaloW * kHaloH;
+// One CTA loops over output SUPER-TILES of 16x16 pixels = two UMMA M-tiles (left / right 16x8
+// halves).  Per channel chunk it loads ONE halo box {KC, 18, 18, 1} at (w0-1, h0-1) -- 324 pixel
+// rows of KC*2 bytes, TMA-swizzled -- and all nine taps of both halves read it through shifted
+// UMMA descriptors: tap (ky,kx) of half h starts at pixel row ky*18 + kx + 8h and its sixteen
+// 8-row groups are one halo row (18 pixels) apart (SBO).  Activation traffic from L2 drops from
+// 9x to 1.27x of the tile, and every weight slab fetched feeds two M-tiles.  Weights are either
+// RESIDENT in smem for the whole kernel (small layers: 9*Cin*BN*2 bytes) or streamed per
+// (chunk, tap) through a deep second ring.  Accumulators are double-buffered in TMEM so the
+// epilogue of super-tile i overlaps the MMAs of i+1; TMA runs ahead across tile boundaries.
+// The single MMA-issuing thread only does 32-bit adds on precomputed descriptor words: the
+// descriptor high words are loop constants (an issue loop with per-MMA descriptor construction
+// measured ~300 clk/MMA, 10x the MMA itself).
+constexpr int kHaloW = 18, kHaloH = 18, kHaloRows = kHaloW * kHaloH;
 
 struct Conv2Params {
-  CUtensorMap a_map[2][2];  // [source][plane]  halo boxes {kc, 10, 18, 1}
-  CUtensorMap w_map[2];     // [plane]          {kc, BN, 1} over {Cin, Cout, 9}
-  int nchunk0, nchunk1, kc, nprod;
+  CUtensorMap a_map[2][2];  // [source][plane]  halo boxes {KC, 18, 18, 1}
+  CUtensorMap w_map[2];     // [plane]          {KC, BN, 1} over {Cin, Cout, 9}
+  int nchunk0, nchunk1, nprod;
   int tiles_w, tiles_h, num_m_tiles, num_n_tiles;
   int B, H, W, Cout;
   int a_stage_bytes, num_a_stages;   // A ring
   int b_stage_bytes, num_b_stages;   // B ring (streamed) -- or resident slab size, 0 stages
-  int desc_bo_mode;                  // 0: base_offset 0 (absolute-address swizzle); 1: (addr>>7)&7
   const float* bias;
   __half* out_hi;
   __half* out_lo;
 };
 
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;
 
-template <int BN, bool RESIDENT>
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+template <int BN, int KC, bool RESIDENT>
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t ROW = KC * 2;                 // bytes per pixel row of a chunk
+  constexpr int KSTEPS = KC / 16;
+  constexpr uint32_t SLAB = BN * ROW;              // one (tap, chunk) weight slab
   const int nchunks = p.nchunk0 + p.nchunk1;
   const int SA = p.num_a_stages, SB = p.num_b_stages;
   uint8_t* sA = smem;
   uint8_t* sW = smem + SA * p.a_stage_bytes;   // resident weights or the B ring
-  const int w_region = RESIDENT ? 9 * nchunks * p.b_stage_bytes : SB * p.b_stage_bytes;
+  const int w_region = RESIDENT ? 9 * nchunks * (int)SLAB : SB * (int)SLAB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + w_region);
   uint64_t* full_a = bars;
   uint64_t* empty_a = bars + kMaxStages;
   uint64_t* full_b = bars + 2 * kMaxStages;
   uint64_t* empty_b = bars + 3 * kMaxStages;
   uint64_t* w_full = bars + 4 * kMaxStages;
-  uint64_t* tmem_full = w_full + 1;    // [2]
+  uint64_t* tmem_full = w_full + 1;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
-  constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  const uint32_t row_bytes = p.kc * 2;
+  constexpr uint32_t kTmemCols = 4 * BN;           // 2 buffers x 2 M-tiles x BN (128..512, power of 2)
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.a_map[0][0]);
@@ -257,31 +268,33 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       if (RESIDENT) {
-        mbar_arrive_expect_tx(w_full, (uint32_t)(9 * nchunks) * BN * row_bytes);
+        mbar_arrive_expect_tx(w_full, (uint32_t)(9 * nchunks) * SLAB);
         for (int tap = 0; tap < 9; ++tap)
           for (int c = 0; c < nchunks; ++c)
-            tma_load_3d(sW + (tap * nchunks + c) * p.b_stage_bytes, &p.w_map[0], w_full, c * p.kc, 0, tap);
+            tma_load_3d(sW + (tap * nchunks + c) * SLAB, &p.w_map[0], w_full, c * KC, 0, tap);
       }
       uint32_t ia = 0, ib = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
-        const int w0 = (m % p.tiles_w) * 8, h0 = ((m / p.tiles_w) % p.tiles_h) * 16;
+        const int w0 = (m % p.tiles_w) * 16, h0 = ((m / p.tiles_w) % p.tiles_h) * 16;
         const int b = m / (p.tiles_w * p.tiles_h);
         for (int c = 0; c < nchunks; ++c) {
           const int src = c < p.nchunk0 ? 0 : 1;
-          const int cc = (src == 0 ? c : c - p.nchunk0) * p.kc;
+          const int cc = (src == 0 ? c : c - p.nchunk0) * KC;
           for (int prod = 0; prod < p.nprod; ++prod) {
             const int s = ia % SA;
             mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full_a[s], (uint32_t)kHaloRows * row_bytes);
+            mbar_arrive_expect_tx(&full_a[s], (uint32_t)kHaloRows * ROW);
             tma_load_4d(sA + s * p.a_stage_bytes, &p.a_map[src][prod == 1 ? 1 : 0], &full_a[s], cc, w0 - 1, h0 - 1, b);
             ++ia;
             if (!RESIDENT) {
+              const CUtensorMap* wm = &p.w_map[prod == 2 ? 1 : 0];
+#pragma unroll 1
               for (int tap = 0; tap < 9; ++tap) {
                 const int sb = ib % SB;
                 mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full_b[sb], (uint32_t)BN * row_bytes);
-                tma_load_3d(sW + sb * p.b_stage_bytes, &p.w_map[prod == 2 ? 1 : 0], &full_b[sb], c * p.kc, nt * BN, tap);
+                mbar_arrive_expect_tx(&full_b[sb], SLAB);
+                tma_load_3d(sW + sb * SLAB, wm, &full_b[sb], c * KC, nt * BN, tap);
                 ++ib;
               }
             }
@@ -293,49 +306,57 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = make_idesc_f16(kTileM, BN);
-      const int ksteps = p.kc / 16;
-      const uint32_t sbo_a = kHaloW * row_bytes;
+      // descriptor words: hi = {SBO, version, swizzle} is constant per operand; lo = addr>>4 | LBO
+      const uint32_t a_hi = (uint32_t)(make_smem_desc_ex(0, ROW, kHaloW * ROW, 0) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_smem_desc(0, ROW) >> 32);
+      const uint32_t lo_flags = 1u << 16;
+      const uint32_t sA_lo = (smem_u32(sA) >> 4) | lo_flags;
+      const uint32_t sW_lo = (smem_u32(sW) >> 4) | lo_flags;
+      const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4;
       if (RESIDENT) { mbar_wait(w_full, 0); tc_fence_after(); }
       uint32_t ia = 0, ib = 0, it = 0;
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;     // ring cursors (stage, phase)
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
+        const uint32_t d0 = tmem_base + buf * (2 * BN);   // left half; right half at +BN
         uint32_t accumulate = 0;
         for (int c = 0; c < nchunks; ++c) {
           for (int prod = 0; prod < p.nprod; ++prod) {
-            const int s = ia % SA;
-            mbar_wait(&full_a[s], (ia / SA) & 1);
+            mbar_wait(&full_a[sa], pha);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + s * p.a_stage_bytes);
+            const uint32_t a_lo = sA_lo + sa * a_stage16;
+#pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_addr = a_base + ((tap / 3) * kHaloW + tap % 3) * row_bytes;
-              uint32_t b_addr;
-              int sb = 0;
+              const uint32_t a_tap = a_lo + (((tap / 3) * kHaloW + tap % 3) * ROW >> 4);
+              uint32_t b_lo;
               if (RESIDENT) {
-                b_addr = smem_u32(sW + (tap * nchunks + c) * p.b_stage_bytes);
+                b_lo = sW_lo + (uint32_t)(tap * nchunks + c) * (SLAB >> 4);
               } else {
-                sb = ib % SB;
-                mbar_wait(&full_b[sb], (ib / SB) & 1);
+                mbar_wait(&full_b[sb], phb);
                 tc_fence_after();
-                b_addr = smem_u32(sW + sb * p.b_stage_bytes);
+                b_lo = sW_lo + sb * (SLAB >> 4);
               }
-              for (int kk = 0; kk < ksteps; ++kk) {
-                const uint32_t aa = a_addr + kk * 32;
-                const uint32_t bo = p.desc_bo_mode ? ((aa >> 7) & 7) : 0;
-                umma_f16(d_tmem, make_smem_desc_ex(aa, row_bytes, sbo_a, bo),
-                         make_smem_desc(b_addr + kk * 32, row_bytes), idesc, accumulate);
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
+                umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
+                umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
                 accumulate = 1;
               }
-              if (!RESIDENT) { umma_commit(&empty_b[sb]); ++ib; }
+              if (!RESIDENT) {
+                umma_commit(&empty_b[sb]);
+                if (++sb == (uint32_t)SB) { sb = 0; phb ^= 1; }
+              }
             }
-            umma_commit(&empty_a[s]);
-            ++ia;
+            umma_commit(&empty_a[sa]);
+            if (++sa == (uint32_t)SA) { sa = 0; pha ^= 1; }
           }
         }
         umma_commit(&tmem_full[buf]);
       }
+      (void)ia; (void)ib;
     }
   } else {
     // ---------------- epilogue ----------------
@@ -345,7 +366,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
-      const int w = (m % p.tiles_w) * 8 + tw, h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
+      const int w = (m % p.tiles_w) * 16 + tw, h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
       const int b = m / (p.tiles_w * p.tiles_h);
       const int n0 = nt * BN;
       const size_t pix = ((size_t)b * p.H + h) * p.W + w;
@@ -353,32 +374,43 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c0, r);
-        tmem_ld_wait();
-        uint32_t hi[16], lo[16];
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + half * BN + c0, r);
+          tmem_ld_wait();
+          uint32_t hi[16], lo[16];
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float v0 = __uint_as_float(r[j]) + __ldg(p.bias + n0 + c0 + j);
-          float v1 = __uint_as_float(r[j + 1]) + __ldg(p.bias + n0 + c0 + j + 1);
-          v0 = v0 > 0.f ? v0 : 0.2f * v0;
-          v1 = v1 > 0.f ? v1 : 0.2f * v1;
-          __half2 hh = __floats2half2_rn(v0, v1);
-          hi[j / 2] = *reinterpret_cast<uint32_t*>(&hh);
-          if (p.out_lo) {
-            float2 back = __half22float2(hh);
-            __half2 ll = __floats2half2_rn(v0 - back.x, v1 - back.y);
-            lo[j / 2] = *reinterpret_cast<uint32_t*>(&ll);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = __ldg(bp + j4);
+            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              const int j = j4 * 4 + e;
+              float v0 = __uint_as_float(r[j]) + bv[e];
+              float v1 = __uint_as_float(r[j + 1]) + bv[e + 1];
+              v0 = fmaxf(v0, 0.2f * v0);               // LeakyReLU(0.2)
+              v1 = fmaxf(v1, 0.2f * v1);
+              __half2 hh = __floats2half2_rn(v0, v1);
+              hi[j / 2] = *reinterpret_cast<uint32_t*>(&hh);
+              if (p.out_lo) {
+                float2 back = __half22float2(hh);
+                __half2 ll = __floats2half2_rn(v0 - back.x, v1 - back.y);
+                lo[j / 2] = *reinterpret_cast<uint32_t*>(&ll);
+              }
+            }
           }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + n0 + c0);
+          const size_t off = (pix + half * 8) * p.Cout + n0 + c0;
+          uint4* dst = reinterpret_cast<uint4*>(p.out_hi + off);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) dst[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-        if (p.out_lo) {
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + n0 + c0);
+          for (int v = 0; v < 4; ++v) dst[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+          if (p.out_lo) {
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) dl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+            for (int v = 0; v < 4; ++v) dl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+          }
         }
       }
       tc_fence_before();
@@ -596,6 +628,7 @@ int set_conv_attrs() {
 struct Conv2Plan {
   Conv2Params p;
   int BN = 0;
+  int kc = 0;
   bool resident = false;
   int smem_bytes = 0;
   int grid = 0;
@@ -606,32 +639,34 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <int BN, bool RES>
+template <int BN, int KC, bool RES>
 int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
-  static int attr_set = 0;
-  if (attr_set < c.smem_bytes) {
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = 227 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
   }
-  conv3x3_tc2<BN, RES><<<c.grid, kConvThreads, c.smem_bytes, st>>>(c.p);
+  conv3x3_tc2<BN, KC, RES><<<c.grid, kConvThreads, c.smem_bytes, st>>>(c.p);
   TFPNP_COUNT_LAUNCH();
   return 0;
 }
 
 int launch_conv2(const Conv2Plan& c, cudaStream_t st) {
-  if (c.resident) {
-    if (c.BN == 32) return launch_conv2_t<32, true>(c, st);
-    if (c.BN == 64) return launch_conv2_t<64, true>(c, st);
-  } else {
-    if (c.BN == 32) return launch_conv2_t<32, false>(c, st);
-    if (c.BN == 64) return launch_conv2_t<64, false>(c, st);
-    if (c.BN == 128) return launch_conv2_t<128, false>(c, st);
+  const int key = c.BN * 1000 + c.kc * 10 + (c.resident ? 1 : 0);
+  switch (key) {
+    case 32321: return launch_conv2_t<32, 32, true>(c, st);
+    case 64321: return launch_conv2_t<64, 32, true>(c, st);
+    case 64641: return launch_conv2_t<64, 64, true>(c, st);
+    case 32320: return launch_conv2_t<32, 32, false>(c, st);
+    case 64320: return launch_conv2_t<64, 32, false>(c, st);
+    case 64640: return launch_conv2_t<64, 64, false>(c, st);
+    case 128640: return launch_conv2_t<128, 64, false>(c, st);
   }
-  set_error("conv2: unsupported BN %d (resident %d)", c.BN, (int)c.resident);
+  set_error("conv2: unsupported BN %d KC %d (resident %d)", c.BN, c.kc, (int)c.resident);
   return TFPNP_ERR_INVALID;
 }
 
-bool conv2_eligible(int H, int W) { return env_int("TFPNP_CONV_V2", 1) != 0 && W % 8 == 0 && H % 16 == 0; }
+bool conv2_eligible(int H, int W) { return env_int("TFPNP_CONV_V2", 1) != 0 && W % 16 == 0 && H % 16 == 0; }
 
 int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                const cuuint32_t* box, int inner_bytes);
@@ -641,30 +676,41 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   Conv2Params& p = c.p;
   const int Cin = C0 + C1;
   const int kc = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  c.kc = kc;
   c.BN = Cout >= 128 ? 128 : Cout;
-  p.kc = kc; p.nchunk0 = C0 / kc; p.nchunk1 = C1 / kc; p.nprod = x3 ? 3 : 1;
-  p.tiles_w = W / 8; p.tiles_h = H / 16;
+  if (kc == 32 && c.BN == 128) c.BN = 64;                   // (not a UNet(2,1) shape; keeps the variant table small)
+  p.nchunk0 = C0 / kc; p.nchunk1 = C1 / kc; p.nprod = x3 ? 3 : 1;
+  p.tiles_w = W / 16; p.tiles_h = H / 16;
   p.num_m_tiles = p.tiles_w * p.tiles_h * B;
   p.num_n_tiles = Cout / c.BN;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
-  p.desc_bo_mode = env_int("TFPNP_DESC_BO", 0);
   const int row_bytes = kc * 2;
   p.a_stage_bytes = (kHaloRows * row_bytes + 1023) & ~1023;
   p.b_stage_bytes = c.BN * row_bytes;                       // multiple of 1024 for all (BN, kc) used
   const int w_bytes = 9 * (Cin / kc) * p.b_stage_bytes;
+  const int misc = 1024 + 1024;                             // alignment slack + barriers
   c.resident = !x3 && p.num_n_tiles == 1 && c.BN <= 64 && w_bytes <= 100 * 1024 &&
                env_int("TFPNP_CONV_RESIDENT", 1) != 0;
   if (c.resident) {
-    p.num_a_stages = 4; p.num_b_stages = 0;
-    c.smem_bytes = p.num_a_stages * p.a_stage_bytes + w_bytes + 1024 + 512;
+    p.num_b_stages = 0;
+    // 3 A stages if that lets two CTAs share an SM, else as many (<= 4) as fit one CTA
+    if (3 * p.a_stage_bytes + w_bytes + misc <= 112 * 1024) p.num_a_stages = 3;
+    else {
+      p.num_a_stages = 4;
+      while (p.num_a_stages > 2 && p.num_a_stages * p.a_stage_bytes + w_bytes + misc > 224 * 1024) --p.num_a_stages;
+    }
+    c.smem_bytes = p.num_a_stages * p.a_stage_bytes + w_bytes + misc;
   } else {
-    p.num_a_stages = 3; p.num_b_stages = 4;
-    c.smem_bytes = p.num_a_stages * p.a_stage_bytes + p.num_b_stages * p.b_stage_bytes + 1024 + 512;
+    p.num_a_stages = 2;
+    const int budget = 224 * 1024 - misc - p.num_a_stages * p.a_stage_bytes;
+    int sb = budget / p.b_stage_bytes;
+    p.num_b_stages = sb > kMaxStages ? kMaxStages : sb;
+    c.smem_bytes = p.num_a_stages * p.a_stage_bytes + p.num_b_stages * p.b_stage_bytes + misc;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int occ = c.smem_bytes <= 112 * 1024 ? 2 : 1;
+  const int occ = (c.smem_bytes <= 112 * 1024 && c.BN <= 64) ? 2 : 1;
   const int total = p.num_m_tiles * p.num_n_tiles;
   c.grid = total < sms * occ ? total : sms * occ;
   return 0;
@@ -792,15 +838,15 @@ struct UNetTc : Denoiser {
     const Act* srcs[2] = {&s0, s1};
     for (int s = 0; s < 2; ++s) {
       if (!srcs[s]) { p.a_map[s][0] = p.a_map[0][0]; p.a_map[s][1] = p.a_map[0][1]; continue; }
-      TFPNP_TRY(encode_halo_map(&p.a_map[s][0], srcs[s]->hi, srcs[s]->C, B, dst.H, dst.W, p.kc));
-      if (x3) TFPNP_TRY(encode_halo_map(&p.a_map[s][1], srcs[s]->lo, srcs[s]->C, B, dst.H, dst.W, p.kc));
+      TFPNP_TRY(encode_halo_map(&p.a_map[s][0], srcs[s]->hi, srcs[s]->C, B, dst.H, dst.W, c.kc));
+      if (x3) TFPNP_TRY(encode_halo_map(&p.a_map[s][1], srcs[s]->lo, srcs[s]->C, B, dst.H, dst.W, c.kc));
       else p.a_map[s][1] = p.a_map[s][0];
     }
     cuuint64_t wd[3] = {(cuuint64_t)sp.cin, (cuuint64_t)sp.cout, 9};
     cuuint64_t ws[2] = {(cuuint64_t)sp.cin * 2, (cuuint64_t)sp.cin * sp.cout * 2};
-    cuuint32_t wb[3] = {(cuuint32_t)p.kc, (cuuint32_t)c.BN, 1};
-    TFPNP_TRY(encode_map(&p.w_map[0], w_hi.as<__half>() + w_off[l], 3, wd, ws, wb, p.kc * 2));
-    if (x3) TFPNP_TRY(encode_map(&p.w_map[1], w_lo.as<__half>() + w_off[l], 3, wd, ws, wb, p.kc * 2));
+    cuuint32_t wb[3] = {(cuuint32_t)c.kc, (cuuint32_t)c.BN, 1};
+    TFPNP_TRY(encode_map(&p.w_map[0], w_hi.as<__half>() + w_off[l], 3, wd, ws, wb, c.kc * 2));
+    if (x3) TFPNP_TRY(encode_map(&p.w_map[1], w_lo.as<__half>() + w_off[l], 3, wd, ws, wb, c.kc * 2));
     else p.w_map[1] = p.w_map[0];
     return 0;
   }
@@ -945,15 +991,15 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
     TFPNP_TRY(plan_conv2_geometry(c, C0, C1, Cout, B, H, W, false));
     Conv2Params& q = c.p;
     q.bias = bias; q.out_hi = out; q.out_lo = nullptr;
-    TFPNP_TRY(encode_halo_map(&q.a_map[0][0], x0, C0, B, H, W, q.kc));
+    TFPNP_TRY(encode_halo_map(&q.a_map[0][0], x0, C0, B, H, W, c.kc));
     q.a_map[0][1] = q.a_map[0][0];
-    if (x1) TFPNP_TRY(encode_halo_map(&q.a_map[1][0], x1, C1, B, H, W, q.kc));
+    if (x1) TFPNP_TRY(encode_halo_map(&q.a_map[1][0], x1, C1, B, H, W, c.kc));
     else q.a_map[1][0] = q.a_map[0][0];
     q.a_map[1][1] = q.a_map[1][0];
     cuuint64_t wd2[3] = {(cuuint64_t)(C0 + C1), (cuuint64_t)Cout, 9};
     cuuint64_t ws2[2] = {(cuuint64_t)(C0 + C1) * 2, (cuuint64_t)(C0 + C1) * Cout * 2};
-    cuuint32_t wb2[3] = {(cuuint32_t)q.kc, (cuuint32_t)c.BN, 1};
-    TFPNP_TRY(encode_map(&q.w_map[0], const_cast<__half*>(w_taps), 3, wd2, ws2, wb2, q.kc * 2));
+    cuuint32_t wb2[3] = {(cuuint32_t)c.kc, (cuuint32_t)c.BN, 1};
+    TFPNP_TRY(encode_map(&q.w_map[0], const_cast<__half*>(w_taps), 3, wd2, ws2, wb2, c.kc * 2));
     q.w_map[1] = q.w_map[0];
     TFPNP_TRY(launch_conv2(c, st));
     TFPNP_CUDA_OK(cudaGetLastError());
