@@ -43,6 +43,53 @@ struct ConvParams {
   __half* out_lo;           // nullptr unless FP16X3
 };
 
+
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+// Epilogue of one 32-column slice of an accumulator row: + bias (from smem), LeakyReLU(0.2), pack to
+// fp16 (hi) and, in FP16X3 mode, the fp16 residual (lo); 64-byte NHWC stores per plane.
+__device__ __forceinline__ void epilogue_store32(const uint32_t (&r)[32], const float* __restrict__ sbias,
+                                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                 size_t off, bool store) {
+  float v[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 bb = *reinterpret_cast<const float4*>(sbias + 4 * j4);   // smem broadcast
+    v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + bb.x;
+    v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + bb.y;
+    v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + bb.z;
+    v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + bb.w;
+  }
+  uint32_t hi[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[2 * j] = fmaxf(v[2 * j], 0.2f * v[2 * j]);             // LeakyReLU(0.2), unet.py:22
+    v[2 * j + 1] = fmaxf(v[2 * j + 1], 0.2f * v[2 * j + 1]);
+    __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    hi[j] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  if (!store) return;
+  uint4* dst = reinterpret_cast<uint4*>(out_hi + off);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dst[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+  if (out_lo) {
+    uint32_t lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float2 back = __half22float2(*reinterpret_cast<__half2*>(&hi[j]));
+      __half2 ll = __floats2half2_rn(v[2 * j] - back.x, v[2 * j + 1] - back.y);
+      lo[j] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    uint4* dl = reinterpret_cast<uint4*>(out_lo + off);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+  }
+}
+
 template <int BN>
 struct ConvCfg {
   static constexpr int kStages = BN >= 128 ? 3 : 4;
@@ -50,7 +97,7 @@ struct ConvCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
 
 template <int BN>
@@ -64,6 +111,7 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
   uint64_t* empty = full + S;
   uint64_t* accum = empty + S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  float* sbias = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x;
@@ -85,6 +133,7 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) sbias[threadIdx.x - 64] = p.bias[n0 + threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -117,16 +166,17 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
       const uint32_t idesc = make_idesc_f16(kTileM, BN);
       const uint32_t row_bytes = p.kc * 2;
       const int ksteps = p.kc / 16;
+      const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, row_bytes) >> 32);
       for (int it = 0; it < kiters; ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t b_addr = a_addr + Cfg::kABytes;
+        const uint32_t a_lo = ((smem_u32(smem) + s * Cfg::kStageBytes) >> 4) | (1u << 16);
+        const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
         for (int kk = 0; kk < ksteps; ++kk) {
-          umma_f16(tmem_base, make_smem_desc(a_addr + kk * 32, row_bytes),
-                   make_smem_desc(b_addr + kk * 32, row_bytes), idesc, (it | kk) != 0);
+          umma_f16(tmem_base, pack_desc(a_lo + kk * 2, desc_hi), pack_desc(b_lo + kk * 2, desc_hi), idesc,
+                   (it | kk) != 0);
         }
         umma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
       }
@@ -147,31 +197,7 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
       tmem_ld_wait();
-      if (valid) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float v0 = __uint_as_float(r[j]) + __ldg(p.bias + n0 + c0 + j);
-          float v1 = __uint_as_float(r[j + 1]) + __ldg(p.bias + n0 + c0 + j + 1);
-          v0 = v0 > 0.f ? v0 : 0.2f * v0;   // LeakyReLU(0.2), unet.py:22
-          v1 = v1 > 0.f ? v1 : 0.2f * v1;
-          __half2 hh = __floats2half2_rn(v0, v1);
-          hi[j / 2] = *reinterpret_cast<uint32_t*>(&hh);
-          if (p.out_lo) {
-            float2 back = __half22float2(hh);
-            __half2 ll = __floats2half2_rn(v0 - back.x, v1 - back.y);
-            lo[j / 2] = *reinterpret_cast<uint32_t*>(&ll);
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + n0 + c0);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) dst[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-        if (p.out_lo) {
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + n0 + c0);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) dl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
-        }
-      }
+      epilogue_store32(r, sbias + c0, p.out_hi, p.out_lo, pix * p.Cout + n0 + c0, valid);
     }
   }
   tc_fence_before();
@@ -204,6 +230,9 @@ struct Conv2Params {
   int B, H, W, Cout;
   int a_stage_bytes, num_a_stages;   // A ring
   int b_stage_bytes, num_b_stages;   // B ring (streamed) -- or resident slab size, 0 stages
+  int dbg;                           // knock-out switches for bottleneck hunting (TFPNP_DBG): 1 = no stores,
+                                     // 2 = no MMA issue, 4 = no activation TMA, 8 = no weight TMA
+  unsigned long long* trace;         // optional [8][1024] globaltimer samples of CTA 0 (TFPNP_TRACE_FILE)
   const float* bias;
   __half* out_hi;
   __half* out_lo;
@@ -211,11 +240,15 @@ struct Conv2Params {
 
 constexpr int kMaxStages = 16;
 
-__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
-  uint64_t d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
-  return d;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
+#define TRACE(row, idx)                                                                         \
+  do {                                                                                          \
+    if (p.trace && blockIdx.x == 0 && (idx) < 1024) p.trace[(row) * 1024 + (idx)] = gtimer();  \
+  } while (0)
 
 template <int BN, int KC, bool RESIDENT>
 __global__ void __launch_bounds__(kConvThreads, 2)
@@ -239,6 +272,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   uint64_t* tmem_full = w_full + 1;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 8);   // [Cout] <= 512 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -259,6 +293,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  for (int i = threadIdx.x; i < p.Cout; i += kConvThreads) sbias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -284,8 +319,12 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
           for (int prod = 0; prod < p.nprod; ++prod) {
             const int s = ia % SA;
             mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full_a[s], (uint32_t)kHaloRows * ROW);
-            tma_load_4d(sA + s * p.a_stage_bytes, &p.a_map[src][prod == 1 ? 1 : 0], &full_a[s], cc, w0 - 1, h0 - 1, b);
+            TRACE(0, ia);
+            if (p.dbg & 4) mbar_arrive(&full_a[s]);
+            else {
+              mbar_arrive_expect_tx(&full_a[s], (uint32_t)kHaloRows * ROW);
+              tma_load_4d(sA + s * p.a_stage_bytes, &p.a_map[src][prod == 1 ? 1 : 0], &full_a[s], cc, w0 - 1, h0 - 1, b);
+            }
             ++ia;
             if (!RESIDENT) {
               const CUtensorMap* wm = &p.w_map[prod == 2 ? 1 : 0];
@@ -293,8 +332,11 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
               for (int tap = 0; tap < 9; ++tap) {
                 const int sb = ib % SB;
                 mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full_b[sb], SLAB);
-                tma_load_3d(sW + sb * SLAB, wm, &full_b[sb], c * KC, nt * BN, tap);
+                if (p.dbg & 8) mbar_arrive(&full_b[sb]);
+                else {
+                  mbar_arrive_expect_tx(&full_b[sb], SLAB);
+                  tma_load_3d(sW + sb * SLAB, wm, &full_b[sb], c * KC, nt * BN, tap);
+                }
                 ++ib;
               }
             }
@@ -318,14 +360,17 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;     // ring cursors (stage, phase)
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const uint32_t buf = it & 1;
+        TRACE(1, it);
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
+        TRACE(2, it);
         const uint32_t d0 = tmem_base + buf * (2 * BN);   // left half; right half at +BN
         uint32_t accumulate = 0;
         for (int c = 0; c < nchunks; ++c) {
           for (int prod = 0; prod < p.nprod; ++prod) {
             mbar_wait(&full_a[sa], pha);
             tc_fence_after();
+            TRACE(3, ia); ++ia;
             const uint32_t a_lo = sA_lo + sa * a_stage16;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
@@ -341,8 +386,10 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
 #pragma unroll
               for (int kk = 0; kk < KSTEPS; ++kk) {
                 const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
-                umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
-                umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
+                if (!(p.dbg & 2)) {
+                  umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
+                  umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
+                }
                 accumulate = 1;
               }
               if (!RESIDENT) {
@@ -355,6 +402,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
           }
         }
         umma_commit(&tmem_full[buf]);
+        TRACE(4, it);
       }
       (void)ia; (void)ib;
     }
@@ -371,8 +419,10 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       const int n0 = nt * BN;
       const size_t pix = ((size_t)b * p.H + h) * p.W + w;
       const uint32_t buf = it & 1;
+      if (warp == 2 && lane == 0) TRACE(5, it);
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) TRACE(6, it);
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
 #pragma unroll 1
@@ -380,42 +430,14 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + half * BN + c0, r);
           tmem_ld_wait();
-          uint32_t hi[16], lo[16];
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = __ldg(bp + j4);
-            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-            for (int e = 0; e < 4; e += 2) {
-              const int j = j4 * 4 + e;
-              float v0 = __uint_as_float(r[j]) + bv[e];
-              float v1 = __uint_as_float(r[j + 1]) + bv[e + 1];
-              v0 = fmaxf(v0, 0.2f * v0);               // LeakyReLU(0.2)
-              v1 = fmaxf(v1, 0.2f * v1);
-              __half2 hh = __floats2half2_rn(v0, v1);
-              hi[j / 2] = *reinterpret_cast<uint32_t*>(&hh);
-              if (p.out_lo) {
-                float2 back = __half22float2(hh);
-                __half2 ll = __floats2half2_rn(v0 - back.x, v1 - back.y);
-                lo[j / 2] = *reinterpret_cast<uint32_t*>(&ll);
-              }
-            }
-          }
-          const size_t off = (pix + half * 8) * p.Cout + n0 + c0;
-          uint4* dst = reinterpret_cast<uint4*>(p.out_hi + off);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) dst[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-          if (p.out_lo) {
-            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) dl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
-          }
+          epilogue_store32(r, sbias + n0 + c0, p.out_hi, p.out_lo, (pix + half * 8) * p.Cout + n0 + c0,
+                           !(p.dbg & 1));
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (warp == 2 && lane == 0) TRACE(7, it);
     }
   }
   tc_fence_before();
@@ -426,23 +448,17 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
 // ---- CUDA-core layers around the tensor-core convs ---------------------------------------
 
 // inc.conv-0: 3x3 conv over cat[d, sigma*ones] (2 ch, denoiser/base.py:29-30) -> 32 ch, fp32 FFMA
-// (K = 18: 0.2 % of the FLOPs), bias + LeakyReLU, NHWC fp16 out.
+// (K = 18: 0.2 % of the FLOPs), bias + LeakyReLU, NHWC fp16 out.  The 576 weights + 32 biases travel
+// as kernel parameters, so every FFMA takes its weight straight from the constant bank.
+struct FirstLayerW { float w[32 * 18]; float b[32]; };
+
 __global__ void __launch_bounds__(128)
 conv_first_kernel(const float* __restrict__ d, const float* __restrict__ sigma, int64_t sstride,
-                  const float* __restrict__ w /*[32][2][9]*/, const float* __restrict__ bias,
-                  __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W) {
-  __shared__ float sw[18][32];
-  __shared__ float sb[32];
-  for (int i = threadIdx.x; i < 576; i += blockDim.x) {
-    int co = i / 18, k = i % 18;
-    sw[k][co] = w[i];
-  }
-  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int b = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= H * W) return;
-  const int y = p / W, x = p % W;
+                  const __grid_constant__ FirstLayerW wb, __half* __restrict__ out_hi,
+                  __half* __restrict__ out_lo, int H, int W) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
   const float sg = sigma[b * sstride];
   float in[18];
 #pragma unroll
@@ -458,14 +474,14 @@ conv_first_kernel(const float* __restrict__ d, const float* __restrict__ sigma, 
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-      float a0 = sb[c0 + j], a1 = sb[c0 + j + 1];
+      float a0 = wb.b[c0 + j], a1 = wb.b[c0 + j + 1];
 #pragma unroll
       for (int k = 0; k < 18; ++k) {
-        a0 = fmaf(sw[k][c0 + j], in[k], a0);
-        a1 = fmaf(sw[k][c0 + j + 1], in[k], a1);
+        a0 = fmaf(wb.w[(c0 + j) * 18 + k], in[k], a0);
+        a1 = fmaf(wb.w[(c0 + j + 1) * 18 + k], in[k], a1);
       }
-      a0 = a0 > 0.f ? a0 : 0.2f * a0;
-      a1 = a1 > 0.f ? a1 : 0.2f * a1;
+      a0 = fmaxf(a0, 0.2f * a0);
+      a1 = fmaxf(a1, 0.2f * a1);
       __half2 hh = __floats2half2_rn(a0, a1);
       hi[j / 2] = *reinterpret_cast<uint32_t*>(&hh);
       float2 back = __half22float2(hh);
@@ -501,19 +517,17 @@ __device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const
   if (lo) *reinterpret_cast<H8*>(lo + off) = l;
 }
 
-// nn.MaxPool2d(2) (unet.py:83), NHWC, 8 channels per thread
-__global__ void maxpool2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
-                              __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B, int H, int W,
-                              int C) {
+// nn.MaxPool2d(2) (unet.py:83), NHWC, 8 channels per thread; grid (x*C8 blocks, Ho, B)
+__global__ void __launch_bounds__(256)
+maxpool2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, __half* __restrict__ out_hi,
+              __half* __restrict__ out_lo, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * Ho * Wo * C8) return;
-  int c8 = i % C8;
-  size_t pix = i / C8;
-  int x = pix % Wo, y = (pix / Wo) % Ho;
-  size_t b = pix / ((size_t)Wo * Ho);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Wo * C8) return;
+  const int c8 = idx % C8, x = idx / C8, y = blockIdx.y;
+  const size_t b = blockIdx.z;
   float m[8], t[8];
-  size_t base = ((b * H + 2 * y) * W + 2 * x) * C + c8 * 8;
+  const size_t base = ((b * H + 2 * y) * W + 2 * x) * C + c8 * 8;
   load8(in_hi, in_lo, base, m);
   load8(in_hi, in_lo, base + C, t);
 #pragma unroll
@@ -524,27 +538,26 @@ __global__ void maxpool2_nhwc(const __half* __restrict__ in_hi, const __half* __
   load8(in_hi, in_lo, base + (size_t)W * C + C, t);
 #pragma unroll
   for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], t[k]);
-  store8(out_hi, out_lo, pix * C + c8 * 8, m);
+  store8(out_hi, out_lo, ((b * Ho + y) * Wo + x) * C + c8 * 8, m);
 }
 
-// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet.py:99), NHWC
-__global__ void upsample2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
-                               __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B, int H, int W,
-                               int C) {
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet.py:99), NHWC;
+// grid (x*C8 blocks, Ho, B): the row interpolation set-up is per block row, not per thread
+__global__ void __launch_bounds__(256)
+upsample2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, __half* __restrict__ out_hi,
+               __half* __restrict__ out_lo, int H, int W, int C) {
   const int Ho = 2 * H, Wo = 2 * W, C8 = C / 8;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * Ho * Wo * C8) return;
-  int c8 = i % C8;
-  size_t pix = i / C8;
-  int x = pix % Wo, y = (pix / Wo) % Ho;
-  size_t b = pix / ((size_t)Wo * Ho);
-  float sy = (float)(H - 1) / (float)(Ho - 1), sx = (float)(W - 1) / (float)(Wo - 1);
-  float fy = sy * y, fx = sx * x;
-  int y0 = (int)fy, x0 = (int)fx;
-  int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
-  float ly = fy - y0, lx = fx - x0;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Wo * C8) return;
+  const int c8 = idx % C8, x = idx / C8, y = blockIdx.y;
+  const size_t b = blockIdx.z;
+  const float sy = (float)(H - 1) / (float)(Ho - 1), sx = (float)(W - 1) / (float)(Wo - 1);
+  const float fy = sy * y, fx = sx * x;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0;
   float v00[8], v01[8], v10[8], v11[8], r[8];
-  size_t ib = b * H * W;
+  const size_t ib = b * H * W;
   load8(in_hi, in_lo, ((ib + (size_t)y0 * W + x0) * C) + c8 * 8, v00);
   load8(in_hi, in_lo, ((ib + (size_t)y0 * W + x1) * C) + c8 * 8, v01);
   load8(in_hi, in_lo, ((ib + (size_t)y1 * W + x0) * C) + c8 * 8, v10);
@@ -555,7 +568,7 @@ __global__ void upsample2_nhwc(const __half* __restrict__ in_hi, const __half* _
     float bot = (1.f - lx) * v10[k] + lx * v11[k];
     r[k] = (1.f - ly) * top + ly * bot;
   }
-  store8(out_hi, out_lo, pix * C + c8 * 8, r);
+  store8(out_hi, out_lo, ((b * Ho + y) * Wo + x) * C + c8 * 8, r);
 }
 
 // outconv 1x1 32->1 (unet.py:124-131) + residual (unet.py:65-66) + clamp (denoiser/base.py:32)
@@ -684,11 +697,12 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   p.num_m_tiles = p.tiles_w * p.tiles_h * B;
   p.num_n_tiles = Cout / c.BN;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.dbg = env_int("TFPNP_DBG", 0);
   const int row_bytes = kc * 2;
   p.a_stage_bytes = (kHaloRows * row_bytes + 1023) & ~1023;
   p.b_stage_bytes = c.BN * row_bytes;                       // multiple of 1024 for all (BN, kc) used
   const int w_bytes = 9 * (Cin / kc) * p.b_stage_bytes;
-  const int misc = 1024 + 1024;                             // alignment slack + barriers
+  const int misc = 1024 + 1024 + 2048;                      // alignment slack + barriers + bias[<=512]
   c.resident = !x3 && p.num_n_tiles == 1 && c.BN <= 64 && w_bytes <= 100 * 1024 &&
                env_int("TFPNP_CONV_RESIDENT", 1) != 0;
   if (c.resident) {
@@ -750,7 +764,8 @@ struct Act {            // NHWC fp16 activation tensor (hi plane, optional lo pl
 struct UNetTc : Denoiser {
   bool x3 = false;
   // weights
-  DevBuf w_first, w_hi, w_lo, biases, w_out;
+  DevBuf w_hi, w_lo, biases, w_out;
+  FirstLayerW first_w;          // inc.conv-0 weights [32][2*9] + bias, passed by value
   size_t w_off[kNumUnetConv3];   // element offset of layer l in w_hi / w_lo ([9][Cout][Cin])
   size_t b_off[kNumUnetConv3];
   // plan for one (B,H,W)
@@ -768,7 +783,6 @@ struct UNetTc : Denoiser {
     for (int l = 0; l < kNumUnetConv3; ++l) { total_b += sp[l].cout; if (l) total_w += (size_t)9 * sp[l].cout * sp[l].cin; }
     std::vector<float> hb(total_b);
     std::vector<__half> hhi(total_w), hlo(total_w);
-    std::vector<float> hfirst(576);
     for (int l = 0; l < kNumUnetConv3; ++l) {
       const int ci = sp[l].cin, co = sp[l].cout;
       const float* w = host + off;
@@ -779,7 +793,8 @@ struct UNetTc : Denoiser {
       for (int i = 0; i < co; ++i) hb[boff + i] = b[i];
       boff += co;
       if (l == 0) {
-        for (int i = 0; i < 576; ++i) hfirst[i] = w[i];   // [32][2][9]
+        for (int i = 0; i < 576; ++i) first_w.w[i] = w[i];   // [32][2][9]
+        for (int i = 0; i < 32; ++i) first_w.b[i] = b[i];
         w_off[l] = 0;
         continue;
       }
@@ -800,11 +815,9 @@ struct UNetTc : Denoiser {
     for (int i = 0; i < 33; ++i) hout[i] = host[off + i];
     off += 33;
     if (off != kUnetParamCount) { set_error("unet param table mismatch"); return TFPNP_ERR_INVALID; }
-    TFPNP_TRY(w_first.alloc(576 * sizeof(float)));
     TFPNP_TRY(biases.alloc(total_b * sizeof(float)));
     TFPNP_TRY(w_out.alloc(33 * sizeof(float)));
     TFPNP_TRY(w_hi.alloc(total_w * sizeof(__half)));
-    TFPNP_CUDA_OK(cudaMemcpy(w_first.p, hfirst.data(), 576 * sizeof(float), cudaMemcpyHostToDevice));
     TFPNP_CUDA_OK(cudaMemcpy(biases.p, hb.data(), total_b * sizeof(float), cudaMemcpyHostToDevice));
     TFPNP_CUDA_OK(cudaMemcpy(w_out.p, hout.data(), 33 * sizeof(float), cudaMemcpyHostToDevice));
     TFPNP_CUDA_OK(cudaMemcpy(w_hi.p, hhi.data(), total_w * sizeof(__half), cudaMemcpyHostToDevice));
@@ -942,26 +955,23 @@ struct UNetTc : Denoiser {
     TFPNP_CHECK(B == pB && H == pH && W == pW, "prepare(%d,%d,%d) not called (plan is %d,%d,%d)", B, H, W, pB, pH, pW);
     const int ch[5] = {32, 64, 128, 256, 512};
     const int T = 256;
-    conv_first_kernel<<<dim3(cdiv(H * W, 128), B), 128, 0, st>>>(x, sigma, sstride, w_first.as<float>(),
-                                                                biases.as<float>() + b_off[0], S0.hi,
-                                                                x3 ? S0.lo : nullptr, H, W);
+    conv_first_kernel<<<dim3(cdiv(W, 128), H, B), 128, 0, st>>>(x, sigma, sstride, first_w, S0.hi,
+                                                               x3 ? S0.lo : nullptr, H, W);
     TFPNP_COUNT_LAUNCH();
     TFPNP_TRY(launch_conv(1, st));
     TFPNP_TRY(launch_conv(2, st));
     for (int lv = 1; lv <= 4; ++lv) {
       int h = H >> lv, w = W >> lv;
-      size_t n = (size_t)B * h * w * (ch[lv - 1] / 8);
-      maxpool2_nhwc<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(skip[lv - 1].hi, skip[lv - 1].lo, S0.hi, S0.lo, B,
-                                                                2 * h, 2 * w, ch[lv - 1]);
+      maxpool2_nhwc<<<dim3(cdiv(w * (ch[lv - 1] / 8), T), h, B), T, 0, st>>>(skip[lv - 1].hi, skip[lv - 1].lo, S0.hi,
+                                                                              S0.lo, 2 * h, 2 * w, ch[lv - 1]);
       TFPNP_COUNT_LAUNCH();
       for (int k = 0; k < 3; ++k) TFPNP_TRY(launch_conv(3 * lv + k, st));
     }
     for (int k = 0; k < 4; ++k) {
       int lv = 3 - k, h = H >> lv, w = W >> lv;
       const Act& src = k == 0 ? skip[4] : S2;
-      size_t n = (size_t)B * h * w * (ch[lv + 1] / 8);
-      upsample2_nhwc<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(src.hi, src.lo, S0.hi, S0.lo, B, h / 2, w / 2,
-                                                                 ch[lv + 1]);
+      upsample2_nhwc<<<dim3(cdiv(w * (ch[lv + 1] / 8), T), h, B), T, 0, st>>>(src.hi, src.lo, S0.hi, S0.lo, h / 2,
+                                                                               w / 2, ch[lv + 1]);
       TFPNP_COUNT_LAUNCH();
       for (int j = 0; j < 3; ++j) TFPNP_TRY(launch_conv(15 + 3 * k + j, st));
     }
@@ -974,7 +984,7 @@ struct UNetTc : Denoiser {
   }
 
   ~UNetTc() override {
-    w_first.release(); w_hi.release(); w_lo.release(); biases.release(); w_out.release(); act.release();
+    w_hi.release(); w_lo.release(); biases.release(); w_out.release(); act.release();
   }
 };
 
@@ -1001,8 +1011,23 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
     cuuint32_t wb2[3] = {(cuuint32_t)c.kc, (cuuint32_t)c.BN, 1};
     TFPNP_TRY(encode_map(&q.w_map[0], const_cast<__half*>(w_taps), 3, wd2, ws2, wb2, c.kc * 2));
     q.w_map[1] = q.w_map[0];
+    const char* tf = getenv("TFPNP_TRACE_FILE");
+    unsigned long long* dtrace = nullptr;
+    if (tf) {
+      TFPNP_CUDA_OK(cudaMalloc(&dtrace, 8 * 1024 * 8));
+      TFPNP_CUDA_OK(cudaMemset(dtrace, 0, 8 * 1024 * 8));
+      q.trace = dtrace;
+    }
     TFPNP_TRY(launch_conv2(c, st));
     TFPNP_CUDA_OK(cudaGetLastError());
+    if (tf) {
+      std::vector<unsigned long long> h(8 * 1024);
+      TFPNP_CUDA_OK(cudaStreamSynchronize(st));
+      TFPNP_CUDA_OK(cudaMemcpy(h.data(), dtrace, h.size() * 8, cudaMemcpyDeviceToHost));
+      cudaFree(dtrace);
+      FILE* f = fopen(tf, "wb");
+      if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    }
     return 0;
   }
   ConvParams p;
