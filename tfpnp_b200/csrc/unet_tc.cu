@@ -161,8 +161,8 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+    {
+      // ---------------- MMA issuer (whole warp converged; one elected lane issues) ----------------
       const uint32_t idesc = make_idesc_f16(kTileM, BN);
       const uint32_t row_bytes = p.kc * 2;
       const int ksteps = p.kc / 16;
@@ -174,13 +174,17 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
         tc_fence_after();
         const uint32_t a_lo = ((smem_u32(smem) + s * Cfg::kStageBytes) >> 4) | (1u << 16);
         const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
-        for (int kk = 0; kk < ksteps; ++kk) {
-          umma_f16(tmem_base, pack_desc(a_lo + kk * 2, desc_hi), pack_desc(b_lo + kk * 2, desc_hi), idesc,
-                   (it | kk) != 0);
+        if (elect_one()) {
+          for (int kk = 0; kk < ksteps; ++kk) {
+            umma_f16(tmem_base, pack_desc(a_lo + kk * 2, desc_hi), pack_desc(b_lo + kk * 2, desc_hi), idesc,
+                     (it | kk) != 0);
+          }
+          umma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
+        __syncwarp();
       }
-      umma_commit(accum);          // accumulator complete
+      if (elect_one()) umma_commit(accum);          // accumulator complete
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue: TMEM -> bias -> LeakyReLU -> fp16 NHWC ----------------
@@ -276,6 +280,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  if (threadIdx.x == 0) TRACE(0, 1000);
   constexpr uint32_t kTmemCols = 4 * BN;           // 2 buffers x 2 M-tiles x BN (128..512, power of 2)
 
   if (warp == 0 && lane == 0) {
@@ -294,10 +299,12 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
   for (int i = threadIdx.x; i < p.Cout; i += kConvThreads) sbias[i] = p.bias[i];
+  if (threadIdx.x == 64) TRACE(0, 1001);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TRACE(0, 1002);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -345,8 +352,8 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+    {
+      // ---------------- MMA issuer (whole warp converged; one elected lane issues) ----------------
       const uint32_t idesc = make_idesc_f16(kTileM, BN);
       // descriptor words: hi = {SBO, version, swizzle} is constant per operand; lo = addr>>4 | LBO
       const uint32_t a_hi = (uint32_t)(make_smem_desc_ex(0, ROW, kHaloW * ROW, 0) >> 32);
@@ -360,49 +367,68 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;     // ring cursors (stage, phase)
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const uint32_t buf = it & 1;
-        TRACE(1, it);
+        if (lane == 0) TRACE(1, it);
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        TRACE(2, it);
+        if (lane == 0) TRACE(2, it);
         const uint32_t d0 = tmem_base + buf * (2 * BN);   // left half; right half at +BN
         uint32_t accumulate = 0;
         for (int c = 0; c < nchunks; ++c) {
           for (int prod = 0; prod < p.nprod; ++prod) {
             mbar_wait(&full_a[sa], pha);
             tc_fence_after();
-            TRACE(3, ia); ++ia;
+            if (lane == 0) TRACE(3, ia);
+            ++ia;
             const uint32_t a_lo = sA_lo + sa * a_stage16;
+            if (RESIDENT) {
+              if (!(p.dbg & 2) && elect_one()) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_tap = a_lo + (((tap / 3) * kHaloW + tap % 3) * ROW >> 4);
-              uint32_t b_lo;
-              if (RESIDENT) {
-                b_lo = sW_lo + (uint32_t)(tap * nchunks + c) * (SLAB >> 4);
-              } else {
+                for (int tap = 0; tap < 9; ++tap) {
+                  const uint32_t a_tap = a_lo + (((tap / 3) * kHaloW + tap % 3) * ROW >> 4);
+                  const uint32_t b_lo = sW_lo + (uint32_t)(tap * nchunks + c) * (SLAB >> 4);
+#pragma unroll
+                  for (int kk = 0; kk < KSTEPS; ++kk) {
+                    const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
+                    umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
+                    umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
+                    accumulate = 1;
+                  }
+                }
+              }
+              accumulate = 1;
+              __syncwarp();
+            } else {
+#pragma unroll 1
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t a_tap = a_lo + (((tap / 3) * kHaloW + tap % 3) * ROW >> 4);
                 mbar_wait(&full_b[sb], phb);
                 tc_fence_after();
-                b_lo = sW_lo + sb * (SLAB >> 4);
-              }
+                const uint32_t b_lo = sW_lo + sb * (SLAB >> 4);
+                if (elect_one()) {
+                  if (!(p.dbg & 2)) {
 #pragma unroll
-              for (int kk = 0; kk < KSTEPS; ++kk) {
-                const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
-                if (!(p.dbg & 2)) {
-                  umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
-                  umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
+                    for (int kk = 0; kk < KSTEPS; ++kk) {
+                      const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
+                      umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
+                      umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
+                      accumulate = 1;
+                    }
+                  }
+                  umma_commit(&empty_b[sb]);
                 }
                 accumulate = 1;
-              }
-              if (!RESIDENT) {
-                umma_commit(&empty_b[sb]);
+                __syncwarp();
                 if (++sb == (uint32_t)SB) { sb = 0; phb ^= 1; }
               }
             }
-            umma_commit(&empty_a[sa]);
+            if (elect_one()) umma_commit(&empty_a[sa]);
+            __syncwarp();
             if (++sa == (uint32_t)SA) { sa = 0; pha ^= 1; }
           }
         }
-        umma_commit(&tmem_full[buf]);
-        TRACE(4, it);
+        if (elect_one()) umma_commit(&tmem_full[buf]);
+        __syncwarp();
+        if (lane == 0) TRACE(4, it);
       }
       (void)ia; (void)ib;
     }
@@ -440,9 +466,12 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       if (warp == 2 && lane == 0) TRACE(7, it);
     }
   }
+  if (lane == 0) TRACE(0, 1010 + warp);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TRACE(0, 1003);
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (threadIdx.x == 64) TRACE(0, 1004);
 }
 
 // ---- CUDA-core layers around the tensor-core convs ---------------------------------------

@@ -32,10 +32,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         torch.cuda.synchronize()
         t = sorted(a.elapsed_time(e) for a, e in evs)[len(evs) // 2] * 1e3
         gf = 2 * 9 * (C0 + C1) * Cout * H * W * B / 1e9
-        res[f"{C0}+{C1}->{Cout}@{H}"] = (round(t, 1), round(gf / t * 1e3 / 1e3, 1))
+        res[f"{C0}+{C1}->{Cout}@{H}"] = (round(t, 1), round(gf / t / 1e3, 1))
     print(json.dumps(res))
 else:
-    for dbg in [0, 1, 2, 3, 4, 8, 12, 6, 14, 15]:
+    for dbg in [0, 1, 2, 16, 3, 4, 15]:
         env = dict(os.environ, TFPNP_DBG=str(dbg))
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
         line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:]

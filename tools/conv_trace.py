@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch, tfpnp_b200 as T
 dev = torch.device("cuda:0")
 names = ["P: A slot free", "M: tile start", "M: tmem free", "M: A landed", "M: tile issued", "E: tile wait", "E: accum ready", "E: tile done"]
-for (C0, C1, Cout, H, W, B) in [(32, 0, 32, 128, 128, 48), (64, 0, 64, 64, 64, 48), (128, 0, 128, 32, 32, 48)]:
+for (C0, C1, Cout, H, W, B) in [(32, 0, 32, 128, 128, 48), (64, 0, 64, 64, 64, 48), (256, 0, 256, 16, 16, 48)]:
     x0 = torch.randn(B, H, W, C0, device=dev).half()
     w = torch.randn(Cout, C0 + C1, 3, 3) * 0.05
     b = torch.zeros(Cout)
@@ -19,6 +19,9 @@ for (C0, C1, Cout, H, W, B) in [(32, 0, 32, 128, 128, 48), (64, 0, 64, 64, 64, 4
     del os.environ["TFPNP_TRACE_FILE"]
     tr = np.fromfile("/tmp/trace.bin", dtype=np.uint64).reshape(8, 1024).astype(np.int64)
     t0 = tr[tr > 0].min()
+    extra = tr[0, 1000:1016].copy(); tr[0, 1000:] = 0
+    print("  kernel entry, prologue pre-sync, post-sync, post-final-sync, post-dealloc:", [int(x - t0) if x else None for x in extra[:5]],
+          " role loops done (warps 0..5):", [int(x - t0) if x else None for x in extra[10:16]])
     print(f"=== {C0}->{Cout} @{H}x{W} B={B}  (ns since first sample; first 8 tiles and last 2)")
     for r in range(8):
         row = tr[r][tr[r] > 0] - t0
