@@ -234,6 +234,7 @@ struct Conv2Params {
   int B, H, W, Cout;
   int a_stage_bytes, num_a_stages;   // A ring
   int b_stage_bytes, num_b_stages;   // B ring (streamed) -- or resident slab size, 0 stages
+  int cluster;                       // CTAs per cluster sharing each streamed weight slab via TMA multicast (1, 2, 4)
   int dbg;                           // knock-out switches for bottleneck hunting (TFPNP_DBG): 1 = no stores,
                                      // 2 = no MMA issue, 4 = no activation TMA, 8 = no weight TMA
   unsigned long long* trace;         // optional [8][1024] globaltimer samples of CTA 0 (TFPNP_TRACE_FILE)
@@ -266,7 +267,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   const int SA = p.num_a_stages, SB = p.num_b_stages;
   uint8_t* sA = smem;
   uint8_t* sW = smem + SA * p.a_stage_bytes;   // resident weights or the B ring
-  const int w_region = RESIDENT ? 9 * nchunks * (int)SLAB : SB * (int)SLAB;
+  const int w_region = RESIDENT ? 9 * nchunks * (int)SLAB : SB * 3 * (int)SLAB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + w_region);
   uint64_t* full_a = bars;
   uint64_t* empty_a = bars + kMaxStages;
@@ -279,9 +280,15 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   float* sbias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 8);   // [Cout] <= 512 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   if (threadIdx.x == 0) TRACE(0, 1000);
-  constexpr uint32_t kTmemCols = 4 * BN;           // 2 buffers x 2 M-tiles x BN (128..512, power of 2)
+  constexpr uint32_t kTmemCols = 4 * BN;
+  // work items: (group of `cs` consecutive super-tiles, n-tile); CTA `crank` of a cluster takes
+  // super-tile g*cs + crank, all CTAs of the cluster walk the same (n-tile, chunk, tap) sequence
+  const int cs = RESIDENT ? 1 : p.cluster;
+  const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1);
+  const int total_items = ((p.num_m_tiles + cs - 1) / cs) * p.num_n_tiles;
+  const int item0 = blockIdx.x / cs, item_step = gridDim.x / cs;           // 2 buffers x 2 M-tiles x BN (128..512, power of 2)
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.a_map[0][0]);
@@ -291,7 +298,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1);
-      mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1);
+      mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], cs);   // a weight slot is free when ALL cluster CTAs released it
     }
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
@@ -303,6 +310,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TRACE(0, 1002);
 
@@ -316,8 +324,11 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
             tma_load_3d(sW + (tap * nchunks + c) * SLAB, &p.w_map[0], w_full, c * KC, 0, tap);
       }
       uint32_t ia = 0, ib = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
+      const int rows_mc = BN / cs;   // weight-slab rows this CTA fetches (and multicasts)
+      for (int t = item0; t < total_items; t += item_step) {
+        const int nt = t % p.num_n_tiles;
+        int m = (t / p.num_n_tiles) * cs + crank;
+        if (m >= p.num_m_tiles) m = p.num_m_tiles - 1;      // padding CTA: recompute the last tile, stores masked
         const int w0 = (m % p.tiles_w) * 16, h0 = ((m / p.tiles_w) % p.tiles_h) * 16;
         const int b = m / (p.tiles_w * p.tiles_h);
         for (int c = 0; c < nchunks; ++c) {
@@ -336,13 +347,19 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
             if (!RESIDENT) {
               const CUtensorMap* wm = &p.w_map[prod == 2 ? 1 : 0];
 #pragma unroll 1
-              for (int tap = 0; tap < 9; ++tap) {
+              for (int tg = 0; tg < 3; ++tg) {           // one ring stage = the 3 taps of a kernel row
                 const int sb = ib % SB;
                 mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
                 if (p.dbg & 8) mbar_arrive(&full_b[sb]);
                 else {
-                  mbar_arrive_expect_tx(&full_b[sb], SLAB);
-                  tma_load_3d(sW + sb * SLAB, wm, &full_b[sb], c * KC, nt * BN, tap);
+                  mbar_arrive_expect_tx(&full_b[sb], 3 * SLAB);
+#pragma unroll
+                  for (int tt = 0; tt < 3; ++tt) {
+                    uint8_t* dst = sW + sb * (3 * SLAB) + tt * SLAB;
+                    if (cs == 1) tma_load_3d(dst, wm, &full_b[sb], c * KC, nt * BN, tg * 3 + tt);
+                    else tma_load_3d_mc(dst + crank * rows_mc * ROW, wm, &full_b[sb], cmask, c * KC,
+                                        nt * BN + crank * rows_mc, tg * 3 + tt);
+                  }
                 }
                 ++ib;
               }
@@ -365,7 +382,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       if (RESIDENT) { mbar_wait(w_full, 0); tc_fence_after(); }
       uint32_t ia = 0, ib = 0, it = 0;
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;     // ring cursors (stage, phase)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = item0; t < total_items; t += item_step, ++it) {
         const uint32_t buf = it & 1;
         if (lane == 0) TRACE(1, it);
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -399,22 +416,28 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
               __syncwarp();
             } else {
 #pragma unroll 1
-              for (int tap = 0; tap < 9; ++tap) {
-                const uint32_t a_tap = a_lo + (((tap / 3) * kHaloW + tap % 3) * ROW >> 4);
+              for (int tg = 0; tg < 3; ++tg) {
                 mbar_wait(&full_b[sb], phb);
                 tc_fence_after();
-                const uint32_t b_lo = sW_lo + sb * (SLAB >> 4);
+                const uint32_t b_stage = sW_lo + sb * (3 * SLAB >> 4);
+                const uint32_t a_row = a_lo + (tg * kHaloW * ROW >> 4);
                 if (elect_one()) {
                   if (!(p.dbg & 2)) {
 #pragma unroll
-                    for (int kk = 0; kk < KSTEPS; ++kk) {
-                      const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
-                      umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
-                      umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
-                      accumulate = 1;
+                    for (int tt = 0; tt < 3; ++tt) {
+                      const uint32_t a_tap = a_row + (tt * ROW >> 4);
+                      const uint32_t b_lo = b_stage + tt * (SLAB >> 4);
+#pragma unroll
+                      for (int kk = 0; kk < KSTEPS; ++kk) {
+                        const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
+                        umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
+                        umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
+                        accumulate = 1;
+                      }
                     }
                   }
-                  umma_commit(&empty_b[sb]);
+                  if (cs == 1) umma_commit(&empty_b[sb]);
+                  else umma_commit_mc(&empty_b[sb], cmask);
                 }
                 accumulate = 1;
                 __syncwarp();
@@ -438,14 +461,16 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
     const int ml = q * 32 + lane;
     const int tw = ml & 7, th = ml >> 3;
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
+    for (int t = item0; t < total_items; t += item_step, ++it) {
+      const int nt = t % p.num_n_tiles;
+      int m = (t / p.num_n_tiles) * cs + crank;
+      const bool real_tile = m < p.num_m_tiles;
+      if (!real_tile) m = p.num_m_tiles - 1;
       const int w = (m % p.tiles_w) * 16 + tw, h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
       const int b = m / (p.tiles_w * p.tiles_h);
       const int n0 = nt * BN;
       const size_t pix = ((size_t)b * p.H + h) * p.W + w;
       const uint32_t buf = it & 1;
-      if (warp == 2 && lane == 0) TRACE(5, it);
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       if (warp == 2 && lane == 0) TRACE(6, it);
@@ -457,7 +482,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + half * BN + c0, r);
           tmem_ld_wait();
           epilogue_store32(r, sbias + n0 + c0, p.out_hi, p.out_lo, (pix + half * 8) * p.Cout + n0 + c0,
-                           !(p.dbg & 1));
+                           real_tile && !(p.dbg & 1));
         }
       }
       tc_fence_before();
@@ -469,6 +494,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   if (lane == 0) TRACE(0, 1010 + warp);
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // no CTA exits while a peer may still arrive on its barriers
   if (threadIdx.x == 0) TRACE(0, 1003);
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
   if (threadIdx.x == 64) TRACE(0, 1004);
@@ -688,7 +714,20 @@ int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
     TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv3x3_tc2<BN, KC, RES><<<c.grid, kConvThreads, c.smem_bytes, st>>>(c.p);
+  if (c.p.cluster > 1) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(c.grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = c.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c.p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    TFPNP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_tc2<BN, KC, RES>, c.p));
+  } else {
+    conv3x3_tc2<BN, KC, RES><<<c.grid, kConvThreads, c.smem_bytes, st>>>(c.p);
+  }
   TFPNP_COUNT_LAUNCH();
   return 0;
 }
@@ -746,16 +785,24 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   } else {
     p.num_a_stages = 2;
     const int budget = 224 * 1024 - misc - p.num_a_stages * p.a_stage_bytes;
-    int sb = budget / p.b_stage_bytes;
+    int sb = budget / (3 * p.b_stage_bytes);                // a ring stage holds the 3 taps of one kernel row
     p.num_b_stages = sb > kMaxStages ? kMaxStages : sb;
-    c.smem_bytes = p.num_a_stages * p.a_stage_bytes + p.num_b_stages * p.b_stage_bytes + misc;
+    c.smem_bytes = p.num_a_stages * p.a_stage_bytes + p.num_b_stages * 3 * p.b_stage_bytes + misc;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int occ = (c.smem_bytes <= 112 * 1024 && c.BN <= 64) ? 2 : 1;
-  const int total = p.num_m_tiles * p.num_n_tiles;
-  c.grid = total < sms * occ ? total : sms * occ;
+  // streamed weights: clusters of 2 (or 4) CTAs fetch each slab once and multicast it
+  int cs = 1;
+  if (!c.resident) {
+    cs = env_int("TFPNP_CONV_CLUSTER", 2);
+    while (cs > 1 && (p.num_m_tiles < cs || (c.BN / cs) * row_bytes % 1024 != 0)) cs /= 2;
+  }
+  p.cluster = cs;
+  const int items = ((p.num_m_tiles + cs - 1) / cs) * p.num_n_tiles;
+  const int max_clusters = (sms * occ) / cs;
+  c.grid = (items < max_clusters ? items : max_clusters) * cs;
   return 0;
 }
 
@@ -886,7 +933,7 @@ struct UNetTc : Denoiser {
     }
     cuuint64_t wd[3] = {(cuuint64_t)sp.cin, (cuuint64_t)sp.cout, 9};
     cuuint64_t ws[2] = {(cuuint64_t)sp.cin * 2, (cuuint64_t)sp.cin * sp.cout * 2};
-    cuuint32_t wb[3] = {(cuuint32_t)c.kc, (cuuint32_t)c.BN, 1};
+    cuuint32_t wb[3] = {(cuuint32_t)c.kc, (cuuint32_t)(c.BN / p.cluster), 1};   // each cluster CTA fetches BN/cluster rows
     TFPNP_TRY(encode_map(&p.w_map[0], w_hi.as<__half>() + w_off[l], 3, wd, ws, wb, c.kc * 2));
     if (x3) TFPNP_TRY(encode_map(&p.w_map[1], w_lo.as<__half>() + w_off[l], 3, wd, ws, wb, c.kc * 2));
     else p.w_map[1] = p.w_map[0];
@@ -1037,7 +1084,7 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
     q.a_map[1][1] = q.a_map[1][0];
     cuuint64_t wd2[3] = {(cuuint64_t)(C0 + C1), (cuuint64_t)Cout, 9};
     cuuint64_t ws2[2] = {(cuuint64_t)(C0 + C1) * 2, (cuuint64_t)(C0 + C1) * Cout * 2};
-    cuuint32_t wb2[3] = {(cuuint32_t)c.kc, (cuuint32_t)c.BN, 1};
+    cuuint32_t wb2[3] = {(cuuint32_t)c.kc, (cuuint32_t)(c.BN / q.cluster), 1};
     TFPNP_TRY(encode_map(&q.w_map[0], const_cast<__half*>(w_taps), 3, wd2, ws2, wb2, c.kc * 2));
     q.w_map[1] = q.w_map[0];
     const char* tf = getenv("TFPNP_TRACE_FILE");
