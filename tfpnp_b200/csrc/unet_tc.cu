@@ -50,29 +50,29 @@ __device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
   return d;
 }
 
-// Epilogue of one 32-column slice of an accumulator row: + bias (from smem), LeakyReLU(0.2), pack to
-// fp16 (hi) and, in FP16X3 mode, the fp16 residual (lo); 64-byte NHWC stores per plane.
-__device__ __forceinline__ void epilogue_store32(const uint32_t (&r)[32], const float* __restrict__ sbias,
-                                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                                 size_t off, bool store) {
-  float v[32];
+// Epilogue pieces for one 32-column slice of an accumulator row.
+// act: + bias (smem broadcast), LeakyReLU(0.2) (unet.py:22) in fp32
+__device__ __forceinline__ void epilogue_act32(const uint32_t (&r)[32], const float* __restrict__ sbias, float (&v)[32]) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 bb = *reinterpret_cast<const float4*>(sbias + 4 * j4);   // smem broadcast
+    const float4 bb = *reinterpret_cast<const float4*>(sbias + 4 * j4);
     v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + bb.x;
     v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + bb.y;
     v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + bb.z;
     v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + bb.w;
   }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+}
+// store: pack to fp16 (hi) and, in FP16X3 mode, the fp16 residual (lo); 64-byte NHWC stores per plane
+__device__ __forceinline__ void epilogue_store_nhwc32(const float (&v)[32], __half* __restrict__ out_hi,
+                                                      __half* __restrict__ out_lo, size_t off) {
   uint32_t hi[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    v[2 * j] = fmaxf(v[2 * j], 0.2f * v[2 * j]);             // LeakyReLU(0.2), unet.py:22
-    v[2 * j + 1] = fmaxf(v[2 * j + 1], 0.2f * v[2 * j + 1]);
     __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
     hi[j] = *reinterpret_cast<uint32_t*>(&hh);
   }
-  if (!store) return;
   uint4* dst = reinterpret_cast<uint4*>(out_hi + off);
 #pragma unroll
   for (int q = 0; q < 4; ++q) dst[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
@@ -88,6 +88,13 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t (&r)[32], const 
 #pragma unroll
     for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
   }
+}
+__device__ __forceinline__ void epilogue_store32(const uint32_t (&r)[32], const float* __restrict__ sbias,
+                                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                 size_t off, bool store) {
+  float v[32];
+  epilogue_act32(r, sbias, v);
+  if (store) epilogue_store_nhwc32(v, out_hi, out_lo, off);
 }
 
 template <int BN>
@@ -241,6 +248,14 @@ struct Conv2Params {
   const float* bias;
   __half* out_hi;
   __half* out_lo;
+  // fused nn.MaxPool2d(2) of the output (unet.py:83): pooled NHWC tensor [B,H/2,W/2,Cout] (nullptr = off)
+  __half* pool_hi;
+  __half* pool_lo;
+  // fused outconv 1x1 (Cout=32 -> 1) + residual + clamp (unet.py:124-131,65-66; denoiser/base.py:32):
+  // x_out[pix] = clamp(d_in[pix] + b + sum_c w[c] * act[c], 0, 1); the 32-channel tensor is not stored
+  const float* outc_w;               // [33] = w[32], b  (nullptr = off)
+  const float* d_in;
+  float* x_out;
 };
 
 constexpr int kMaxStages = 16;
@@ -306,6 +321,8 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
   for (int i = threadIdx.x; i < p.Cout; i += kConvThreads) sbias[i] = p.bias[i];
+  float* soutc = sbias + 512;                                    // [33] fused outconv weights + bias
+  if (p.outc_w && threadIdx.x < 33) soutc[threadIdx.x] = p.outc_w[threadIdx.x];
   if (threadIdx.x == 64) TRACE(0, 1001);
   tc_fence_before();
   __syncthreads();
@@ -481,8 +498,28 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + half * BN + c0, r);
           tmem_ld_wait();
-          epilogue_store32(r, sbias + n0 + c0, p.out_hi, p.out_lo, (pix + half * 8) * p.Cout + n0 + c0,
-                           real_tile && !(p.dbg & 1));
+          float v[32];
+          epilogue_act32(r, sbias + n0 + c0, v);
+          const bool st_ok = real_tile && !(p.dbg & 1);
+          if (p.outc_w) {                       // last layer: 1x1 conv + residual + clamp, fp32 out (BN == 32)
+            float acc = soutc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc = fmaf(soutc[j], v[j], acc);
+            if (st_ok) p.x_out[pix + half * 8] = fminf(fmaxf(p.d_in[pix + half * 8] + acc, 0.f), 1.f);
+            continue;
+          }
+          if (st_ok) epilogue_store_nhwc32(v, p.out_hi, p.out_lo, (pix + half * 8) * p.Cout + n0 + c0);
+          if (p.pool_hi) {                      // 2x2 max over (tw^1, th^1) = lanes ^1 and ^8
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+              v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
+            }
+            if (st_ok && !(lane & 9)) {
+              const size_t ppix = ((size_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + ((w + half * 8) >> 1);
+              epilogue_store_nhwc32(v, p.pool_hi, p.pool_lo, ppix * p.Cout + n0 + c0);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -770,7 +807,7 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   p.a_stage_bytes = (kHaloRows * row_bytes + 1023) & ~1023;
   p.b_stage_bytes = c.BN * row_bytes;                       // multiple of 1024 for all (BN, kc) used
   const int w_bytes = 9 * (Cin / kc) * p.b_stage_bytes;
-  const int misc = 1024 + 1024 + 2048;                      // alignment slack + barriers + bias[<=512]
+  const int misc = 1024 + 1024 + 2048 + 256;                // alignment slack + barriers + bias[<=512] + outc[33]
   c.resident = !x3 && p.num_n_tiles == 1 && c.BN <= 64 && w_bytes <= 100 * 1024 &&
                env_int("TFPNP_CONV_RESIDENT", 1) != 0;
   if (c.resident) {
@@ -914,6 +951,9 @@ struct UNetTc : Denoiser {
     return 0;
   }
 
+  bool fused_pool[kNumUnetConv3] = {};   // layer l also wrote its 2x2-max-pooled output (into S2)
+  bool fused_outc = false;               // layer 26 produced x directly
+
   int plan_conv_v2(int l, const Act& s0, const Act* s1, const Act& dst, int B) {
     const ConvSpec& sp = unet_conv_specs()[l];
     Conv2Plan& c = convs2[l];
@@ -924,6 +964,13 @@ struct UNetTc : Denoiser {
     p.bias = biases.as<float>() + b_off[l];
     p.out_hi = dst.hi;
     p.out_lo = x3 ? dst.lo : nullptr;
+    const bool fuse = env_int("TFPNP_CONV_FUSE", 1) != 0;
+    fused_pool[l] = fuse && (l == 2 || l == 5 || l == 8 || l == 11);   // conv-2 of inc / down1..3 feeds a MaxPool2d
+    if (fused_pool[l]) { p.pool_hi = S2.hi; p.pool_lo = x3 ? S2.lo : nullptr; }   // S2 is idle in the encoder
+    if (l == 26) {
+      fused_outc = fuse;
+      if (fuse) p.outc_w = w_out.as<float>();      // d_in / x_out are per-call pointers, set in forward()
+    }
     const Act* srcs[2] = {&s0, s1};
     for (int s = 0; s < 2; ++s) {
       if (!srcs[s]) { p.a_map[s][0] = p.a_map[0][0]; p.a_map[s][1] = p.a_map[0][1]; continue; }
@@ -944,6 +991,8 @@ struct UNetTc : Denoiser {
   int plan_conv(int l, const Act& s0, const Act* s1, const Act& dst, int B) {
     if (conv2_eligible(dst.H, dst.W)) return plan_conv_v2(l, s0, s1, dst, B);
     convs2[l].grid = 0;
+    fused_pool[l] = false;
+    if (l == 26) fused_outc = false;
     const ConvSpec& sp = unet_conv_specs()[l];
     ConvParams& p = convs[l];
     memset(&p, 0, sizeof(p));
@@ -1006,7 +1055,9 @@ struct UNetTc : Denoiser {
     TFPNP_TRY(plan_conv(2, view(S1, 32, H, W), nullptr, skip[0], B));
     for (int lv = 1; lv <= 4; ++lv) {
       int h = H >> lv, w = W >> lv, l0 = 3 * lv;
-      TFPNP_TRY(plan_conv(l0, view(S0, ch[lv - 1], h, w), nullptr, view(S1, ch[lv], h, w), B));
+      // pooled input: written by the fused epilogue of the previous block (-> S2) or by maxpool2_nhwc (-> S0)
+      const Act& pooled = fused_pool[l0 - 1] ? S2 : S0;
+      TFPNP_TRY(plan_conv(l0, view(pooled, ch[lv - 1], h, w), nullptr, view(S1, ch[lv], h, w), B));
       TFPNP_TRY(plan_conv(l0 + 1, view(S1, ch[lv], h, w), nullptr, view(S0, ch[lv], h, w), B));
       TFPNP_TRY(plan_conv(l0 + 2, view(S0, ch[lv], h, w), nullptr, skip[lv], B));
     }
@@ -1038,9 +1089,11 @@ struct UNetTc : Denoiser {
     TFPNP_TRY(launch_conv(2, st));
     for (int lv = 1; lv <= 4; ++lv) {
       int h = H >> lv, w = W >> lv;
-      maxpool2_nhwc<<<dim3(cdiv(w * (ch[lv - 1] / 8), T), h, B), T, 0, st>>>(skip[lv - 1].hi, skip[lv - 1].lo, S0.hi,
-                                                                              S0.lo, 2 * h, 2 * w, ch[lv - 1]);
-      TFPNP_COUNT_LAUNCH();
+      if (!fused_pool[3 * lv - 1]) {
+        maxpool2_nhwc<<<dim3(cdiv(w * (ch[lv - 1] / 8), T), h, B), T, 0, st>>>(skip[lv - 1].hi, skip[lv - 1].lo,
+                                                                                S0.hi, S0.lo, 2 * h, 2 * w, ch[lv - 1]);
+        TFPNP_COUNT_LAUNCH();
+      }
       for (int k = 0; k < 3; ++k) TFPNP_TRY(launch_conv(3 * lv + k, st));
     }
     for (int k = 0; k < 4; ++k) {
@@ -1049,12 +1102,18 @@ struct UNetTc : Denoiser {
       upsample2_nhwc<<<dim3(cdiv(w * (ch[lv + 1] / 8), T), h, B), T, 0, st>>>(src.hi, src.lo, S0.hi, S0.lo, h / 2,
                                                                                w / 2, ch[lv + 1]);
       TFPNP_COUNT_LAUNCH();
-      for (int j = 0; j < 3; ++j) TFPNP_TRY(launch_conv(15 + 3 * k + j, st));
+      for (int j = 0; j < 3; ++j) {
+        const int l = 15 + 3 * k + j;
+        if (l == 26 && fused_outc) { convs2[l].p.d_in = x; convs2[l].p.x_out = out; }
+        TFPNP_TRY(launch_conv(l, st));
+      }
     }
-    size_t npix = (size_t)B * H * W;
-    outc_nhwc<<<(unsigned)((npix + T - 1) / T), T, 0, st>>>(S2.hi, S2.lo, w_out.as<float>(), w_out.as<float>() + 32,
-                                                            x, out, npix);
-    TFPNP_COUNT_LAUNCH();
+    if (!fused_outc) {
+      size_t npix = (size_t)B * H * W;
+      outc_nhwc<<<(unsigned)((npix + T - 1) / T), T, 0, st>>>(S2.hi, S2.lo, w_out.as<float>(), w_out.as<float>() + 32,
+                                                              x, out, npix);
+      TFPNP_COUNT_LAUNCH();
+    }
     TFPNP_CUDA_OK(cudaGetLastError());
     return 0;
   }
