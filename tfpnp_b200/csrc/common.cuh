@@ -47,6 +47,34 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 extern thread_local int64_t g_launch_count;
 #define TFPNP_COUNT_LAUNCH() (++::tfpnp::g_launch_count)
 
+// Launch with optional programmatic dependent launch (PDL) and thread-block-cluster attributes.
+// With pdl = true the kernel may begin (its prologue) before the previous kernel in the stream has
+// drained; the kernel itself must execute griddepcontrol.wait before touching dependent data.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                             int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // simple owned device buffer
 struct DevBuf {
   void* p = nullptr;

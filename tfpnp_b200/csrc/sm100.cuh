@@ -97,6 +97,13 @@ __device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap
       : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------
+// launch_dependents: the next kernel in the stream (launched with the programmatic-serialization
+// attribute) may start being scheduled once every CTA of this grid has executed this or exited;
+// wait: block until the preceding grid has fully completed and its memory is visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- clusters -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -121,6 +121,7 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
   float* sbias = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int mt = blockIdx.x;
   const int w0 = (mt % p.tiles_w) * p.TW;
   const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
@@ -145,6 +146,7 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous layer's tail; its activations are needed from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -295,6 +297,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   float* sbias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 8);   // [Cout] <= 512 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) TRACE(0, 1000);
   constexpr uint32_t kTmemCols = 4 * BN;
   // work items: (group of `cs` consecutive super-tiles, n-tile); CTA `crank` of a cluster takes
@@ -329,17 +332,18 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   tc_fence_after();
   if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast
   const uint32_t tmem_base = *tmem_slot;
+  if (RESIDENT && warp == 0 && lane == 0) {     // weights are constants: fetch them before the dependency wait
+    mbar_arrive_expect_tx(w_full, (uint32_t)(9 * nchunks) * SLAB);
+    for (int tap = 0; tap < 9; ++tap)
+      for (int c = 0; c < nchunks; ++c)
+        tma_load_3d(sW + (tap * nchunks + c) * SLAB, &p.w_map[0], w_full, c * KC, 0, tap);
+  }
+  pdl_wait();   // prologue + weight prefetch overlapped the previous layer's tail
   if (threadIdx.x == 0) TRACE(0, 1002);
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      if (RESIDENT) {
-        mbar_arrive_expect_tx(w_full, (uint32_t)(9 * nchunks) * SLAB);
-        for (int tap = 0; tap < 9; ++tap)
-          for (int c = 0; c < nchunks; ++c)
-            tma_load_3d(sW + (tap * nchunks + c) * SLAB, &p.w_map[0], w_full, c * KC, 0, tap);
-      }
       uint32_t ia = 0, ib = 0;
       const int rows_mc = BN / cs;   // weight-slab rows this CTA fetches (and multicasts)
       for (int t = item0; t < total_items; t += item_step) {
@@ -548,6 +552,8 @@ __global__ void __launch_bounds__(128)
 conv_first_kernel(const float* __restrict__ d, const float* __restrict__ sigma, int64_t sstride,
                   const __grid_constant__ FirstLayerW wb, __half* __restrict__ out_hi,
                   __half* __restrict__ out_lo, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z, y = blockIdx.y;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= W) return;
@@ -613,6 +619,8 @@ __device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const
 __global__ void __launch_bounds__(256)
 maxpool2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, __half* __restrict__ out_hi,
               __half* __restrict__ out_lo, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Wo * C8) return;
@@ -638,6 +646,8 @@ maxpool2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo
 __global__ void __launch_bounds__(256)
 upsample2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, __half* __restrict__ out_hi,
                __half* __restrict__ out_lo, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = 2 * H, Wo = 2 * W, C8 = C / 8;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Wo * C8) return;
@@ -667,6 +677,8 @@ upsample2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
 __global__ void outc_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                           const float* __restrict__ w, const float* __restrict__ bias,
                           const float* __restrict__ d, float* __restrict__ out, size_t npix) {
+  pdl_launch_dependents();
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   float acc = bias[0];
@@ -743,6 +755,11 @@ int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+// programmatic dependent launch between the kernels of one denoiser call (TFPNP_PDL=0 disables)
+bool use_pdl() {
+  static int v = env_int("TFPNP_PDL", 1);
+  return v != 0;
+}
 
 template <int BN, int KC, bool RES>
 int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
@@ -751,20 +768,8 @@ int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
     TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (c.p.cluster > 1) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(c.grid);
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = c.smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = c.p.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    TFPNP_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_tc2<BN, KC, RES>, c.p));
-  } else {
-    conv3x3_tc2<BN, KC, RES><<<c.grid, kConvThreads, c.smem_bytes, st>>>(c.p);
-  }
+  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES>, dim3(c.grid), dim3(kConvThreads), c.smem_bytes, st, use_pdl(),
+                          c.p.cluster, c.p));
   TFPNP_COUNT_LAUNCH();
   return 0;
 }
@@ -853,9 +858,9 @@ int encode_halo_map(CUtensorMap* m, const __half* base, int C, int B, int H, int
 int launch_conv_params(const ConvParams& p, int BN, cudaStream_t st) {
   dim3 grid(p.tiles_w * p.tiles_h * cdiv(p.B, p.TB), p.Cout / BN);
   switch (BN) {
-    case 32: conv3x3_tc<32><<<grid, kConvThreads, ConvCfg<32>::kSmemBytes, st>>>(p); break;
-    case 64: conv3x3_tc<64><<<grid, kConvThreads, ConvCfg<64>::kSmemBytes, st>>>(p); break;
-    case 128: conv3x3_tc<128><<<grid, kConvThreads, ConvCfg<128>::kSmemBytes, st>>>(p); break;
+    case 32: TFPNP_CUDA_OK(launch_ex(conv3x3_tc<32>, grid, dim3(kConvThreads), ConvCfg<32>::kSmemBytes, st, use_pdl(), 1, p)); break;
+    case 64: TFPNP_CUDA_OK(launch_ex(conv3x3_tc<64>, grid, dim3(kConvThreads), ConvCfg<64>::kSmemBytes, st, use_pdl(), 1, p)); break;
+    case 128: TFPNP_CUDA_OK(launch_ex(conv3x3_tc<128>, grid, dim3(kConvThreads), ConvCfg<128>::kSmemBytes, st, use_pdl(), 1, p)); break;
     default: set_error("unsupported BN %d", BN); return TFPNP_ERR_INVALID;
   }
   TFPNP_COUNT_LAUNCH();
@@ -1082,6 +1087,8 @@ struct UNetTc : Denoiser {
     TFPNP_CHECK(B == pB && H == pH && W == pW, "prepare(%d,%d,%d) not called (plan is %d,%d,%d)", B, H, W, pB, pH, pW);
     const int ch[5] = {32, 64, 128, 256, 512};
     const int T = 256;
+    // head of the chain: a normal (fully serialised) launch; every later kernel of this call may overlap its
+    // prologue with its predecessor's tail (PDL)
     conv_first_kernel<<<dim3(cdiv(W, 128), H, B), 128, 0, st>>>(x, sigma, sstride, first_w, S0.hi,
                                                                x3 ? S0.lo : nullptr, H, W);
     TFPNP_COUNT_LAUNCH();
@@ -1090,8 +1097,8 @@ struct UNetTc : Denoiser {
     for (int lv = 1; lv <= 4; ++lv) {
       int h = H >> lv, w = W >> lv;
       if (!fused_pool[3 * lv - 1]) {
-        maxpool2_nhwc<<<dim3(cdiv(w * (ch[lv - 1] / 8), T), h, B), T, 0, st>>>(skip[lv - 1].hi, skip[lv - 1].lo,
-                                                                                S0.hi, S0.lo, 2 * h, 2 * w, ch[lv - 1]);
+        TFPNP_CUDA_OK(launch_ex(maxpool2_nhwc, dim3(cdiv(w * (ch[lv - 1] / 8), T), h, B), dim3(T), 0, st, use_pdl(), 1,
+                                skip[lv - 1].hi, skip[lv - 1].lo, S0.hi, S0.lo, 2 * h, 2 * w, ch[lv - 1]));
         TFPNP_COUNT_LAUNCH();
       }
       for (int k = 0; k < 3; ++k) TFPNP_TRY(launch_conv(3 * lv + k, st));
@@ -1099,8 +1106,8 @@ struct UNetTc : Denoiser {
     for (int k = 0; k < 4; ++k) {
       int lv = 3 - k, h = H >> lv, w = W >> lv;
       const Act& src = k == 0 ? skip[4] : S2;
-      upsample2_nhwc<<<dim3(cdiv(w * (ch[lv + 1] / 8), T), h, B), T, 0, st>>>(src.hi, src.lo, S0.hi, S0.lo, h / 2,
-                                                                               w / 2, ch[lv + 1]);
+      TFPNP_CUDA_OK(launch_ex(upsample2_nhwc, dim3(cdiv(w * (ch[lv + 1] / 8), T), h, B), dim3(T), 0, st, use_pdl(), 1,
+                              src.hi, src.lo, S0.hi, S0.lo, h / 2, w / 2, ch[lv + 1]));
       TFPNP_COUNT_LAUNCH();
       for (int j = 0; j < 3; ++j) {
         const int l = 15 + 3 * k + j;
@@ -1110,8 +1117,8 @@ struct UNetTc : Denoiser {
     }
     if (!fused_outc) {
       size_t npix = (size_t)B * H * W;
-      outc_nhwc<<<(unsigned)((npix + T - 1) / T), T, 0, st>>>(S2.hi, S2.lo, w_out.as<float>(), w_out.as<float>() + 32,
-                                                              x, out, npix);
+      TFPNP_CUDA_OK(launch_ex(outc_nhwc, dim3((unsigned)((npix + T - 1) / T)), dim3(T), 0, st, use_pdl(), 1, S2.hi, S2.lo,
+                              w_out.as<float>(), w_out.as<float>() + 32, x, out, npix));
       TFPNP_COUNT_LAUNCH();
     }
     TFPNP_CUDA_OK(cudaGetLastError());
