@@ -418,8 +418,9 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
             if (lane == 0) TRACE(3, ia);
             ++ia;
             const uint32_t a_lo = sA_lo + sa * a_stage16;
+            const bool last_item = (c == nchunks - 1) && (prod == p.nprod - 1);
             if (RESIDENT) {
-              if (!(p.dbg & 2) && elect_one()) {
+              if (elect_one()) {
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                   const uint32_t a_tap = a_lo + (((tap / 3) * kHaloW + tap % 3) * ROW >> 4);
@@ -432,6 +433,8 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
                     accumulate = 1;
                   }
                 }
+                umma_commit(&empty_a[sa]);                 // smem slot free once these MMAs have read it
+                if (last_item) umma_commit(&tmem_full[buf]);   // accumulator complete
               }
               accumulate = 1;
               __syncwarp();
@@ -465,13 +468,16 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
                 if (++sb == (uint32_t)SB) { sb = 0; phb ^= 1; }
               }
             }
-            if (elect_one()) umma_commit(&empty_a[sa]);
-            __syncwarp();
+            if (!RESIDENT) {
+              if (elect_one()) {
+                umma_commit(&empty_a[sa]);
+                if (last_item) umma_commit(&tmem_full[buf]);
+              }
+              __syncwarp();
+            }
             if (++sa == (uint32_t)SA) { sa = 0; pha ^= 1; }
           }
         }
-        if (elect_one()) umma_commit(&tmem_full[buf]);
-        __syncwarp();
         if (lane == 0) TRACE(4, it);
       }
       (void)ia; (void)ib;
@@ -495,13 +501,18 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       if (warp == 2 && lane == 0) TRACE(6, it);
+      // the two M-tile halves sit side by side in TMEM: walk their 2*BN columns in blocks of 64
+      // (one tcgen05.ld round trip per two 32-column slices)
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + half * BN + c0, r);
-          tmem_ld_wait();
+      for (int cb = 0; cb < 2 * BN; cb += 64) {
+        uint32_t r64[64];
+        tmem_ld_32x64(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + cb, r64);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int col = cb + 32 * sl;
+          const int half = col / BN, c0 = col % BN;
+          uint32_t (&r)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r64[32 * sl]);
           float v[32];
           epilogue_act32(r, sbias + n0 + c0, v);
           const bool st_ok = real_tile && !(p.dbg & 1);

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch, tfpnp_b200 as T
 dev = torch.device("cuda:0")
 names = ["P: A slot free", "M: tile start", "M: tmem free", "M: A landed", "M: tile issued", "E: tile wait", "E: accum ready", "E: tile done"]
-for (C0, C1, Cout, H, W, B) in [(256, 0, 256, 16, 16, 48)]:
+for (C0, C1, Cout, H, W, B) in [(64, 0, 64, 64, 64, 48), (32, 0, 32, 128, 128, 48)]:
     x0 = torch.randn(B, H, W, C0, device=dev).half()
     w = torch.randn(Cout, C0 + C1, 3, 3) * 0.05
     b = torch.zeros(Cout)
@@ -23,10 +23,10 @@ for (C0, C1, Cout, H, W, B) in [(256, 0, 256, 16, 16, 48)]:
     print("  kernel entry, prologue pre-sync, post-sync, post-final-sync, post-dealloc:", [int(x - t0) if x else None for x in extra[:5]],
           " role loops done (warps 0..5):", [int(x - t0) if x else None for x in extra[10:16]])
     print(f"=== {C0}->{Cout} @{H}x{W} B={B}  (ns since first sample; first 8 tiles and last 2)")
-    fine = tr[5][:160] - t0
-    print("  MMA per-tap (before wait, after wait, after issue, after commit+syncwarp), first 12 taps + taps 20-23:")
-    for k in list(range(12)) + [20, 21, 22, 23]:
-        print("     ", fine[4 * k: 4 * k + 4].tolist())
+    fine = tr[5][:60] - t0
+    print("  resident MMA issue: time before each tap's MMAs (9 taps) + after the block, tiles 1..4 (ia=1..4):")
+    for k in range(1, 5):
+        print("     ", fine[10 * k: 10 * k + 10].tolist())
     tr[5] = 0
     for r in range(8):
         row = tr[r][tr[r] > 0] - t0
