@@ -44,6 +44,8 @@ struct ConvParams {
 };
 
 
+struct H8 { __half2 v[4]; };  // 8 channels = 16 bytes
+
 __device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
@@ -99,7 +101,7 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t (&r)[32], const 
 
 template <int BN>
 struct ConvCfg {
-  static constexpr int kStages = BN >= 128 ? 3 : 4;
+  static constexpr int kStages = BN >= 128 ? 6 : 4;   // BN=128: 192 KB, 1 CTA/SM (these grids are < 148 CTAs anyway)
   static constexpr int kABytes = kTileM * 128;   // room for kc = 64
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -243,6 +245,12 @@ struct Conv2Params {
   int B, H, W, Cout;
   int a_stage_bytes, num_a_stages;   // A ring
   int b_stage_bytes, num_b_stages;   // B ring (streamed) -- or resident slab size, 0 stages
+  // fused nn.Upsample(x2, bilinear, align_corners=True) of source 1 (unet.py:99): a_map[1] then addresses the
+  // LOW-RES tensor [B, H/2, W/2, C1] with an (unswizzled) 11x11 box and four transform warps interpolate the
+  // 18x18 halo tile straight into the swizzled A stage; the up-sampled tensor is never materialised.
+  int up_fused;
+  float up_sy, up_sx;                // (Hin-1)/(H-1), (Win-1)/(W-1)
+  int stg_bytes;                     // staging slot size (121 rows, 1024-aligned)
   int cluster;                       // CTAs per cluster sharing each streamed weight slab via TMA multicast (1, 2, 4)
   int dbg;                           // knock-out switches for bottleneck hunting (TFPNP_DBG): 1 = no stores,
                                      // 2 = no MMA issue, 4 = no activation TMA, 8 = no weight TMA
@@ -272,8 +280,12 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (p.trace && blockIdx.x == 0 && (idx) < 1024) p.trace[(row) * 1024 + (idx)] = gtimer();  \
   } while (0)
 
-template <int BN, int KC, bool RESIDENT>
-__global__ void __launch_bounds__(kConvThreads, 2)
+constexpr int kUpBox = 11;                     // low-res window edge feeding an 18-pixel halo edge
+constexpr int kXformThreads = 288;                      // 9 transform warps
+constexpr int kConvFuseThreads = kConvThreads + kXformThreads;
+
+template <int BN, int KC, bool RESIDENT, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? kConvFuseThreads : kConvThreads, FUSE ? 1 : 2)
 conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -285,7 +297,8 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   uint8_t* sA = smem;
   uint8_t* sW = smem + SA * p.a_stage_bytes;   // resident weights or the B ring
   const int w_region = RESIDENT ? 9 * nchunks * (int)SLAB : SB * 3 * (int)SLAB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + w_region);
+  uint8_t* sStg = sW + w_region;                                  // [2][stg_bytes] low-res windows (FUSE only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + (FUSE ? 2 * p.stg_bytes : 0));
   uint64_t* full_a = bars;
   uint64_t* empty_a = bars + kMaxStages;
   uint64_t* full_b = bars + 2 * kMaxStages;
@@ -293,8 +306,10 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   uint64_t* w_full = bars + 4 * kMaxStages;
   uint64_t* tmem_full = w_full + 1;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* sbias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 8);   // [Cout] <= 512 floats
+  uint64_t* stg_full = tmem_empty + 2;   // [2]
+  uint64_t* stg_empty = stg_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + 2);
+  float* sbias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 12);   // [Cout] <= 512 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -319,11 +334,14 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], cs);   // a weight slot is free when ALL cluster CTAs released it
     }
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
+      mbar_init(&stg_full[i], 1); mbar_init(&stg_empty[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
-  for (int i = threadIdx.x; i < p.Cout; i += kConvThreads) sbias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = p.bias[i];
   float* soutc = sbias + 512;                                    // [33] fused outconv weights + bias
   if (p.outc_w && threadIdx.x < 33) soutc[threadIdx.x] = p.outc_w[threadIdx.x];
   if (threadIdx.x == 64) TRACE(0, 1001);
@@ -344,7 +362,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      uint32_t ia = 0, ib = 0;
+      uint32_t ia = 0, ib = 0, iu = 0;
       const int rows_mc = BN / cs;   // weight-slab rows this CTA fetches (and multicasts)
       for (int t = item0; t < total_items; t += item_step) {
         const int nt = t % p.num_n_tiles;
@@ -359,7 +377,16 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
             const int s = ia % SA;
             mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);
             TRACE(0, ia);
-            if (p.dbg & 4) mbar_arrive(&full_a[s]);
+            if (FUSE && src == 1) {
+              // A stage s is free: hand the low-res window to the transform warps, they fill the stage
+              const int st = iu & 1;
+              mbar_wait(&stg_empty[st], ((iu >> 1) & 1) ^ 1);
+              mbar_arrive_expect_tx(&stg_full[st], (uint32_t)(kUpBox * kUpBox) * ROW);
+              const int ys = (int)(p.up_sy * (float)(h0 > 0 ? h0 - 1 : 0));
+              const int xs = (int)(p.up_sx * (float)(w0 > 0 ? w0 - 1 : 0));
+              tma_load_4d(sStg + st * p.stg_bytes, &p.a_map[1][0], &stg_full[st], cc, xs, ys, b);
+              ++iu;
+            } else if (p.dbg & 4) mbar_arrive(&full_a[s]);
             else {
               mbar_arrive_expect_tx(&full_a[s], (uint32_t)kHaloRows * ROW);
               tma_load_4d(sA + s * p.a_stage_bytes, &p.a_map[src][prod == 1 ? 1 : 0], &full_a[s], cc, w0 - 1, h0 - 1, b);
@@ -482,7 +509,99 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       }
       (void)ia; (void)ib;
     }
-  } else {
+  } else if (FUSE && warp >= 6) {
+    // ---------------- transform warps: bilinear x2 (align_corners) of the low-res window into the A stage ------
+    // Thread = (halo column k, 16-byte channel group j, row group g): the column interpolation set-up is done
+    // once per tile, the thread then walks its rows top-down keeping the horizontally interpolated source rows
+    // in registers (consecutive output rows share them), so a row costs at most one new source row.
+    const int tid = threadIdx.x - kConvThreads;            // 0..287
+    constexpr int CH16 = KC / 8;                           // 16-byte channel groups per pixel row
+    constexpr int SLOTS = kHaloW * CH16;                   // 144 (KC=64) / 72 (KC=32)
+    constexpr int GROUPS = kXformThreads / SLOTS;          // 2 / 4 row groups
+    constexpr int RPG = (kHaloH + GROUPS - 1) / GROUPS;    // rows per group: 9 / 5
+    constexpr int iROW = (int)ROW;
+    const int g = tid / SLOTS, slot = tid % SLOTS;
+    const int k = slot / CH16, j = slot % CH16;
+    const int Hin = p.H >> 1, Win = p.W >> 1;
+    const int r_begin = g * RPG, r_end = (r_begin + RPG < kHaloH) ? r_begin + RPG : kHaloH;
+    uint32_t ia = 0, iu = 0;
+    for (int t = item0; t < total_items; t += item_step) {
+      int m = (t / p.num_n_tiles) * cs + crank;
+      if (m >= p.num_m_tiles) m = p.num_m_tiles - 1;
+      const int w0 = (m % p.tiles_w) * 16, h0 = ((m / p.tiles_w) % p.tiles_h) * 16;
+      const int ys = (int)(p.up_sy * (float)(h0 > 0 ? h0 - 1 : 0));
+      const int xs = (int)(p.up_sx * (float)(w0 > 0 ? w0 - 1 : 0));
+      // column set-up (fixed for the tile)
+      const int xo = w0 - 1 + k;
+      const bool x_ok = g < GROUPS && xo >= 0 && xo < p.W;
+      const float fx = p.up_sx * (float)xo;
+      const int x0 = (int)fx;
+      const int x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+      const float lx = fx - (float)x0;
+      const int ox0 = (x0 - xs) * iROW + j * 16, ox1 = (x1 - xs) * iROW + j * 16;
+      for (int c = 0; c < nchunks; ++c) {
+        for (int prod = 0; prod < p.nprod; ++prod, ++ia) {
+          if (c < p.nchunk0) continue;                      // source 0 comes by TMA
+          const int s = ia % SA, st = iu & 1;
+          mbar_wait(&stg_full[st], (iu >> 1) & 1);
+          const uint8_t* stg = sStg + st * p.stg_bytes;
+          uint8_t* dstA = sA + s * p.a_stage_bytes;
+          if (g < GROUPS) {
+            float ha[8], hb[8];                             // horizontally interpolated source rows ya, yb
+            int ya = -1, yb = -1;
+            auto hrow = [&](int y, float (&hr)[8]) {
+              const uint8_t* rp = stg + (y - ys) * (kUpBox * iROW);
+              const H8 a = *reinterpret_cast<const H8*>(rp + ox0), bq = *reinterpret_cast<const H8*>(rp + ox1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 fa = __half22float2(a.v[e]), fb = __half22float2(bq.v[e]);
+                hr[2 * e] = (1.f - lx) * fa.x + lx * fb.x;
+                hr[2 * e + 1] = (1.f - lx) * fa.y + lx * fb.y;
+              }
+            };
+            for (int r = r_begin; r < r_end; ++r) {
+              const int yo = h0 - 1 + r;
+              const int pr = r * kHaloW + k;
+              uint4 outv = make_uint4(0, 0, 0, 0);           // conv zero padding outside the image
+              if (x_ok && yo >= 0 && yo < p.H) {
+                const float fy = p.up_sy * (float)yo;
+                const int y0 = (int)fy;
+                const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0);
+                const float ly = fy - (float)y0;
+                if (y0 != ya) {
+                  if (y0 == yb) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ha[e] = hb[e];
+                  } else hrow(y0, ha);
+                  ya = y0;
+                }
+                if (y1 != yb) {
+                  if (y1 == ya) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) hb[e] = ha[e];
+                  } else hrow(y1, hb);
+                  yb = y1;
+                }
+                H8 o;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  o.v[e] = __floats2half2_rn((1.f - ly) * ha[2 * e] + ly * hb[2 * e],
+                                             (1.f - ly) * ha[2 * e + 1] + ly * hb[2 * e + 1]);
+                outv = *reinterpret_cast<uint4*>(&o);
+              }
+              // TMA-compatible swizzle of the A stage: 16-byte chunk index ^= row bits
+              const int swz = (ROW == 128) ? (pr & 7) : ((pr >> 1) & 3);
+              *reinterpret_cast<uint4*>(dstA + pr * iROW + ((j ^ swz) << 4)) = outv;
+            }
+          }
+          fence_proxy_async();                               // generic-proxy smem writes -> visible to the MMA (async proxy)
+          asm volatile("bar.sync 1, 288;" ::: "memory");     // the nine transform warps
+          if (tid == 0) { mbar_arrive(&full_a[s]); mbar_arrive(&stg_empty[st]); }
+          ++iu;
+        }
+      }
+    }
+  } else if (warp >= 2 && warp <= 5) {
     // ---------------- epilogue ----------------
     const int q = warp & 3;
     const int ml = q * 32 + lane;
@@ -602,7 +721,6 @@ conv_first_kernel(const float* __restrict__ d, const float* __restrict__ sigma, 
   }
 }
 
-struct H8 { __half2 v[4]; };  // 8 channels = 16 bytes
 
 __device__ __forceinline__ void load8(const __half* hi, const __half* lo, size_t off, float (&f)[8]) {
   H8 a = *reinterpret_cast<const H8*>(hi + off);
@@ -760,7 +878,8 @@ int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, con
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return TFPNP_ERR_CUDA;
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+  CUtensorMapSwizzle sw = inner_bytes < 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                          : inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -803,29 +922,39 @@ bool use_pdl() {
   return v != 0;
 }
 
-template <int BN, int KC, bool RES>
+template <int BN, int KC, bool RES, bool FUSE>
 int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
     attr_set = true;
   }
-  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES>, dim3(c.grid), dim3(kConvThreads), c.smem_bytes, st, use_pdl(),
-                          c.p.cluster, c.p));
+  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE>, dim3(c.grid), dim3(FUSE ? kConvFuseThreads : kConvThreads),
+                          c.smem_bytes, st, use_pdl(), c.p.cluster, c.p));
   TFPNP_COUNT_LAUNCH();
   return 0;
 }
 
 int launch_conv2(const Conv2Plan& c, cudaStream_t st) {
   const int key = c.BN * 1000 + c.kc * 10 + (c.resident ? 1 : 0);
+  if (c.p.up_fused) {
+    switch (key) {      // the four decoder conv-0 layers of UNet(2,1): 96->32, 192->64, 384->128, 768->256
+      case 32321: return launch_conv2_t<32, 32, true, true>(c, st);
+      case 64640: return launch_conv2_t<64, 64, false, true>(c, st);
+      case 128640: return launch_conv2_t<128, 64, false, true>(c, st);
+    }
+    set_error("conv2: no fused-upsample variant for BN %d KC %d (resident %d)", c.BN, c.kc, (int)c.resident);
+    return TFPNP_ERR_INVALID;
+  }
   switch (key) {
-    case 32321: return launch_conv2_t<32, 32, true>(c, st);
-    case 64321: return launch_conv2_t<64, 32, true>(c, st);
-    case 64641: return launch_conv2_t<64, 64, true>(c, st);
-    case 32320: return launch_conv2_t<32, 32, false>(c, st);
-    case 64320: return launch_conv2_t<64, 32, false>(c, st);
-    case 64640: return launch_conv2_t<64, 64, false>(c, st);
-    case 128640: return launch_conv2_t<128, 64, false>(c, st);
+    case 32321: return launch_conv2_t<32, 32, true, false>(c, st);
+    case 64321: return launch_conv2_t<64, 32, true, false>(c, st);
+    case 64641: return launch_conv2_t<64, 64, true, false>(c, st);
+    case 32320: return launch_conv2_t<32, 32, false, false>(c, st);
+    case 64320: return launch_conv2_t<64, 32, false, false>(c, st);
+    case 64640: return launch_conv2_t<64, 64, false, false>(c, st);
+    case 128640: return launch_conv2_t<128, 64, false, false>(c, st);
   }
   set_error("conv2: unsupported BN %d KC %d (resident %d)", c.BN, c.kc, (int)c.resident);
   return TFPNP_ERR_INVALID;
@@ -837,7 +966,7 @@ int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, con
                const cuuint32_t* box, int inner_bytes);
 
 // Fill everything of a Conv2Plan except the tensor maps.
-int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, int W, bool x3) {
+int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, int W, bool x3, bool fuse_up = false) {
   Conv2Params& p = c.p;
   const int Cin = C0 + C1;
   const int kc = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
@@ -854,7 +983,12 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   p.a_stage_bytes = (kHaloRows * row_bytes + 1023) & ~1023;
   p.b_stage_bytes = c.BN * row_bytes;                       // multiple of 1024 for all (BN, kc) used
   const int w_bytes = 9 * (Cin / kc) * p.b_stage_bytes;
-  const int misc = 1024 + 1024 + 2048 + 256;                // alignment slack + barriers + bias[<=512] + outc[33]
+  p.up_fused = fuse_up ? 1 : 0;
+  p.stg_bytes = (kUpBox * kUpBox * row_bytes + 1023) & ~1023;
+  p.up_sy = (float)(H / 2 - 1) / (float)(H - 1);
+  p.up_sx = (float)(W / 2 - 1) / (float)(W - 1);
+  // alignment slack + barriers + bias[<=512] + outc[33] (+ two low-res staging slots when the upsample is fused)
+  const int misc = 1024 + 1024 + 2048 + 256 + (fuse_up ? 2 * p.stg_bytes : 0);
   c.resident = !x3 && p.num_n_tiles == 1 && c.BN <= 64 && w_bytes <= 100 * 1024 &&
                env_int("TFPNP_CONV_RESIDENT", 1) != 0;
   if (c.resident) {
@@ -876,7 +1010,7 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int occ = (c.smem_bytes <= 112 * 1024 && c.BN <= 64) ? 2 : 1;
+  const int occ = (c.smem_bytes <= 112 * 1024 && c.BN <= 64 && !fuse_up) ? 2 : 1;
   // streamed weights: clusters of 2 (or 4) CTAs fetch each slab once and multicast it
   int cs = 1;
   if (!c.resident) {
@@ -1001,12 +1135,16 @@ struct UNetTc : Denoiser {
   bool fused_pool[kNumUnetConv3] = {};   // layer l also wrote its 2x2-max-pooled output (into S2)
   bool fused_outc = false;               // layer 26 produced x directly
 
-  int plan_conv_v2(int l, const Act& s0, const Act* s1, const Act& dst, int B) {
+  bool fused_up[kNumUnetConv3] = {};     // decoder conv-0 layer l interpolates its second source itself
+
+  // `low`: when non-null, source 1 is the bilinear x2 up-sampling of this low-resolution tensor, fused into the layer
+  int plan_conv_v2(int l, const Act& s0, const Act* s1, const Act& dst, int B, const Act* low = nullptr) {
     const ConvSpec& sp = unet_conv_specs()[l];
     Conv2Plan& c = convs2[l];
     memset(&c.p, 0, sizeof(c.p));
     const int c1 = s1 ? s1->C : 0;
-    TFPNP_TRY(plan_conv2_geometry(c, s0.C, c1, sp.cout, B, dst.H, dst.W, x3));
+    fused_up[l] = low != nullptr;
+    TFPNP_TRY(plan_conv2_geometry(c, s0.C, c1, sp.cout, B, dst.H, dst.W, x3, low != nullptr));
     Conv2Params& p = c.p;
     p.bias = biases.as<float>() + b_off[l];
     p.out_hi = dst.hi;
@@ -1021,6 +1159,15 @@ struct UNetTc : Denoiser {
     const Act* srcs[2] = {&s0, s1};
     for (int s = 0; s < 2; ++s) {
       if (!srcs[s]) { p.a_map[s][0] = p.a_map[0][0]; p.a_map[s][1] = p.a_map[0][1]; continue; }
+      if (s == 1 && low) {       // unswizzled 11x11 window of the low-resolution tensor
+        cuuint64_t dims[4] = {(cuuint64_t)low->C, (cuuint64_t)low->W, (cuuint64_t)low->H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)low->C * 2, (cuuint64_t)low->W * low->C * 2,
+                                 (cuuint64_t)low->H * low->W * low->C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)c.kc, (cuuint32_t)kUpBox, (cuuint32_t)kUpBox, 1};
+        TFPNP_TRY(encode_map(&p.a_map[1][0], low->hi, 4, dims, strides, box, -1));
+        p.a_map[1][1] = p.a_map[1][0];
+        continue;
+      }
       TFPNP_TRY(encode_halo_map(&p.a_map[s][0], srcs[s]->hi, srcs[s]->C, B, dst.H, dst.W, c.kc));
       if (x3) TFPNP_TRY(encode_halo_map(&p.a_map[s][1], srcs[s]->lo, srcs[s]->C, B, dst.H, dst.W, c.kc));
       else p.a_map[s][1] = p.a_map[s][0];
@@ -1035,10 +1182,11 @@ struct UNetTc : Denoiser {
   }
 
   // build ConvParams for layer l reading (src0 [, src1]) and writing dst
-  int plan_conv(int l, const Act& s0, const Act* s1, const Act& dst, int B) {
-    if (conv2_eligible(dst.H, dst.W)) return plan_conv_v2(l, s0, s1, dst, B);
+  int plan_conv(int l, const Act& s0, const Act* s1, const Act& dst, int B, const Act* low = nullptr) {
+    if (conv2_eligible(dst.H, dst.W)) return plan_conv_v2(l, s0, s1, dst, B, low);
     convs2[l].grid = 0;
     fused_pool[l] = false;
+    fused_up[l] = false;
     if (l == 26) fused_outc = false;
     const ConvSpec& sp = unet_conv_specs()[l];
     ConvParams& p = convs[l];
@@ -1111,7 +1259,10 @@ struct UNetTc : Denoiser {
     for (int k = 0; k < 4; ++k) {
       int lv = 3 - k, h = H >> lv, w = W >> lv, l0 = 15 + 3 * k;
       Act up = view(S0, ch[lv + 1], h, w);
-      TFPNP_TRY(plan_conv(l0, skip[lv], &up, view(S1, ch[lv], h, w), B));
+      // the block input: x5 for the first block, else the previous block's output in S2
+      Act low = view(k == 0 ? skip[4] : S2, ch[lv + 1], h / 2, w / 2);
+      const bool fuse_up = !x3 && conv2_eligible(h, w) && env_int("TFPNP_CONV_FUSE_UP", 1) != 0;
+      TFPNP_TRY(plan_conv(l0, skip[lv], &up, view(S1, ch[lv], h, w), B, fuse_up ? &low : nullptr));
       TFPNP_TRY(plan_conv(l0 + 1, view(S1, ch[lv], h, w), nullptr, view(S0, ch[lv], h, w), B));
       TFPNP_TRY(plan_conv(l0 + 2, view(S0, ch[lv], h, w), nullptr, view(S2, ch[lv], h, w), B));
     }
@@ -1148,9 +1299,10 @@ struct UNetTc : Denoiser {
     for (int k = 0; k < 4; ++k) {
       int lv = 3 - k, h = H >> lv, w = W >> lv;
       const Act& src = k == 0 ? skip[4] : S2;
+      if (!fused_up[15 + 3 * k])
       TFPNP_CUDA_OK(launch_ex(x3 ? upsample2_nhwc<true> : upsample2_nhwc<false>, dim3(cdiv(w * (ch[lv + 1] / 8), T), h, B),
                               dim3(T), 0, st, use_pdl(), 1, src.hi, src.lo, S0.hi, S0.lo, h / 2, w / 2, ch[lv + 1]));
-      TFPNP_COUNT_LAUNCH();
+      if (!fused_up[15 + 3 * k]) TFPNP_COUNT_LAUNCH();
       for (int j = 0; j < 3; ++j) {
         const int l = 15 + 3 * k + j;
         if (l == 26 && fused_outc) { convs2[l].p.d_in = x; convs2[l].p.x_out = out; }
