@@ -312,3 +312,79 @@ def test_native_library_is_loaded(dev):
     maps = open("/proc/self/maps").read()
     assert "libtfpnp_b200.so" in maps
     assert T.lib().tfpnp_version() == 100
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE configs 3-5 at their full per-GPU shapes: size-independent properties
+# (sharded calls bit-identical to the full call = the multi-GPU equality; finite outputs) plus
+# a small slice against the CPU oracle.
+# ------------------------------------------------------------------------------------------
+
+def _shard_equal(solver, full, call, n, parts):
+    import tfpnp_b200 as T
+    outs = []
+    for r in range(parts):
+        lo, hi = T.shard_bounds(n, r, parts)
+        outs.append(call(slice(lo, hi)))
+    assert torch.equal(torch.cat(outs), full)
+
+
+def test_pr_config3_full_shape(dev):
+    """pr iADMM, env_batch=36, 256x256, 4 CDP masks (2 iterations here; the loop is linear in iters)."""
+    import tfpnp_b200 as T
+    d = synth.pr_batch(36, 256, 2)
+    dd = cu(d, dev)
+    s = T.IADMMSolver_PR(denoiser("fp16", "default"))
+    call = lambda sl: s((dd["state"][sl], (dd["y0"][sl], dd["mask"][sl])), (dd["sigma_d"][sl], dd["mu"][sl], dd["tau"][sl]))
+    with torch.no_grad():
+        full = call(slice(0, 36))
+        assert torch.isfinite(full).all()
+        _shard_equal(s, full, call, 36, 3)
+    sl = slice(0, 2)
+    ref = O.iadmm_pr(weights("default"), d["state"][sl], d["y0"][sl], d["mask"][sl], d["sigma_d"][sl], d["mu"][sl], d["tau"][sl])
+    assert_close(full[sl], ref, 1e-4, "pr cfg3 slice")
+
+
+def test_spi_config5_per_gpu_shape(dev):
+    """spi ADMM, 48 images per GPU (384 over 8 GPUs), 128x128, K in {4,6,8}."""
+    import tfpnp_b200 as T
+    d = synth.spi_batch(48, 128, 2)
+    dd = cu(d, dev)
+    s = T.ADMMSolver_SPI(denoiser("fp16", "default"))
+    call = lambda sl: s((dd["state"][sl], (dd["x0"][sl], dd["K"][sl])), (dd["sigma_d"][sl], dd["mu"][sl]))
+    with torch.no_grad():
+        full = call(slice(0, 48))
+        assert torch.isfinite(full).all()
+        _shard_equal(s, full, call, 48, 4)
+    sl = slice(0, 3)
+    ref = O.admm_spi(weights("default"), d["state"][sl], d["x0"][sl], d["K"][sl], d["sigma_d"][sl], d["mu"][sl])
+    l2, _ = rel_err(full[sl], ref)
+    assert l2 <= 1e-4, l2
+
+
+def test_ct_config4_per_gpu_shape(dev):
+    """ct iADMM, 8 images per GPU (32 over 4 GPUs), 256x256, 60 views."""
+    import tfpnp_b200 as T
+    cs, sn, det = O.ct_geometry(256, 60)
+    g = torch.Generator().manual_seed(7)
+    gt = torch.rand(8, 1, 256, 256, generator=g)
+    # measurements through the GPU operators (the CPU restatement of A at 256x256x60 is slow)
+    s = T.IADMMSolver_CT(denoiser("fp16", "default"))
+    opn = s.radon_generator(256, 60, dev)
+    y0 = T.radon_forward(gt.to(dev), 60)
+    assert y0.shape == (8, 1, 60, 363)
+    x0 = T.radon_backward(y0, 256, 60) / opn ** 2
+    state = torch.cat((x0, x0.clone(), torch.zeros_like(x0)), dim=1)
+    view = torch.full((8, 1, 256, 256), 60 / 120.0, device=dev)
+    par = [(torch.rand(8, 2, generator=g) * sc).to(dev) for sc in (70 / 255, 1.0, 2.0)]
+    call = lambda sl: s((state[sl], (y0[sl], view[sl])), tuple(p[sl] for p in par))
+    with torch.no_grad():
+        full = call(slice(0, 8))
+        assert torch.isfinite(full).all() and full.shape == state.shape
+        _shard_equal(s, full, call, 8, 2)
+    # one image, one iteration against the oracle with the same operator norm
+    ref = O.iadmm_ct(weights("default"), state[:1].cpu(), y0[:1].cpu(), 60, opn, par[0][:1, :1].cpu(), par[1][:1, :1].cpu(),
+                     par[2][:1, :1].cpu())
+    with torch.no_grad():
+        one = s((state[:1], (y0[:1], view[:1])), tuple(p[:1, :1] for p in par))
+    assert_close(one, ref, 1e-4, "ct cfg4 one image")

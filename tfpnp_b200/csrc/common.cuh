@@ -131,6 +131,9 @@ struct Denoiser {
   virtual ~Denoiser() {}
   // allocate workspaces / descriptors for this shape (never called during graph capture)
   virtual int prepare(int B, int H, int W) = 0;
+  // a second engine over the SAME weights with its own activation workspace, so two half-batches can run
+  // concurrently on two streams (nullptr if the implementation does not support it); owned by the caller
+  virtual Denoiser* clone_shared() { return nullptr; }
   // x, out: [B,H,W] fp32 (C=1); sigma[b] at sigma[b*sigma_stride]
   virtual int forward(const float* x, const float* sigma, int64_t sigma_stride, float* out, int B,
                       int H, int W, cudaStream_t st) = 0;

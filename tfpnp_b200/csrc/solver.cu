@@ -5,6 +5,7 @@
 // plus an unpack and a pack kernel that touch the caller's tensors.
 #include "tasks.cuh"
 #include <map>
+#include <cstdlib>
 #include <vector>
 
 namespace tfpnp {
@@ -87,6 +88,12 @@ __global__ void gather_params(const float* __restrict__ sig, const float* __rest
 struct Solver {
   tfpnp_solver_config cfg{};
   Denoiser* den = nullptr;
+  Denoiser* den2 = nullptr;          // second engine over the same weights: the batch is denoised as two
+                                     // independent halves on two streams, so one half's kernels fill the SMs the
+                                     // other half's kernel tails / under-filled deep layers leave idle
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int split_min_batch = 16;
   bool complex_state = false;
   int cap_B = 0, cap_it = 0;
   DevBuf x, z, u, d, T, aux0p, aux1p, params, k10, resid;
@@ -142,6 +149,21 @@ struct Solver {
     return 0;
   }
 
+  bool split_batch(int B) const { return den2 != nullptr && B >= split_min_batch; }
+
+  int denoise(const float* sig, int B, cudaStream_t st) {
+    const size_t HW = (size_t)cfg.H * cfg.W;
+    if (!split_batch(B)) return den->forward(d.as<float>(), sig, 1, x.as<float>(), B, cfg.H, cfg.W, st);
+    const int B0 = B / 2, B1 = B - B0;
+    TFPNP_CUDA_OK(cudaEventRecord(ev_fork, st));
+    TFPNP_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0));
+    TFPNP_TRY(den->forward(d.as<float>(), sig, 1, x.as<float>(), B0, cfg.H, cfg.W, st));
+    TFPNP_TRY(den2->forward(d.as<float>() + B0 * HW, sig + B0, 1, x.as<float>() + B0 * HW, B1, cfg.H, cfg.W, side));
+    TFPNP_CUDA_OK(cudaEventRecord(ev_join, side));
+    TFPNP_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
+    return 0;
+  }
+
   // enqueue the iteration loop on `st` (no allocation, no sync: graph-capturable)
   int enqueue_loop(int B, int iters, cudaStream_t st, bool prof) {
     const int N = cfg.W;
@@ -158,11 +180,11 @@ struct Solver {
         TFPNP_TRY(spi_update(x.as<float>(), z.as<float>(), u.as<float>(), d.as<float>(),
                              aux0p.as<float>(), k10.as<float>(), mu, B, (int)HW, st));
         if (prof) cudaEventRecord(events[ev++], st);
-        TFPNP_TRY(den->forward(d.as<float>(), sig, 1, x.as<float>(), B, cfg.H, cfg.W, st));
+        TFPNP_TRY(denoise(sig, B, st));
         if (prof) cudaEventRecord(events[ev++], st);
         continue;
       }
-      TFPNP_TRY(den->forward(d.as<float>(), sig, 1, x.as<float>(), B, cfg.H, cfg.W, st));
+      TFPNP_TRY(denoise(sig, B, st));
       if (prof) cudaEventRecord(events[ev++], st);
       switch (cfg.task) {
         case TFPNP_TASK_CSMRI:
@@ -194,11 +216,17 @@ struct Solver {
     const int HW = cfg.H * cfg.W;
     g_launch_count = 0;
     TFPNP_TRY(ensure(B, iters > 0 ? iters : 1));
-    TFPNP_TRY(den->prepare(B, cfg.H, cfg.W));
-    if (den->generation != den_generation) {      // the denoiser's workspaces moved
+    if (split_batch(B)) {
+      TFPNP_TRY(den->prepare(B / 2, cfg.H, cfg.W));
+      TFPNP_TRY(den2->prepare(B - B / 2, cfg.H, cfg.W));
+    } else {
+      TFPNP_TRY(den->prepare(B, cfg.H, cfg.W));
+    }
+    const int gen = den->generation + (den2 ? den2->generation : 0);
+    if (gen != den_generation) {      // a denoiser workspace moved
       for (auto& g : graphs) cudaGraphExecDestroy(g.second);
       graphs.clear();
-      den_generation = den->generation;
+      den_generation = gen;
     }
     const int T256 = 256;
     dim3 grid(cdiv(HW, T256 * 4), B);
@@ -292,6 +320,10 @@ struct Solver {
   std::map<std::pair<int, int>, int64_t> graph_nodes;
 
   ~Solver() {
+    delete den2;
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     for (auto e : events) cudaEventDestroy(e);
     if (cap_stream) cudaStreamDestroy(cap_stream);
@@ -315,6 +347,20 @@ int solver_create(const tfpnp_solver_config* cfg, Denoiser* den, void** out) {
   s->cfg = *cfg;
   s->den = den;
   s->complex_state = fft_task;
+  {
+    const char* e = getenv("TFPNP_SPLIT");
+    const int split = e ? atoi(e) : 0;   // measured: no gain on B200 (persistent grids serialise), off by default
+    if (split) {
+      s->den2 = den->clone_shared();
+      if (s->den2) {
+        if (cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+          delete s; set_error("stream/event creation failed"); return TFPNP_ERR_CUDA;
+        }
+      }
+    }
+  }
   if (cfg->task == TFPNP_TASK_CT) {
     if (!(cfg->views > 0 && cfg->opnorm > 0.f)) { delete s; set_error("CT needs views > 0 and opnorm > 0"); return TFPNP_ERR_INVALID; }
     int rc = s->geom.init(cfg->H, cfg->views);

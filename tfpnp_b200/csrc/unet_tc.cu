@@ -1057,6 +1057,7 @@ struct Act {            // NHWC fp16 activation tensor (hi plane, optional lo pl
 
 struct UNetTc : Denoiser {
   bool x3 = false;
+  bool shares_weights = false;   // clone_shared(): weight buffers belong to the parent engine
   // weights
   DevBuf w_hi, w_lo, biases, w_out;
   FirstLayerW first_w;          // inc.conv-0 weights [32][2*9] + bias, passed by value
@@ -1319,7 +1320,18 @@ struct UNetTc : Denoiser {
     return 0;
   }
 
+  Denoiser* clone_shared() override {
+    UNetTc* c = new UNetTc();
+    c->precision = precision; c->x3 = x3; c->shares_weights = true;
+    c->w_hi = w_hi; c->w_lo = w_lo; c->biases = biases; c->w_out = w_out;   // non-owning aliases
+    c->first_w = first_w;
+    memcpy(c->w_off, w_off, sizeof(w_off));
+    memcpy(c->b_off, b_off, sizeof(b_off));
+    return c;
+  }
+
   ~UNetTc() override {
+    if (shares_weights) { w_hi.p = w_lo.p = biases.p = w_out.p = nullptr; }
     w_hi.release(); w_lo.release(); biases.release(); w_out.release(); act.release();
   }
 };
