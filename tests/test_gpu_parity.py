@@ -356,10 +356,16 @@ def test_spi_config5_per_gpu_shape(dev):
         full = call(slice(0, 48))
         assert torch.isfinite(full).all()
         _shard_equal(s, full, call, 48, 4)
+    # The 10-step bisection prox is piecewise constant (1e-3 cells): a denoiser perturbation delta moves a
+    # fraction ~delta/1e-3 of the pixels by one cell, so this loop amplifies rounding differences.  The fp32-
+    # equivalent mode meets 1e-4; the fp16 mode (10-bit operands, like TF32) is held to 2e-3.
     sl = slice(0, 3)
     ref = O.admm_spi(weights("default"), d["state"][sl], d["x0"][sl], d["K"][sl], d["sigma_d"][sl], d["mu"][sl])
-    l2, _ = rel_err(full[sl], ref)
-    assert l2 <= 1e-4, l2
+    assert rel_err(full[sl], ref)[0] <= 2e-3
+    s3 = T.ADMMSolver_SPI(denoiser("fp16x3", "default"))
+    with torch.no_grad():
+        out3 = s3((dd["state"][sl], (dd["x0"][sl], dd["K"][sl])), (dd["sigma_d"][sl], dd["mu"][sl]))
+    assert rel_err(out3, ref)[0] <= 1e-4
 
 
 def test_ct_config4_per_gpu_shape(dev):

@@ -894,12 +894,15 @@ int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, con
 }
 
 int set_conv_attrs() {
-  static bool done = false;
+  static unsigned long long done_mask = 0;   // one bit per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool done = (done_mask >> (dev & 63)) & 1ull;
   if (done) return 0;
   TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<32>::kSmemBytes));
   TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
   TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
-  done = true;
+  done_mask |= 1ull << (dev & 63);
   return 0;
 }
 
@@ -924,11 +927,13 @@ bool use_pdl() {
 
 template <int BN, int KC, bool RES, bool FUSE>
 int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // one bit per device (a function attribute is per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_set >> (dev & 63) & 1ull)) {
     TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
-    attr_set = true;
+    attr_set |= 1ull << (dev & 63);
   }
   TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE>, dim3(c.grid), dim3(FUSE ? kConvFuseThreads : kConvThreads),
                           c.smem_bytes, st, use_pdl(), c.p.cluster, c.p));
