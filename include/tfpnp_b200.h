@@ -128,6 +128,32 @@ int tfpnp_radon_backward(const float* sino, float* img, int B, int N, int views,
  * psnr[b] = 10 log10(1 / mean((clamp(out[b],0,1) - gt[b])^2)); out, gt: [B,HW] */
 int tfpnp_psnr(const float* out, const float* gt, float* psnr, int B, int64_t HW, void* stream);
 
+/* ---- environment bookkeeping: PnPEnv.step (tfpnp/env/base.py:157-191) ----------
+ * The caller side of the solver on every episode step.  `idx` is a DEVICE vector of int64 row
+ * indices (the env's idx_left, base.py:154,181); NULL means the identity.  `items` / `ch` are HOST
+ * arrays (copied into the kernel parameters). */
+
+/* dst_t[r] = src_t[idx[r]] for every tensor t of an observation in ONE launch -- replaces the
+ * per-tensor fancy indexing of `_observation` (tasks/csmri/env.py:49-57).  Rows are raw bytes. */
+typedef struct { const void* src; void* dst; int64_t row_bytes; } tfpnp_gather_item;
+int tfpnp_env_gather(const tfpnp_gather_item* items, int n_items, const int64_t* idx, int n_rows,
+                     void* stream);
+
+/* state['solver'][idx] = solver_state; state['output'][idx] = solver.get_output(solver_state)
+ * (base.py:171-172 with base.py:101-104 / tasks/csmri/solver.py:9-18) fused.
+ * solver_state [n_rows,3,HW(,2)]; state_solver [B,3,HW(,2)]; state_output [B,1,HW]. */
+int tfpnp_env_scatter_state(const float* solver_state, const int64_t* idx, int n_rows,
+                            float* state_solver, float* state_output, int64_t HW, int complex_state,
+                            void* stream);
+
+/* get_policy_ob (tasks/{csmri,pr,ct,spi}/env.py get_policy_ob): dst [n_rows, n_ch, HW] fp32 with
+ * dst[r,c,i] = float(src_c[idx[r]*img_stride_c + offset_c + i*pix_stride_c]).  complex2real /
+ * complex2channel (transforms.py:16-26) are pix_stride 2 with offset 0 / 1; dtype 1 reads a
+ * torch.bool / uint8 plane (mask.float()). */
+typedef struct { const void* src; int64_t img_stride; int64_t offset; int32_t pix_stride; int32_t dtype; } tfpnp_ob_channel;
+int tfpnp_env_policy_ob(const tfpnp_ob_channel* ch, int n_ch, const int64_t* idx, int n_rows,
+                        int64_t HW, float* dst, void* stream);
+
 /* ---- introspection used by tests / bench ---------------------------------- */
 /* measured device time (ms) of the denoiser part and the data-fidelity part of the last
  * forward when profiling is enabled with tfpnp_solver_set_profiling(handle, 1) */

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import pnp_oracle as O
+from . import env_oracle as E
 from . import refshim, synth
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
@@ -127,7 +128,61 @@ def main():
         assert torch.equal(O.cdp_backward(gg, m), T.cdp_backward(gg, m))
         save("transforms", x=x.numpy(), fft2=T.fft2(x).numpy(), ifft2=T.ifft2(x).numpy(), mask=m.numpy(),
              cdp_fwd=T.cdp_forward(x, m).numpy(), g=gg.numpy(), cdp_bwd=T.cdp_backward(gg, m).numpy())
+
+        # 6. environment bookkeeping (tfpnp/env/base.py:121-191 + tasks/{csmri,spi}/env.py): a 3-step episode with
+        #    images dropping out, driven through the UNMODIFIED reference env + solver classes
+        env_fixture("csmri", weights[("he", 0)])
+        env_fixture("spi", weights[("he", 0)])
     print("done")
+
+
+def _load_ref_env(task):
+    import importlib.util
+    path = os.path.join(refshim.REFERENCE_ROOT, "tasks", task, "env.py")
+    spec = importlib.util.spec_from_file_location(f"_ref_{task}_env", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return getattr(mod, {"csmri": "CSMRIEnv", "spi": "SPIEnv"}[task])
+
+
+def env_fixture(task, sd, B=4, n=32, steps=3, pack=2):
+    d = {"csmri": synth.csmri_batch, "spi": synth.spi_batch}[task](B, n, steps * pack)
+    data = E.env_data(task, d)
+    actions = E.episode_actions(task, d, B, steps, pack)
+    ref_env = _load_ref_env(task)(None, refshim.reference_solver(task, sd), steps)
+    ora = E.EnvOracle(task, sd, steps)
+    clone = lambda x: {k: v.clone() for k, v in x.items()}
+    ob_r = ref_env.reset(data=clone(data))
+    ob_o = ora.reset(clone(data))
+    rec = {}
+
+    def check_ob(tag, r, o):
+        pr, po = ref_env.get_policy_ob(r), ora.policy_ob(o)
+        assert pr.shape == po.shape and (pr.shape[0] == 0 or close(po, pr) <= 2e-6), tag
+        assert pr.shape[1] == ref_env.ob_base_dim + 3
+        for k in o:
+            assert torch.equal(torch.as_tensor(getattr(r, k)).float(), o[k].float()) or close(o[k].float(), torch.as_tensor(getattr(r, k)).float()) <= 2e-6, (tag, k)
+        rec[tag + "_policy_ob"] = pr.numpy()
+        rec[tag + "_variables"] = r.variables.numpy()
+
+    check_ob("reset", ob_r, ob_o)
+    for s, a in enumerate(actions):
+        r = ref_env.step({k: v.clone() for k, v in a.items()})
+        o = ora.step({k: v.clone() for k, v in a.items()})
+        check_ob(f"step{s}_ob", r[0], o[0])
+        check_ob(f"step{s}_masked", r[1], o[1])
+        assert close(o[2], r[2], 1e-4) >= 0 and r[3] == o[3] and torch.equal(r[4]["done"], o[4]["done"])
+        rec[f"step{s}_reward"] = r[2].numpy()
+        rec[f"step{s}_all_done"] = np.asarray(r[3])
+        rec[f"step{s}_done"] = r[4]["done"].numpy()
+        for k, v in a.items():
+            rec[f"step{s}_action_{k}"] = v.numpy()
+        if r[3]:
+            break
+    rec["n_steps"] = np.asarray(s + 1)
+    save(f"env_{task}", **{"data_" + k: v.numpy() for k, v in data.items()}, **rec, wsum=weight_checksum(sd), init="he",
+         seed=0, max_episode_step=steps)
+    print(f"  env_{task}: reference env vs oracle env agree over {s + 1} steps")
 
 
 if __name__ == "__main__":

@@ -12,3 +12,4 @@ from .solver import (PnPSolver, ADMMSolver, IADMMSolver, ADMMSolver_CSMRI, IADMM
                      create_solver_pr, create_solver_ct, create_solver_spi)
 from .ops import radon_forward, radon_backward, torch_psnr, conv3x3_lrelu_nhwc  # noqa: F401
 from .dist import shard_batch, shard_bounds, all_gather_psnr  # noqa: F401
+from .env import Batch, Env, DifferentiableEnv, PnPEnv, CSMRIEnv, PREnv, CTEnv, SPIEnv  # noqa: F401

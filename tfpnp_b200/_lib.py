@@ -24,6 +24,15 @@ class SolverConfig(C.Structure):
                 ("ct_sin", C.POINTER(C.c_float)), ("use_graph", C.c_int)]
 
 
+class GatherItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("row_bytes", C.c_int64)]
+
+
+class ObChannel(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("img_stride", C.c_int64), ("offset", C.c_int64),
+                ("pix_stride", C.c_int32), ("dtype", C.c_int32)]
+
+
 # every symbol include/tfpnp_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "tfpnp_version": (C.c_int, []),
@@ -45,6 +54,11 @@ SIGNATURES = {
     "tfpnp_radon_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "tfpnp_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "tfpnp_env_gather": (C.c_int, [C.POINTER(GatherItem), C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "tfpnp_env_scatter_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_int, C.c_void_p]),
+    "tfpnp_env_policy_ob": (C.c_int, [C.POINTER(ObChannel), C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                      C.c_void_p]),
     "tfpnp_solver_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "tfpnp_solver_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }

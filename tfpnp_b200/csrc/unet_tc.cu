@@ -52,6 +52,12 @@ __device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
   return d;
 }
 
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // Epilogue pieces for one 32-column slice of an accumulator row.
 // act: + bias (smem broadcast), LeakyReLU(0.2) (unet.py:22) in fp32
 __device__ __forceinline__ void epilogue_act32(const uint32_t (&r)[32], const float* __restrict__ sbias, float (&v)[32]) {
@@ -75,9 +81,9 @@ __device__ __forceinline__ void epilogue_store_nhwc32(const float (&v)[32], __ha
     __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
     hi[j] = *reinterpret_cast<uint32_t*>(&hh);
   }
-  uint4* dst = reinterpret_cast<uint4*>(out_hi + off);
+  // 32-byte (sector-sized) stores: STG.256, two per 32 channels
 #pragma unroll
-  for (int q = 0; q < 4; ++q) dst[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+  for (int q = 0; q < 2; ++q) st_global_256(out_hi + off + 16 * q, &hi[8 * q]);
   if (out_lo) {
     uint32_t lo[16];
 #pragma unroll
@@ -86,9 +92,8 @@ __device__ __forceinline__ void epilogue_store_nhwc32(const float (&v)[32], __ha
       __half2 ll = __floats2half2_rn(v[2 * j] - back.x, v[2 * j + 1] - back.y);
       lo[j] = *reinterpret_cast<uint32_t*>(&ll);
     }
-    uint4* dl = reinterpret_cast<uint4*>(out_lo + off);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    for (int q = 0; q < 2; ++q) st_global_256(out_lo + off + 16 * q, &lo[8 * q]);
   }
 }
 __device__ __forceinline__ void epilogue_store32(const uint32_t (&r)[32], const float* __restrict__ sbias,
@@ -282,11 +287,18 @@ __device__ __forceinline__ unsigned long long gtimer() {
 
 constexpr int kUpBox = 11;                     // low-res window edge feeding an 18-pixel halo edge
 constexpr int kXformThreads = 288;                      // 9 transform warps
-constexpr int kConvFuseThreads = kConvThreads + kXformThreads;
+// Epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, one per M-tile half).  The epilogue of a
+// 256-pixel x BN tile is a long dependent instruction stream (~5 instructions per value); with one warp per quadrant
+// it is as long as the tile's MMAs for BN >= 64 (measured: 64->64 @64x64 ran at the epilogue's pace, and a one-tile
+// CTA exposes all of it).  The 64-channel-chunk variants run one CTA per SM and have the registers for 8 warps.
+template <int KC, bool FUSE> constexpr int conv2_nepi() { return (KC == 64 && !FUSE) ? 8 : 4; }
+template <int KC, bool FUSE> constexpr int conv2_threads() { return 64 + 32 * conv2_nepi<KC, FUSE>() + (FUSE ? kXformThreads : 0); }
 
 template <int BN, int KC, bool RESIDENT, bool FUSE>
-__global__ void __launch_bounds__(FUSE ? kConvFuseThreads : kConvThreads, FUSE ? 1 : 2)
+__global__ void __launch_bounds__(conv2_threads<KC, FUSE>(), (FUSE || KC == 64) ? 1 : 2)
 conv3x3_tc2(const __grid_constant__ Conv2Params p) {
+  constexpr int NEPI = conv2_nepi<KC, FUSE>();
+  static_assert(NEPI == 4 || BN >= 64, "two epilogue warps per quadrant split the tile by M-tile half in 64-column blocks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t ROW = KC * 2;                 // bytes per pixel row of a chunk
@@ -328,15 +340,16 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
     prefetch_tensormap(&p.w_map[0]);
     if (p.nchunk1) prefetch_tensormap(&p.a_map[1][0]);
   }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1);
-      mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], cs);   // a weight slot is free when ALL cluster CTAs released it
-    }
-    mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
+  if (warp == 1) {
+    if (lane < kMaxStages) {                                   // one ring slot per lane
+      mbar_init(&full_a[lane], 1); mbar_init(&empty_a[lane], 1);
+      mbar_init(&full_b[lane], 1); mbar_init(&empty_b[lane], cs);   // a weight slot is free when ALL cluster CTAs released it
+    } else if (lane < kMaxStages + 2) {
+      const int i = lane - kMaxStages;
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NEPI);
       mbar_init(&stg_full[i], 1); mbar_init(&stg_empty[i], 1);
+    } else if (lane == kMaxStages + 2) {
+      mbar_init(w_full, 1);
     }
     fence_barrier_init();
   }
@@ -448,6 +461,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
             const bool last_item = (c == nchunks - 1) && (prod == p.nprod - 1);
             if (RESIDENT) {
               if (elect_one()) {
+                if (!(p.dbg & 2))
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                   const uint32_t a_tap = a_lo + (((tap / 3) * kHaloW + tap % 3) * ROW >> 4);
@@ -509,12 +523,12 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       }
       (void)ia; (void)ib;
     }
-  } else if (FUSE && warp >= 6) {
+  } else if (FUSE && warp >= 2 + NEPI) {
     // ---------------- transform warps: bilinear x2 (align_corners) of the low-res window into the A stage ------
     // Thread = (halo column k, 16-byte channel group j, row group g): the column interpolation set-up is done
     // once per tile, the thread then walks its rows top-down keeping the horizontally interpolated source rows
     // in registers (consecutive output rows share them), so a row costs at most one new source row.
-    const int tid = threadIdx.x - kConvThreads;            // 0..287
+    const int tid = threadIdx.x - (64 + 32 * NEPI);        // 0..287
     constexpr int CH16 = KC / 8;                           // 16-byte channel groups per pixel row
     constexpr int SLOTS = kHaloW * CH16;                   // 144 (KC=64) / 72 (KC=32)
     constexpr int GROUPS = kXformThreads / SLOTS;          // 2 / 4 row groups
@@ -601,9 +615,12 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
         }
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
+  } else if (warp >= 2 && warp < 2 + NEPI) {
     // ---------------- epilogue ----------------
-    const int q = warp & 3;
+    const int q = warp & 3;                                // TMEM lane quadrant this warp may access
+    // with 8 epilogue warps, warp pair member e handles M-tile half e (columns [e*BN, (e+1)*BN) of the tile's 2*BN)
+    const int cb_begin = NEPI == 8 ? ((warp - 2) >> 2) * BN : 0;
+    const int cb_end = NEPI == 8 ? cb_begin + BN : 2 * BN;
     const int ml = q * 32 + lane;
     const int tw = ml & 7, th = ml >> 3;
     uint32_t it = 0;
@@ -623,7 +640,8 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       // the two M-tile halves sit side by side in TMEM: walk their 2*BN columns in blocks of 64
       // (one tcgen05.ld round trip per two 32-column slices)
 #pragma unroll 1
-      for (int cb = 0; cb < 2 * BN; cb += 64) {
+      for (int cb = cb_begin; cb < cb_end; cb += 64) {
+        if (p.dbg & 32) break;                  // knock-out: no TMEM reads, no epilogue math
         uint32_t r64[64];
         tmem_ld_32x64(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + cb, r64);
         tmem_ld_wait();
@@ -935,7 +953,7 @@ int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
                                        227 * 1024));
     attr_set |= 1ull << (dev & 63);
   }
-  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE>, dim3(c.grid), dim3(FUSE ? kConvFuseThreads : kConvThreads),
+  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE>, dim3(c.grid), dim3(conv2_threads<KC, FUSE>()),
                           c.smem_bytes, st, use_pdl(), c.p.cluster, c.p));
   TFPNP_COUNT_LAUNCH();
   return 0;
@@ -1015,7 +1033,7 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int occ = (c.smem_bytes <= 112 * 1024 && c.BN <= 64 && !fuse_up) ? 2 : 1;
+  const int occ = (c.smem_bytes <= 112 * 1024 && c.BN <= 64 && !fuse_up && kc == 32) ? 2 : 1;   // = the kernel's launch bounds
   // streamed weights: clusters of 2 (or 4) CTAs fetch each slab once and multicast it
   int cs = 1;
   if (!c.resident) {

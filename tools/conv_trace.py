@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch, tfpnp_b200 as T
 dev = torch.device("cuda:0")
 names = ["P: A slot free", "M: tile start", "M: tmem free", "M: A landed", "M: tile issued", "E: tile wait", "E: accum ready", "E: tile done"]
-for (C0, C1, Cout, H, W, B) in [(64, 0, 64, 64, 64, 48), (32, 0, 32, 128, 128, 48)]:
+for (C0, C1, Cout, H, W, B) in [(64, 0, 64, 64, 64, 48), (32, 0, 32, 128, 128, 48), (128, 0, 128, 32, 32, 48), (256, 0, 256, 16, 16, 48)]:
     x0 = torch.randn(B, H, W, C0, device=dev).half()
     w = torch.randn(Cout, C0 + C1, 3, 3) * 0.05
     b = torch.zeros(Cout)

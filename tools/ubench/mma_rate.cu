@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate(long long* out, int iters, in
 template <int N, int MODE>
 void run(const char* name, int sbo_rows) {
   long long* d; cudaMalloc(&d, 16);
-  const int iters = 50, smem = 64 * 1024;
+  const int iters = 50, smem = 100 * 1024;
   cudaFuncSetAttribute(mma_rate<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   mma_rate<N, MODE><<<1, 128, smem>>>(d, iters, sbo_rows);
   mma_rate<N, MODE><<<1, 128, smem>>>(d, iters, sbo_rows);
@@ -84,5 +84,10 @@ int main() {
   run<128, 0>("1 accum, fixed desc", 8);
   run<256, 0>("1 accum, fixed desc", 8);
   run<32, 0>("1 accum, fixed desc", 8);
+  run<96, 0>("1 accum, fixed desc", 8);
+  run<96, 3>("2 accum, conv desc pattern", 18);
+  run<192, 0>("1 accum, fixed desc", 8);
+  run<192, 3>("2 accum, conv desc pattern", 18);
+  run<256, 3>("2 accum, conv desc pattern", 18);
   return 0;
 }
