@@ -100,14 +100,17 @@ def test_native_env_matches_reference_fixture(task, dev):
     env = _native_env(task, dev, steps)
     ob = env.reset(data={k: v.clone() for k, v in data.items()})
     assert torch.equal(env.get_policy_ob(ob).cpu(), g["reset_policy_ob"])          # pure data movement: bit-exact
+    # SPI: the 10-step bisection prox has a 1e-3 resolution, a last-ulp difference flips isolated pixels by one cell
+    # (tests/test_gpu_parity.py::test_spi_golden) -> judged by the relative L2 error; CS-MRI by the max error
+    k, t = (0, 5e-4) if task == "spi" else (1, 1e-4)
     for s, a in enumerate(actions):
         ob, ob_m, reward, all_done, info = env.step(_cu(a, dev))
-        assert rel_err(ob.variables, g[f"step{s}_ob_variables"])[1] <= 1e-4
-        assert rel_err(env.get_policy_ob(ob), g[f"step{s}_ob_policy_ob"])[1] <= 1e-4
+        assert rel_err(ob.variables, g[f"step{s}_ob_variables"])[k] <= t
+        assert rel_err(env.get_policy_ob(ob), g[f"step{s}_ob_policy_ob"])[k] <= t
         pm = env.get_policy_ob(ob_m)
         assert tuple(pm.shape) == tuple(g[f"step{s}_masked_policy_ob"].shape)
         if pm.shape[0]:
-            assert rel_err(pm, g[f"step{s}_masked_policy_ob"])[1] <= 1e-4
+            assert rel_err(pm, g[f"step{s}_masked_policy_ob"])[k] <= t
         assert torch.allclose(reward.cpu(), g[f"step{s}_reward"], rtol=1e-3, atol=2e-3)   # dB
         assert bool(all_done) == bool(g[f"step{s}_all_done"])
         assert torch.equal(info["done"].cpu(), g[f"step{s}_done"])

@@ -31,6 +31,9 @@ CASES = [
     (64, 0, 64, 64, 64, 8),       # resident 72 KB weights, 1 CTA/SM
     (128, 0, 128, 32, 32, 6),     # streamed weights, multi-tile
     (64, 128, 64, 64, 64, 3),     # streamed weights, concat, 3 chunks
+    (512, 0, 512, 8, 8, 48),      # 8x8 level at the bench shape: two-image M-tiles, 4 N tiles, weight multicast
+    (256, 512, 256, 8, 8, 5),     # 8x8 level, concat of two sources, ragged (odd) batch
+    (512, 0, 512, 8, 8, 1),       # a single 8x8 image: falls back to the one-tile-per-CTA kernel
 ]
 
 

@@ -52,6 +52,27 @@ __device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
   return d;
 }
 
+// packed fp32 arithmetic (sm_100 FFMA2 / FMUL2): two lanes per instruction, scalar first operand broadcast
+__device__ __forceinline__ float2 fmul2(float s, float2 a) {
+  unsigned long long rs, ra, rd;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rs) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(rs), "l"(ra));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float s, float2 a, float2 c) {   // s * a + c
+  unsigned long long rs, ra, rc, rd;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rs) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rs), "l"(ra), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
 __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* v) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -294,10 +315,18 @@ constexpr int kXformThreads = 288;                      // 9 transform warps
 template <int KC, bool FUSE> constexpr int conv2_nepi() { return (KC == 64 && !FUSE) ? 8 : 4; }
 template <int KC, bool FUSE> constexpr int conv2_threads() { return 64 + 32 * conv2_nepi<KC, FUSE>() + (FUSE ? kXformThreads : 0); }
 
-template <int BN, int KC, bool RESIDENT, bool FUSE>
+// SMALL: 8x8 images (the bottleneck level of a 128x128 input).  One UMMA M-tile = TWO images: the A box is
+// {KC, 10 (x), 2 (image), 10 (y)} over the tensor viewed as {C, W, B, H}, i.e. smem row = y'*20 + img*10 + x', so the
+// sixteen 8-pixel row groups (y, img) of tap (ky,kx) start at row ky*20 + kx and are uniformly 10 rows apart (SBO) --
+// the same shifted-descriptor scheme as the 18x18 halo tile, one M-tile (one accumulator) per work item.
+template <int BN, int KC, bool RESIDENT, bool FUSE, bool SMALL = false>
 __global__ void __launch_bounds__(conv2_threads<KC, FUSE>(), (FUSE || KC == 64) ? 1 : 2)
 conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   constexpr int NEPI = conv2_nepi<KC, FUSE>();
+  static_assert(!SMALL || (!FUSE && !RESIDENT && KC == 64 && NEPI == 8), "SMALL is built for the streamed 64-channel-chunk variant");
+  constexpr int TAP_ROWS = SMALL ? 20 : kHaloW;          // smem rows between kernel rows ky
+  constexpr int SBO_ROWS = SMALL ? 10 : kHaloW;          // smem rows between the M-tile's 8-pixel row groups
+  constexpr int A_ROWS = SMALL ? 200 : kHaloRows;        // rows one A stage receives
   static_assert(NEPI == 4 || BN >= 64, "two epilogue warps per quadrant split the tile by M-tile half in 64-column blocks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -325,6 +354,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
+  if (p.dbg & 64) { pdl_wait(); return; }   // knock-out: launch + dependency wait only
   if (threadIdx.x == 0) TRACE(0, 1000);
   constexpr uint32_t kTmemCols = 4 * BN;
   // work items: (group of `cs` consecutive super-tiles, n-tile); CTA `crank` of a cluster takes
@@ -371,8 +401,11 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   }
   pdl_wait();   // prologue + weight prefetch overlapped the previous layer's tail
   if (threadIdx.x == 0) TRACE(0, 1002);
+  const bool skip_roles = (p.dbg & 128) != 0;   // knock-out: prologue + teardown only
 
-  if (warp == 0) {
+  if (skip_roles) {
+    if (RESIDENT && warp == 1) mbar_wait(w_full, 0);   // do not exit with the weight TMA in flight
+  } else if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       uint32_t ia = 0, ib = 0, iu = 0;
@@ -388,10 +421,11 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
           const int cc = (src == 0 ? c : c - p.nchunk0) * KC;
           for (int prod = 0; prod < p.nprod; ++prod) {
             const int s = ia % SA;
-            mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);
+            if (!(FUSE && src == 1)) mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);
             TRACE(0, ia);
             if (FUSE && src == 1) {
-              // A stage s is free: hand the low-res window to the transform warps, they fill the stage
+              // hand the low-res window to the transform warps as soon as a staging slot is free (the load runs
+              // ahead of the A ring); they wait for A stage s themselves and fill it
               const int st = iu & 1;
               mbar_wait(&stg_empty[st], ((iu >> 1) & 1) ^ 1);
               mbar_arrive_expect_tx(&stg_full[st], (uint32_t)(kUpBox * kUpBox) * ROW);
@@ -401,8 +435,9 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
               ++iu;
             } else if (p.dbg & 4) mbar_arrive(&full_a[s]);
             else {
-              mbar_arrive_expect_tx(&full_a[s], (uint32_t)kHaloRows * ROW);
-              tma_load_4d(sA + s * p.a_stage_bytes, &p.a_map[src][prod == 1 ? 1 : 0], &full_a[s], cc, w0 - 1, h0 - 1, b);
+              mbar_arrive_expect_tx(&full_a[s], (uint32_t)A_ROWS * ROW);
+              if (SMALL) tma_load_4d(sA + s * p.a_stage_bytes, &p.a_map[src][prod == 1 ? 1 : 0], &full_a[s], cc, -1, 2 * m, -1);
+              else tma_load_4d(sA + s * p.a_stage_bytes, &p.a_map[src][prod == 1 ? 1 : 0], &full_a[s], cc, w0 - 1, h0 - 1, b);
             }
             ++ia;
             if (!RESIDENT) {
@@ -434,7 +469,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       // ---------------- MMA issuer (whole warp converged; one elected lane issues) ----------------
       const uint32_t idesc = make_idesc_f16(kTileM, BN);
       // descriptor words: hi = {SBO, version, swizzle} is constant per operand; lo = addr>>4 | LBO
-      const uint32_t a_hi = (uint32_t)(make_smem_desc_ex(0, ROW, kHaloW * ROW, 0) >> 32);
+      const uint32_t a_hi = (uint32_t)(make_smem_desc_ex(0, ROW, SBO_ROWS * ROW, 0) >> 32);
       const uint32_t b_hi = (uint32_t)(make_smem_desc(0, ROW) >> 32);
       const uint32_t lo_flags = 1u << 16;
       const uint32_t sA_lo = (smem_u32(sA) >> 4) | lo_flags;
@@ -464,7 +499,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
                 if (!(p.dbg & 2))
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                  const uint32_t a_tap = a_lo + (((tap / 3) * kHaloW + tap % 3) * ROW >> 4);
+                  const uint32_t a_tap = a_lo + (((tap / 3) * TAP_ROWS + tap % 3) * ROW >> 4);
                   const uint32_t b_lo = sW_lo + (uint32_t)(tap * nchunks + c) * (SLAB >> 4);
 #pragma unroll
                   for (int kk = 0; kk < KSTEPS; ++kk) {
@@ -485,7 +520,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
                 mbar_wait(&full_b[sb], phb);
                 tc_fence_after();
                 const uint32_t b_stage = sW_lo + sb * (3 * SLAB >> 4);
-                const uint32_t a_row = a_lo + (tg * kHaloW * ROW >> 4);
+                const uint32_t a_row = a_lo + (tg * TAP_ROWS * ROW >> 4);
                 if (elect_one()) {
                   if (!(p.dbg & 2)) {
 #pragma unroll
@@ -496,7 +531,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
                       for (int kk = 0; kk < KSTEPS; ++kk) {
                         const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
                         umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
-                        umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
+                        if (!SMALL) umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
                         accumulate = 1;
                       }
                     }
@@ -525,19 +560,21 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
     }
   } else if (FUSE && warp >= 2 + NEPI) {
     // ---------------- transform warps: bilinear x2 (align_corners) of the low-res window into the A stage ------
-    // Thread = (halo column k, 16-byte channel group j, row group g): the column interpolation set-up is done
-    // once per tile, the thread then walks its rows top-down keeping the horizontally interpolated source rows
-    // in registers (consecutive output rows share them), so a row costs at most one new source row.
+    // Thread = (halo column k, 16-byte channel group j, row group g).  All index arithmetic of the interpolation is
+    // done once per TILE (column set-up: source offsets + lx; row set-up: source row + ly for each of the thread's
+    // RPG rows, kept in registers); per chunk the thread walks its rows top-down keeping the horizontally
+    // interpolated source rows in registers (consecutive output rows share them) and uses packed fp32 FMAs
+    // (FFMA2 / FMUL2), so an output row of 8 channels costs ~40 instructions instead of ~90.
     const int tid = threadIdx.x - (64 + 32 * NEPI);        // 0..287
     constexpr int CH16 = KC / 8;                           // 16-byte channel groups per pixel row
     constexpr int SLOTS = kHaloW * CH16;                   // 144 (KC=64) / 72 (KC=32)
-    constexpr int GROUPS = kXformThreads / SLOTS;          // 2 / 4 row groups
+    constexpr int GROUPS = kXformThreads / SLOTS;          // 2 / 4 row groups (SLOTS * GROUPS == 288)
     constexpr int RPG = (kHaloH + GROUPS - 1) / GROUPS;    // rows per group: 9 / 5
     constexpr int iROW = (int)ROW;
     const int g = tid / SLOTS, slot = tid % SLOTS;
     const int k = slot / CH16, j = slot % CH16;
     const int Hin = p.H >> 1, Win = p.W >> 1;
-    const int r_begin = g * RPG, r_end = (r_begin + RPG < kHaloH) ? r_begin + RPG : kHaloH;
+    const int r_begin = g * RPG;
     uint32_t ia = 0, iu = 0;
     for (int t = item0; t < total_items; t += item_step) {
       int m = (t / p.num_n_tiles) * cs + crank;
@@ -547,70 +584,80 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       const int xs = (int)(p.up_sx * (float)(w0 > 0 ? w0 - 1 : 0));
       // column set-up (fixed for the tile)
       const int xo = w0 - 1 + k;
-      const bool x_ok = g < GROUPS && xo >= 0 && xo < p.W;
+      const bool x_ok = xo >= 0 && xo < p.W;
       const float fx = p.up_sx * (float)xo;
       const int x0 = (int)fx;
       const int x1 = x0 + (x0 < Win - 1 ? 1 : 0);
-      const float lx = fx - (float)x0;
+      const float lx = fx - (float)x0, wx = 1.f - lx;
       const int ox0 = (x0 - xs) * iROW + j * 16, ox1 = (x1 - xs) * iROW + j * 16;
+      // row set-up (fixed for the tile): yrow = (staging row of y0) * 2 + (y1 != y0), or -1 for conv zero padding
+      int yrow[RPG];
+      float lyv[RPG];
+#pragma unroll
+      for (int rr = 0; rr < RPG; ++rr) {
+        const int r = r_begin + rr;
+        const int yo = h0 - 1 + r;
+        const float fy = p.up_sy * (float)yo;
+        const int y0 = (int)fy;
+        lyv[rr] = fy - (float)y0;
+        yrow[rr] = (x_ok && r < kHaloH && yo >= 0 && yo < p.H) ? (((y0 - ys) << 1) | (y0 < Hin - 1 ? 1 : 0)) : -1;
+      }
       for (int c = 0; c < nchunks; ++c) {
         for (int prod = 0; prod < p.nprod; ++prod, ++ia) {
           if (c < p.nchunk0) continue;                      // source 0 comes by TMA
           const int s = ia % SA, st = iu & 1;
           mbar_wait(&stg_full[st], (iu >> 1) & 1);
+          mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);      // the staging load ran ahead of the A ring: claim the stage here
+          if (tid == 0) TRACE(5, 2 * iu);
           const uint8_t* stg = sStg + st * p.stg_bytes;
           uint8_t* dstA = sA + s * p.a_stage_bytes;
-          if (g < GROUPS) {
-            float ha[8], hb[8];                             // horizontally interpolated source rows ya, yb
-            int ya = -1, yb = -1;
-            auto hrow = [&](int y, float (&hr)[8]) {
-              const uint8_t* rp = stg + (y - ys) * (kUpBox * iROW);
-              const H8 a = *reinterpret_cast<const H8*>(rp + ox0), bq = *reinterpret_cast<const H8*>(rp + ox1);
+          float2 ha[4], hb[4];                              // horizontally interpolated source rows ya, yb
+          int ya = -1, yb = -1;
+          auto hrow = [&](int y, float2 (&hr)[4]) {
+            const uint8_t* rp = stg + y * (kUpBox * iROW);
+            const H8 a = *reinterpret_cast<const H8*>(rp + ox0), bq = *reinterpret_cast<const H8*>(rp + ox1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hr[e] = ffma2(lx, __half22float2(bq.v[e]), fmul2(wx, __half22float2(a.v[e])));
+          };
+#pragma unroll
+          for (int rr = 0; rr < RPG; ++rr) {
+            const int r = r_begin + rr;
+            uint4 outv = make_uint4(0, 0, 0, 0);            // conv zero padding outside the image
+            if (yrow[rr] >= 0) {
+              const int y0 = yrow[rr] >> 1, y1 = y0 + (yrow[rr] & 1);
+              if (y0 != ya) {
+                if (y0 == yb) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) ha[e] = hb[e];
+                } else hrow(y0, ha);
+                ya = y0;
+              }
+              if (y1 != yb) {
+                if (y1 == ya) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) hb[e] = ha[e];
+                } else hrow(y1, hb);
+                yb = y1;
+              }
+              const float ly = lyv[rr], wy = 1.f - ly;
+              H8 o;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 fa = __half22float2(a.v[e]), fb = __half22float2(bq.v[e]);
-                hr[2 * e] = (1.f - lx) * fa.x + lx * fb.x;
-                hr[2 * e + 1] = (1.f - lx) * fa.y + lx * fb.y;
+                const float2 v = ffma2(ly, hb[e], fmul2(wy, ha[e]));
+                o.v[e] = __floats2half2_rn(v.x, v.y);
               }
-            };
-            for (int r = r_begin; r < r_end; ++r) {
-              const int yo = h0 - 1 + r;
-              const int pr = r * kHaloW + k;
-              uint4 outv = make_uint4(0, 0, 0, 0);           // conv zero padding outside the image
-              if (x_ok && yo >= 0 && yo < p.H) {
-                const float fy = p.up_sy * (float)yo;
-                const int y0 = (int)fy;
-                const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0);
-                const float ly = fy - (float)y0;
-                if (y0 != ya) {
-                  if (y0 == yb) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) ha[e] = hb[e];
-                  } else hrow(y0, ha);
-                  ya = y0;
-                }
-                if (y1 != yb) {
-                  if (y1 == ya) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) hb[e] = ha[e];
-                  } else hrow(y1, hb);
-                  yb = y1;
-                }
-                H8 o;
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  o.v[e] = __floats2half2_rn((1.f - ly) * ha[2 * e] + ly * hb[2 * e],
-                                             (1.f - ly) * ha[2 * e + 1] + ly * hb[2 * e + 1]);
-                outv = *reinterpret_cast<uint4*>(&o);
-              }
+              outv = *reinterpret_cast<uint4*>(&o);
+            }
+            if (r < kHaloH) {
               // TMA-compatible swizzle of the A stage: 16-byte chunk index ^= row bits
+              const int pr = r * kHaloW + k;
               const int swz = (ROW == 128) ? (pr & 7) : ((pr >> 1) & 3);
               *reinterpret_cast<uint4*>(dstA + pr * iROW + ((j ^ swz) << 4)) = outv;
             }
           }
           fence_proxy_async();                               // generic-proxy smem writes -> visible to the MMA (async proxy)
           asm volatile("bar.sync 1, 288;" ::: "memory");     // the nine transform warps
-          if (tid == 0) { mbar_arrive(&full_a[s]); mbar_arrive(&stg_empty[st]); }
+          if (tid == 0) { mbar_arrive(&full_a[s]); mbar_arrive(&stg_empty[st]); TRACE(5, 2 * iu + 1); }
           ++iu;
         }
       }
@@ -619,8 +666,9 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
     // ---------------- epilogue ----------------
     const int q = warp & 3;                                // TMEM lane quadrant this warp may access
     // with 8 epilogue warps, warp pair member e handles M-tile half e (columns [e*BN, (e+1)*BN) of the tile's 2*BN)
-    const int cb_begin = NEPI == 8 ? ((warp - 2) >> 2) * BN : 0;
-    const int cb_end = NEPI == 8 ? cb_begin + BN : 2 * BN;
+    // (SMALL has one M-tile per item: the two warps of a quadrant split its BN columns instead)
+    const int cb_begin = SMALL ? ((warp - 2) >> 2) * (BN / 2) : (NEPI == 8 ? ((warp - 2) >> 2) * BN : 0);
+    const int cb_end = SMALL ? cb_begin + BN / 2 : (NEPI == 8 ? cb_begin + BN : 2 * BN);
     const int ml = q * 32 + lane;
     const int tw = ml & 7, th = ml >> 3;
     uint32_t it = 0;
@@ -629,8 +677,10 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       int m = (t / p.num_n_tiles) * cs + crank;
       const bool real_tile = m < p.num_m_tiles;
       if (!real_tile) m = p.num_m_tiles - 1;
-      const int w = (m % p.tiles_w) * 16 + tw, h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
-      const int b = m / (p.tiles_w * p.tiles_h);
+      // SMALL: M row = (y*2 + img)*8 + x of images 2m, 2m+1
+      const int w = SMALL ? tw : (m % p.tiles_w) * 16 + tw;
+      const int h = SMALL ? (th >> 1) : ((m / p.tiles_w) % p.tiles_h) * 16 + th;
+      const int b = SMALL ? 2 * m + (th & 1) : m / (p.tiles_w * p.tiles_h);
       const int n0 = nt * BN;
       const size_t pix = ((size_t)b * p.H + h) * p.W + w;
       const uint32_t buf = it & 1;
@@ -652,7 +702,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
           uint32_t (&r)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r64[32 * sl]);
           float v[32];
           epilogue_act32(r, sbias + n0 + c0, v);
-          const bool st_ok = real_tile && !(p.dbg & 1);
+          const bool st_ok = real_tile && !(p.dbg & 1) && (!SMALL || b < p.B);
           if (p.outc_w) {                       // last layer: 1x1 conv + residual + clamp, fp32 out (BN == 32)
             float acc = soutc[32];
 #pragma unroll
@@ -929,6 +979,7 @@ struct Conv2Plan {
   int BN = 0;
   int kc = 0;
   bool resident = false;
+  bool small = false;      // 8x8 images, two per M-tile (conv3x3_tc2<..., SMALL>)
   int smem_bytes = 0;
   int grid = 0;
 };
@@ -943,17 +994,17 @@ bool use_pdl() {
   return v != 0;
 }
 
-template <int BN, int KC, bool RES, bool FUSE>
+template <int BN, int KC, bool RES, bool FUSE, bool SMALL = false>
 int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
   static unsigned long long attr_set = 0;   // one bit per device (a function attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES, FUSE, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
     attr_set |= 1ull << (dev & 63);
   }
-  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE>, dim3(c.grid), dim3(conv2_threads<KC, FUSE>()),
+  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE, SMALL>, dim3(c.grid), dim3(conv2_threads<KC, FUSE>()),
                           c.smem_bytes, st, use_pdl(), c.p.cluster, c.p));
   TFPNP_COUNT_LAUNCH();
   return 0;
@@ -961,6 +1012,11 @@ int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
 
 int launch_conv2(const Conv2Plan& c, cudaStream_t st) {
   const int key = c.BN * 1000 + c.kc * 10 + (c.resident ? 1 : 0);
+  if (c.small) {
+    if (key == 128640 && !c.p.up_fused) return launch_conv2_t<128, 64, false, false, true>(c, st);
+    set_error("conv2: no 8x8 variant for BN %d KC %d (resident %d)", c.BN, c.kc, (int)c.resident);
+    return TFPNP_ERR_INVALID;
+  }
   if (c.p.up_fused) {
     switch (key) {      // the four decoder conv-0 layers of UNet(2,1): 96->32, 192->64, 384->128, 768->256
       case 32321: return launch_conv2_t<32, 32, true, true>(c, st);
@@ -984,6 +1040,11 @@ int launch_conv2(const Conv2Plan& c, cudaStream_t st) {
 }
 
 bool conv2_eligible(int H, int W) { return env_int("TFPNP_CONV_V2", 1) != 0 && W % 16 == 0 && H % 16 == 0; }
+// 8x8 images with >= 2 images, 64-channel chunks and Cout a multiple of 128 (the 512-channel level of a 128x128 input)
+bool conv2_small_eligible(int H, int W, int B, int C0, int C1, int Cout) {
+  return env_int("TFPNP_CONV_V2", 1) != 0 && env_int("TFPNP_CONV_SMALL", 1) != 0 && H == 8 && W == 8 && B >= 2 &&
+         C0 % 64 == 0 && C1 % 64 == 0 && Cout % 128 == 0;
+}
 
 int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                const cuuint32_t* box, int inner_bytes);
@@ -991,19 +1052,20 @@ int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, con
 // Fill everything of a Conv2Plan except the tensor maps.
 int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, int W, bool x3, bool fuse_up = false) {
   Conv2Params& p = c.p;
+  c.small = (H == 8 && W == 8);
   const int Cin = C0 + C1;
   const int kc = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   c.kc = kc;
   c.BN = Cout >= 128 ? 128 : Cout;
   if (kc == 32 && c.BN == 128) c.BN = 64;                   // (not a UNet(2,1) shape; keeps the variant table small)
   p.nchunk0 = C0 / kc; p.nchunk1 = C1 / kc; p.nprod = x3 ? 3 : 1;
-  p.tiles_w = W / 16; p.tiles_h = H / 16;
-  p.num_m_tiles = p.tiles_w * p.tiles_h * B;
+  p.tiles_w = c.small ? 1 : W / 16; p.tiles_h = c.small ? 1 : H / 16;
+  p.num_m_tiles = c.small ? (B + 1) / 2 : p.tiles_w * p.tiles_h * B;
   p.num_n_tiles = Cout / c.BN;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
   p.dbg = env_int("TFPNP_DBG", 0);
   const int row_bytes = kc * 2;
-  p.a_stage_bytes = (kHaloRows * row_bytes + 1023) & ~1023;
+  p.a_stage_bytes = ((c.small ? 200 : kHaloRows) * row_bytes + 1023) & ~1023;
   p.b_stage_bytes = c.BN * row_bytes;                       // multiple of 1024 for all (BN, kc) used
   const int w_bytes = 9 * (Cin / kc) * p.b_stage_bytes;
   p.up_fused = fuse_up ? 1 : 0;
@@ -1012,7 +1074,7 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   p.up_sx = (float)(W / 2 - 1) / (float)(W - 1);
   // alignment slack + barriers + bias[<=512] + outc[33] (+ two low-res staging slots when the upsample is fused)
   const int misc = 1024 + 1024 + 2048 + 256 + (fuse_up ? 2 * p.stg_bytes : 0);
-  c.resident = !x3 && p.num_n_tiles == 1 && c.BN <= 64 && w_bytes <= 100 * 1024 &&
+  c.resident = !x3 && !c.small && p.num_n_tiles == 1 && c.BN <= 64 && w_bytes <= 100 * 1024 &&
                env_int("TFPNP_CONV_RESIDENT", 1) != 0;
   if (c.resident) {
     p.num_b_stages = 0;
@@ -1024,7 +1086,7 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
     }
     c.smem_bytes = p.num_a_stages * p.a_stage_bytes + w_bytes + misc;
   } else {
-    p.num_a_stages = 2;
+    p.num_a_stages = c.small ? 3 : 2;
     const int budget = 224 * 1024 - misc - p.num_a_stages * p.a_stage_bytes;
     int sb = budget / (3 * p.b_stage_bytes);                // a ring stage holds the 3 taps of one kernel row
     p.num_b_stages = sb > kMaxStages ? kMaxStages : sb;
@@ -1047,7 +1109,16 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   return 0;
 }
 
+// 8x8 level: tensor viewed as {C, W, B, H}; box {kc, 10, 2, 10} -> smem row = y'*20 + img*10 + x'
+int encode_small_map(CUtensorMap* m, const __half* base, int C, int B, int H, int W, int kc) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)B, (cuuint64_t)H};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, 10, 2, 10};
+  return encode_map(m, const_cast<__half*>(base), 4, dims, strides, box, kc * 2);
+}
+
 int encode_halo_map(CUtensorMap* m, const __half* base, int C, int B, int H, int W, int kc) {
+  if (H == 8 && W == 8) return encode_small_map(m, base, C, B, H, W, kc);
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
@@ -1174,7 +1245,7 @@ struct UNetTc : Denoiser {
     p.out_hi = dst.hi;
     p.out_lo = x3 ? dst.lo : nullptr;
     const bool fuse = env_int("TFPNP_CONV_FUSE", 1) != 0;
-    fused_pool[l] = fuse && (l == 2 || l == 5 || l == 8 || l == 11);   // conv-2 of inc / down1..3 feeds a MaxPool2d
+    fused_pool[l] = fuse && !c.small && (l == 2 || l == 5 || l == 8 || l == 11);   // conv-2 of inc / down1..3 feeds a MaxPool2d
     if (fused_pool[l]) { p.pool_hi = S2.hi; p.pool_lo = x3 ? S2.lo : nullptr; }   // S2 is idle in the encoder
     if (l == 26) {
       fused_outc = fuse;
@@ -1207,7 +1278,9 @@ struct UNetTc : Denoiser {
 
   // build ConvParams for layer l reading (src0 [, src1]) and writing dst
   int plan_conv(int l, const Act& s0, const Act* s1, const Act& dst, int B, const Act* low = nullptr) {
-    if (conv2_eligible(dst.H, dst.W)) return plan_conv_v2(l, s0, s1, dst, B, low);
+    if (conv2_eligible(dst.H, dst.W) ||
+        (!low && conv2_small_eligible(dst.H, dst.W, B, s0.C, s1 ? s1->C : 0, unet_conv_specs()[l].cout)))
+      return plan_conv_v2(l, s0, s1, dst, B, low);
     convs2[l].grid = 0;
     fused_pool[l] = false;
     fused_up[l] = false;
@@ -1295,7 +1368,27 @@ struct UNetTc : Denoiser {
   }
 
   int launch_conv(int l, cudaStream_t st) {
-    if (convs2[l].grid > 0) return launch_conv2(convs2[l], st);
+    if (convs2[l].grid > 0) {
+      // debugging aid: TFPNP_TRACE_LAYER=l + TFPNP_TRACE_FILE dump CTA 0's role timeline of layer l (eager calls only)
+      static const int trace_layer = env_int("TFPNP_TRACE_LAYER", -1);
+      const char* tf = trace_layer == l ? getenv("TFPNP_TRACE_FILE") : nullptr;
+      if (tf) {
+        unsigned long long* dtrace = nullptr;
+        TFPNP_CUDA_OK(cudaMalloc(&dtrace, 8 * 1024 * 8));
+        TFPNP_CUDA_OK(cudaMemset(dtrace, 0, 8 * 1024 * 8));
+        Conv2Plan c = convs2[l];
+        c.p.trace = dtrace;
+        TFPNP_TRY(launch_conv2(c, st));
+        std::vector<unsigned long long> h(8 * 1024);
+        TFPNP_CUDA_OK(cudaStreamSynchronize(st));
+        TFPNP_CUDA_OK(cudaMemcpy(h.data(), dtrace, h.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(dtrace);
+        FILE* f = fopen(tf, "wb");
+        if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+        return 0;
+      }
+      return launch_conv2(convs2[l], st);
+    }
     return launch_conv_params(convs[l], conv_bn[l], st);
   }
 
@@ -1366,7 +1459,7 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
   TFPNP_CHECK(C0 > 0 && C0 % 32 == 0 && C1 % 32 == 0, "channel counts must be multiples of 32");
   TFPNP_CHECK(Cout == 32 || Cout == 64 || Cout % 128 == 0, "Cout must be 32, 64 or a multiple of 128");
   TFPNP_TRY(set_conv_attrs());
-  if (conv2_eligible(H, W)) {
+  if (conv2_eligible(H, W) || conv2_small_eligible(H, W, B, C0, C1, Cout)) {
     Conv2Plan c;
     memset(&c.p, 0, sizeof(c.p));
     TFPNP_TRY(plan_conv2_geometry(c, C0, C1, Cout, B, H, W, false));

@@ -44,7 +44,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         res[f"{C0}+{C1}->{Cout}@{H}"] = (round(t, 1), round(gf / t * 1e3, 1))
     print(json.dumps(res))
 else:
-    for dbg in ([0, 1, 2, 3, 4, 8, 15] if os.environ.get("KNOCK_ALL") else [0, 2, 15, 32, 33]):
+    for dbg in ([0, 1, 2, 3, 4, 8, 15] if os.environ.get("KNOCK_ALL") else [0, 32, 15, 128, 64]):
         env = dict(os.environ, TFPNP_DBG=str(dbg))
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
         line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:]
