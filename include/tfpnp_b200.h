@@ -65,6 +65,13 @@ const char* tfpnp_last_error(void);
  * replicate.py:50-75). */
 int tfpnp_denoiser_create(const float* weights_host, size_t n_floats, int precision,
                           void** out_handle);
+/* IRCNN prox_sigma denoiser (BASELINE configs[0]).  Absent from the reference (tfpnp/pnp/__init__.py:5-13 only
+ * knows 'unet'): the published 7-layer, 64-channel, dilation 1-2-3-4-3-2-1 network in inference form,
+ * wrapped like UNetDenoiser2D: out = clamp(x - net(cat[x, sigma*ones]), 0, 1).  `weights_host`: the 14 tensors
+ * model.{0,2,...,12}.{weight,bias} ([64,2,3,3],[64], 5 x ([64,64,3,3],[64]), [1,64,3,3],[1]) flattened in that
+ * order (n_floats = 186,433).  precision: TFPNP_PREC_FP16 or TFPNP_PREC_FP16X3.  The handle is a denoiser
+ * handle: use it with tfpnp_denoiser_forward / _destroy and tfpnp_solver_create. */
+int tfpnp_ircnn_create(const float* weights_host, size_t n_floats, int precision, void** out_handle);
 int tfpnp_denoiser_destroy(void* handle);
 
 /* out[b] = clamp(UNet(cat[x[b], sigma[b]]) , 0, 1)   denoiser/base.py:23-32

@@ -103,6 +103,8 @@ def unet_forward(sd: Dict[str, Tensor], x: Tensor,
 
 def denoise(sd: Dict[str, Tensor], x: Tensor, sigma: Tensor, quant=None) -> Tensor:
     """UNetDenoiser2D.forward (denoiser/base.py:23-32): x [B,1,H,W], sigma [B]."""
+    if "model.0.weight" in sd:          # an IRCNN state_dict (self-defined, see ircnn_denoise)
+        return ircnn_denoise(sd, x, sigma)
     n, _, h, w = x.shape
     noise_map = torch.ones(n, 1, h, w, dtype=x.dtype) * sigma.reshape(n, 1, 1, 1).to(x.dtype)
     out = unet_forward(sd, torch.cat([x, noise_map], dim=1), quant)
@@ -281,6 +283,32 @@ def radon_opnorm(N: int, cs: Tensor, sn: Tensor, det: int, seed: int = 0,
         v = float(x.norm())
         x = x / v
     return v ** 0.5
+
+
+# ----------------------------------------------------------------------------
+# IRCNN.  ABSENT from the reference (tfpnp/pnp/__init__.py:5-13): PARITY UNPINNED.
+# Restates the published network (Zhang et al., CVPR 2017; inference form, BatchNorm folded): seven
+# 3x3 convolutions, 64 channels, dilations 1,2,3,4,3,2,1, ReLU between them, residual output, wrapped
+# like UNetDenoiser2D (tfpnp/pnp/denoiser/base.py:23-32).
+# ----------------------------------------------------------------------------
+IRCNN_DILATIONS = (1, 2, 3, 4, 3, 2, 1)
+
+
+def ircnn_param_shapes():
+    out = []
+    for i, (ci, co) in enumerate([(2, 64)] + [(64, 64)] * 5 + [(64, 1)]):
+        out += [(f"model.{2 * i}.weight", (co, ci, 3, 3)), (f"model.{2 * i}.bias", (co,))]
+    return out
+
+
+def ircnn_denoise(sd: Dict[str, Tensor], x: Tensor, sigma: Tensor) -> Tensor:
+    N, _, H, W = x.shape
+    h = torch.cat([x, torch.ones(N, 1, H, W, dtype=x.dtype) * sigma.reshape(N, 1, 1, 1).to(x.dtype)], dim=1)
+    for i, d in enumerate(IRCNN_DILATIONS):
+        h = F.conv2d(h, sd[f"model.{2 * i}.weight"].to(x.dtype), sd[f"model.{2 * i}.bias"].to(x.dtype), padding=d, dilation=d)
+        if i < 6:
+            h = F.relu(h)
+    return torch.clamp(x - h, 0, 1)
 
 
 # ----------------------------------------------------------------------------

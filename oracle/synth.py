@@ -55,6 +55,25 @@ def unet_state_dict(seed: int = 0, init: str = "he", out_scale: float = 0.1, dty
     return sd
 
 
+def ircnn_state_dict(seed: int = 0, out_scale: float = 0.1):
+    """Seeded IRCNN(2,1,64) weights (oracle/pnp_oracle.py: ircnn_param_shapes): variance-preserving
+    He-uniform for the ReLU layers, the last layer scaled so the predicted residual is a moderate correction."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    sd = {}
+    shapes = O.ircnn_param_shapes()
+    for name, shape in shapes:
+        if name.endswith("weight"):
+            fan_in = shape[1] * 9
+            bound = math.sqrt(6.0 / fan_in)
+            w = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            if name == shapes[-2][0]:
+                w = w * out_scale
+            sd[name] = w
+        else:
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+    return sd
+
+
 def radial_mask(n: int, lines: int) -> torch.Tensor:
     """Boolean union of ``lines`` straight lines through the centre at angles
     k*pi/lines (stand-in for the absent radial_128_{2,4,8}.mat,

@@ -91,7 +91,7 @@ def test_factories_and_errors():
     opt.solver = "hqs"                   # other algorithms are out of scope -> same error as an unknown name
     with pytest.raises(NotImplementedError):
         T.create_solver_csmri(opt, den)
-    opt.denoiser = "ircnn"               # tfpnp/pnp/__init__.py:8-13
+    opt.denoiser = "dncnn"               # unknown names raise as upstream (tfpnp/pnp/__init__.py:8-13)
     with pytest.raises(NotImplementedError):
         T.create_denoiser(opt, state_dict=weights("he"))
     with pytest.raises(TypeError):

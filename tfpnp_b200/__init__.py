@@ -6,7 +6,7 @@ single-photon imaging, with the UNet prox_sigma denoiser, implemented as hand-wr
 sm_100a CUDA in ``libtfpnp_b200.so`` (C ABI: include/tfpnp_b200.h).  No fallback paths.
 """
 from ._lib import build, lib, LIB_PATH  # noqa: F401
-from .denoiser import UNetDenoiser2D, create_denoiser  # noqa: F401
+from .denoiser import UNetDenoiser2D, IRCNNDenoiser2D, create_denoiser  # noqa: F401
 from .solver import (PnPSolver, ADMMSolver, IADMMSolver, ADMMSolver_CSMRI, IADMMSolver_PR,  # noqa: F401
                      IADMMSolver_CT, ADMMSolver_SPI, RadonGenerator, create_solver_csmri,
                      create_solver_pr, create_solver_ct, create_solver_spi)

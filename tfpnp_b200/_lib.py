@@ -38,6 +38,7 @@ SIGNATURES = {
     "tfpnp_version": (C.c_int, []),
     "tfpnp_last_error": (C.c_char_p, []),
     "tfpnp_denoiser_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "tfpnp_ircnn_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "tfpnp_denoiser_destroy": (C.c_int, [C.c_void_p]),
     "tfpnp_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -139,6 +139,18 @@ struct Denoiser {
                       int H, int W, cudaStream_t st) = 0;
 };
 
+// pre-planned one-tile-per-CTA tensor-core 3x3 conv layer (unet_tc.cu): NHWC fp16 (hi [+ lo residual plane]) in/out,
+// weights [tap][Cout][Cin] fp16, act = max(v, slope*v), tap spacing `dil`
+struct ConvV1Layer;
+int conv_v1_plan(ConvV1Layer** out, const __half* x_hi, const __half* x_lo, int Cin, const __half* w_hi,
+                 const __half* w_lo, const float* bias, __half* out_hi, __half* out_lo, int B, int H, int W,
+                 int Cout, int dil, float slope);
+int conv_v1_launch(const ConvV1Layer* L, cudaStream_t st);
+void conv_v1_free(ConvV1Layer* L);
+
+Denoiser* make_ircnn_tc(const float* weights_host, int precision);   // ircnn.cu
+constexpr size_t kIrcnnParamCount = (size_t)64 * 2 * 9 + 64 + 5 * ((size_t)64 * 64 * 9 + 64) + (size_t)1 * 64 * 9 + 1;
+
 Denoiser* make_unet_simt(const float* weights_host);                 // unet_simt.cu
 Denoiser* make_unet_tc(const float* weights_host, int precision);    // unet_tc.cu
 int conv3x3_nhwc(const void* x0, int C0, const void* x1, int C1, const void* w_taps, const float* bias,

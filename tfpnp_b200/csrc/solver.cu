@@ -401,6 +401,27 @@ int tfpnp_denoiser_create(const float* weights_host, size_t n_floats, int precis
   return 0;
 }
 
+int tfpnp_ircnn_create(const float* weights_host, size_t n_floats, int precision, void** out) {
+  TFPNP_CHECK(weights_host && out, "null argument");
+  TFPNP_CHECK(n_floats == kIrcnnParamCount, "IRCNN(2,1,64) has %zu parameters, got %zu", kIrcnnParamCount, n_floats);
+  int dev = 0;
+  TFPNP_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  TFPNP_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("tfpnp_b200 needs an sm_100 device (B200); found sm_%d%d", prop.major, prop.minor);
+    return TFPNP_ERR_UNSUPPORTED;
+  }
+  if (precision != TFPNP_PREC_FP16 && precision != TFPNP_PREC_FP16X3) {
+    set_error("IRCNN supports precision fp16 / fp16x3, got %d", precision);
+    return TFPNP_ERR_INVALID;
+  }
+  Denoiser* d = make_ircnn_tc(weights_host, precision);
+  if (!d) return TFPNP_ERR_CUDA;
+  *out = d;
+  return 0;
+}
+
 int tfpnp_denoiser_destroy(void* h) {
   delete static_cast<Denoiser*>(h);
   return 0;

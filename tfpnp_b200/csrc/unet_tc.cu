@@ -38,6 +38,8 @@ struct ConvParams {
   int box_rows;             // pixel rows one A box really carries (TB clamped to B)
   int tiles_w, tiles_h;
   int B, H, W, Cout;
+  int dil;                  // tap spacing (1 for the UNet; 1..4 for the dilated IRCNN layers)
+  float slope;              // activation max(v, slope*v): 0.2 = LeakyReLU(0.2), 0 = ReLU
   const float* bias;
   __half* out_hi;
   __half* out_lo;           // nullptr unless FP16X3
@@ -81,7 +83,8 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* v) {
 
 // Epilogue pieces for one 32-column slice of an accumulator row.
 // act: + bias (smem broadcast), LeakyReLU(0.2) (unet.py:22) in fp32
-__device__ __forceinline__ void epilogue_act32(const uint32_t (&r)[32], const float* __restrict__ sbias, float (&v)[32]) {
+__device__ __forceinline__ void epilogue_act32(const uint32_t (&r)[32], const float* __restrict__ sbias, float (&v)[32],
+                                               const float slope = 0.2f) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     const float4 bb = *reinterpret_cast<const float4*>(sbias + 4 * j4);
@@ -91,7 +94,7 @@ __device__ __forceinline__ void epilogue_act32(const uint32_t (&r)[32], const fl
     v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + bb.w;
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+  for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], slope * v[j]);
 }
 // store: pack to fp16 (hi) and, in FP16X3 mode, the fp16 residual (lo); 64-byte NHWC stores per plane
 __device__ __forceinline__ void epilogue_store_nhwc32(const float (&v)[32], __half* __restrict__ out_hi,
@@ -119,9 +122,9 @@ __device__ __forceinline__ void epilogue_store_nhwc32(const float (&v)[32], __ha
 }
 __device__ __forceinline__ void epilogue_store32(const uint32_t (&r)[32], const float* __restrict__ sbias,
                                                  __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                                 size_t off, bool store) {
+                                                 size_t off, bool store, float slope) {
   float v[32];
-  epilogue_act32(r, sbias, v);
+  epilogue_act32(r, sbias, v, slope);
   if (store) epilogue_store_nhwc32(v, out_hi, out_lo, off);
 }
 
@@ -193,7 +196,7 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
         uint8_t* sA = smem + s * Cfg::kStageBytes;
         uint8_t* sB = sA + Cfg::kABytes;
         mbar_arrive_expect_tx(&full[s], stage_tx);
-        tma_load_4d(sA, &p.a_map[src][prod == 1 ? 1 : 0], &full[s], cc, w0 + dx, h0 + dy, b0);
+        tma_load_4d(sA, &p.a_map[src][prod == 1 ? 1 : 0], &full[s], cc, w0 + dx * p.dil, h0 + dy * p.dil, b0);
         tma_load_3d(sB, &p.w_map[prod == 2 ? 1 : 0], &full[s], chunk * p.kc, n0, tap);
       }
     }
@@ -238,7 +241,7 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
       tmem_ld_wait();
-      epilogue_store32(r, sbias + c0, p.out_hi, p.out_lo, pix * p.Cout + n0 + c0, valid);
+      epilogue_store32(r, sbias + c0, p.out_hi, p.out_lo, pix * p.Cout + n0 + c0, valid, p.slope);
     }
   }
   tc_fence_before();
@@ -1302,6 +1305,7 @@ struct UNetTc : Denoiser {
     p.tiles_w = dst.W / p.TW;
     p.tiles_h = dst.H / p.TH;
     p.B = B; p.H = dst.H; p.W = dst.W; p.Cout = sp.cout;
+    p.dil = 1; p.slope = 0.2f;
     p.bias = biases.as<float>() + b_off[l];
     p.out_hi = dst.hi;
     p.out_lo = x3 ? dst.lo : nullptr;
@@ -1358,7 +1362,9 @@ struct UNetTc : Denoiser {
       Act up = view(S0, ch[lv + 1], h, w);
       // the block input: x5 for the first block, else the previous block's output in S2
       Act low = view(k == 0 ? skip[4] : S2, ch[lv + 1], h / 2, w / 2);
-      const bool fuse_up = !x3 && conv2_eligible(h, w) && env_int("TFPNP_CONV_FUSE_UP", 1) != 0;
+      // fused up-sampling pays where the up-sampled tensor is large; TFPNP_FUSE_UP_MIN = smallest output height fused
+      const bool fuse_up = !x3 && conv2_eligible(h, w) && env_int("TFPNP_CONV_FUSE_UP", 1) != 0 &&
+                           h >= env_int("TFPNP_FUSE_UP_MIN", 32);   // measured: 16x16 outputs are faster un-fused
       TFPNP_TRY(plan_conv(l0, skip[lv], &up, view(S1, ch[lv], h, w), B, fuse_up ? &low : nullptr));
       TFPNP_TRY(plan_conv(l0 + 1, view(S1, ch[lv], h, w), nullptr, view(S0, ch[lv], h, w), B));
       TFPNP_TRY(plan_conv(l0 + 2, view(S0, ch[lv], h, w), nullptr, view(S2, ch[lv], h, w), B));
@@ -1505,6 +1511,7 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
   p.box_rows = p.TW * p.TH * (p.TB < B ? p.TB : B);
   p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.dil = 1; p.slope = 0.2f;
   p.bias = bias; p.out_hi = out; p.out_lo = nullptr;
   const __half* srcs[2] = {x0, x1};
   const int cs[2] = {C0, C1};
@@ -1527,6 +1534,55 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
 }
 
 }  // namespace
+
+// ---- one-tile-per-CTA tensor-core conv as a reusable, pre-planned layer (used by ircnn.cu) -------------
+struct ConvV1Layer { ConvParams p; int BN; };
+
+int conv_v1_plan(ConvV1Layer** out, const __half* x_hi, const __half* x_lo, int Cin, const __half* w_hi,
+                 const __half* w_lo, const float* bias, __half* out_hi, __half* out_lo, int B, int H, int W,
+                 int Cout, int dil, float slope) {
+  TFPNP_CHECK(Cin % 32 == 0 && (Cout == 32 || Cout == 64 || Cout % 128 == 0), "conv_v1_plan: unsupported channels %d -> %d", Cin, Cout);
+  TFPNP_TRY(set_conv_attrs());
+  const bool x3 = x_lo != nullptr;
+  ConvV1Layer* L = new ConvV1Layer();
+  ConvParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  const int kc = Cin % 64 == 0 ? 64 : 32;
+  L->BN = Cout >= 128 ? 128 : Cout;
+  p.kc = kc; p.nchunk0 = Cin / kc; p.nchunk1 = 0; p.nprod = x3 ? 3 : 1;
+  tile_geom(H, W, p.TW, p.TH, p.TB);
+  if (W % p.TW != 0 || H % p.TH != 0) {
+    set_error("conv_v1_plan: H, W must tile by %dx%d", p.TH, p.TW);
+    delete L;
+    return TFPNP_ERR_INVALID;
+  }
+  p.box_rows = p.TW * p.TH * (p.TB < B ? p.TB : B);
+  p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.dil = dil; p.slope = slope;
+  p.bias = bias; p.out_hi = out_hi; p.out_lo = x3 ? out_lo : nullptr;
+  cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)(p.TB < B ? p.TB : B)};
+  int rc = encode_map(&p.a_map[0][0], const_cast<__half*>(x_hi), 4, dims, strides, box, kc * 2);
+  if (rc == 0 && x3) rc = encode_map(&p.a_map[0][1], const_cast<__half*>(x_lo), 4, dims, strides, box, kc * 2);
+  if (!x3) p.a_map[0][1] = p.a_map[0][0];
+  p.a_map[1][0] = p.a_map[0][0]; p.a_map[1][1] = p.a_map[0][1];
+  cuuint64_t wd[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+  cuuint64_t ws[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
+  cuuint32_t wb[3] = {(cuuint32_t)kc, (cuuint32_t)L->BN, 1};
+  if (rc == 0) rc = encode_map(&p.w_map[0], const_cast<__half*>(w_hi), 3, wd, ws, wb, kc * 2);
+  if (rc == 0 && x3) rc = encode_map(&p.w_map[1], const_cast<__half*>(w_lo), 3, wd, ws, wb, kc * 2);
+  if (!x3) p.w_map[1] = p.w_map[0];
+  if (rc != 0) { delete L; return rc; }
+  *out = L;
+  return 0;
+}
+int conv_v1_launch(const ConvV1Layer* L, cudaStream_t st) {
+  TFPNP_TRY(launch_conv_params(L->p, L->BN, st));
+  return 0;
+}
+void conv_v1_free(ConvV1Layer* L) { delete L; }
 
 int conv3x3_nhwc(const void* x0, int C0, const void* x1, int C1, const void* w_taps, const float* bias,
                  void* out, int B, int H, int W, int Cout, cudaStream_t st) {

@@ -100,9 +100,63 @@ class UNetDenoiser2D(torch.nn.Module):
             pass
 
 
+#: IRCNN(in_nc=2, out_nc=1, nc=64) inference-form state_dict (BatchNorm folded): seven Conv2d at sequential
+#: indices 0,2,...,12 with ReLU between them, dilations 1,2,3,4,3,2,1
+IRCNN_DILATIONS = (1, 2, 3, 4, 3, 2, 1)
+
+
+def ircnn_state_dict_layout():
+    out = []
+    for i, (ci, co) in enumerate([(2, 64)] + [(64, 64)] * 5 + [(64, 1)]):
+        out.append((f"model.{2 * i}.weight", (co, ci, 3, 3)))
+        out.append((f"model.{2 * i}.bias", (co,)))
+    return out
+
+
+class IRCNNDenoiser2D(UNetDenoiser2D):
+    """IRCNN prox_sigma denoiser (BASELINE configs[0]).  The reference has no IRCNN
+    (tfpnp/pnp/__init__.py:5-13); this is the published network wrapped like UNetDenoiser2D
+    (tfpnp/pnp/denoiser/base.py:23-32): ``clamp(x - net(cat[x, sigma map]), 0, 1)``.  Same call signature,
+    usable with every solver of this package."""
+
+    def __init__(self, ckpt_path=None, state_dict=None, precision="fp16"):
+        torch.nn.Module.__init__(self)
+        if state_dict is None:
+            if ckpt_path is None:
+                raise ValueError('Default ckpt not found, you have to provide a ckpt path')
+            state_dict = torch.load(ckpt_path, map_location="cpu")
+        if precision not in ("fp16", "fp16x3"):
+            raise ValueError("IRCNNDenoiser2D precision must be 'fp16' or 'fp16x3'")
+        self.precision = precision
+        parts = []
+        for key, shape in ircnn_state_dict_layout():
+            if key not in state_dict:
+                raise KeyError(f"IRCNN checkpoint is missing '{key}'")
+            t = state_dict[key]
+            if tuple(t.shape) != shape:
+                raise ValueError(f"'{key}' has shape {tuple(t.shape)}, expected {shape}")
+            parts.append(t.detach().to(torch.float32).cpu().contiguous().reshape(-1))
+        self._flat = torch.cat(parts).contiguous()
+        self._handles = {}
+
+    def _handle(self, device: torch.device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            with torch.cuda.device(idx):
+                out = C.c_void_p()
+                _lib.check(_lib.lib().tfpnp_ircnn_create(self._flat.data_ptr(), self._flat.numel(),
+                                                         _lib.PRECISIONS[self.precision], C.byref(out)),
+                           "tfpnp_ircnn_create")
+            self._handles[idx] = h = out
+        return h
+
+
 def create_denoiser(opt, ckpt_path=None, state_dict=None, precision="fp16"):
-    """Mirror of tfpnp.pnp.create_denoiser (tfpnp/pnp/__init__.py:5-13)."""
+    """Mirror of tfpnp.pnp.create_denoiser (tfpnp/pnp/__init__.py:5-13), plus 'ircnn'."""
     print(f'[i] use denoiser: {opt.denoiser}')
     if opt.denoiser == 'unet':
         return UNetDenoiser2D(ckpt_path, state_dict, precision)
+    if opt.denoiser == 'ircnn':
+        return IRCNNDenoiser2D(ckpt_path, state_dict, precision)
     raise NotImplementedError

@@ -65,9 +65,9 @@ class _NativeADMM(PnPSolver):
     use_graph = True
 
     def __init__(self, denoiser):
-        if not isinstance(denoiser, UNetDenoiser2D):
-            raise TypeError("tfpnp_b200 solvers need a tfpnp_b200.UNetDenoiser2D (the denoiser runs inside "
-                            "the fused CUDA path)")
+        if not isinstance(denoiser, UNetDenoiser2D):      # IRCNNDenoiser2D derives from it
+            raise TypeError("tfpnp_b200 solvers need a tfpnp_b200.UNetDenoiser2D / IRCNNDenoiser2D (the denoiser "
+                            "runs inside the fused CUDA path)")
         super().__init__(denoiser)
         self._solvers = {}      # (device idx, H, W, extra) -> handle
         self.last_launch_count = 0
