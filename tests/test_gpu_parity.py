@@ -394,3 +394,30 @@ def test_ct_config4_per_gpu_shape(dev):
     with torch.no_grad():
         one = s((state[:1], (y0[:1], view[:1])), tuple(p[:1, :1] for p in par))
     assert_close(one, ref, 1e-4, "ct cfg4 one image")
+
+
+def test_csmri_fused_update_bit_identical_to_three_kernel_path(dev):
+    """The one-launch cluster kernel (csmri.cu: csmri_fused) does the same arithmetic in the same order as the
+    rows_fwd / cols / rows_inv kernels: identical bits (the flag is read once per process -> subprocess)."""
+    import subprocess, sys, os
+    code = (
+        "import sys, torch; sys.path.insert(0, %r);\n"
+        "import tfpnp_b200 as T\nfrom oracle import synth\n"
+        "dev = torch.device('cuda:0'); sd = synth.unet_state_dict(0, 'default')\n"
+        "outs = []\n"
+        "for n, B in ((128, 5), (64, 3)):\n"
+        "    d = synth.csmri_batch(B, n, 3)\n"
+        "    s = T.ADMMSolver_CSMRI(T.UNetDenoiser2D(state_dict=sd, precision='fp16'))\n"
+        "    with torch.no_grad():\n"
+        "        o = s((d['state'].to(dev), (d['y0'].to(dev), d['mask'].to(dev))), (d['sigma_d'].to(dev), d['mu'].to(dev)))\n"
+        "    outs.append(o.cpu())\n"
+        "torch.save(outs, sys.argv[1])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = {}
+    for flag in ("0", "1"):
+        path = f"/tmp/csmri_fused_{flag}.pt"
+        env = dict(os.environ, TFPNP_CSMRI_FUSED=flag)
+        r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[flag] = torch.load(path)
+    for a, b in zip(res["0"], res["1"]):
+        assert torch.isfinite(a).all() and torch.equal(a, b)

@@ -15,6 +15,7 @@
 //   rows_inv : warp per image row   inverse row FFT -> z, u, d
 #include "tasks.cuh"
 #include "fft.cuh"
+#include <cstdlib>
 
 namespace tfpnp {
 namespace {
@@ -130,10 +131,167 @@ csmri_rows_inv(const float2* __restrict__ T, const float* __restrict__ x, float2
   }
 }
 
+// ---- one launch per iteration: the whole update of an image inside a 2-CTA cluster -------------------------------
+// CTA `rank` of the cluster owns image rows [rank*N/2, (rank+1)*N/2) for the two row passes and columns (frequency
+// positions) [rank*N/2, ...) for the column pass.  The two transposes between the passes go through shared memory:
+// every warp scatters its FFT output into the [col][row] (then [row][col]) tile of the CTA that owns the column (row)
+// -- its own tile or, through distributed shared memory (st.shared::cluster), its peer's -- so the intermediate T
+// never touches L2/HBM and the twiddle set-up is paid once per warp instead of once per row.  Same arithmetic, in the
+// same order, as the three-kernel path above (bit-identical results).
+__device__ __forceinline__ void st_cluster_f2(const float2* local_ptr, uint32_t cta, float2 v) {
+  uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr)), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(ra), "f"(v.x), "f"(v.y) : "memory");
+}
+
+constexpr int FUSED_WARPS = 16;
+
+template <int R>
+__global__ void __launch_bounds__(FUSED_WARPS * 32, 1)
+csmri_fused(const float* __restrict__ x, float2* __restrict__ z, float2* __restrict__ u, float* __restrict__ d,
+            const float2* __restrict__ y0p, const uint8_t* __restrict__ maskp, const float* __restrict__ mu) {
+  constexpr int N = 32 * R, HALF = N / 2, PITCH = N + 1, RPW = HALF / FUSED_WARPS;
+  static_assert(RPW >= 1, "csmri_fused needs N >= 64");
+  extern __shared__ float2 fsm[];
+  float2* tA = fsm;                     // [HALF cols][PITCH]: column-major input of the column pass
+  float2* tB = fsm + HALF * PITCH;      // [HALF rows][PITCH]: row-major input of the inverse row pass
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int b = blockIdx.x >> 1;
+  const int warp = threadIdx.x >> 5;
+  WarpFFT<R> f;
+  f.init();                             // twiddles: overlaps the tail of the denoiser's last kernel
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const size_t img = (size_t)b * N * N;
+  float2 v[R];
+  // Every pass first issues ALL the global loads of the warp's RPW rows / columns (one latency per pass instead of
+  // one per row), then runs the FFTs out of registers.
+  // ---- pass 1: (x + u) -> row FFT -> scatter by column owner
+  {
+    float2 in[RPW][R];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = rank * HALF + warp * RPW + i;
+      const float* xr = x + img + (size_t)r * N;
+      const float2* ur = u + img + (size_t)r * N;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const float2 uu = ur[32 * j + f.lane];
+        in[i][j] = make_float2(xr[32 * j + f.lane] + uu.x, uu.y);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = rank * HALF + warp * RPW + i;
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = in[i][j];
+      f.forward(v);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int c = 32 * j + f.lane;
+        st_cluster_f2(tA + (c % HALF) * PITCH + r, c / HALF, v[j]);
+      }
+    }
+  }
+  // data-consistency operands of this warp's columns: constant during the solver call, fetched before the barrier
+  float2 yv[RPW][R];
+  bool mk[RPW][R];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const size_t col = ((size_t)b * N + rank * HALF + warp * RPW + i) * N;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      mk[i][j] = maskp[col + 32 * j + f.lane] != 0;
+      yv[i][j] = y0p[col + 32 * j + f.lane];
+    }
+  }
+  const float m = mu[b];
+  const float inv_n = 1.0f / (float)N;
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  // ---- pass 2: column FFT -> masked data consistency -> inverse column FFT -> scatter by row owner
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int cc = warp * RPW + i, c = rank * HALF + cc;
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = tA[cc * PITCH + 32 * j + f.lane];
+    f.forward(v);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      float2 zf = make_float2(v[j].x * inv_n, v[j].y * inv_n);
+      if (mk[i][j]) {                            // z[mask] = ((mu z + y0)/(1+mu))[mask], solver.py:50-51
+        zf.x = (m * zf.x + yv[i][j].x) / (1.0f + m);
+        zf.y = (m * zf.y + yv[i][j].y) / (1.0f + m);
+      }
+      v[j] = zf;
+    }
+    f.inverse(v);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int r = 32 * j + f.lane;
+      st_cluster_f2(tB + (r % HALF) * PITCH + c, r / HALF, v[j]);
+    }
+  }
+  // the dual-update operands of this warp's rows (x, u): fetched before the barrier
+  float2 uv[RPW][R];
+  float xv[RPW][R];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const size_t row = img + (size_t)(rank * HALF + warp * RPW + i) * N;
+#pragma unroll
+    for (int j = 0; j < R; ++j) { uv[i][j] = u[row + 32 * j + f.lane]; xv[i][j] = x[row + 32 * j + f.lane]; }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  // ---- pass 3: inverse row FFT -> z, u += x - z, d = Re(z - u)
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int rr = warp * RPW + i, r = rank * HALF + rr;
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = tB[rr * PITCH + 32 * j + f.lane];
+    f.inverse(v);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const size_t idx = img + (size_t)r * N + 32 * j + f.lane;
+      const float2 zz = make_float2(v[j].x * inv_n, v[j].y * inv_n);
+      float2 uu = uv[i][j];
+      uu.x = uu.x + xv[i][j] - zz.x;   // u = u + x - z (solver.py:55), Im(x) = 0
+      uu.y = uu.y - zz.y;
+      z[idx] = zz;
+      u[idx] = uu;
+      d[idx] = zz.x - uu.x;            // complex2real(z - u) (solver.py:45)
+    }
+  }
+}
+
+template <int R>
+int launch_fused(const float* x, float2* z, float2* u, float* d, const float2* y0p, const uint8_t* maskp,
+                 const float* mu, int B, cudaStream_t st) {
+  constexpr int N = 32 * R;
+  constexpr int smem = 2 * (N / 2) * (N + 1) * (int)sizeof(float2);
+  static unsigned long long attr_set = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_set >> (dev & 63) & 1ull)) {
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(csmri_fused<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set |= 1ull << (dev & 63);
+  }
+  TFPNP_CUDA_OK(launch_ex(csmri_fused<R>, dim3(2 * B), dim3(FUSED_WARPS * 32), smem, st, true, 2, x, z, u, d, y0p, maskp, mu));
+  TFPNP_COUNT_LAUNCH();
+  return 0;
+}
+
 template <int R>
 int launch_update(const float* x, float2* z, float2* u, float* d, float2* T, const float2* y0p,
                   const uint8_t* maskp, const float* mu, int B, cudaStream_t st) {
   constexpr int N = 32 * R;
+  if constexpr (R == 2 || R == 4) {
+    // Opt-in (TFPNP_CSMRI_FUSED=1).  Measured on B200 at 48 x 128^2: the update segment drops from 34 to 29 us per
+    // iteration, but the whole step gets 1.9 % SLOWER (24.39 vs 23.93 ms): 96 clusters with 132 KB of shared memory each
+    // and scattered 8-byte DSMEM stores hold up the start of the next denoiser call more than the two saved launches
+    // give back.  Kept (bit-identical, tested) as the base for a bulk-DSMEM transpose.
+    static const bool fused = getenv("TFPNP_CSMRI_FUSED") != nullptr && atoi(getenv("TFPNP_CSMRI_FUSED")) != 0;
+    if (fused) return launch_fused<R>(x, z, u, d, y0p, maskp, mu, B, st);
+  }
   const int row_blocks = B * N / ROWS_PER_CTA;
   csmri_rows_fwd<R><<<row_blocks, ROWS_PER_CTA * 32, 0, st>>>(x, u, T);
   TFPNP_COUNT_LAUNCH();

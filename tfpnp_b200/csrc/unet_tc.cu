@@ -315,6 +315,11 @@ constexpr int kXformThreads = 288;                      // 9 transform warps
 // 256-pixel x BN tile is a long dependent instruction stream (~5 instructions per value); with one warp per quadrant
 // it is as long as the tile's MMAs for BN >= 64 (measured: 64->64 @64x64 ran at the epilogue's pace, and a one-tile
 // CTA exposes all of it).  The 64-channel-chunk variants run one CTA per SM and have the registers for 8 warps.
+// Streamed weights: one ring stage holds TPS taps of one (n-tile, chunk): the three taps of a kernel row.  Measured on
+// B200: per-tap stages for BN = 128 (8 x 16 KB instead of 2 x 48 KB) are SLOWER (60.0k -> 55.7k image-iters/s): the
+// extra full/empty handshakes on the single MMA-issuing thread cost more than the deeper ring hides.
+template <int BN> constexpr int conv2_taps_per_stage() { return 3; }
+inline int conv2_taps_per_stage_rt(int) { return 3; }
 template <int KC, bool FUSE> constexpr int conv2_nepi() { return (KC == 64 && !FUSE) ? 8 : 4; }
 template <int KC, bool FUSE> constexpr int conv2_threads() { return 64 + 32 * conv2_nepi<KC, FUSE>() + (FUSE ? kXformThreads : 0); }
 
@@ -327,6 +332,7 @@ __global__ void __launch_bounds__(conv2_threads<KC, FUSE>(), (FUSE || KC == 64) 
 conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   constexpr int NEPI = conv2_nepi<KC, FUSE>();
   static_assert(!SMALL || (!FUSE && !RESIDENT && KC == 64 && NEPI == 8), "SMALL is built for the streamed 64-channel-chunk variant");
+  constexpr int TPS = conv2_taps_per_stage<BN>();        // taps per weight-ring stage
   constexpr int TAP_ROWS = SMALL ? 20 : kHaloW;          // smem rows between kernel rows ky
   constexpr int SBO_ROWS = SMALL ? 10 : kHaloW;          // smem rows between the M-tile's 8-pixel row groups
   constexpr int A_ROWS = SMALL ? 200 : kHaloRows;        // rows one A stage receives
@@ -340,7 +346,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   const int SA = p.num_a_stages, SB = p.num_b_stages;
   uint8_t* sA = smem;
   uint8_t* sW = smem + SA * p.a_stage_bytes;   // resident weights or the B ring
-  const int w_region = RESIDENT ? 9 * nchunks * (int)SLAB : SB * 3 * (int)SLAB;
+  const int w_region = RESIDENT ? 9 * nchunks * (int)SLAB : SB * TPS * (int)SLAB;
   uint8_t* sStg = sW + w_region;                                  // [2][stg_bytes] low-res windows (FUSE only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + (FUSE ? 2 * p.stg_bytes : 0));
   uint64_t* full_a = bars;
@@ -446,18 +452,18 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
             if (!RESIDENT) {
               const CUtensorMap* wm = &p.w_map[prod == 2 ? 1 : 0];
 #pragma unroll 1
-              for (int tg = 0; tg < 3; ++tg) {           // one ring stage = the 3 taps of a kernel row
+              for (int tg = 0; tg < 9 / TPS; ++tg) {     // one ring stage = TPS taps
                 const int sb = ib % SB;
                 mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
                 if (p.dbg & 8) mbar_arrive(&full_b[sb]);
                 else {
-                  mbar_arrive_expect_tx(&full_b[sb], 3 * SLAB);
+                  mbar_arrive_expect_tx(&full_b[sb], TPS * SLAB);
 #pragma unroll
-                  for (int tt = 0; tt < 3; ++tt) {
-                    uint8_t* dst = sW + sb * (3 * SLAB) + tt * SLAB;
-                    if (cs == 1) tma_load_3d(dst, wm, &full_b[sb], c * KC, nt * BN, tg * 3 + tt);
+                  for (int tt = 0; tt < TPS; ++tt) {
+                    uint8_t* dst = sW + sb * (TPS * SLAB) + tt * SLAB;
+                    if (cs == 1) tma_load_3d(dst, wm, &full_b[sb], c * KC, nt * BN, tg * TPS + tt);
                     else tma_load_3d_mc(dst + crank * rows_mc * ROW, wm, &full_b[sb], cmask, c * KC,
-                                        nt * BN + crank * rows_mc, tg * 3 + tt);
+                                        nt * BN + crank * rows_mc, tg * TPS + tt);
                   }
                 }
                 ++ib;
@@ -519,15 +525,16 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
               __syncwarp();
             } else {
 #pragma unroll 1
-              for (int tg = 0; tg < 3; ++tg) {
+              for (int tg = 0; tg < 9 / TPS; ++tg) {
                 mbar_wait(&full_b[sb], phb);
                 tc_fence_after();
-                const uint32_t b_stage = sW_lo + sb * (3 * SLAB >> 4);
-                const uint32_t a_row = a_lo + (tg * TAP_ROWS * ROW >> 4);
+                const uint32_t b_stage = sW_lo + sb * (TPS * SLAB >> 4);
+                // first tap of the stage: kernel row (tg*TPS)/3, column (tg*TPS)%3
+                const uint32_t a_row = a_lo + ((((tg * TPS) / 3) * TAP_ROWS + (tg * TPS) % 3) * ROW >> 4);
                 if (elect_one()) {
                   if (!(p.dbg & 2)) {
 #pragma unroll
-                    for (int tt = 0; tt < 3; ++tt) {
+                    for (int tt = 0; tt < TPS; ++tt) {
                       const uint32_t a_tap = a_row + (tt * ROW >> 4);
                       const uint32_t b_lo = b_stage + tt * (SLAB >> 4);
 #pragma unroll
@@ -1091,9 +1098,10 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   } else {
     p.num_a_stages = c.small ? 3 : 2;
     const int budget = 224 * 1024 - misc - p.num_a_stages * p.a_stage_bytes;
-    int sb = budget / (3 * p.b_stage_bytes);                // a ring stage holds the 3 taps of one kernel row
+    const int tps = conv2_taps_per_stage_rt(c.BN);          // taps per ring stage (1 for BN = 128, else a kernel row)
+    int sb = budget / (tps * p.b_stage_bytes);
     p.num_b_stages = sb > kMaxStages ? kMaxStages : sb;
-    c.smem_bytes = p.num_a_stages * p.a_stage_bytes + p.num_b_stages * 3 * p.b_stage_bytes + misc;
+    c.smem_bytes = p.num_a_stages * p.a_stage_bytes + p.num_b_stages * tps * p.b_stage_bytes + misc;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -1405,8 +1413,8 @@ struct UNetTc : Denoiser {
     const int T = 256;
     // head of the chain: a normal (fully serialised) launch; every later kernel of this call may overlap its
     // prologue with its predecessor's tail (PDL)
-    conv_first_kernel<<<dim3(cdiv(W, 128), H, B), 128, 0, st>>>(x, sigma, sstride, first_w, S0.hi,
-                                                               x3 ? S0.lo : nullptr, H, W);
+    TFPNP_CUDA_OK(launch_ex(conv_first_kernel, dim3(cdiv(W, 128), H, B), dim3(128), 0, st, use_pdl(), 1, x, sigma, sstride,
+                            first_w, S0.hi, x3 ? S0.lo : nullptr, H, W));
     TFPNP_COUNT_LAUNCH();
     TFPNP_TRY(launch_conv(1, st));
     TFPNP_TRY(launch_conv(2, st));
