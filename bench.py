@@ -46,6 +46,15 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def ncu_traffic():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one inner iteration's kernels from the committed
+    `ncu --set full` capture of this same command (profiles/r01_traffic.json, written by tools/ncu_traffic.py)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -240,6 +249,9 @@ def main():
     h2d = sum(host[k].numel() * host[k].element_size() for k in ("state", "y0", "mask", "sigma_d", "mu", "gt"))
     d2h = out_host.numel() * 4 + B_total * 4
 
+    tr = ncu_traffic()
+    den_traffic = tr["denoiser_dram_bytes_per_iter"] * ITERS if tr else None       # per step, like `achieved`
+    upd_traffic = tr["update_dram_bytes_per_iter"] * ITERS if tr else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak",
@@ -254,10 +266,13 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv3x3_tc (tcgen05 implicit-GEMM, denoiser segment)",
                      "achieved": den_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                     "frac": den_tflops / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                     "frac": den_tflops / pk["tf_sust"], "traffic": den_traffic,
+                     "traffic_note": "DRAM bytes per step (30 denoiser calls) from profiles/r01_traffic.json (ncu --set full)",
+                     "peak_source": pk["src"] + " bf16 sustained",
                      "denoiser_ms_per_step": den_ms.value, "update_ms_per_step": upd_ms.value},
         "roofline_update": {"bound": "hbm", "kernel": "csmri rows_fwd+cols+rows_inv", "achieved": upd_gbs,
-                            "peak": pk["hbm"], "unit": "GB/s", "frac": upd_gbs / pk["hbm"], "traffic": None},
+                            "peak": pk["hbm"], "unit": "GB/s", "frac": upd_gbs / pk["hbm"], "traffic": upd_traffic,
+                            "algorithmic_bytes_per_step": B_PER_GPU * N_PIX * N_PIX * UPDATE_BYTES_PER_PX * ITERS},
     }
 
     if rank == 0 and not args.no_cpu_baseline:
