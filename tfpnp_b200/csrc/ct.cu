@@ -11,7 +11,8 @@
 //   A^T : its exact transpose written as a gather (each pixel reads <= 2 detector bins per view),
 // so both directions are atomic-free gathers; parity is against oracle/pnp_oracle.py's
 // restatement of the same formulas (PARITY UNPINNED w.r.t. torch_radon).
-// Two launches per iteration: forward (+ "- y0") and backprojection fused with the update.
+// Three launches per iteration: transpose (for the column-driven views), forward (+ "- y0") and backprojection
+// fused with the update.
 #include "tasks.cuh"
 #include <cmath>
 #include <vector>
@@ -19,45 +20,60 @@
 namespace tfpnp {
 namespace {
 
-// sino[b,v,d] = sum over driving axis ... (- y0[b,v,d] if y0 != nullptr)
+// imgT[b][j][i] = img[b][i][j]: the column-driven views walk the image column by column, so reading the TRANSPOSED
+// image makes consecutive detector bins (consecutive lanes) touch consecutive addresses (measured: the uncoalesced
+// walk made the projector L1-wavefront bound, 170 us for 8 x 256^2 x 60 views)
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ img, float* __restrict__ imgT, int N) {
+  __shared__ float tile[32][33];
+  const size_t base = (size_t)blockIdx.z * N * N;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int x = x0 + tx, y = y0 + ty + k;
+    tile[ty + k][tx] = (x < N && y < N) ? img[base + (size_t)y * N + x] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int x = y0 + tx, y = x0 + ty + k;                  // transposed coordinates
+    if (x < N && y < N) imgT[base + (size_t)y * N + x] = tile[tx][ty + k];
+  }
+}
+
+// sino[b,v,d] = sum over the driving axis of the linearly interpolated image / max(|cos|,|sin|)  (- y0[b,v,d] if y0)
+// Both branches walk `line` = a row of `src` (the image for row-driven views, its transpose for column-driven ones).
 __global__ void __launch_bounds__(128)
-radon_fwd_kernel(const float* __restrict__ img, const float* __restrict__ y0, float* __restrict__ sino,
-                 const float* __restrict__ cs, const float* __restrict__ sn, int N, int D) {
+radon_fwd_kernel(const float* __restrict__ img, const float* __restrict__ imgT, const float* __restrict__ y0,
+                 float* __restrict__ sino, const float* __restrict__ cs, const float* __restrict__ sn, int N, int D) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   const int v = blockIdx.y, b = blockIdx.z, V = gridDim.y;
   if (d >= D) return;
   const float co = cs[v], si = sn[v];
   const float c = (N - 1) * 0.5f;
   const float s = (float)d - (D - 1) * 0.5f;
-  const float* im = img + (size_t)b * N * N;
   const bool col_drive = fabsf(si) >= fabsf(co);
   const float m = col_drive ? fabsf(si) : fabsf(co);
+  // position along the interpolated axis at driving index k:  r(k) = (s - (k - c) * a) / bq + c
+  const float a = col_drive ? co : si, bq = col_drive ? si : co;
+  const float inv_b = 1.0f / bq;
+  const float* src = (col_drive ? imgT : img) + (size_t)b * N * N;
   float acc = 0.f;
-  if (col_drive) {
-    for (int j = 0; j < N; ++j) {
-      float t = (float)j - c;
-      float r = __fadd_rn(__fdiv_rn(__fsub_rn(s, __fmul_rn(t, co)), si), c);   // row index at column j
-      float fl = floorf(r);
-      float f = r - fl;
-      int i0 = (int)fl;
-      float v0 = (i0 >= 0 && i0 < N) ? im[(size_t)i0 * N + j] : 0.f;
-      float v1 = (i0 + 1 >= 0 && i0 + 1 < N) ? im[(size_t)(i0 + 1) * N + j] : 0.f;
-      acc += (1.f - f) * v0 + f * v1;
-    }
-  } else {
-    for (int i = 0; i < N; ++i) {
-      float t = (float)i - c;
-      float r = __fadd_rn(__fdiv_rn(__fsub_rn(s, __fmul_rn(t, si)), co), c);   // column index at row i
-      float fl = floorf(r);
-      float f = r - fl;
-      int j0 = (int)fl;
-      float v0 = (j0 >= 0 && j0 < N) ? im[(size_t)i * N + j0] : 0.f;
-      float v1 = (j0 + 1 >= 0 && j0 + 1 < N) ? im[(size_t)i * N + j0 + 1] : 0.f;
-      acc += (1.f - f) * v0 + f * v1;
-    }
+#pragma unroll 4
+  for (int k = 0; k < N; ++k) {
+    const float t = (float)k - c;
+    const float r = __fadd_rn(__fmul_rn(__fsub_rn(s, __fmul_rn(t, a)), inv_b), c);
+    const float fl = floorf(r);
+    const float f = r - fl;
+    const int i0 = (int)fl;
+    const float* line = src + (size_t)k * N;
+    const float v0 = (i0 >= 0 && i0 < N) ? line[i0] : 0.f;
+    const float v1 = (i0 + 1 >= 0 && i0 + 1 < N) ? line[i0 + 1] : 0.f;
+    acc += (1.f - f) * v0 + f * v1;
   }
-  size_t o = ((size_t)b * V + v) * D + d;
-  float r = acc / m;
+  const size_t o = ((size_t)b * V + v) * D + d;
+  const float r = acc / m;
   sino[o] = y0 ? r - y0[o] : r;
 }
 
@@ -68,7 +84,7 @@ __device__ __forceinline__ float backproject_pixel(const float* __restrict__ sg,
   const float half = (D - 1) * 0.5f;
   for (int v = 0; v < V; ++v) {
     const float co = cs[v], si = sn[v];
-    const float m = fmaxf(fabsf(si), fabsf(co));
+    const float inv_m = 1.0f / fmaxf(fabsf(si), fabsf(co));     // one division per view instead of four
     float dstar = __fadd_rn(__fadd_rn(__fmul_rn(xx, co), __fmul_rn(yy, si)), half);
     float fl = floorf(dstar);
     int d0 = (int)fl;
@@ -76,7 +92,7 @@ __device__ __forceinline__ float backproject_pixel(const float* __restrict__ sg,
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       int dd = d0 + k;
-      float w = fmaxf(1.f - fabsf((fl + (float)k) - dstar) / m, 0.f) / m;
+      float w = fmaxf(1.f - fabsf((fl + (float)k) - dstar) * inv_m, 0.f) * inv_m;
       if (dd >= 0 && dd < D) acc += row[dd] * w;
     }
   }
@@ -137,8 +153,15 @@ int CtGeom::set_tables(const float* cos_host, const float* sin_host) {
   return 0;
 }
 
+int CtGeom::reserve(int B) const {
+  return tbuf.alloc((size_t)B * N * N * sizeof(float));
+}
+
 int radon_forward(const CtGeom& g, const float* img, const float* y0, float* sino, int B, cudaStream_t st) {
-  radon_fwd_kernel<<<dim3(cdiv(g.det, 128), g.views, B), 128, 0, st>>>(img, y0, sino, g.cs.as<float>(),
+  TFPNP_CHECK(g.tbuf.bytes >= (size_t)B * g.N * g.N * sizeof(float), "CtGeom::reserve(%d) not called", B);
+  transpose_kernel<<<dim3(cdiv(g.N, 32), cdiv(g.N, 32), B), 256, 0, st>>>(img, g.tbuf.as<float>(), g.N);
+  TFPNP_COUNT_LAUNCH();
+  radon_fwd_kernel<<<dim3(cdiv(g.det, 128), g.views, B), 128, 0, st>>>(img, g.tbuf.as<float>(), y0, sino, g.cs.as<float>(),
                                                                         g.sn.as<float>(), g.N, g.det);
   TFPNP_COUNT_LAUNCH();
   TFPNP_CUDA_OK(cudaGetLastError());

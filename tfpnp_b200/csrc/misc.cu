@@ -72,6 +72,7 @@ int tfpnp_radon_forward(const float* img, float* sino, int B, int N, int views, 
   TFPNP_CHECK(img && sino && B > 0 && N > 0 && views > 0, "bad argument");
   CtGeom* g = geom_cache().get(N, views, cos_host, sin_host);
   if (!g) return TFPNP_ERR_CUDA;
+  TFPNP_TRY(g->reserve(B));
   return radon_forward(*g, img, nullptr, sino, B, static_cast<cudaStream_t>(stream));
 }
 

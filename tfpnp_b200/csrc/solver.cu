@@ -131,6 +131,7 @@ struct Solver {
           break;
         case TFPNP_TASK_CT:
           TFPNP_TRY(resid.alloc((size_t)B * geom.views * geom.det * sizeof(float)));
+          TFPNP_TRY(geom.reserve(B));
           TFPNP_TRY(aux0p.alloc((size_t)B * geom.views * geom.det * sizeof(float)));
           break;
         case TFPNP_TASK_SPI:
@@ -328,7 +329,7 @@ struct Solver {
     for (auto e : events) cudaEventDestroy(e);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     x.release(); z.release(); u.release(); d.release(); T.release(); aux0p.release(); aux1p.release();
-    params.release(); k10.release(); resid.release(); geom.cs.release(); geom.sn.release();
+    params.release(); k10.release(); resid.release(); geom.cs.release(); geom.sn.release(); geom.tbuf.release();
   }
 };
 

@@ -33,6 +33,8 @@ int pr_update(const float* x, float2* z, float2* u, float* d, float2* T, const f
 struct CtGeom {
   int N = 0, views = 0, det = 0;
   DevBuf cs, sn;  // fp32 cos/sin tables [views]
+  mutable DevBuf tbuf;                                       // transposed image scratch [B,N,N] for the column-driven views
+  int reserve(int B) const;                                  // size tbuf (never during graph capture)
   int init(int N, int views);                                // tables as torch.linspace would give
   int set_tables(const float* cos_host, const float* sin_host);  // caller-supplied tables [views]
 };
