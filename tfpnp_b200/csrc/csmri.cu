@@ -21,7 +21,7 @@ namespace tfpnp {
 namespace {
 
 constexpr int ROWS_PER_CTA = 8;   // warps per CTA in the row kernels
-constexpr int COLS_PER_CTA = 16;  // columns (= warps) per CTA in the column kernel
+constexpr int COLS_PER_CTA = 8;   // columns (= warps) per CTA in the column kernel: more, smaller CTAs per SM overlap the load / FFT / store phases
 
 __global__ void csmri_prep_kernel(const float2* __restrict__ y0, const uint8_t* __restrict__ mask,
                                   float2* __restrict__ y0p, uint8_t* __restrict__ maskp, int N, int R) {
@@ -136,8 +136,8 @@ csmri_rows_inv(const float2* __restrict__ T, const float* __restrict__ x, float2
 // positions) [rank*N/2, ...) for the column pass.  The two transposes between the passes go through shared memory:
 // every warp scatters its FFT output into the [col][row] (then [row][col]) tile of the CTA that owns the column (row)
 // -- its own tile or, through distributed shared memory (st.shared::cluster), its peer's -- so the intermediate T
-// never touches L2/HBM and the twiddle set-up is paid once per warp instead of once per row.  Same arithmetic, in the
-// same order, as the three-kernel path above (bit-identical results).
+// never touches L2/HBM.  Same arithmetic, in the same order, as the three-kernel path above (equal up to the
+// compiler's FMA contraction inside the butterflies).
 __device__ __forceinline__ void st_cluster_f2(const float2* local_ptr, uint32_t cta, float2 v) {
   uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr)), ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
@@ -288,7 +288,7 @@ int launch_update(const float* x, float2* z, float2* u, float* d, float2* T, con
     // Opt-in (TFPNP_CSMRI_FUSED=1).  Measured on B200 at 48 x 128^2: the update segment drops from 34 to 29 us per
     // iteration, but the whole step gets 1.9 % SLOWER (24.39 vs 23.93 ms): 96 clusters with 132 KB of shared memory each
     // and scattered 8-byte DSMEM stores hold up the start of the next denoiser call more than the two saved launches
-    // give back.  Kept (bit-identical, tested) as the base for a bulk-DSMEM transpose.
+    // give back.  Kept (tested against the three-kernel path) as the base for a bulk-DSMEM transpose.
     static const bool fused = getenv("TFPNP_CSMRI_FUSED") != nullptr && atoi(getenv("TFPNP_CSMRI_FUSED")) != 0;
     if (fused) return launch_fused<R>(x, z, u, d, y0p, maskp, mu, B, st);
   }
@@ -307,6 +307,7 @@ int launch_update(const float* x, float2* z, float2* u, float* d, float2* T, con
 
 int csmri_prep(const float* y0, const uint8_t* mask, float2* y0p, uint8_t* maskp, int B, int N,
                cudaStream_t st) {
+  TFPNP_CUDA_OK(fft_tables_init());   // twiddles: once per device, outside any graph capture
   TFPNP_CHECK(N == 32 || N == 64 || N == 128 || N == 256, "csmri: N must be 32/64/128/256, got %d", N);
   size_t n = (size_t)B * N * N;
   csmri_prep_kernel<<<(unsigned)(n / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(y0), mask, y0p,

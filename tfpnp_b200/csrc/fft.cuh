@@ -15,6 +15,7 @@
 // tfpnp/utils/transforms.py:68-103,215-257.
 #pragma once
 #include <cuda_runtime.h>
+#include <cmath>
 
 namespace tfpnp {
 
@@ -74,6 +75,41 @@ __device__ __forceinline__ void dft_regs(float2 (&v)[R]) {
   }
 }
 
+// Twiddle table, filled once per device from the host in double precision (fft_tables_init): a warp that does ONE
+// transform spent as many instructions on its 5 + R sincospif calls as on the FFT itself.
+//   g_fft_tw[log2 R][i][lane], i < 5 : W_{2s}^{lane & (s-1)}, s = 16 >> i ;   i = 5 + k : W_{32R}^{lane * k}
+constexpr int kFftTwRows = 13;
+static __device__ float2 g_fft_tw[4][kFftTwRows][32];
+
+static inline cudaError_t fft_tables_init() {
+  static unsigned long long done_mask = 0;   // one bit per device (the table is per translation unit and device)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if ((done_mask >> (dev & 63)) & 1ull) return cudaSuccess;
+  static float2 h[4][kFftTwRows][32];
+  const double pi = 3.14159265358979323846;
+  for (int lr = 0; lr < 4; ++lr) {
+    const int R = 1 << lr;
+    for (int lane = 0; lane < 32; ++lane) {
+      for (int i = 0; i < 5; ++i) {
+        const int s = 16 >> i;
+        const double a = pi * (double)(lane & (s - 1)) / (double)s;
+        h[lr][i][lane].x = (float)cos(a);
+        h[lr][i][lane].y = (float)(-sin(a));
+      }
+      for (int k = 0; k < 8; ++k) {
+        const double a = pi * (double)(2 * lane * k) / (double)(32 * R);
+        h[lr][5 + k][lane].x = k < R ? (float)cos(a) : 1.f;
+        h[lr][5 + k][lane].y = k < R ? (float)(-sin(a)) : 0.f;
+      }
+    }
+  }
+  e = cudaMemcpyToSymbol(g_fft_tw, h, sizeof(h));
+  if (e == cudaSuccess) done_mask |= 1ull << (dev & 63);
+  return e;
+}
+
 template <int R>
 struct WarpFFT {
   float2 tw_lane[5];  // W_{2s}^{lane & (s-1)}, s = 16,8,4,2,1
@@ -82,21 +118,11 @@ struct WarpFFT {
 
   __device__ __forceinline__ void init() {
     lane = threadIdx.x & 31;
+    constexpr int LR = R == 1 ? 0 : (R == 2 ? 1 : (R == 4 ? 2 : 3));
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      int s = 16 >> i;
-      float t = (float)(lane & (s - 1)) / (float)s;
-      float sn, cs;
-      sincospif(t, &sn, &cs);
-      tw_lane[i] = make_float2(cs, -sn);
-    }
+    for (int i = 0; i < 5; ++i) tw_lane[i] = g_fft_tw[LR][i][lane];
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-      float t = (float)(2 * lane * k) / (float)(32 * R);
-      float sn, cs;
-      sincospif(t, &sn, &cs);
-      tw_reg[k] = make_float2(cs, -sn);
-    }
+    for (int k = 0; k < R; ++k) tw_reg[k] = g_fft_tw[LR][5 + k][lane];
   }
 
   __device__ __forceinline__ void forward(float2 (&v)[R]) {

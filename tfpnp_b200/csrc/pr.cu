@@ -18,7 +18,7 @@ namespace tfpnp {
 namespace {
 
 constexpr int ROWS_PER_CTA = 8;
-constexpr int COLS_PER_CTA = 16;
+constexpr int COLS_PER_CTA = 8;   // columns (= warps) per CTA in the column kernel: more, smaller CTAs per SM overlap the load / FFT / store phases
 
 __global__ void pr_prep_kernel(const float* __restrict__ y0, float* __restrict__ y0p, int N, int R) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (bm, c, r), r fastest
@@ -150,6 +150,7 @@ int launch_update(const float* x, float2* z, float2* u, float* d, float2* T, con
 }  // namespace
 
 int pr_prep(const float* y0, float* y0p, int B, int M, int N, cudaStream_t st) {
+  TFPNP_CUDA_OK(fft_tables_init());   // twiddles: once per device, outside any graph capture
   size_t n = (size_t)B * M * N * N;
   pr_prep_kernel<<<(unsigned)(n / 256), 256, 0, st>>>(y0, y0p, N, N / 32);
   TFPNP_COUNT_LAUNCH();
