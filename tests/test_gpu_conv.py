@@ -34,6 +34,8 @@ CASES = [
     (512, 0, 512, 8, 8, 48),      # 8x8 level at the bench shape: two-image M-tiles, 4 N tiles, weight multicast
     (256, 512, 256, 8, 8, 5),     # 8x8 level, concat of two sources, ragged (odd) batch
     (512, 0, 512, 8, 8, 1),       # a single 8x8 image: falls back to the one-tile-per-CTA kernel
+    (32, 0, 64, 64, 64, 3),       # down1.conv-0: 32-channel chunk, N = 64, resident weights, 2 CTAs / SM
+    (64, 0, 64, 64, 64, 48),      # the bench shape of the 64-channel level (768 tiles on 148 persistent CTAs)
 ]
 
 
