@@ -131,6 +131,16 @@ int tfpnp_radon_forward(const float* img, float* sino, int B, int N, int views,
 int tfpnp_radon_backward(const float* sino, float* img, int B, int N, int views,
                          const float* cos_host, const float* sin_host, void* stream);
 
+/* ---- stand-alone transforms (tfpnp/utils/transforms.py:68-103, 282-320) ------
+ * out = FFT2 (inverse = 0) or IFFT2 (inverse = 1), ortho-normalised, of n_imgs complex images
+ * [n_imgs, N, N, 2] (fp32 interleaved), over the two image dims.  centered = 1 is the reference's
+ * fft2 / ifft2 (fftshift(FFT(ifftshift(x)))); centered = 0 is the plain pair used by
+ * cdp_forward / cdp_backward.  N in {32, 64, 128, 256}.  workspace: n_imgs*N*N*2 floats; in, out
+ * and workspace must not alias.  (The solvers' FFTs are fused with their data-fidelity steps; this
+ * operator serves the measurement synthesis and the per-transform parity tests.) */
+int tfpnp_fft2(const float* in, float* out, float* workspace, int n_imgs, int N, int inverse,
+               int centered, void* stream);
+
 /* ---- reward metric: torch_psnr (tfpnp/env/base.py:237-242) ------------------
  * psnr[b] = 10 log10(1 / mean((clamp(out[b],0,1) - gt[b])^2)); out, gt: [B,HW] */
 int tfpnp_psnr(const float* out, const float* gt, float* psnr, int B, int64_t HW, void* stream);

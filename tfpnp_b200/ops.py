@@ -75,3 +75,52 @@ def conv3x3_lrelu_nhwc(x0: torch.Tensor, weight: torch.Tensor, bias: torch.Tenso
                                                  wt.data_ptr(), b.data_ptr(), out.data_ptr(), B, H, W, Cout,
                                                  torch.cuda.current_stream().cuda_stream), "tfpnp_conv3x3_nhwc")
     return out
+
+
+# ---- stand-alone transforms (tfpnp/utils/transforms.py) ----------------------------------------------------
+
+def _fft2_native(x: torch.Tensor, inverse: bool, centered: bool) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("tfpnp_b200 transforms run on CUDA (sm_100) tensors only; there is no CPU fallback")
+    assert x.shape[-1] == 2 and x.shape[-2] == x.shape[-3], "expected [..., N, N, 2]"
+    N = x.shape[-2]
+    xin = x.contiguous().float()
+    n = xin.numel() // (N * N * 2)
+    out = torch.empty_like(xin)
+    ws = torch.empty_like(xin)
+    if n:
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().tfpnp_fft2(xin.data_ptr(), out.data_ptr(), ws.data_ptr(), n, N, 1 if inverse else 0,
+                                             1 if centered else 0, torch.cuda.current_stream().cuda_stream), "tfpnp_fft2")
+    return out
+
+
+def fft2(data: torch.Tensor) -> torch.Tensor:
+    """transforms.fft2 (transforms.py:68-84): centred ortho 2-D FFT of [..., N, N, 2]."""
+    return _fft2_native(data, False, True)
+
+
+def ifft2(data: torch.Tensor) -> torch.Tensor:
+    """transforms.ifft2 (transforms.py:87-103)."""
+    return _fft2_native(data, True, True)
+
+
+def complex_mul(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """transforms.complex_mul (transforms.py:260-270)."""
+    re = x[..., 0] * y[..., 0] - x[..., 1] * y[..., 1]
+    im = x[..., 0] * y[..., 1] + x[..., 1] * y[..., 0]
+    return torch.stack((re, im), dim=-1)
+
+
+def cdp_forward(data: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """transforms.cdp_forward (transforms.py:282-301): FFT2_ortho(data * mask_j), j = 1..M, un-centred.
+    data [B,1,N,N,2], mask [B,M,N,N,2] -> [B,M,N,N,2]."""
+    if data.dim() == 4:
+        data = torch.stack([data, torch.zeros_like(data)], -1)
+    return _fft2_native(complex_mul(data, mask), False, False)
+
+
+def cdp_backward(data: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """transforms.cdp_backward (transforms.py:304-320): mean_j(IFFT2_ortho(data_j) * conj(mask_j)) -> [B,1,N,N,2]."""
+    conj = torch.stack((mask[..., 0], -mask[..., 1]), dim=-1)
+    return complex_mul(_fft2_native(data, True, False), conj).mean(dim=1, keepdim=True)
