@@ -98,6 +98,24 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def synth_inputs(T, dev, B, n, iters, seed):
+    """Synthetic CS-MRI batch of the BASELINE shape, built with the PRODUCT's own operators on the GPU:
+    gt ~ U[0,1), radial masks cycling over ~50/25/12.5 % sampling, y0 = fft2(gt) + N(0,(15/255)^2) on the mask,
+    x0 = ifft2(y0), state = ADMMSolver.reset, sigma_d ~ U[0,70/255], mu ~ U[0,1].  Returned on the HOST (pinned)."""
+    g = torch.Generator(dev).manual_seed(seed)
+    gt = torch.rand(B, 1, n, n, device=dev, generator=g)
+    opts = [max(2, n // 3), max(2, n // 6), max(2, n // 12)]
+    masks = [T.radial_mask(n, L, device=dev) for L in opts]
+    mask = torch.stack([masks[b % 3] for b in range(B)])[:, None]
+    m = T.csmri_measure(gt, mask, sigma_n=15 / 255, generator=g)
+    x0 = m["x0"]
+    state = torch.cat((x0, x0.clone(), torch.zeros_like(x0)), dim=1)          # ADMMSolver.reset (base.py:95-99)
+    sigma_d = torch.rand(B, iters, device=dev, generator=g) * (70 / 255)
+    mu = torch.rand(B, iters, device=dev, generator=g)
+    d = dict(state=state, y0=m["y0"], mask=m["mask"], sigma_d=sigma_d, mu=mu, gt=gt)
+    return {k: v.cpu().contiguous() for k, v in d.items()}
+
+
 def cpu_reference_rate(sd, d, B, iters, repeats=1):
     """The reference algorithm (oracle port of tasks/csmri/solver.py:29-57 + UNetDenoiser2D) on the host."""
     from oracle import pnp_oracle as O
@@ -160,8 +178,7 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    import tfpnp_b200 as T
-    from oracle import synth     # input synthesis + (rank 0) the cpu_baseline / parity checker only
+    import tfpnp_b200 as T       # the product arm imports nothing from oracle/ (only the cpu_baseline / parity leg below does)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,8 +190,8 @@ def main():
     dev = torch.device("cuda", local)
 
     # ---- inputs: weak scaling, 48 images per GPU, different seed per rank --------------------
-    sd = synth.unet_state_dict(0, "default")
-    d = synth.csmri_batch(B_PER_GPU, N_PIX, ITERS, seed=synth.SEED + rank)
+    sd = T.random_unet_state_dict(0)
+    d = synth_inputs(T, dev, B_PER_GPU, N_PIX, ITERS, seed=1234 + rank)
     B_total = B_PER_GPU * world
     solver = T.ADMMSolver_CSMRI(T.UNetDenoiser2D(state_dict=sd, precision=args.precision))
     host = {k: d[k].contiguous().pin_memory() for k in ("state", "y0", "mask", "sigma_d", "mu", "gt")}
@@ -259,7 +276,8 @@ def main():
         "config": {"workload": "csmri ADMM, env_batch=48/GPU, 128x128, action_pack=5 x max_episode_step=6 "
                                "(30 inner iters per call), UNet denoiser (BASELINE configs[1])",
                    "precision": args.precision, "global_batch": B_total, "iters_per_step": ITERS,
-                   "l2": "256 MiB flush write between timed steps", "weights": "seeded default-init UNet(2,1)"},
+                   "l2": "256 MiB flush write between timed steps", "weights": "seeded default-init UNet(2,1)",
+                   "inputs": "synthesised on the GPU by tfpnp_b200.csmri_measure (radial masks, sigma_n = 15/255)"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches * args.steps),

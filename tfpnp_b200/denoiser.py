@@ -100,6 +100,23 @@ class UNetDenoiser2D(torch.nn.Module):
             pass
 
 
+def random_unet_state_dict(seed: int = 0):
+    """A seeded UNet(2,1) state_dict with nn.Conv2d's default initialisation (weights and biases
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in))): benchmarks and smoke tests need weights of the right architecture, the
+    pretrained unet-nm.pt is not distributed with the reference."""
+    import math
+    from collections import OrderedDict
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    fan_in = 1
+    for key, shape in unet_state_dict_layout():
+        if key.endswith("weight"):
+            fan_in = shape[1] * shape[2] * shape[3]
+        b = 1.0 / math.sqrt(fan_in)
+        sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * b
+    return sd
+
+
 #: IRCNN(in_nc=2, out_nc=1, nc=64) inference-form state_dict (BatchNorm folded): seven Conv2d at sequential
 #: indices 0,2,...,12 with ReLU between them, dilations 1,2,3,4,3,2,1
 IRCNN_DILATIONS = (1, 2, 3, 4, 3, 2, 1)

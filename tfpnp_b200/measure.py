@@ -20,6 +20,21 @@ def _randn_like(x, generator):
     return torch.randn(x.shape, device=x.device, dtype=x.dtype, generator=generator)
 
 
+def radial_mask(n: int, lines: int, device=None) -> torch.Tensor:
+    """A radial k-space sampling mask [n, n] (bool): the union of `lines` straight lines through the centre at angles
+    k*pi/lines -- the role of the reference's (undistributed) radial_128_{2,4,8}.mat masks (tasks/csmri/main.py:22)."""
+    c = (n - 1) / 2.0
+    t = torch.linspace(-c * 1.5, c * 1.5, 4 * n, device=device)
+    m = torch.zeros(n, n, dtype=torch.bool, device=device)
+    for k in range(lines):
+        a = torch.tensor(k * 3.141592653589793 / lines, device=device)
+        i = torch.round(c + t * torch.sin(a)).long()
+        j = torch.round(c + t * torch.cos(a)).long()
+        ok = (i >= 0) & (i < n) & (j >= 0) & (j < n)
+        m[i[ok], j[ok]] = True
+    return m
+
+
 def csmri_measure(gt: torch.Tensor, mask: torch.Tensor, sigma_n: float = 0.0, generator=None) -> dict:
     """tasks/csmri/dataset.py:52-66.  gt [B,1,N,N] in [0,1]; mask [B,1,N,N] bool (or broadcastable [1,1,N,N]);
     sigma_n = noise level / 255 already applied (GaussianModelD, tfpnp/utils/noise.py:19-33)."""

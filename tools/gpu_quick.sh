@@ -1,4 +1,5 @@
 #!/bin/bash
+# scratch: quick check after a change (edit freely); the end-of-block run is tools/gpu_round.sh
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
-echo "=== pytest measure"; timeout 600 python -m pytest tests/test_measure.py -m gpu -q --timeout 300 -p no:cacheprovider 2>&1 | tail -15
+echo "=== bench"; timeout 600 python bench.py 2>&1 | tail -1 | cut -c1-2600
