@@ -123,6 +123,19 @@ int tfpnp_solver_forward(void* handle, const float* state_in, const void* aux0,
 /* number of kernels the last tfpnp_solver_forward enqueued (graph nodes included) */
 int64_t tfpnp_solver_last_launch_count(void* handle);
 
+/* ---- the other CS-MRI solvers of the reference's _solver_map (tasks/csmri/solver.py:60-204) ----
+ * Same kernels as the ADMM path (denoiser, warp FFT, pre-rolled k-space operands); only the pointwise step in
+ * k-space and the update around the transform differ.  state_in/state_out: cat of V complex variables
+ * [B,V,N,N,2]: HQS (x,z) V=2; PG x V=1; APG (x,s) V=2; RED-ADMM (x,z,u) V=3.  y0 [B,1,N,N,2] f32, mask [B,1,N,N] u8.
+ * Hyper-parameters p0,p1,p2 ([B,iters], strided like tfpnp_solver_forward):
+ *   HQS (sigma_d, mu, NULL); PG (sigma_d, tau, NULL); APG (sigma_d, tau, beta); RED-ADMM (sigma_d, mu, lamda). */
+typedef enum { TFPNP_ALGO_HQS = 1, TFPNP_ALGO_PG = 2, TFPNP_ALGO_APG = 3, TFPNP_ALGO_REDADMM = 4 } tfpnp_csmri_algo;
+int tfpnp_csmri_variant_create(int algo, int N, void* denoiser, void** out_handle);
+int tfpnp_csmri_variant_destroy(void* handle);
+int tfpnp_csmri_variant_forward(void* handle, const float* state_in, const float* y0, const void* mask,
+                                const float* p0, const float* p1, const float* p2, int64_t row_stride,
+                                int64_t col_stride, int B, int iters, float* state_out, void* stream);
+
 /* ---- CT operators (own discretisation of the reference geometry,
  *      tfpnp/utils/transforms.py:465-491) ------------------------------------- */
 /* img [B,1,N,N] <-> sino [B,1,views,ceil(sqrt(2)N)]; cos/sin: optional HOST tables as above */

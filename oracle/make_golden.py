@@ -129,6 +129,27 @@ def main():
         save("transforms", x=x.numpy(), fft2=T.fft2(x).numpy(), ifft2=T.ifft2(x).numpy(), mask=m.numpy(),
              cdp_fwd=T.cdp_forward(x, m).numpy(), g=gg.numpy(), cdp_bwd=T.cdp_backward(gg, m).numpy())
 
+        # 5b. the other CS-MRI solvers of _solver_map (tasks/csmri/solver.py:60-201), driven through the reference classes
+        d = synth.csmri_batch(2, 32, 3)
+        g7 = torch.Generator().manual_seed(77)
+        extra = {"tau": torch.rand(2, 3, generator=g7) * 1.5, "beta": torch.rand(2, 3, generator=g7) * 0.8,
+                 "lamda": torch.rand(2, 3, generator=g7) * 0.5 + 0.05}
+        x0 = d["x0"]
+        rec = {}
+        for name, fn, pk in (("hqs", O.hqs_csmri, ("sigma_d", "mu")), ("pg", O.pg_csmri, ("sigma_d", "tau")),
+                             ("apg", O.apg_csmri, ("sigma_d", "tau", "beta")),
+                             ("redadmm", O.redadmm_csmri, ("sigma_d", "mu", "lamda"))):
+            sol = refshim.reference_solver("csmri_" + name, sd)
+            state0 = sol.reset({"x0": x0})
+            params = tuple({**d, **extra}[k] for k in pk)
+            ref = sol((state0.clone(), (d["y0"], d["mask"])), params)
+            e = close(fn(sd, state0.clone(), d["y0"], d["mask"], *params), ref)
+            assert torch.equal(sol.get_output(ref), O.complex2real(torch.split(ref, ref.shape[1] // sol.num_var, dim=1)[0]))
+            rec[name + "_state0"] = state0.numpy(); rec[name + "_out"] = ref.numpy()
+            print(f"  csmri {name} oracle-vs-reference rel max err {e:.2e}")
+        save("csmri_variants", **np_({k: d[k] for k in ("y0", "mask", "x0", "gt", "sigma_d", "mu")}), **np_(extra), **rec,
+             wsum=weight_checksum(sd), init="he", seed=0)
+
         # 6. environment bookkeeping (tfpnp/env/base.py:121-191 + tasks/{csmri,spi}/env.py): a 3-step episode with
         #    images dropping out, driven through the UNMODIFIED reference env + solver classes
         env_fixture("csmri", weights[("he", 0)])

@@ -357,6 +357,62 @@ def admm_csmri(sd, state: Tensor, y0: Tensor, mask: Tensor, sigma_d: Tensor, mu:
     return torch.cat((x, z, u), dim=1)
 
 
+def _dc_blend(Z: Tensor, y0: Tensor, m: Tensor, mu: Tensor) -> Tensor:
+    return torch.where(m, (mu * Z + y0) / (1 + mu), Z)
+
+
+def hqs_csmri(sd, state: Tensor, y0: Tensor, mask: Tensor, sigma_d: Tensor, mu: Tensor) -> Tensor:
+    """HQSSolver_CSMRI.forward (tasks/csmri/solver.py:60-88); state = cat[x, z]."""
+    x, z = torch.split(state, state.shape[1] // 2, dim=1)
+    B = x.shape[0]
+    m = mask.bool()[..., None].expand_as(y0)
+    for i in range(sigma_d.shape[-1]):
+        x = real2complex(denoise(sd, complex2real(z), sigma_d[:, i]))
+        z = ifft2c(_dc_blend(fft2c(x), y0, m, mu[:, i].reshape(B, 1, 1, 1, 1)))
+    return torch.cat([x, z], dim=1)
+
+
+def pg_csmri(sd, state: Tensor, y0: Tensor, mask: Tensor, sigma_d: Tensor, tau: Tensor) -> Tensor:
+    """PGSolver_CSMRI.forward (tasks/csmri/solver.py:91-118); state = x."""
+    x = state
+    B = x.shape[0]
+    m = mask.bool()[..., None].expand_as(y0)
+    for i in range(sigma_d.shape[-1]):
+        temp = torch.where(m, fft2c(x) - y0, torch.zeros_like(y0))
+        z = x - tau[:, i].reshape(B, 1, 1, 1, 1) * ifft2c(temp)
+        x = real2complex(denoise(sd, complex2real(z), sigma_d[:, i]))
+    return x
+
+
+def apg_csmri(sd, state: Tensor, y0: Tensor, mask: Tensor, sigma_d: Tensor, tau: Tensor, beta: Tensor) -> Tensor:
+    """APGSolver_CSMRI.forward (tasks/csmri/solver.py:121-161); state = cat[x, s]."""
+    x, s = torch.split(state, state.shape[1] // 2, dim=1)
+    B = x.shape[0]
+    m = mask.bool()[..., None].expand_as(y0)
+    for i in range(sigma_d.shape[-1]):
+        temp = torch.where(m, fft2c(s) - y0, torch.zeros_like(y0))
+        z = s - tau[:, i].reshape(B, 1, 1, 1, 1) * ifft2c(temp)
+        x_prev = x
+        x = real2complex(denoise(sd, complex2real(z), sigma_d[:, i]))
+        s = x + beta[:, i].reshape(B, 1, 1, 1, 1) * (x - x_prev)
+    return torch.cat([x, s], dim=1)
+
+
+def redadmm_csmri(sd, state: Tensor, y0: Tensor, mask: Tensor, sigma_d: Tensor, mu: Tensor, lamda: Tensor) -> Tensor:
+    """REDADMMSolver_CSMRI.forward (tasks/csmri/solver.py:164-201); state = cat[x, z, u]."""
+    x, z, u = _split3(state)
+    B = x.shape[0]
+    m = mask.bool()[..., None].expand_as(y0)
+    for i in range(sigma_d.shape[-1]):
+        _mu = mu[:, i].reshape(B, 1, 1, 1, 1)
+        _l = lamda[:, i].reshape(B, 1, 1, 1, 1)
+        x_half = real2complex(denoise(sd, complex2real(x), sigma_d[:, i]))
+        x = (_l * x_half + _mu * (z - u)) / (_mu + _l)
+        z = ifft2c(_dc_blend(fft2c(x + u), y0, m, _mu))
+        u = u + x - z
+    return torch.cat([x, z, u], dim=1)
+
+
 def iadmm_pr(sd, state: Tensor, y0: Tensor, mask: Tensor, sigma_d: Tensor, mu: Tensor,
              tau: Tensor, iter_num: Optional[int] = None, quant=None) -> Tensor:
     """IADMMSolver_PR.forward (tasks/pr/solver.py:37-76)."""

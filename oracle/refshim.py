@@ -81,6 +81,8 @@ def reference_denoiser(state_dict):
 
 
 def reference_solver(task: str, state_dict):
-    cls = {"csmri": "ADMMSolver_CSMRI", "pr": "IADMMSolver_PR", "spi": "ADMMSolver_SPI"}[task]
-    mod = load_solver_module(task)
+    cls = {"csmri": "ADMMSolver_CSMRI", "pr": "IADMMSolver_PR", "spi": "ADMMSolver_SPI",
+           "csmri_hqs": "HQSSolver_CSMRI", "csmri_pg": "PGSolver_CSMRI", "csmri_apg": "APGSolver_CSMRI",
+           "csmri_redadmm": "REDADMMSolver_CSMRI"}[task]
+    mod = load_solver_module(task.split("_")[0])
     return getattr(mod, cls)(reference_denoiser(state_dict))

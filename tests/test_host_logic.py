@@ -88,7 +88,11 @@ def test_factories_and_errors():
     assert isinstance(T.create_solver_ct(opt, den), T.IADMMSolver_CT)
     opt.solver = "admm_spi"
     assert isinstance(T.create_solver_spi(opt, den), T.ADMMSolver_SPI)
-    opt.solver = "hqs"                   # other algorithms are out of scope -> same error as an unknown name
+    for name, cls in (("hqs", T.HQSSolver_CSMRI), ("pg", T.PGSolver_CSMRI), ("apg", T.APGSolver_CSMRI),
+                      ("redadmm", T.REDADMMSolver_CSMRI)):
+        opt.solver = name
+        assert isinstance(T.create_solver_csmri(opt, den), cls)
+    opt.solver = "amp"                   # draws random numbers inside the loop: not built -> same error as an unknown name
     with pytest.raises(NotImplementedError):
         T.create_solver_csmri(opt, den)
     opt.denoiser = "dncnn"               # unknown names raise as upstream (tfpnp/pnp/__init__.py:8-13)

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtfpnp_b200.so")
 
 TASK_CSMRI, TASK_PR, TASK_CT, TASK_SPI = 0, 1, 2, 3
+ALGO_HQS, ALGO_PG, ALGO_APG, ALGO_REDADMM = 1, 2, 3, 4
 PREC_FP16, PREC_FP16X3, PREC_FP32_SIMT = 0, 1, 2
 PRECISIONS = {"fp16": PREC_FP16, "fp16x3": PREC_FP16X3, "fp32_simt": PREC_FP32_SIMT}
 
@@ -50,6 +51,10 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tfpnp_solver_last_launch_count": (C.c_int64, [C.c_void_p]),
+    "tfpnp_csmri_variant_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tfpnp_csmri_variant_destroy": (C.c_int, [C.c_void_p]),
+    "tfpnp_csmri_variant_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tfpnp_radon_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "tfpnp_radon_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -1,0 +1,356 @@
+// The other CS-MRI plug-and-play solvers of the reference's `_solver_map` (tasks/csmri/solver.py:60-204):
+//   HQS      (:60-88)    x = D(Re z);                         z = ifft2(DC(fft2(x)))
+//   PG       (:91-118)   z = x - tau ifft2(M (fft2(x) - y0));  x = D(Re z)
+//   APG      (:121-161)  z = s - tau ifft2(M (fft2(s) - y0));  x' = x; x = D(Re z); s = x + beta (x - x')
+//   RED-ADMM (:164-201)  x = (lam D(Re x) + mu (z - u)) / (mu + lam);  z = ifft2(DC(fft2(x + u)));  u += x - z
+// with DC(Z)[mask] = (mu Z + y0) / (1 + mu) and M the sampling mask.  They share every kernel with the ADMM path: the
+// denoiser, the warp-register FFT (fft.cuh) and the pre-rolled / sign-folded k-space operands of csmri_prep; only the
+// pointwise step in k-space (blend vs. masked residual) and the AXPY around the transform differ.  Implemented as a
+// generic "masked-FFT step" G = ifft2(op(fft2(in))) on complex images (rows -> columns + pointwise -> rows, the same three
+// launches as csmri.cu) plus one small pointwise kernel per algorithm.  (AMP, :204-245, draws torch.randn_like inside the
+// loop and is not reproducible against a fixture: not built.)
+#include "tasks.cuh"
+#include "fft.cuh"
+
+namespace tfpnp {
+namespace {
+
+constexpr int V_ROWS_PER_CTA = 8;
+constexpr int V_COLS_PER_CTA = 8;
+enum { MODE_BLEND = 0, MODE_RESIDUAL = 1 };
+
+template <int R>
+__global__ void __launch_bounds__(V_ROWS_PER_CTA * 32)
+vstep_rows_fwd(const float2* __restrict__ in, float2* __restrict__ T) {
+  constexpr int N = 32 * R;
+  WarpFFT<R> f;
+  f.init();
+  const size_t row = (size_t)blockIdx.x * V_ROWS_PER_CTA + (threadIdx.x >> 5);
+  const float2* src = in + row * N;
+  float2 v[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) v[j] = src[32 * j + f.lane];
+  f.forward(v);
+  float2* dst = T + row * N;
+#pragma unroll
+  for (int j = 0; j < R; ++j) dst[32 * j + f.lane] = v[j];
+}
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(V_COLS_PER_CTA * 32)
+vstep_cols(float2* __restrict__ T, const float2* __restrict__ y0p, const uint8_t* __restrict__ maskp,
+           const float* __restrict__ mu) {
+  constexpr int N = 32 * R;
+  constexpr int PITCH = V_COLS_PER_CTA + 1;
+  __shared__ float2 tile[N * PITCH];
+  const int b = blockIdx.y, c0 = blockIdx.x * V_COLS_PER_CTA;
+  float2* Tb = T + (size_t)b * N * N;
+  for (int i = threadIdx.x; i < N * V_COLS_PER_CTA; i += V_COLS_PER_CTA * 32) {
+    const int r = i / V_COLS_PER_CTA, cc = i % V_COLS_PER_CTA;
+    tile[r * PITCH + cc] = Tb[(size_t)r * N + c0 + cc];
+  }
+  __syncthreads();
+  WarpFFT<R> f;
+  f.init();
+  const int w = threadIdx.x >> 5;
+  float2 v[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) v[j] = tile[(32 * j + f.lane) * PITCH + w];
+  f.forward(v);
+  const float m = MODE == MODE_BLEND ? mu[b] : 0.f;
+  const float inv_n = 1.0f / (float)N;
+  const size_t col = ((size_t)b * N + c0 + w) * N;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    float2 zf = make_float2(v[j].x * inv_n, v[j].y * inv_n);
+    const bool on = maskp[col + 32 * j + f.lane] != 0;
+    const float2 y = y0p[col + 32 * j + f.lane];
+    if (MODE == MODE_BLEND) {
+      if (on) {                                   // z[mask] = ((mu z + y0)/(1+mu))[mask]   (solver.py:77-79, 191-193)
+        zf.x = (m * zf.x + y.x) / (1.0f + m);
+        zf.y = (m * zf.y + y.y) / (1.0f + m);
+      }
+    } else {                                      // temp = fft2(x) - y0; temp[~mask] = 0      (solver.py:108-109, 144-145)
+      zf = on ? make_float2(zf.x - y.x, zf.y - y.y) : make_float2(0.f, 0.f);
+    }
+    v[j] = zf;
+  }
+  f.inverse(v);
+#pragma unroll
+  for (int j = 0; j < R; ++j) tile[(32 * j + f.lane) * PITCH + w] = v[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < N * V_COLS_PER_CTA; i += V_COLS_PER_CTA * 32) {
+    const int r = i / V_COLS_PER_CTA, cc = i % V_COLS_PER_CTA;
+    Tb[(size_t)r * N + c0 + cc] = tile[r * PITCH + cc];
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(V_ROWS_PER_CTA * 32)
+vstep_rows_inv(const float2* __restrict__ T, float2* __restrict__ out) {
+  constexpr int N = 32 * R;
+  WarpFFT<R> f;
+  f.init();
+  const size_t row = (size_t)blockIdx.x * V_ROWS_PER_CTA + (threadIdx.x >> 5);
+  const float2* src = T + row * N;
+  float2 v[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) v[j] = src[32 * j + f.lane];
+  f.inverse(v);
+  const float inv_n = 1.0f / (float)N;
+  float2* dst = out + row * N;
+#pragma unroll
+  for (int j = 0; j < R; ++j) dst[32 * j + f.lane] = make_float2(v[j].x * inv_n, v[j].y * inv_n);
+}
+
+template <int R>
+int masked_fft_step(const float2* in, float2* G, float2* T, const float2* y0p, const uint8_t* maskp, const float* mu,
+                    int mode, int B, cudaStream_t st) {
+  constexpr int N = 32 * R;
+  const int row_blocks = B * N / V_ROWS_PER_CTA;
+  vstep_rows_fwd<R><<<row_blocks, V_ROWS_PER_CTA * 32, 0, st>>>(in, T);
+  if (mode == MODE_BLEND)
+    vstep_cols<R, MODE_BLEND><<<dim3(N / V_COLS_PER_CTA, B), V_COLS_PER_CTA * 32, 0, st>>>(T, y0p, maskp, mu);
+  else
+    vstep_cols<R, MODE_RESIDUAL><<<dim3(N / V_COLS_PER_CTA, B), V_COLS_PER_CTA * 32, 0, st>>>(T, y0p, maskp, mu);
+  vstep_rows_inv<R><<<row_blocks, V_ROWS_PER_CTA * 32, 0, st>>>(T, G);
+  TFPNP_COUNT_LAUNCH(); TFPNP_COUNT_LAUNCH(); TFPNP_COUNT_LAUNCH();
+  TFPNP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- pointwise pieces (one thread per pixel; per-image parameters p[b]) -----------------------------------------
+// HQS: z = G; d = Re z
+__global__ void hqs_finish(const float2* __restrict__ G, float2* __restrict__ z, float* __restrict__ d, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 g = G[i];
+  z[i] = g; d[i] = g.x;
+}
+// x (real, denoiser output) -> complex (x, 0): real2complex (transforms.py:12-13)
+__global__ void real_to_complex(const float* __restrict__ x, float2* __restrict__ xc, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) xc[i] = make_float2(x[i], 0.f);
+}
+// PG / APG: z = in - tau G; d = Re z                                              (solver.py:110-111, 146)
+__global__ void grad_step(const float2* __restrict__ in, const float2* __restrict__ G, const float* __restrict__ tau,
+                          float* __restrict__ d, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = tau[i / HW];
+  d[i] = in[i].x - t * G[i].x;          // only Re z feeds the denoiser; z itself is not part of the state
+}
+// APG: s = x + beta (x - x_prev); x_prev = x   (x real from the denoiser, as complex)   (solver.py:149-158)
+__global__ void apg_extrapolate(const float* __restrict__ x, float2* __restrict__ xprev, float2* __restrict__ s,
+                                const float* __restrict__ beta, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float bt = beta[i / HW];
+  const float2 xc = make_float2(x[i], 0.f), xp = xprev[i];
+  s[i] = make_float2(xc.x + bt * (xc.x - xp.x), xc.y + bt * (xc.y - xp.y));
+  xprev[i] = xc;
+}
+// RED-ADMM x step: x = (lam x_half + mu (z - u)) / (mu + lam); in = x + u             (solver.py:184-188)
+__global__ void red_xstep(const float* __restrict__ xh, float2* __restrict__ xc, const float2* __restrict__ z,
+                          const float2* __restrict__ u, float2* __restrict__ in, const float* __restrict__ mu,
+                          const float* __restrict__ lam, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float m = mu[i / HW], l = lam[i / HW];
+  const float2 zz = z[i], uu = u[i];
+  const float2 xn = make_float2((l * xh[i] + m * (zz.x - uu.x)) / (m + l), (l * 0.f + m * (zz.y - uu.y)) / (m + l));
+  xc[i] = xn;
+  in[i] = make_float2(xn.x + uu.x, xn.y + uu.y);
+}
+// RED-ADMM z / u step: z = G; u = u + x - z; d = Re x (the next denoiser input)       (solver.py:190-197, 184)
+__global__ void red_finish(const float2* __restrict__ G, const float2* __restrict__ xc, float2* __restrict__ z,
+                           float2* __restrict__ u, float* __restrict__ d, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 g = G[i], x = xc[i];
+  float2 uu = u[i];
+  uu.x = uu.x + x.x - g.x;
+  uu.y = uu.y + x.y - g.y;
+  z[i] = g; u[i] = uu; d[i] = x.x;
+}
+// slot k of a [B, V, HW] complex state <-> a [B, HW] complex buffer
+__global__ void slot_copy(const float2* __restrict__ state, float2* __restrict__ buf, float* __restrict__ re, int V, int k,
+                          int HW, size_t n, int to_state) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t b = i / HW, p = i % HW;
+  float2* s = const_cast<float2*>(state) + (b * V + k) * HW + p;
+  if (to_state) *s = buf[i];
+  else { const float2 v = *s; buf[i] = v; if (re) re[i] = v.x; }
+}
+__global__ void gather_params3(const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2,
+                               int64_t rs, int64_t cs, float* __restrict__ P, int B, int iters) {
+  const int n = B * iters;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = t / B, b = t % B;
+    const int64_t src = b * rs + i * cs;
+    P[t] = p0[src];
+    if (p1) P[n + t] = p1[src];
+    if (p2) P[2 * n + t] = p2[src];
+  }
+}
+
+struct VariantSolver {
+  int algo = 0, N = 0;
+  Denoiser* den = nullptr;
+  int cap_B = 0;
+  size_t cap_params = 0;
+  DevBuf c0, c1, c2, c3, G, T, xr, d, y0p, maskp, params;   // complex images c0..c3, G, T; real x, d
+  int64_t last_launches = 0;
+
+  int ensure(int B, int iters) {
+    const size_t HW = (size_t)N * N;
+    if (B > cap_B) {
+      for (DevBuf* b : {&c0, &c1, &c2, &c3, &G, &T, &y0p}) TFPNP_TRY(b->alloc(B * HW * sizeof(float2)));
+      TFPNP_TRY(xr.alloc(B * HW * sizeof(float)));
+      TFPNP_TRY(d.alloc(B * HW * sizeof(float)));
+      TFPNP_TRY(maskp.alloc(B * HW));
+      cap_B = B;
+    }
+    const size_t need = (size_t)B * (iters > 0 ? iters : 1) * 3 * sizeof(float);
+    if (need > cap_params) { TFPNP_TRY(params.alloc(need)); cap_params = params.bytes; }
+    return 0;
+  }
+
+  template <int R>
+  int run(const float* state_in, const float* y0, const uint8_t* mask, const float* p0, const float* p1, const float* p2,
+          int64_t rs, int64_t cs, int B, int iters, float* state_out, cudaStream_t st) {
+    const int HW = N * N;
+    const size_t n = (size_t)B * HW;
+    const int T256 = 256;
+    const unsigned nb = (unsigned)((n + T256 - 1) / T256);
+    const int V = algo == TFPNP_ALGO_PG ? 1 : (algo == TFPNP_ALGO_REDADMM ? 3 : 2);
+    const float2* sin = reinterpret_cast<const float2*>(state_in);
+    float2* sout = reinterpret_cast<float2*>(state_out);
+    TFPNP_CUDA_OK(cudaMemcpyAsync(state_out, state_in, n * V * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    if (iters == 0) return 0;                                    // the reference returns the state unchanged
+    gather_params3<<<cdiv(B * iters, T256), T256, 0, st>>>(p0, p1, p2, rs, cs, params.as<float>(), B, iters);
+    TFPNP_COUNT_LAUNCH();
+    TFPNP_TRY(csmri_prep(y0, mask, y0p.as<float2>(), maskp.as<uint8_t>(), B, N, st));
+    TFPNP_TRY(den->prepare(B, N, N));
+    const float* P = params.as<float>();
+    const size_t np = (size_t)B * iters;
+    float2 *X = c0.as<float2>(), *Z = c1.as<float2>(), *U = c2.as<float2>(), *IN = c3.as<float2>(), *g = G.as<float2>();
+    float *x = xr.as<float>(), *dd = d.as<float>();
+    auto step = [&](const float2* in, int mode, const float* mu) {
+      return masked_fft_step<R>(in, g, T.as<float2>(), y0p.as<float2>(), maskp.as<uint8_t>(), mu, mode, B, st);
+    };
+    auto denoise = [&](const float* sig) { return den->forward(dd, sig, 1, x, B, N, N, st); };
+#define VLAUNCH(kernel, ...) do { kernel<<<nb, T256, 0, st>>>(__VA_ARGS__); TFPNP_COUNT_LAUNCH(); } while (0)
+    switch (algo) {
+      case TFPNP_ALGO_HQS: {            // state (x, z); params (sigma_d, mu)
+        VLAUNCH(slot_copy, sin, Z, dd, V, 1, HW, n, 0);                   // d = Re z
+        for (int i = 0; i < iters; ++i) {
+          TFPNP_TRY(denoise(P + (size_t)i * B));
+          VLAUNCH(real_to_complex, x, X, n);
+          TFPNP_TRY(step(X, MODE_BLEND, P + np + (size_t)i * B));
+          VLAUNCH(hqs_finish, g, Z, dd, n);
+        }
+        VLAUNCH(slot_copy, sout, X, nullptr, V, 0, HW, n, 1);
+        VLAUNCH(slot_copy, sout, Z, nullptr, V, 1, HW, n, 1);
+        break;
+      }
+      case TFPNP_ALGO_PG: {             // state x; params (sigma_d, tau)
+        VLAUNCH(slot_copy, sin, X, nullptr, V, 0, HW, n, 0);
+        for (int i = 0; i < iters; ++i) {
+          TFPNP_TRY(step(X, MODE_RESIDUAL, nullptr));
+          VLAUNCH(grad_step, X, g, P + np + (size_t)i * B, dd, HW, n);
+          TFPNP_TRY(denoise(P + (size_t)i * B));
+          VLAUNCH(real_to_complex, x, X, n);
+        }
+        VLAUNCH(slot_copy, sout, X, nullptr, V, 0, HW, n, 1);
+        break;
+      }
+      case TFPNP_ALGO_APG: {            // state (x, s); params (sigma_d, tau, beta)
+        VLAUNCH(slot_copy, sin, X, nullptr, V, 0, HW, n, 0);             // X holds x_prev
+        VLAUNCH(slot_copy, sin, U, nullptr, V, 1, HW, n, 0);             // U holds s
+        for (int i = 0; i < iters; ++i) {
+          TFPNP_TRY(step(U, MODE_RESIDUAL, nullptr));
+          VLAUNCH(grad_step, U, g, P + np + (size_t)i * B, dd, HW, n);
+          TFPNP_TRY(denoise(P + (size_t)i * B));
+          VLAUNCH(apg_extrapolate, x, X, U, P + 2 * np + (size_t)i * B, HW, n);
+        }
+        VLAUNCH(slot_copy, sout, X, nullptr, V, 0, HW, n, 1);
+        VLAUNCH(slot_copy, sout, U, nullptr, V, 1, HW, n, 1);
+        break;
+      }
+      case TFPNP_ALGO_REDADMM: {        // state (x, z, u); params (sigma_d, mu, lamda)
+        VLAUNCH(slot_copy, sin, X, dd, V, 0, HW, n, 0);                  // d = Re x
+        VLAUNCH(slot_copy, sin, Z, nullptr, V, 1, HW, n, 0);
+        VLAUNCH(slot_copy, sin, U, nullptr, V, 2, HW, n, 0);
+        for (int i = 0; i < iters; ++i) {
+          const float* mu = P + np + (size_t)i * B;
+          TFPNP_TRY(denoise(P + (size_t)i * B));
+          VLAUNCH(red_xstep, x, X, Z, U, IN, mu, P + 2 * np + (size_t)i * B, HW, n);
+          TFPNP_TRY(step(IN, MODE_BLEND, mu));
+          VLAUNCH(red_finish, g, X, Z, U, dd, n);
+        }
+        VLAUNCH(slot_copy, sout, X, nullptr, V, 0, HW, n, 1);
+        VLAUNCH(slot_copy, sout, Z, nullptr, V, 1, HW, n, 1);
+        VLAUNCH(slot_copy, sout, U, nullptr, V, 2, HW, n, 1);
+        break;
+      }
+      default:
+        set_error("unknown CS-MRI solver variant %d", algo);
+        return TFPNP_ERR_INVALID;
+    }
+#undef VLAUNCH
+    TFPNP_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  ~VariantSolver() {
+    for (DevBuf* b : {&c0, &c1, &c2, &c3, &G, &T, &xr, &d, &y0p, &maskp, &params}) b->release();
+  }
+};
+
+}  // namespace
+}  // namespace tfpnp
+
+using namespace tfpnp;
+
+extern "C" {
+
+int tfpnp_csmri_variant_create(int algo, int N, void* denoiser, void** out) {
+  TFPNP_CHECK(denoiser && out, "null argument");
+  TFPNP_CHECK(algo >= TFPNP_ALGO_HQS && algo <= TFPNP_ALGO_REDADMM, "unknown CS-MRI solver variant %d", algo);
+  TFPNP_CHECK(N == 32 || N == 64 || N == 128 || N == 256, "FFT tasks support N in {32,64,128,256}, got %d", N);
+  VariantSolver* s = new VariantSolver();
+  s->algo = algo; s->N = N; s->den = static_cast<Denoiser*>(denoiser);
+  *out = s;
+  return 0;
+}
+
+int tfpnp_csmri_variant_destroy(void* h) {
+  delete static_cast<VariantSolver*>(h);
+  return 0;
+}
+
+int tfpnp_csmri_variant_forward(void* h, const float* state_in, const float* y0, const void* mask, const float* p0,
+                                const float* p1, const float* p2, int64_t row_stride, int64_t col_stride, int B,
+                                int iters, float* state_out, void* stream) {
+  TFPNP_CHECK(h && state_in && state_out && state_in != state_out && y0 && mask && B > 0 && iters >= 0, "bad argument");
+  VariantSolver* s = static_cast<VariantSolver*>(h);
+  TFPNP_CHECK(iters == 0 || (p0 && p1 && (s->algo < TFPNP_ALGO_APG || p2)), "missing hyper-parameter pointer");
+  g_launch_count = 0;
+  TFPNP_CUDA_OK(fft_tables_init());     // this translation unit's copy of the twiddle table
+  TFPNP_TRY(s->ensure(B, iters));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* m8 = static_cast<const uint8_t*>(mask);
+  int rc;
+  switch (s->N) {
+    case 32: rc = s->run<1>(state_in, y0, m8, p0, p1, p2, row_stride, col_stride, B, iters, state_out, st); break;
+    case 64: rc = s->run<2>(state_in, y0, m8, p0, p1, p2, row_stride, col_stride, B, iters, state_out, st); break;
+    case 128: rc = s->run<4>(state_in, y0, m8, p0, p1, p2, row_stride, col_stride, B, iters, state_out, st); break;
+    default: rc = s->run<8>(state_in, y0, m8, p0, p1, p2, row_stride, col_stride, B, iters, state_out, st); break;
+  }
+  s->last_launches = g_launch_count;
+  return rc;
+}
+
+}  // extern "C"

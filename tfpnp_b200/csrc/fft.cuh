@@ -78,6 +78,9 @@ __device__ __forceinline__ void dft_regs(float2 (&v)[R]) {
 // Twiddle table, filled once per device from the host in double precision (fft_tables_init): a warp that does ONE
 // transform spent as many instructions on its 5 + R sincospif calls as on the FFT itself.
 //   g_fft_tw[log2 R][i][lane], i < 5 : W_{2s}^{lane & (s-1)}, s = 16 >> i ;   i = 5 + k : W_{32R}^{lane * k}
+// NOTE: the table is `static` = one copy per translation unit (no relocatable device code in this build): every entry
+// point of a .cu file that launches WarpFFT kernels must call fft_tables_init() itself (csmri_prep, pr_prep,
+// tfpnp_fft2, tfpnp_csmri_variant_forward do).
 constexpr int kFftTwRows = 13;
 static __device__ float2 g_fft_tw[4][kFftTwRows][32];
 

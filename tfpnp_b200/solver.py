@@ -178,6 +178,114 @@ class ADMMSolver_CSMRI(ADMMSolver):
         return self._run(h, variables, _f32c(y0), m8, 0, (sigma_d, mu), iter_num)
 
 
+class _CSMRIVariant(PnPSolver):
+    """Host logic shared by the other CS-MRI solvers (tasks/csmri/solver.py:60-204): same kernels, different update."""
+    _algo = None
+    _nvar = None
+    _param_keys = ()
+
+    def __init__(self, denoiser):
+        if not isinstance(denoiser, UNetDenoiser2D):
+            raise TypeError("tfpnp_b200 solvers need a tfpnp_b200.UNetDenoiser2D / IRCNNDenoiser2D")
+        super().__init__(denoiser)
+        self._solvers = {}
+        self.last_launch_count = 0
+
+    @property
+    def num_var(self):
+        return self._nvar
+
+    def get_output(self, state):            # CSMRIMixin.get_output: complex2real of the first variable
+        x = torch.split(state, state.shape[1] // self._nvar, dim=1)[0]
+        return x[..., 0]
+
+    def filter_aux_inputs(self, state):     # solver.py:20-21
+        return (state['y0'], state['mask'])
+
+    def filter_hyperparameter(self, action):
+        return tuple(action[k] for k in self._param_keys)
+
+    def forward(self, inputs, parameters, iter_num=None):
+        variables, aux = inputs
+        y0, mask = tuple(aux)
+        params = tuple(parameters)
+        if not variables.is_cuda:
+            raise RuntimeError("tfpnp_b200 solvers run on CUDA (sm_100) tensors only; there is no CPU fallback")
+        if torch.is_grad_enabled() and (variables.requires_grad or any(p.requires_grad for p in params)):
+            raise NotImplementedError("the differentiable solver path is out of scope (SURVEY 8f N4)")
+        B, _, H, W, _ = variables.shape
+        if iter_num is None:
+            iter_num = params[0].shape[-1]
+        dev = variables.device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        h = self._solvers.get((idx, H))
+        if h is None:
+            h = C.c_void_p()
+            with torch.cuda.device(idx):
+                _lib.check(_lib.lib().tfpnp_csmri_variant_create(self._algo, H, self.denoiser._handle(dev), C.byref(h)),
+                           "tfpnp_csmri_variant_create")
+            self._solvers[(idx, H)] = h
+        m8 = mask.contiguous()
+        m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else (m8 != 0).view(torch.uint8)
+        ps = [(p if p.dtype == torch.float32 else p.float()).reshape(B, -1) for p in params]
+        if any(p.stride() != ps[0].stride() for p in ps):
+            ps = [p.contiguous() for p in ps]
+        if any(p.shape[1] < iter_num for p in ps):
+            raise IndexError(f"iter_num={iter_num} exceeds the hyper-parameter width {ps[0].shape[1]}")
+        rs, cs = ps[0].stride()
+        state_in = _f32c(variables)
+        out = torch.empty_like(state_in)
+        y0c = _f32c(y0)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().tfpnp_csmri_variant_forward(
+                h, state_in.data_ptr(), y0c.data_ptr(), m8.data_ptr(), ps[0].data_ptr(), ps[1].data_ptr(),
+                ps[2].data_ptr() if len(ps) > 2 else None, rs, cs, B, int(iter_num), out.data_ptr(),
+                torch.cuda.current_stream().cuda_stream), "tfpnp_csmri_variant_forward")
+        return out
+
+    def __del__(self):
+        try:
+            for h in self._solvers.values():
+                _lib.lib().tfpnp_csmri_variant_destroy(h)
+        except Exception:
+            pass
+
+
+class HQSSolver_CSMRI(_CSMRIVariant):
+    """tasks/csmri/solver.py:60-88 + HQSSolver (tfpnp/pnp/solver/base.py:118-139)."""
+    _algo, _nvar, _param_keys = _lib.ALGO_HQS, 2, ('sigma_d', 'mu')
+
+    def reset(self, data):
+        x = data['x0'].clone().detach()
+        return torch.cat([x, x.clone().detach()], dim=1)
+
+
+class PGSolver_CSMRI(_CSMRIVariant):
+    """tasks/csmri/solver.py:91-118 + PGSolver (base.py:141-160)."""
+    _algo, _nvar, _param_keys = _lib.ALGO_PG, 1, ('sigma_d', 'tau')
+
+    def reset(self, data):
+        return data['x0'].clone().detach()
+
+
+class APGSolver_CSMRI(_CSMRIVariant):
+    """tasks/csmri/solver.py:121-161 + APGSolver (base.py:162-189); beta comes from the action, as upstream."""
+    _algo, _nvar, _param_keys = _lib.ALGO_APG, 2, ('sigma_d', 'tau', 'beta')
+
+    def reset(self, data):
+        x = data['x0'].clone().detach()
+        return torch.cat([x, x.clone().detach()], dim=1)
+
+
+class REDADMMSolver_CSMRI(_CSMRIVariant):
+    """tasks/csmri/solver.py:164-201 + REDADMMSolver (base.py:192-214)."""
+    _algo, _nvar, _param_keys = _lib.ALGO_REDADMM, 3, ('sigma_d', 'mu', 'lamda')
+
+    def reset(self, data):
+        x = data['x0'].clone().detach()
+        return torch.cat([x, x.clone().detach(), torch.zeros_like(x)], dim=1)
+
+
 class IADMMSolver_PR(IADMMSolver):
     """tasks/pr/solver.py:15-76."""
     _task = _lib.TASK_PR
@@ -276,7 +384,8 @@ class ADMMSolver_SPI(ADMMSolver):
 
 
 # ---- factories, same names / error behaviour as the reference ---------------------------------
-_csmri_map = {'admm': ADMMSolver_CSMRI}      # tasks/csmri/solver.py:253-270 (hqs/pg/apg/redadmm/amp: out of scope)
+_csmri_map = {'admm': ADMMSolver_CSMRI, 'hqs': HQSSolver_CSMRI, 'pg': PGSolver_CSMRI, 'apg': APGSolver_CSMRI,
+              'redadmm': REDADMMSolver_CSMRI}    # tasks/csmri/solver.py:253-270 ('amp' draws random numbers in the loop: not built)
 _pr_map = {'iadmm': IADMMSolver_PR}          # tasks/pr/solver.py:115-128
 _ct_map = {'iadmm': IADMMSolver_CT}          # tasks/ct/solver.py:90-103
 _spi_map = {'admm_spi': ADMMSolver_SPI}      # tasks/spi/solver.py:54-66
