@@ -450,6 +450,18 @@ def iadmm_ct(sd, state: Tensor, y0: Tensor, views: int, opnorm: float, sigma_d: 
     return torch.cat((x, z, u), dim=1)
 
 
+def pg_ct(sd, state: Tensor, y0: Tensor, views: int, opnorm: float, sigma_d: Tensor, tau: Tensor) -> Tensor:
+    """PGSolver_CT.forward (tasks/ct/solver.py:56-87) on this build's Radon pair (PARITY UNPINNED w.r.t. torch_radon)."""
+    x = state
+    B, n = x.shape[0], x.shape[-1]
+    cs, sn, det = ct_geometry(n, views)
+    for i in range(sigma_d.shape[-1]):
+        g = radon_backward(radon_forward(x, cs, sn, det) - y0, cs, sn, n) / opnorm ** 2
+        z = x - tau[:, i].reshape(B, 1, 1, 1) * g
+        x = denoise(sd, z, sigma_d[:, i])
+    return x
+
+
 def admm_spi(sd, state: Tensor, x0: Tensor, K: Tensor, sigma_d: Tensor, mu: Tensor,
              iter_num: Optional[int] = None, quant=None) -> Tensor:
     """ADMMSolver_SPI.forward (tasks/spi/solver.py:17-51); order z, u, then x."""

@@ -51,3 +51,19 @@ def test_native_variants_match_reference_fixture(dev, name, prec, tol):
     with torch.no_grad():
         same = s((state0, (g["y0"].to(dev), g["mask"].to(dev))), tuple(a[:, :0] for a in s.filter_hyperparameter(action)), iter_num=0)
     assert torch.equal(same, state0)
+
+
+@pytest.mark.gpu
+def test_pg_ct_vs_oracle(dev):
+    """PGSolver_CT (tasks/ct/solver.py:56-87) on this build's Radon pair against the CPU restatement."""
+    import tfpnp_b200 as T
+    from oracle import synth
+    d = synth.ct_batch(2, 64, 24, 3, seed=5)
+    ref = O.pg_ct(weights("he"), d["x0"], d["y0"], d["views"], d["opnorm"], d["sigma_d"], d["tau"])
+    s = T.PGSolver_CT(T.UNetDenoiser2D(state_dict=weights("he"), precision="fp16x3"))
+    s.opnorm_override = d["opnorm"]
+    state0 = s.reset({"x0": d["x0"].to(dev)})
+    with torch.no_grad():
+        out = s((state0, (d["y0"].to(dev), d["view"].to(dev))), (d["sigma_d"].to(dev), d["tau"].to(dev)))
+    assert rel_err(out, ref)[1] <= 1e-4
+    assert s.num_var == 1 and torch.equal(s.get_output(out), out)

@@ -92,6 +92,8 @@ def test_factories_and_errors():
                       ("redadmm", T.REDADMMSolver_CSMRI)):
         opt.solver = name
         assert isinstance(T.create_solver_csmri(opt, den), cls)
+    opt.solver = "pg"
+    assert isinstance(T.create_solver_ct(opt, den), T.PGSolver_CT)
     opt.solver = "amp"                   # draws random numbers inside the loop: not built -> same error as an unknown name
     with pytest.raises(NotImplementedError):
         T.create_solver_csmri(opt, den)

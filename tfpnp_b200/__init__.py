@@ -8,7 +8,7 @@ sm_100a CUDA in ``libtfpnp_b200.so`` (C ABI: include/tfpnp_b200.h).  No fallback
 from ._lib import build, lib, LIB_PATH  # noqa: F401
 from .denoiser import UNetDenoiser2D, IRCNNDenoiser2D, create_denoiser, random_unet_state_dict  # noqa: F401
 from .solver import (PnPSolver, ADMMSolver, IADMMSolver, ADMMSolver_CSMRI, IADMMSolver_PR,  # noqa: F401
-                     HQSSolver_CSMRI, PGSolver_CSMRI, APGSolver_CSMRI, REDADMMSolver_CSMRI,
+                     HQSSolver_CSMRI, PGSolver_CSMRI, APGSolver_CSMRI, REDADMMSolver_CSMRI, PGSolver_CT,
                      IADMMSolver_CT, ADMMSolver_SPI, RadonGenerator, create_solver_csmri,
                      create_solver_pr, create_solver_ct, create_solver_spi)
 from .ops import (radon_forward, radon_backward, torch_psnr, conv3x3_lrelu_nhwc, fft2, ifft2, complex_mul,  # noqa: F401

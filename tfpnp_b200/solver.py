@@ -364,6 +364,57 @@ class IADMMSolver_CT(IADMMSolver):
         return self._run(h, variables, _f32c(y0), None, 0, (sigma_d, mu, tau), iter_num)
 
 
+class PGSolver_CT(PnPSolver):
+    """tasks/ct/solver.py:56-87 + PGSolver (tfpnp/pnp/solver/base.py:141-160): proximal gradient with this build's
+    Radon pair.  A composition of the native operators (projector, backprojector, denoiser); the AXPYs around them are
+    torch element-wise glue.  (PGSolver_PR, tasks/pr/solver.py:79-112, applies the CS-MRI gradient with a boolean
+    index on the complex CDP masks and cannot run upstream: not built.)"""
+
+    def __init__(self, denoiser):
+        if not isinstance(denoiser, UNetDenoiser2D):
+            raise TypeError("tfpnp_b200 solvers need a tfpnp_b200.UNetDenoiser2D / IRCNNDenoiser2D")
+        super().__init__(denoiser)
+        self.radon_generator = RadonGenerator()
+        self.opnorm_override = None
+
+    @property
+    def num_var(self):
+        return 1
+
+    def reset(self, data):
+        return data['x0'].clone().detach()
+
+    def get_output(self, state):
+        return state
+
+    def filter_aux_inputs(self, state):
+        return (state['y0'], state['view'])
+
+    def filter_hyperparameter(self, action):
+        return action['sigma_d'], action['tau']
+
+    def forward(self, inputs, parameters, iter_num=None):
+        from .ops import radon_forward, radon_backward
+        variables, aux = inputs
+        y0, view = tuple(aux)
+        sigma_d, tau = parameters
+        if not variables.is_cuda:
+            raise RuntimeError("tfpnp_b200 solvers run on CUDA (sm_100) tensors only; there is no CPU fallback")
+        if torch.is_grad_enabled() and (variables.requires_grad or sigma_d.requires_grad or tau.requires_grad):
+            raise NotImplementedError("the differentiable solver path is out of scope (SURVEY 8f N4)")
+        x = variables
+        B, n = x.shape[0], x.shape[-1]
+        views = int(view[0, 0, 0, 0].item() * 120)          # solver.py:67
+        opnorm = self.opnorm_override or self.radon_generator(n, views, x.device)
+        if iter_num is None:
+            iter_num = sigma_d.shape[-1]
+        for i in range(iter_num):
+            _tau = tau[:, i].reshape(B, 1, 1, 1)
+            z = x - _tau * (radon_backward(radon_forward(x, views) - y0, n, views) / opnorm ** 2)   # solver.py:79
+            x = self.prox_mapping(z, sigma_d[:, i])                                                 # solver.py:82
+        return x
+
+
 class ADMMSolver_SPI(ADMMSolver):
     """tasks/spi/solver.py:8-51."""
     _task = _lib.TASK_SPI
@@ -387,7 +438,7 @@ class ADMMSolver_SPI(ADMMSolver):
 _csmri_map = {'admm': ADMMSolver_CSMRI, 'hqs': HQSSolver_CSMRI, 'pg': PGSolver_CSMRI, 'apg': APGSolver_CSMRI,
               'redadmm': REDADMMSolver_CSMRI}    # tasks/csmri/solver.py:253-270 ('amp' draws random numbers in the loop: not built)
 _pr_map = {'iadmm': IADMMSolver_PR}          # tasks/pr/solver.py:115-128
-_ct_map = {'iadmm': IADMMSolver_CT}          # tasks/ct/solver.py:90-103
+_ct_map = {'iadmm': IADMMSolver_CT, 'pg': PGSolver_CT}          # tasks/ct/solver.py:90-103
 _spi_map = {'admm_spi': ADMMSolver_SPI}      # tasks/spi/solver.py:54-66
 
 
