@@ -156,6 +156,9 @@ csmri_fused(const float* __restrict__ x, float2* __restrict__ z, float2* __restr
   float2* tA = fsm;                     // [HALF cols][PITCH]: column-major input of the column pass
   float2* tB = fsm + HALF * PITCH;      // [HALF rows][PITCH]: row-major input of the inverse row pass
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // distributed shared memory may only be touched once the peer CTA has started: arrive now, wait before the first
+  // remote store (without this the scatter of pass 1 raced with the peer's launch as soon as the prologue got short)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int b = blockIdx.x >> 1;
@@ -163,6 +166,7 @@ csmri_fused(const float* __restrict__ x, float2* __restrict__ z, float2* __restr
   WarpFFT<R> f;
   f.init();                             // twiddles: overlaps the tail of the denoiser's last kernel
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   const size_t img = (size_t)b * N * N;
   float2 v[R];
   // Every pass first issues ALL the global loads of the warp's RPW rows / columns (one latency per pass instead of

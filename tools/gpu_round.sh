@@ -18,7 +18,8 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 cut -c1-900 gpurun_out/bench_reference.json
 if [ "$1" != "noncu" ]; then
 echo "=== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv \
+# (the bench builds its inputs on the GPU with many small torch kernels first: list this repo's kernels only)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"conv|upsample|csmri|psnr|pack|gather_params" -s 100 -c 300 --csv \
   --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
 python tools/launch_summary.py gpurun_out/launches.csv | tee gpurun_out/launches_summary.txt | head -24
 echo "=== ncu full: every kernel of one inner iteration"
