@@ -153,6 +153,8 @@ mine = O.psnr(out[lo:hi], gt[lo:hi])                # rank-local metric (oracle 
 gathered = T.all_gather_psnr(mine, B)
 assert gathered.shape == (B, 1), gathered.shape
 assert torch.equal(gathered, full), (gathered, full)
+imgs = T.all_gather_batch(out[lo:hi], B)               # optional image gather (uneven shards: 3 + 2)
+assert torch.equal(imgs, out)
 # sharded batches are bit-identical slices
 d = synth.spi_batch(4, 16, 1)
 sh = T.shard_batch(d, rank, 2)

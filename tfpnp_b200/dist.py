@@ -32,6 +32,22 @@ def shard_batch(obj, rank: int, world: int):
     return obj
 
 
+def all_gather_batch(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Gather dim-0 shards of any tensor (e.g. ``solver.get_output`` images [B_local,1,H,W]) from all ranks into
+    [n_total, ...] in batch order -- the optional second exchange of SURVEY 8e, for callers that need every image on
+    every rank (the reference's DataParallel gather, replicate.py:50-75)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    sizes = [shard_bounds(n_total, r, world) for r in range(world)]
+    pad = max(hi - lo for lo, hi in sizes)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
+
+
 def all_gather_psnr(local: torch.Tensor, n_total: int) -> torch.Tensor:
     """Gather the [B_local,1] PSNR vectors of all ranks into [n_total,1] (rank order = batch order)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
