@@ -2,5 +2,4 @@
 # scratch: quick check after a change (edit freely); the end-of-block run is tools/gpu_round.sh
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
-echo "=== pytest -m gpu"; timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider 2>&1 | tail -4
-echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+for sa in 3 2; do echo "=== TFPNP_SMALL_SA=$sa"; TFPNP_SMALL_SA=$sa timeout 300 python tools/conv_knockout.py 2>&1 | head -1 | cut -c1-330; done
