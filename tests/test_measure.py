@@ -94,3 +94,20 @@ def test_episode_on_gpu_synthesised_data(dev):
         total += reward
     assert all_done and torch.isfinite(total).all()
     assert torch.allclose(env.last_metric, psnr0 + total, atol=1e-3)
+
+
+def test_radial_mask_and_seeded_weights_cpu():
+    """Host-side helpers of the benchmark inputs run anywhere (no kernels involved)."""
+    import tfpnp_b200 as T
+    from oracle import pnp_oracle as O
+    for n, lines, lo, hi in ((128, 42, 0.30, 0.45), (128, 21, 0.15, 0.25), (64, 10, 0.10, 0.22)):
+        m = T.radial_mask(n, lines)
+        assert m.dtype == torch.bool and tuple(m.shape) == (n, n)
+        assert lo <= float(m.float().mean()) <= hi
+        assert bool(m[n // 2 - 1:n // 2 + 1, n // 2 - 1:n // 2 + 1].any())      # lines pass through the centre
+    sd = T.random_unet_state_dict(3)
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == O.unet_param_shapes()
+    sd2 = T.random_unet_state_dict(3)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)                          # seeded
+    w = sd["inc.conv.conv-1.conv2d.weight"]
+    assert float(w.abs().max()) <= 1 / (32 * 9) ** 0.5 + 1e-7                   # U(+-1/sqrt(fan_in)), nn.Conv2d's default
