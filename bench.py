@@ -40,10 +40,18 @@ UNIT = "image-iters/s"
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    fb = dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+        try:
+            d = json.load(open(p))
+            hbm = d.get("hbm_gbs")
+            burst = d.get("bf16_tflops")
+            sust = d.get("bf16_tflops_sustained", burst)
+            if hbm and (sust or burst):
+                return dict(hbm=float(hbm), tf_burst=float(burst or sust), tf_sust=float(sust or burst), src="measured")
+        except Exception:
+            pass
+    return fb
 
 
 def ncu_traffic():
