@@ -58,3 +58,13 @@ def test_conv3x3_tc_vs_torch(C0, C1, Cout, H, W, B):
     assert out.shape == ref.shape
     l2, mx = rel_err(out.float(), ref)
     assert l2 < 6e-4 and mx < 2e-3, (l2, mx)      # fp16 output rounding: 2^-11 relative
+
+
+PAIR_CASES = [(128, 0, 128, 32, 32, 6), (256, 0, 256, 16, 16, 5), (256, 512, 256, 16, 16, 2), (64, 0, 128, 32, 16, 3)]
+
+
+@pytest.mark.parametrize("C0,C1,Cout,H,W,B", PAIR_CASES)
+def test_conv3x3_pair_kernel_vs_torch(C0, C1, Cout, H, W, B, monkeypatch):
+    """The opt-in CTA-pair kernel (tcgen05.mma.cta_group::2, DESIGN 9.1): same check as above with TFPNP_CONV_PAIR=1."""
+    monkeypatch.setenv("TFPNP_CONV_PAIR", "1")
+    test_conv3x3_tc_vs_torch(C0, C1, Cout, H, W, B)

@@ -749,6 +749,213 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   if (threadIdx.x == 64) TRACE(0, 1004);
 }
 
+// ==========================================================================================
+// v2-pair: the streamed-weight kernel on CTA PAIRS (tcgen05.mma.cta_group::2) for the 128/256/512-channel levels
+// ==========================================================================================
+// A work item = (16x16 super-tile, 128-cout n-tile) on a cluster of two CTAs.  CTA r owns the 16-row x 8-column half r of
+// the tile = one 128-row M-tile; the MMA runs M = 256 over the pair.  Per CTA: the half-halo A box {64, 10, 18, 1} (180 rows,
+// 23 KB instead of 41.5 KB; tap (ky,kx) starts at row ky*10 + kx, 8-row groups 10 rows apart) and HALF of each weight slab
+// (rows [64 r, 64 r + 64) of the n-tile: 8 KB per tap instead of 16 KB), so the weight ring is six 3-tap stages deep where
+// the single-CTA kernel fits two, and every SM ingests half the weight bytes.  Only the leader (rank 0) issues MMAs; its
+// full_* barriers collect the TMA bytes of BOTH CTAs (the peer's loads name the leader's barrier), completions are multicast
+// to both CTAs (empty_* and tmem_full), and the peer's epilogue releases the accumulator on the leader's tmem_empty.
+// (Bring-up: tools/ubench/mma_pair.cu.)
+struct ConvPairParams {
+  CUtensorMap a_map[2];     // [source] half-halo boxes {64, 10, 18, 1}
+  CUtensorMap w_map;        // {64, 64 rows, 1 tap} over {Cin, Cout, 9}
+  int nchunk0, nchunk1;
+  int tiles_w, tiles_h, num_m_tiles, num_n_tiles;
+  int B, H, W, Cout;
+  int num_a_stages, num_b_stages;
+  const float* bias;
+  __half* out_hi;
+  __half* pool_hi;          // fused nn.MaxPool2d(2) output or nullptr
+};
+
+constexpr int kPairThreads = 64 + 32 * 8;
+constexpr int kPairARows = 180, kPairABytes = 23552;            // 180 x 128 B, padded to a multiple of 1024
+constexpr int kPairSlab = 64 * 128;                             // one tap's half slab
+constexpr int kPairBStage = 3 * kPairSlab;
+
+__global__ void __launch_bounds__(kPairThreads, 1)
+conv3x3_pair(const __grid_constant__ ConvPairParams p) {
+  constexpr int BN = 128, KC = 64, KSTEPS = 4;
+  constexpr uint32_t ROW = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int SA = p.num_a_stages, SB = p.num_b_stages;
+  const int nchunks = p.nchunk0 + p.nchunk1;
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + SA * kPairABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + SB * kPairBStage);
+  uint64_t* full_a = bars;                      // [8]   (leader's are the ones waited on)
+  uint64_t* empty_a = bars + 8;                 // [8]
+  uint64_t* full_b = bars + 16;                 // [16]
+  uint64_t* empty_b = bars + 32;                // [16]
+  uint64_t* tmem_full = bars + 48;              // [2]
+  uint64_t* tmem_empty = bars + 50;             // [2]  (leader's collects both CTAs' epilogues)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 52);
+  float* sbias = reinterpret_cast<float*>(bars + 54);           // [Cout] <= 512
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.a_map[0]);
+    prefetch_tensormap(&p.w_map);
+    if (p.nchunk1) prefetch_tensormap(&p.a_map[1]);
+  }
+  if (warp == 1) {
+    if (lane < 8) { mbar_init(&full_a[lane], 2); mbar_init(&empty_a[lane], 1); }
+    if (lane < 16) { mbar_init(&full_b[lane], 2); mbar_init(&empty_b[lane], 1); }
+    if (lane < 2) { mbar_init(&tmem_full[lane], 1); mbar_init(&tmem_empty[lane], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 256);
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // peer's barriers initialised, TMEM allocated in both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int total_items = p.num_m_tiles * p.num_n_tiles;
+  const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs): own half-halo + own half of every weight slab ----------------
+      uint32_t ia = 0, ib = 0;
+      for (int t = item0; t < total_items; t += item_step) {
+        const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
+        const int w0 = (m % p.tiles_w) * 16, h0 = ((m / p.tiles_w) % p.tiles_h) * 16;
+        const int b = m / (p.tiles_w * p.tiles_h);
+        for (int c = 0; c < nchunks; ++c, ++ia) {
+          const int src = c < p.nchunk0 ? 0 : 1;
+          const int cc = (src == 0 ? c : c - p.nchunk0) * KC;
+          const int s = ia % SA;
+          mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);
+          const uint32_t fa = mapa_u32(&full_a[s], 0);          // the LEADER's barrier
+          if (rank == 0) mbar_arrive_expect_tx(&full_a[s], 2u * kPairARows * ROW);
+          else mbar_arrive_cluster(fa);
+          tma_load_4d_2sm(sA + s * kPairABytes, &p.a_map[src], fa, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
+#pragma unroll 1
+          for (int tg = 0; tg < 3; ++tg, ++ib) {
+            const int sb = ib % SB;
+            mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
+            const uint32_t fb = mapa_u32(&full_b[sb], 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_b[sb], 2u * kPairBStage);
+            else mbar_arrive_cluster(fb);
+#pragma unroll
+            for (int tt = 0; tt < 3; ++tt)
+              tma_load_3d_2sm(sW + sb * kPairBStage + tt * kPairSlab, &p.w_map, fb, c * KC, nt * BN + 64 * (int)rank, tg * 3 + tt);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ---------------- MMA issuer (leader only) ----------------
+      const uint32_t idesc = make_idesc_f16(256, BN);
+      const uint32_t a_hi = (uint32_t)(make_smem_desc_ex(0, ROW, 10 * ROW, 0) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_smem_desc(0, ROW) >> 32);
+      const uint32_t lo_flags = 1u << 16;
+      const uint32_t sA_lo = (smem_u32(sA) >> 4) | lo_flags;
+      const uint32_t sW_lo = (smem_u32(sW) >> 4) | lo_flags;
+      uint32_t ia = 0, ib = 0, it = 0;
+      for (int t = item0; t < total_items; t += item_step, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * BN;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < nchunks; ++c, ++ia) {
+          const int sa = ia % SA;
+          mbar_wait(&full_a[sa], (ia / SA) & 1);
+          tc_fence_after();
+          const uint32_t a_lo = sA_lo + sa * (kPairABytes >> 4);
+#pragma unroll 1
+          for (int tg = 0; tg < 3; ++tg, ++ib) {
+            const int sb = ib % SB;
+            mbar_wait(&full_b[sb], (ib / SB) & 1);
+            tc_fence_after();
+            const uint32_t b_stage = sW_lo + sb * (kPairBStage >> 4);
+            const uint32_t a_row = a_lo + (tg * 10 * ROW >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int tt = 0; tt < 3; ++tt) {
+                const uint32_t a_tap = a_row + (tt * ROW >> 4);
+                const uint32_t b_lo = b_stage + tt * (kPairSlab >> 4);
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) {
+                  umma2_f16(d0, pack_desc(a_tap + kk * 2, a_hi), pack_desc(b_lo + kk * 2, b_hi), idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma2_commit_mc(&empty_b[sb], 3);                 // frees the weight stage in BOTH CTAs
+            }
+            accumulate = 1;
+            __syncwarp();
+          }
+          if (elect_one()) {
+            umma2_commit_mc(&empty_a[sa], 3);
+            if (c == nchunks - 1) umma2_commit_mc(&tmem_full[buf], 3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): own 128 rows; the two warps of a quadrant split the 128 columns ----------------
+    const int q = warp & 3;
+    const int e = (warp - 2) >> 2;
+    const int ml = q * 32 + lane;
+    const int tw = ml & 7, th = ml >> 3;
+    const uint32_t te = mapa_u32(&tmem_empty[0], 0);            // the leader's tmem_empty[0]; [1] is 8 bytes further
+    uint32_t it = 0;
+    for (int t = item0; t < total_items; t += item_step, ++it) {
+      const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
+      const int w = (m % p.tiles_w) * 16 + 8 * (int)rank + tw, h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
+      const int b = m / (p.tiles_w * p.tiles_h);
+      const int n0 = nt * BN;
+      const size_t pix = ((size_t)b * p.H + h) * p.W + w;
+      const uint32_t buf = it & 1;
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t r64[64];
+      tmem_ld_32x64(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + e * 64, r64);
+      tmem_ld_wait();
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int c0 = e * 64 + 32 * sl;
+        uint32_t (&r)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r64[32 * sl]);
+        float v[32];
+        epilogue_act32(r, sbias + n0 + c0, v);
+        epilogue_store_nhwc32(v, p.out_hi, nullptr, pix * p.Cout + n0 + c0);
+        if (p.pool_hi) {                      // 2x2 max over (tw^1, th^1) = lanes ^1 and ^8
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
+          }
+          if (!(lane & 9)) {
+            const size_t ppix = ((size_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+            epilogue_store_nhwc32(v, p.pool_hi, nullptr, ppix * p.Cout + n0 + c0);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(te + buf * 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // nobody leaves (or frees TMEM) while the peer may still signal it
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, 256);
+}
+
 // ---- CUDA-core layers around the tensor-core convs ---------------------------------------
 
 // inc.conv-0: 3x3 conv over cat[d, sigma*ones] (2 ch, denoiser/base.py:29-30) -> 32 ch, fp32 FFMA
@@ -1136,6 +1343,69 @@ int encode_halo_map(CUtensorMap* m, const __half* base, int C, int B, int H, int
   return encode_map(m, const_cast<__half*>(base), 4, dims, strides, box, kc * 2);
 }
 
+struct ConvPairPlan {
+  ConvPairParams p;
+  int grid = 0, smem_bytes = 0;
+};
+
+// CTA-pair kernel: streamed weights, 64-channel chunks, Cout a multiple of 128, 16x16 tiling, fp16 mode (opt-in while it is
+// being brought up: TFPNP_CONV_PAIR=1)
+bool conv_pair_eligible(int C0, int C1, int Cout, int H, int W, bool x3, bool fuse_up) {
+  return env_int("TFPNP_CONV_PAIR", 0) != 0 && !x3 && !fuse_up && C0 % 64 == 0 && C1 % 64 == 0 && Cout % 128 == 0 &&
+         H % 16 == 0 && W % 16 == 0;
+}
+
+int plan_conv_pair(ConvPairPlan& c, const __half* x0, int C0, const __half* x1, int C1, const __half* w_taps, const float* bias,
+                   __half* out, int B, int H, int W, int Cout) {
+  ConvPairParams& p = c.p;
+  memset(&p, 0, sizeof(p));
+  p.nchunk0 = C0 / 64; p.nchunk1 = C1 / 64;
+  p.tiles_w = W / 16; p.tiles_h = H / 16;
+  p.num_m_tiles = p.tiles_w * p.tiles_h * B;
+  p.num_n_tiles = Cout / 128;
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.bias = bias; p.out_hi = out;
+  const int misc = 1024 /*align*/ + 512 /*barriers*/ + 2048 /*bias*/ + 256;
+  p.num_a_stages = 3;
+  int sb = (227 * 1024 - misc - p.num_a_stages * kPairABytes) / kPairBStage;
+  p.num_b_stages = sb > 16 ? 16 : sb;
+  c.smem_bytes = p.num_a_stages * kPairABytes + p.num_b_stages * kPairBStage + misc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int items = p.num_m_tiles * p.num_n_tiles;
+  const int pairs = items < sms / 2 ? items : sms / 2;
+  c.grid = 2 * pairs;
+  const __half* srcs[2] = {x0, x1};
+  const int cs[2] = {C0, C1};
+  for (int s = 0; s < 2; ++s) {
+    if (!srcs[s]) { p.a_map[s] = p.a_map[0]; continue; }
+    cuuint64_t dims[4] = {(cuuint64_t)cs[s], (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)cs[s] * 2, (cuuint64_t)W * cs[s] * 2, (cuuint64_t)H * W * cs[s] * 2};
+    cuuint32_t box[4] = {64, 10, 18, 1};
+    TFPNP_TRY(encode_map(&p.a_map[s], const_cast<__half*>(srcs[s]), 4, dims, strides, box, 128));
+  }
+  const int Cin = C0 + C1;
+  cuuint64_t wd[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+  cuuint64_t ws[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
+  cuuint32_t wb[3] = {64, 64, 1};
+  TFPNP_TRY(encode_map(&p.w_map, const_cast<__half*>(w_taps), 3, wd, ws, wb, 128));
+  return 0;
+}
+
+int launch_conv_pair(const ConvPairPlan& c, cudaStream_t st) {
+  static unsigned long long attr_set = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_set >> (dev & 63) & 1ull)) {
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set |= 1ull << (dev & 63);
+  }
+  TFPNP_CUDA_OK(launch_ex(conv3x3_pair, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
+  TFPNP_COUNT_LAUNCH();
+  return 0;
+}
+
 int launch_conv_params(const ConvParams& p, int BN, cudaStream_t st) {
   dim3 grid(p.tiles_w * p.tiles_h * cdiv(p.B, p.TB), p.Cout / BN);
   switch (BN) {
@@ -1175,6 +1445,7 @@ struct UNetTc : Denoiser {
   std::vector<ConvParams> convs; // layers 1..26 -> convs[l]
   std::vector<int> conv_bn;
   std::vector<Conv2Plan> convs2; // v2 (halo-tile) plans; grid == 0 -> layer uses v1
+  std::vector<ConvPairPlan> convsp; // CTA-pair plans (opt-in); grid == 0 -> layer uses v2 / v1
 
   int init(const float* host) {
     const ConvSpec* sp = unet_conv_specs();
@@ -1289,6 +1560,17 @@ struct UNetTc : Denoiser {
 
   // build ConvParams for layer l reading (src0 [, src1]) and writing dst
   int plan_conv(int l, const Act& s0, const Act* s1, const Act& dst, int B, const Act* low = nullptr) {
+    convsp[l].grid = 0;
+    if (conv_pair_eligible(s0.C, s1 ? s1->C : 0, unet_conv_specs()[l].cout, dst.H, dst.W, x3, low != nullptr)) {
+      ConvPairPlan& c = convsp[l];
+      TFPNP_TRY(plan_conv_pair(c, s0.hi, s0.C, s1 ? s1->hi : nullptr, s1 ? s1->C : 0, w_hi.as<__half>() + w_off[l],
+                               biases.as<float>() + b_off[l], dst.hi, B, dst.H, dst.W, unet_conv_specs()[l].cout));
+      convs2[l].grid = 0;
+      fused_up[l] = false;
+      fused_pool[l] = env_int("TFPNP_CONV_FUSE", 1) != 0 && (l == 2 || l == 5 || l == 8 || l == 11);
+      if (fused_pool[l]) c.p.pool_hi = S2.hi;
+      return 0;
+    }
     if (conv2_eligible(dst.H, dst.W) ||
         (!low && conv2_small_eligible(dst.H, dst.W, B, s0.C, s1 ? s1->C : 0, unet_conv_specs()[l].cout)))
       return plan_conv_v2(l, s0, s1, dst, B, low);
@@ -1353,6 +1635,7 @@ struct UNetTc : Denoiser {
     convs.assign(kNumUnetConv3, ConvParams{});
     conv_bn.assign(kNumUnetConv3, 0);
     convs2.assign(kNumUnetConv3, Conv2Plan{});
+    convsp.assign(kNumUnetConv3, ConvPairPlan{});
     auto view = [](const Act& buf, int C, int h, int w) { Act a = buf; a.C = C; a.H = h; a.W = w; return a; };
     // encoder level 0: first -> S0 ; conv1: S0 -> S1 ; conv2: S1 -> x1
     TFPNP_TRY(plan_conv(1, view(S0, 32, H, W), nullptr, view(S1, 32, H, W), B));
@@ -1382,6 +1665,7 @@ struct UNetTc : Denoiser {
   }
 
   int launch_conv(int l, cudaStream_t st) {
+    if (convsp[l].grid > 0) return launch_conv_pair(convsp[l], st);
     if (convs2[l].grid > 0) {
       // debugging aid: TFPNP_TRACE_LAYER=l + TFPNP_TRACE_FILE dump CTA 0's role timeline of layer l (eager calls only)
       static const int trace_layer = env_int("TFPNP_TRACE_LAYER", -1);
@@ -1473,6 +1757,13 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
   TFPNP_CHECK(C0 > 0 && C0 % 32 == 0 && C1 % 32 == 0, "channel counts must be multiples of 32");
   TFPNP_CHECK(Cout == 32 || Cout == 64 || Cout % 128 == 0, "Cout must be 32, 64 or a multiple of 128");
   TFPNP_TRY(set_conv_attrs());
+  if (conv_pair_eligible(C0, C1, Cout, H, W, false, false)) {
+    ConvPairPlan cp;
+    TFPNP_TRY(plan_conv_pair(cp, x0, C0, x1, C1, w_taps, bias, out, B, H, W, Cout));
+    TFPNP_TRY(launch_conv_pair(cp, st));
+    TFPNP_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (conv2_eligible(H, W) || conv2_small_eligible(H, W, B, C0, C1, Cout)) {
     Conv2Plan c;
     memset(&c.p, 0, sizeof(c.p));
