@@ -775,7 +775,8 @@ struct ConvPairParams {
 constexpr int kPairThreads = 64 + 32 * 8;
 constexpr int kPairARows = 180, kPairABytes = 23552;            // 180 x 128 B, padded to a multiple of 1024
 constexpr int kPairSlab = 64 * 128;                             // one tap's half slab
-constexpr int kPairBStage = 3 * kPairSlab;
+constexpr int kPairTPS = 9;                                     // taps per weight-ring stage (3: a kernel row, 9: a whole chunk)
+constexpr int kPairBStage = kPairTPS * kPairSlab;
 
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv3x3_pair(const __grid_constant__ ConvPairParams p) {
@@ -841,15 +842,16 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
           else mbar_arrive_cluster(fa);
           tma_load_4d_2sm(sA + s * kPairABytes, &p.a_map[src], fa, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
 #pragma unroll 1
-          for (int tg = 0; tg < 3; ++tg, ++ib) {
+          for (int tg = 0; tg < 9 / kPairTPS; ++tg, ++ib) {
             const int sb = ib % SB;
             mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
             const uint32_t fb = mapa_u32(&full_b[sb], 0);
             if (rank == 0) mbar_arrive_expect_tx(&full_b[sb], 2u * kPairBStage);
             else mbar_arrive_cluster(fb);
 #pragma unroll
-            for (int tt = 0; tt < 3; ++tt)
-              tma_load_3d_2sm(sW + sb * kPairBStage + tt * kPairSlab, &p.w_map, fb, c * KC, nt * BN + 64 * (int)rank, tg * 3 + tt);
+            for (int tt = 0; tt < kPairTPS; ++tt)
+              tma_load_3d_2sm(sW + sb * kPairBStage + tt * kPairSlab, &p.w_map, fb, c * KC, nt * BN + 64 * (int)rank,
+                              tg * kPairTPS + tt);
           }
         }
       }
@@ -876,16 +878,16 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
           tc_fence_after();
           const uint32_t a_lo = sA_lo + sa * (kPairABytes >> 4);
 #pragma unroll 1
-          for (int tg = 0; tg < 3; ++tg, ++ib) {
+          for (int tg = 0; tg < 9 / kPairTPS; ++tg, ++ib) {
             const int sb = ib % SB;
             mbar_wait(&full_b[sb], (ib / SB) & 1);
             tc_fence_after();
             const uint32_t b_stage = sW_lo + sb * (kPairBStage >> 4);
-            const uint32_t a_row = a_lo + (tg * 10 * ROW >> 4);
             if (elect_one()) {
 #pragma unroll
-              for (int tt = 0; tt < 3; ++tt) {
-                const uint32_t a_tap = a_row + (tt * ROW >> 4);
+              for (int tt = 0; tt < kPairTPS; ++tt) {
+                const int tap = tg * kPairTPS + tt;
+                const uint32_t a_tap = a_lo + (((tap / 3) * 10 + tap % 3) * ROW >> 4);
                 const uint32_t b_lo = b_stage + tt * (kPairSlab >> 4);
 #pragma unroll
                 for (int kk = 0; kk < KSTEPS; ++kk) {
