@@ -65,6 +65,9 @@ PAIR_CASES = [(128, 0, 128, 32, 32, 6), (256, 0, 256, 16, 16, 5), (256, 512, 256
 
 @pytest.mark.parametrize("C0,C1,Cout,H,W,B", PAIR_CASES)
 def test_conv3x3_pair_kernel_vs_torch(C0, C1, Cout, H, W, B, monkeypatch):
-    """The opt-in CTA-pair kernel (tcgen05.mma.cta_group::2, DESIGN 9.1): same check as above with TFPNP_CONV_PAIR=1."""
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2, DESIGN 9.1) and, with TFPNP_CONV_PAIR=0, the single-CTA kernel it
+    replaces on these shapes: both against torch."""
     monkeypatch.setenv("TFPNP_CONV_PAIR", "1")
+    test_conv3x3_tc_vs_torch(C0, C1, Cout, H, W, B)
+    monkeypatch.setenv("TFPNP_CONV_PAIR", "0")
     test_conv3x3_tc_vs_torch(C0, C1, Cout, H, W, B)

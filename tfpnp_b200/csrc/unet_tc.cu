@@ -755,8 +755,10 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
 // A work item = (16x16 super-tile, 128-cout n-tile) on a cluster of two CTAs.  CTA r owns the 16-row x 8-column half r of
 // the tile = one 128-row M-tile; the MMA runs M = 256 over the pair.  Per CTA: the half-halo A box {64, 10, 18, 1} (180 rows,
 // 23 KB instead of 41.5 KB; tap (ky,kx) starts at row ky*10 + kx, 8-row groups 10 rows apart) and HALF of each weight slab
-// (rows [64 r, 64 r + 64) of the n-tile: 8 KB per tap instead of 16 KB), so the weight ring is six 3-tap stages deep where
-// the single-CTA kernel fits two, and every SM ingests half the weight bytes.  Only the leader (rank 0) issues MMAs; its
+// (rows [64 r, 64 r + 64) of the n-tile: 8 KB per tap instead of 16 KB): a whole 64-channel chunk (half-halo + nine half
+// slabs = 95 KB) is ONE ring stage behind ONE full / empty barrier pair, two stages deep, and every SM ingests half the
+// weight bytes.  (Per-kernel-row stages were 1.5x slower than the single-CTA kernel: with M = 256 per MMA a 3-tap stage
+// is 0.39 us of tensor work while each hand-shake crosses SMs twice.)  Only the leader (rank 0) issues MMAs; its
 // full_* barriers collect the TMA bytes of BOTH CTAs (the peer's loads name the leader's barrier), completions are multicast
 // to both CTAs (empty_* and tmem_full), and the peer's epilogue releases the accumulator on the leader's tmem_empty.
 // (Bring-up: tools/ubench/mma_pair.cu.)
@@ -784,15 +786,12 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
   constexpr uint32_t ROW = 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int SA = p.num_a_stages, SB = p.num_b_stages;
+  const int S = p.num_a_stages;                 // ring of chunk stages: [A half-halo | 9 half slabs]
   const int nchunks = p.nchunk0 + p.nchunk1;
-  uint8_t* sA = smem;
-  uint8_t* sW = smem + SA * kPairABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + SB * kPairBStage);
-  uint64_t* full_a = bars;                      // [8]   (leader's are the ones waited on)
-  uint64_t* empty_a = bars + 8;                 // [8]
-  uint64_t* full_b = bars + 16;                 // [16]
-  uint64_t* empty_b = bars + 32;                // [16]
+  constexpr int kStage = kPairABytes + kPairBStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * kStage);
+  uint64_t* full = bars;                        // [8]   (the leader's are the ones waited on)
+  uint64_t* empty = bars + 8;                   // [8]
   uint64_t* tmem_full = bars + 48;              // [2]
   uint64_t* tmem_empty = bars + 50;             // [2]  (leader's collects both CTAs' epilogues)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 52);
@@ -807,8 +806,7 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
     if (p.nchunk1) prefetch_tensormap(&p.a_map[1]);
   }
   if (warp == 1) {
-    if (lane < 8) { mbar_init(&full_a[lane], 2); mbar_init(&empty_a[lane], 1); }
-    if (lane < 16) { mbar_init(&full_b[lane], 2); mbar_init(&empty_b[lane], 1); }
+    if (lane < 8) { mbar_init(&full[lane], 2); mbar_init(&empty[lane], 1); }
     if (lane < 2) { mbar_init(&tmem_full[lane], 1); mbar_init(&tmem_empty[lane], 16); }
     fence_barrier_init();
   }
@@ -826,8 +824,8 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- TMA producer (both CTAs): own half-halo + own half of every weight slab ----------------
-      uint32_t ia = 0, ib = 0;
+      // ---------------- TMA producer (both CTAs): own half-halo + own half of the chunk's nine weight slabs ----------------
+      uint32_t ia = 0;
       for (int t = item0; t < total_items; t += item_step) {
         const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
         const int w0 = (m % p.tiles_w) * 16, h0 = ((m / p.tiles_w) % p.tiles_h) * 16;
@@ -835,37 +833,28 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
         for (int c = 0; c < nchunks; ++c, ++ia) {
           const int src = c < p.nchunk0 ? 0 : 1;
           const int cc = (src == 0 ? c : c - p.nchunk0) * KC;
-          const int s = ia % SA;
-          mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);
-          const uint32_t fa = mapa_u32(&full_a[s], 0);          // the LEADER's barrier
-          if (rank == 0) mbar_arrive_expect_tx(&full_a[s], 2u * kPairARows * ROW);
-          else mbar_arrive_cluster(fa);
-          tma_load_4d_2sm(sA + s * kPairABytes, &p.a_map[src], fa, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
-#pragma unroll 1
-          for (int tg = 0; tg < 9 / kPairTPS; ++tg, ++ib) {
-            const int sb = ib % SB;
-            mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
-            const uint32_t fb = mapa_u32(&full_b[sb], 0);
-            if (rank == 0) mbar_arrive_expect_tx(&full_b[sb], 2u * kPairBStage);
-            else mbar_arrive_cluster(fb);
+          const int s = ia % S;
+          mbar_wait(&empty[s], ((ia / S) & 1) ^ 1);
+          const uint32_t fb = mapa_u32(&full[s], 0);            // the LEADER's barrier
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (kPairARows * ROW + kPairBStage));
+          else mbar_arrive_cluster(fb);
+          uint8_t* st = smem + s * kStage;
+          tma_load_4d_2sm(st, &p.a_map[src], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
 #pragma unroll
-            for (int tt = 0; tt < kPairTPS; ++tt)
-              tma_load_3d_2sm(sW + sb * kPairBStage + tt * kPairSlab, &p.w_map, fb, c * KC, nt * BN + 64 * (int)rank,
-                              tg * kPairTPS + tt);
-          }
+          for (int tt = 0; tt < 9; ++tt)
+            tma_load_3d_2sm(st + kPairABytes + tt * kPairSlab, &p.w_map, fb, c * KC, nt * BN + 64 * (int)rank, tt);
         }
       }
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      // ---------------- MMA issuer (leader only) ----------------
+      // ---------------- MMA issuer (leader only): one barrier wait and one release per chunk ----------------
       const uint32_t idesc = make_idesc_f16(256, BN);
       const uint32_t a_hi = (uint32_t)(make_smem_desc_ex(0, ROW, 10 * ROW, 0) >> 32);
       const uint32_t b_hi = (uint32_t)(make_smem_desc(0, ROW) >> 32);
       const uint32_t lo_flags = 1u << 16;
-      const uint32_t sA_lo = (smem_u32(sA) >> 4) | lo_flags;
-      const uint32_t sW_lo = (smem_u32(sW) >> 4) | lo_flags;
-      uint32_t ia = 0, ib = 0, it = 0;
+      const uint32_t s_lo = (smem_u32(smem) >> 4) | lo_flags;
+      uint32_t ia = 0, it = 0;
       for (int t = item0; t < total_items; t += item_step, ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -873,37 +862,26 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
         const uint32_t d0 = tmem_base + buf * BN;
         uint32_t accumulate = 0;
         for (int c = 0; c < nchunks; ++c, ++ia) {
-          const int sa = ia % SA;
-          mbar_wait(&full_a[sa], (ia / SA) & 1);
+          const int sa = ia % S;
+          mbar_wait(&full[sa], (ia / S) & 1);
           tc_fence_after();
-          const uint32_t a_lo = sA_lo + sa * (kPairABytes >> 4);
-#pragma unroll 1
-          for (int tg = 0; tg < 9 / kPairTPS; ++tg, ++ib) {
-            const int sb = ib % SB;
-            mbar_wait(&full_b[sb], (ib / SB) & 1);
-            tc_fence_after();
-            const uint32_t b_stage = sW_lo + sb * (kPairBStage >> 4);
-            if (elect_one()) {
-#pragma unroll
-              for (int tt = 0; tt < kPairTPS; ++tt) {
-                const int tap = tg * kPairTPS + tt;
-                const uint32_t a_tap = a_lo + (((tap / 3) * 10 + tap % 3) * ROW >> 4);
-                const uint32_t b_lo = b_stage + tt * (kPairSlab >> 4);
-#pragma unroll
-                for (int kk = 0; kk < KSTEPS; ++kk) {
-                  umma2_f16(d0, pack_desc(a_tap + kk * 2, a_hi), pack_desc(b_lo + kk * 2, b_hi), idesc, accumulate);
-                  accumulate = 1;
-                }
-              }
-              umma2_commit_mc(&empty_b[sb], 3);                 // frees the weight stage in BOTH CTAs
-            }
-            accumulate = 1;
-            __syncwarp();
-          }
+          const uint32_t a_lo = s_lo + sa * (kStage >> 4);
+          const uint32_t b_stage = a_lo + (kPairABytes >> 4);
           if (elect_one()) {
-            umma2_commit_mc(&empty_a[sa], 3);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_tap = a_lo + (((tap / 3) * 10 + tap % 3) * ROW >> 4);
+              const uint32_t b_lo = b_stage + tap * (kPairSlab >> 4);
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                umma2_f16(d0, pack_desc(a_tap + kk * 2, a_hi), pack_desc(b_lo + kk * 2, b_hi), idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma2_commit_mc(&empty[sa], 3);                     // frees the chunk stage in BOTH CTAs
             if (c == nchunks - 1) umma2_commit_mc(&tmem_full[buf], 3);
           }
+          accumulate = 1;
           __syncwarp();
         }
       }
@@ -1350,10 +1328,11 @@ struct ConvPairPlan {
   int grid = 0, smem_bytes = 0;
 };
 
-// CTA-pair kernel: streamed weights, 64-channel chunks, Cout a multiple of 128, 16x16 tiling, fp16 mode (opt-in while it is
-// being brought up: TFPNP_CONV_PAIR=1)
+// CTA-pair kernel: streamed weights, 64-channel chunks, Cout a multiple of 128, 16x16 tiling, fp16 mode (TFPNP_CONV_PAIR=0
+// falls back to the single-CTA kernel).  Measured: 14.6 / 16.6 / 39.7 us against 20.4 / 20.4 / 47.5 us (128->128 @32x32,
+// 256->256 @16x16, 768->256 @16x16, 48 images); 60.3k -> 63.8k image-iters/s end to end.
 bool conv_pair_eligible(int C0, int C1, int Cout, int H, int W, bool x3, bool fuse_up) {
-  return env_int("TFPNP_CONV_PAIR", 0) != 0 && !x3 && !fuse_up && C0 % 64 == 0 && C1 % 64 == 0 && Cout % 128 == 0 &&
+  return env_int("TFPNP_CONV_PAIR", 1) != 0 && !x3 && !fuse_up && C0 % 64 == 0 && C1 % 64 == 0 && Cout % 128 == 0 &&
          H % 16 == 0 && W % 16 == 0;
 }
 
@@ -1368,10 +1347,9 @@ int plan_conv_pair(ConvPairPlan& c, const __half* x0, int C0, const __half* x1, 
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
   p.bias = bias; p.out_hi = out;
   const int misc = 1024 /*align*/ + 512 /*barriers*/ + 2048 /*bias*/ + 256;
-  p.num_a_stages = 3;
-  int sb = (227 * 1024 - misc - p.num_a_stages * kPairABytes) / kPairBStage;
-  p.num_b_stages = sb > 16 ? 16 : sb;
-  c.smem_bytes = p.num_a_stages * kPairABytes + p.num_b_stages * kPairBStage + misc;
+  p.num_a_stages = 2;                              // chunk stages: [A half-halo 23 KB | nine half slabs 72 KB]
+  p.num_b_stages = 0;
+  c.smem_bytes = p.num_a_stages * (kPairABytes + kPairBStage) + misc;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
