@@ -80,6 +80,15 @@ int tfpnp_denoiser_destroy(void* handle);
 int tfpnp_denoiser_forward(void* handle, const float* x, const float* sigma,
                            int64_t sigma_stride, float* out, int B, int H, int W, void* stream);
 
+/* Reverse mode of the call above (what autograd computes for the reference's denoiser inside
+ * PnPEnv.forward, tfpnp/env/base.py:193-206): for a cotangent gout [B,1,H,W] of `out`,
+ *   gx [B,1,H,W] = d<out,gout>/dx,   gsigma [B] = d<out,gout>/dsigma   (weights are frozen: denoiser/base.py:19-21).
+ * Recomputes the forward pass keeping every activation (fp32).  Only the TFPNP_PREC_FP32_SIMT engine implements it
+ * (first correct path; others return TFPNP_ERR_UNSUPPORTED).  ROUND-1 STATUS: compiled, host logic and derivation
+ * checked on the CPU; not yet run on a GPU (tests gated behind TFPNP_TEST_GRAD=1). */
+int tfpnp_denoiser_vjp(void* handle, const float* x, const float* sigma, int64_t sigma_stride, const float* gout,
+                       float* gx, float* gsigma, int B, int H, int W, void* stream);
+
 /* One denoiser layer on its own (kernel-level parity tests): ConvLayer = nn.Conv2d(3x3, pad 1,
  * bias) + LeakyReLU(0.2) (unet.py:8-22) over the channel concatenation of x0 [B,H,W,C0] and the
  * optional x1 [B,H,W,C1] (torch.cat, unet.py:119), NHWC fp16 in/out, tcgen05 implicit GEMM.
@@ -135,6 +144,20 @@ int tfpnp_csmri_variant_destroy(void* handle);
 int tfpnp_csmri_variant_forward(void* handle, const float* state_in, const float* y0, const void* mask,
                                 const float* p0, const float* p1, const float* p2, int64_t row_stride,
                                 int64_t col_stride, int B, int iters, float* state_out, void* stream);
+
+/* Reverse mode of ADMMSolver_CSMRI.forward (tasks/csmri/solver.py:29-57) w.r.t. the hyper-parameters, as the
+ * reference's actor update needs it (tfpnp/trainer/mddpg/trainer.py:173 through tfpnp/env/base.py:193-206).
+ *   states        [iters+1][B,3,N,N,2]: the input state followed by the state after each iteration (recorded by the
+ *                 caller with tfpnp_solver_forward(iters = 1) per iteration)
+ *   sigma_d, mu   [B,iters] strided like tfpnp_solver_forward;  y0 [B,1,N,N,2] f32;  mask [B,1,N,N] u8
+ *   grad_out      [B,3,N,N,2] cotangent of the final state
+ *   grad_sigma_d, grad_mu   [B,iters] contiguous (written);  grad_state_in [B,3,N,N,2] or NULL
+ * `denoiser` must implement tfpnp_denoiser_vjp.  Synchronises the stream before returning (scratch is per call).
+ * ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+int tfpnp_csmri_admm_backward(void* denoiser, const float* states, const float* y0, const void* mask,
+                              const float* sigma_d, const float* mu, int64_t row_stride, int64_t col_stride, int B,
+                              int N, int iters, const float* grad_out, float* grad_sigma_d, float* grad_mu,
+                              float* grad_state_in, void* stream);
 
 /* ---- CT operators (own discretisation of the reference geometry,
  *      tfpnp/utils/transforms.py:465-491) ------------------------------------- */

@@ -1,0 +1,65 @@
+"""Generate tests/golden/grad_csmri_small.npz by differentiating the UNMODIFIED reference (build container only).
+
+    PYTHONPATH=/root/repo python -m oracle.make_golden_grad
+
+The reference's actor update back-propagates through ``ADMMSolver_CSMRI.forward`` with PyTorch autograd
+(tfpnp/env/base.py:193-206, tfpnp/trainer/mddpg/trainer.py:173).  This script does the same on the seeded
+``csmri_small`` case (2 images, 32x32, 3 iterations) with a seeded cotangent, records the gradients w.r.t.
+``sigma_d`` / ``mu`` / the input state and the denoiser's vector-Jacobian product on its own, and asserts that both
+restatements of oracle/grad_oracle.py (autograd through the oracle, and the hand-derived adjoint recursion the CUDA
+path implements) agree with the reference.  TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import grad_oracle as G
+from . import refshim, synth
+from .make_golden import close, np_, save, weight_checksum
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    refshim.install()
+    sd = synth.unet_state_dict(0, "he")
+
+    # 1. denoiser VJP (tfpnp/pnp/denoiser/base.py:23-32 under autograd)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(2, 1, 32, 32, generator=g)
+    sigma = torch.tensor([10 / 255, 50 / 255])
+    gout = torch.randn(2, 1, 32, 32, generator=g)
+    den = refshim.reference_denoiser(sd)
+    xr, sr = x.clone().requires_grad_(True), sigma.clone().requires_grad_(True)
+    out = den(xr, sr)
+    den_gx, den_gs = torch.autograd.grad(out, (xr, sr), gout)
+    gx, gs = G.denoise_vjp_autograd(sd, x, sigma, gout)
+    print(f"  denoiser vjp oracle-vs-reference: gx {close(gx, den_gx):.2e}  gsigma {close(gs, den_gs):.2e}")
+
+    # 2. the solver: gradients of <forward(state, params), gout> w.r.t. sigma_d, mu and the state
+    d = synth.csmri_batch(2, 32, 3)
+    g = torch.Generator().manual_seed(13)
+    gstate = torch.randn(d["state"].shape, generator=g)
+    sol = refshim.reference_solver("csmri", sd)
+    st = d["state"].clone().requires_grad_(True)
+    sg = d["sigma_d"].clone().requires_grad_(True)
+    mu = d["mu"].clone().requires_grad_(True)
+    out = sol((st, (d["y0"], d["mask"])), (sg, mu))
+    ref_gs, ref_gm, ref_gst = torch.autograd.grad(out, (sg, mu, st), gstate)
+    a_gs, a_gm, a_gst = G.admm_csmri_vjp_autograd(sd, d["state"], d["y0"], d["mask"], d["sigma_d"], d["mu"], gstate)
+    print(f"  solver vjp (autograd through the oracle) vs reference: sigma_d {close(a_gs, ref_gs, 1e-5):.2e}  "
+          f"mu {close(a_gm, ref_gm, 1e-5):.2e}  state {close(a_gst, ref_gst, 1e-5):.2e}")
+    states = G.admm_csmri_trajectory(sd, d["state"], d["y0"], d["mask"], d["sigma_d"], d["mu"])
+    m_gs, m_gm, m_gst = G.admm_csmri_vjp_manual(sd, states, d["y0"], d["mask"], d["sigma_d"], d["mu"], gstate)
+    print(f"  solver vjp (adjoint recursion) vs reference:           sigma_d {close(m_gs, ref_gs, 1e-4):.2e}  "
+          f"mu {close(m_gm, ref_gm, 1e-4):.2e}  state {close(m_gst, ref_gst, 1e-4):.2e}")
+
+    save("grad_csmri_small", den_x=x.numpy(), den_sigma=sigma.numpy(), den_gout=gout.numpy(), den_gx=den_gx.numpy(),
+         den_gsigma=den_gs.numpy(), **np_({k: d[k] for k in ("state", "y0", "mask", "sigma_d", "mu")}),
+         gout=gstate.numpy(), g_sigma_d=ref_gs.numpy(), g_mu=ref_gm.numpy(), g_state=ref_gst.numpy(),
+         wsum=weight_checksum(sd), init="he", seed=0)
+
+
+if __name__ == "__main__":
+    main()

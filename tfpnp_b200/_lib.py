@@ -43,6 +43,8 @@ SIGNATURES = {
     "tfpnp_denoiser_destroy": (C.c_int, [C.c_void_p]),
     "tfpnp_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tfpnp_denoiser_vjp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tfpnp_conv3x3_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tfpnp_solver_create": (C.c_int, [C.POINTER(SolverConfig), C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -55,6 +57,9 @@ SIGNATURES = {
     "tfpnp_csmri_variant_destroy": (C.c_int, [C.c_void_p]),
     "tfpnp_csmri_variant_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "tfpnp_csmri_admm_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfpnp_radon_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "tfpnp_radon_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -137,6 +137,14 @@ struct Denoiser {
   // x, out: [B,H,W] fp32 (C=1); sigma[b] at sigma[b*sigma_stride]
   virtual int forward(const float* x, const float* sigma, int64_t sigma_stride, float* out, int B,
                       int H, int W, cudaStream_t st) = 0;
+  // reverse mode: gx [B,H,W] = d<out,gout>/dx, gsigma[b*gs_stride] = d<out,gout>/dsigma[b].
+  // Implemented by the fp32 engine (unet_simt.cu); the tensor-core engines report TFPNP_ERR_UNSUPPORTED.
+  virtual int vjp(const float* x, const float* sigma, int64_t sigma_stride, const float* gout, float* gx,
+                  float* gsigma, int64_t gs_stride, int B, int H, int W, cudaStream_t st) {
+    (void)x; (void)sigma; (void)sigma_stride; (void)gout; (void)gx; (void)gsigma; (void)gs_stride; (void)B; (void)H; (void)W; (void)st;
+    set_error("this denoiser engine has no reverse mode: create it with precision fp32_simt");
+    return TFPNP_ERR_UNSUPPORTED;
+  }
 };
 
 // pre-planned one-tile-per-CTA tensor-core 3x3 conv layer (unet_tc.cu): NHWC fp16 (hi [+ lo residual plane]) in/out,

@@ -309,6 +309,127 @@ struct VariantSolver {
   }
 };
 
+
+// ---- reverse mode of the ADMM solver (tfpnp/env/base.py:193-206 under autograd) ------------------------
+// Adjoint of one iteration (x', z', u') = step(z, u; sigma, mu) with incoming (gx', gz', gu'):
+//   gzt = gz' - gu';  q = ifft2c(B_mu fft2c(gzt))  (the k-space blend with y0 = 0 is self-adjoint);
+//   r = ifft2c(M (fft2c(x' + u) - y0));  g_mu = <gzt, r> / (1 + mu)^2;  gxt = Re(gx' + gu' + q);
+//   (gv, g_sigma) = J_D(Re(z - u), sigma)^T gxt;  gz = (gv, 0);  gu = gu' + q - (gv, 0);  gx = 0.
+// Checked on the CPU against autograd through the unmodified reference (oracle/grad_oracle.py, make_golden_grad.py).
+
+// A = gz' - gu';  IN = (Re x' , 0) + u   with x' = slot 0 of the next state, u = slot 2 of this state
+__global__ void grad_pre(const float2* __restrict__ GZ, const float2* __restrict__ GU, const float2* __restrict__ st_i,
+                         const float2* __restrict__ st_n, float2* __restrict__ A, float2* __restrict__ IN, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t b = i / HW, p = i % HW;
+  const float2 gz = GZ[i], gu = GU[i];
+  A[i] = make_float2(gz.x - gu.x, gz.y - gu.y);
+  const float2 u = st_i[(b * 3 + 2) * HW + p];
+  const float xr = st_n[(b * 3 + 0) * HW + p].x;
+  IN[i] = make_float2(xr + u.x, u.y);
+}
+// g_mu[b] = <A, R>_b / (1 + mu[b])^2 ; one CTA per image
+__global__ void __launch_bounds__(256)
+grad_mu_reduce(const float2* __restrict__ A, const float2* __restrict__ R, const float* __restrict__ mu,
+               float* __restrict__ gmu, int64_t stride, int HW) {
+  __shared__ float red[256];
+  const int b = blockIdx.x;
+  const float2* a = A + (size_t)b * HW;
+  const float2* r = R + (size_t)b * HW;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) s += a[p].x * r[p].x + a[p].y * r[p].y;
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { const float m = 1.f + mu[b]; gmu[b * stride] = red[0] / (m * m); }
+}
+// gxt = Re(gx' + gu' + q);  GU += q;  v = Re(z - u) of this state (the denoiser input of the iteration)
+__global__ void grad_mid(const float2* __restrict__ GX, float2* __restrict__ GU, const float2* __restrict__ Q,
+                         const float2* __restrict__ st_i, float* __restrict__ gxt, float* __restrict__ v, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t b = i / HW, p = i % HW;
+  const float2 q = Q[i];
+  float2 gu = GU[i];
+  gxt[i] = GX[i].x + gu.x + q.x;
+  gu.x += q.x; gu.y += q.y;
+  GU[i] = gu;
+  v[i] = st_i[(b * 3 + 1) * HW + p].x - st_i[(b * 3 + 2) * HW + p].x;
+}
+// gz = (gv, 0);  gu -= (gv, 0);  gx = 0
+__global__ void grad_post(const float* __restrict__ gv, float2* __restrict__ GX, float2* __restrict__ GZ,
+                          float2* __restrict__ GU, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = gv[i];
+  GX[i] = make_float2(0.f, 0.f);
+  GZ[i] = make_float2(g, 0.f);
+  GU[i].x -= g;
+}
+
+template <int R>
+int admm_backward(Denoiser* den, const float* states, const float* y0, const uint8_t* mask, const float* sigma_d,
+                  const float* mu, int64_t rs, int64_t cs, int B, int iters, const float* grad_out, float* g_sigma,
+                  float* g_mu, float* g_state_in, cudaStream_t st) {
+  constexpr int N = 32 * R;
+  const int HW = N * N;
+  const size_t n = (size_t)B * HW;
+  const int T256 = 256;
+  const unsigned nb = (unsigned)((n + T256 - 1) / T256);
+  DevBuf gx, gz, gu, A, IN, Q, Rr, T, y0p, zero, gxt, v, gv, maskp, P;
+  int rc = 0;
+  auto body = [&]() -> int {
+    for (DevBuf* b : {&gx, &gz, &gu, &A, &IN, &Q, &Rr, &T, &y0p, &zero}) TFPNP_TRY(b->alloc(n * sizeof(float2)));
+    for (DevBuf* b : {&gxt, &v, &gv}) TFPNP_TRY(b->alloc(n * sizeof(float)));
+    TFPNP_TRY(maskp.alloc(n));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float)));
+    TFPNP_CUDA_OK(cudaMemsetAsync(zero.p, 0, n * sizeof(float2), st));
+    gather_params3<<<cdiv(B * iters, T256), T256, 0, st>>>(sigma_d, mu, nullptr, rs, cs, P.as<float>(), B, iters);
+    TFPNP_COUNT_LAUNCH();
+    TFPNP_TRY(csmri_prep(y0, mask, y0p.as<float2>(), maskp.as<uint8_t>(), B, N, st));
+    const size_t np = (size_t)B * iters;
+    const float2* go = reinterpret_cast<const float2*>(grad_out);
+#define VLAUNCH(kernel, ...) do { kernel<<<nb, T256, 0, st>>>(__VA_ARGS__); TFPNP_COUNT_LAUNCH(); } while (0)
+    VLAUNCH(slot_copy, go, gx.as<float2>(), nullptr, 3, 0, HW, n, 0);
+    VLAUNCH(slot_copy, go, gz.as<float2>(), nullptr, 3, 1, HW, n, 0);
+    VLAUNCH(slot_copy, go, gu.as<float2>(), nullptr, 3, 2, HW, n, 0);
+    const size_t state_elems = n * 3;     // float2 per recorded state
+    for (int i = iters - 1; i >= 0; --i) {
+      const float2* st_i = reinterpret_cast<const float2*>(states) + (size_t)i * state_elems;
+      const float2* st_n = st_i + state_elems;
+      const float* mu_i = P.as<float>() + np + (size_t)i * B;
+      const float* sg_i = P.as<float>() + (size_t)i * B;
+      VLAUNCH(grad_pre, gz.as<float2>(), gu.as<float2>(), st_i, st_n, A.as<float2>(), IN.as<float2>(), HW, n);
+      TFPNP_TRY(masked_fft_step<R>(A.as<float2>(), Q.as<float2>(), T.as<float2>(), zero.as<float2>(), maskp.as<uint8_t>(), mu_i,
+                                   MODE_BLEND, B, st));
+      TFPNP_TRY(masked_fft_step<R>(IN.as<float2>(), Rr.as<float2>(), T.as<float2>(), y0p.as<float2>(), maskp.as<uint8_t>(),
+                                   nullptr, MODE_RESIDUAL, B, st));
+      grad_mu_reduce<<<B, 256, 0, st>>>(A.as<float2>(), Rr.as<float2>(), mu_i, g_mu + i, iters, HW);
+      TFPNP_COUNT_LAUNCH();
+      VLAUNCH(grad_mid, gx.as<float2>(), gu.as<float2>(), Q.as<float2>(), st_i, gxt.as<float>(), v.as<float>(), HW, n);
+      TFPNP_TRY(den->vjp(v.as<float>(), sg_i, 1, gxt.as<float>(), gv.as<float>(), g_sigma + i, iters, B, N, N, st));
+      VLAUNCH(grad_post, gv.as<float>(), gx.as<float2>(), gz.as<float2>(), gu.as<float2>(), n);
+    }
+    if (g_state_in) {
+      float2* gs = reinterpret_cast<float2*>(g_state_in);
+      VLAUNCH(slot_copy, gs, gx.as<float2>(), nullptr, 3, 0, HW, n, 1);
+      VLAUNCH(slot_copy, gs, gz.as<float2>(), nullptr, 3, 1, HW, n, 1);
+      VLAUNCH(slot_copy, gs, gu.as<float2>(), nullptr, 3, 2, HW, n, 1);
+    }
+#undef VLAUNCH
+    TFPNP_CUDA_OK(cudaGetLastError());
+    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers below are freed on return
+    return 0;
+  };
+  rc = body();
+  for (DevBuf* b : {&gx, &gz, &gu, &A, &IN, &Q, &Rr, &T, &y0p, &zero, &gxt, &v, &gv, &maskp, &P}) b->release();
+  return rc;
+}
+
 }  // namespace
 }  // namespace tfpnp
 
@@ -351,6 +472,26 @@ int tfpnp_csmri_variant_forward(void* h, const float* state_in, const float* y0,
   }
   s->last_launches = g_launch_count;
   return rc;
+}
+
+int tfpnp_csmri_admm_backward(void* denoiser, const float* states, const float* y0, const void* mask,
+                              const float* sigma_d, const float* mu, int64_t row_stride, int64_t col_stride, int B, int N,
+                              int iters, const float* grad_out, float* grad_sigma_d, float* grad_mu, float* grad_state_in,
+                              void* stream) {
+  TFPNP_CHECK(denoiser && states && y0 && mask && sigma_d && mu && grad_out && grad_sigma_d && grad_mu && B > 0 && iters > 0,
+              "bad argument");
+  TFPNP_CHECK(N == 32 || N == 64 || N == 128 || N == 256, "FFT tasks support N in {32,64,128,256}, got %d", N);
+  g_launch_count = 0;
+  TFPNP_CUDA_OK(fft_tables_init());
+  Denoiser* den = static_cast<Denoiser*>(denoiser);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* m8 = static_cast<const uint8_t*>(mask);
+  switch (N) {
+    case 32: return admm_backward<1>(den, states, y0, m8, sigma_d, mu, row_stride, col_stride, B, iters, grad_out, grad_sigma_d, grad_mu, grad_state_in, st);
+    case 64: return admm_backward<2>(den, states, y0, m8, sigma_d, mu, row_stride, col_stride, B, iters, grad_out, grad_sigma_d, grad_mu, grad_state_in, st);
+    case 128: return admm_backward<4>(den, states, y0, m8, sigma_d, mu, row_stride, col_stride, B, iters, grad_out, grad_sigma_d, grad_mu, grad_state_in, st);
+    default: return admm_backward<8>(den, states, y0, m8, sigma_d, mu, row_stride, col_stride, B, iters, grad_out, grad_sigma_d, grad_mu, grad_state_in, st);
+  }
 }
 
 }  // extern "C"

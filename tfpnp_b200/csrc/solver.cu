@@ -436,6 +436,12 @@ int tfpnp_denoiser_forward(void* h, const float* x, const float* sigma, int64_t 
   return d->forward(x, sigma, sstride, out, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
+int tfpnp_denoiser_vjp(void* h, const float* x, const float* sigma, int64_t sstride, const float* gout, float* gx,
+                       float* gsigma, int B, int H, int W, void* stream) {
+  TFPNP_CHECK(h && x && sigma && gout && gx && gsigma && B > 0, "bad argument");
+  return static_cast<Denoiser*>(h)->vjp(x, sigma, sstride, gout, gx, gsigma, 1, B, H, W, static_cast<cudaStream_t>(stream));
+}
+
 int tfpnp_solver_create(const tfpnp_solver_config* cfg, void* denoiser, void** out) {
   return solver_create(cfg, static_cast<Denoiser*>(denoiser), out);
 }

@@ -75,11 +75,50 @@ class UNetDenoiser2D(torch.nn.Module):
             self._handles[idx] = h = out
         return h
 
+    # Reverse mode is opt-in: set ``denoiser.differentiable = True``.  It runs on a second, fp32 engine
+    # built from the same weights (tfpnp_denoiser_vjp); round-1 status: compiled, not yet validated on a GPU.
+    differentiable = False
+
+    def _grad_handle(self, device: torch.device):
+        """The fp32 engine that implements tfpnp_denoiser_vjp (this engine itself when precision == 'fp32_simt')."""
+        if self.precision == "fp32_simt":
+            return self._handle(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = ("grad", idx)
+        h = self._handles.get(key)
+        if h is None:
+            with torch.cuda.device(idx):
+                out = C.c_void_p()
+                _lib.check(_lib.lib().tfpnp_denoiser_create(self._flat.data_ptr(), self._flat.numel(),
+                                                            _lib.PREC_FP32_SIMT, C.byref(out)), "tfpnp_denoiser_create")
+            self._handles[key] = h = out
+        return h
+
+    def vjp(self, x, sigma, gout):
+        """(d<out,gout>/dx [N,1,H,W], d<out,gout>/dsigma [N]) of ``forward`` (denoiser/base.py:23-32 under autograd)."""
+        if not x.is_cuda:
+            raise RuntimeError("tfpnp_b200.UNetDenoiser2D runs on CUDA (sm_100) tensors only; no CPU fallback")
+        N, Cc, H, W = x.shape
+        assert Cc == 1
+        x = x.detach().contiguous().float()
+        sigma = sigma.detach().reshape(N).float().contiguous()
+        gout = gout.detach().contiguous().float()
+        gx = torch.empty_like(x)
+        gs = torch.empty(N, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().tfpnp_denoiser_vjp(self._grad_handle(x.device), x.data_ptr(), sigma.data_ptr(), 1,
+                                                     gout.data_ptr(), gx.data_ptr(), gs.data_ptr(), N, H, W, st),
+                       "tfpnp_denoiser_vjp")
+        return gx, gs
+
     def forward(self, x, sigma):
         if not x.is_cuda:
             raise RuntimeError("tfpnp_b200.UNetDenoiser2D runs on CUDA (sm_100) tensors only; no CPU fallback")
         if torch.is_grad_enabled() and (x.requires_grad or sigma.requires_grad):
-            raise NotImplementedError("differentiable denoiser is out of scope (SURVEY 8f, N4)")
+            if not self.differentiable:
+                raise NotImplementedError("differentiable denoiser is opt-in (SURVEY 8f, N4): set .differentiable = True")
+            return _DenoiseFn.apply(self, x, sigma)
         N, Cc, H, W = x.shape
         assert Cc == 1
         x = x.contiguous().float()
@@ -98,6 +137,25 @@ class UNetDenoiser2D(torch.nn.Module):
                 _lib.lib().tfpnp_denoiser_destroy(h)
         except Exception:
             pass
+
+
+class _DenoiseFn(torch.autograd.Function):
+    """autograd node for UNetDenoiser2D.forward: the native forward, tfpnp_denoiser_vjp backward."""
+
+    @staticmethod
+    def forward(ctx, den, x, sigma):
+        with torch.no_grad():
+            out = den.forward(x.detach(), sigma.detach())
+        ctx.den = den
+        ctx.sigma_shape = sigma.shape
+        ctx.save_for_backward(x.detach(), sigma.detach())
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, sigma = ctx.saved_tensors
+        gx, gs = ctx.den.vjp(x, sigma, gout)
+        return None, gx.to(x.dtype), gs.reshape(ctx.sigma_shape).to(sigma.dtype)
 
 
 def random_unet_state_dict(seed: int = 0):
@@ -155,6 +213,9 @@ class IRCNNDenoiser2D(UNetDenoiser2D):
             parts.append(t.detach().to(torch.float32).cpu().contiguous().reshape(-1))
         self._flat = torch.cat(parts).contiguous()
         self._handles = {}
+
+    def _grad_handle(self, device: torch.device):
+        raise NotImplementedError("reverse mode (SURVEY 8f N4) is built for the UNet denoiser only")
 
     def _handle(self, device: torch.device):
         idx = device.index if device.index is not None else torch.cuda.current_device()

@@ -9,8 +9,9 @@ unchanged.  ``forward`` marshals raw device pointers into ``tfpnp_solver_forward
 (include/tfpnp_b200.h); the iterated proximal loop itself is hand-written sm_100a CUDA.
 
 There is no PyTorch/CPU fallback.  The differentiable use (``PnPEnv.forward`` under
-autograd, tfpnp/env/base.py:193-206) is out of scope for this build and
-raises NotImplementedError.
+autograd, tfpnp/env/base.py:193-206) is opt-in and exists for ``ADMMSolver_CSMRI``
+only (``solver.differentiable = True``: gradients w.r.t. sigma_d / mu / the input state through
+``tfpnp_csmri_admm_backward``); everything else raises NotImplementedError under autograd.
 """
 from __future__ import annotations
 
@@ -107,12 +108,20 @@ class _NativeADMM(PnPSolver):
             self._solvers[key] = h = out
         return h
 
+    # reverse mode: opt-in, ADMMSolver_CSMRI only
+    differentiable = False
+    _has_backward = False
+
+    def _wants_grad(self, variables, parameters):
+        return torch.is_grad_enabled() and (variables.requires_grad or any(p.requires_grad for p in parameters))
+
     def _check_inputs(self, variables, parameters):
         if not variables.is_cuda:
             raise RuntimeError("tfpnp_b200 solvers run on CUDA (sm_100) tensors only; there is no CPU fallback")
-        if torch.is_grad_enabled() and (variables.requires_grad or any(p.requires_grad for p in parameters)):
+        if self._wants_grad(variables, parameters) and not (self.differentiable and self._has_backward):
             raise NotImplementedError(
-                "the differentiable solver path (PnPEnv.forward under autograd) is out of scope (SURVEY 8f N4)")
+                "the differentiable solver path (PnPEnv.forward under autograd, SURVEY 8f N4) is opt-in and built for "
+                "ADMMSolver_CSMRI only: set solver.differentiable = True")
 
     def _run(self, handle, variables, aux0, aux1, aux1_stride, params, iter_num):
         B = variables.shape[0]
@@ -162,6 +171,7 @@ class ADMMSolver_CSMRI(ADMMSolver):
     """tasks/csmri/solver.py:9-57."""
     _task = _lib.TASK_CSMRI
     _complex_state = True
+    _has_backward = True
 
     def filter_aux_inputs(self, state):     # solver.py:20-21
         return (state['y0'], state['mask'])
@@ -175,7 +185,58 @@ class ADMMSolver_CSMRI(ADMMSolver):
         m8 = mask.contiguous()
         m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else (m8 != 0).view(torch.uint8)
         h = self._solver_handle(variables.device, H, W)
+        if self._wants_grad(variables, (sigma_d, mu)):
+            if iter_num is None:
+                iter_num = sigma_d.shape[-1]
+            return _CSMRIAdmmFn.apply(self, h, variables, _f32c(y0), m8, sigma_d, mu, int(iter_num))
         return self._run(h, variables, _f32c(y0), m8, 0, (sigma_d, mu), iter_num)
+
+
+class _CSMRIAdmmFn(torch.autograd.Function):
+    """autograd node for ADMMSolver_CSMRI.forward (what tfpnp/trainer/mddpg/trainer.py:173 differentiates).
+
+    forward: the native solver one iteration at a time, recording the trajectory; backward: the adjoint recursion
+    of tfpnp_csmri_admm_backward (csmri_variants.cu) with the denoiser's vector-Jacobian product on the fp32 engine.
+    """
+
+    @staticmethod
+    def forward(ctx, solver, handle, variables, y0, m8, sigma_d, mu, iter_num):
+        B = variables.shape[0]
+        sg = sigma_d.detach().float().reshape(B, -1)[:, :iter_num].contiguous()
+        m = mu.detach().float().reshape(B, -1)[:, :iter_num].contiguous()
+        if sg.shape[1] < iter_num or m.shape[1] < iter_num:
+            raise IndexError(f"iter_num={iter_num} exceeds the hyper-parameter width")
+        states = [_f32c(variables.detach())]
+        with torch.no_grad():
+            for i in range(iter_num):
+                states.append(solver._run(handle, states[-1], y0, m8, 0, (sg[:, i:i + 1], m[:, i:i + 1]), 1))
+        ctx.solver = solver
+        ctx.meta = (sigma_d.shape, mu.shape, sigma_d.dtype, mu.dtype, iter_num)
+        ctx.save_for_backward(torch.stack(states), y0, m8, sg, m)
+        return states[-1].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        states, y0, m8, sg, m = ctx.saved_tensors
+        sshape, mshape, sdt, mdt, it = ctx.meta
+        B, _, H, W, _ = gout.shape
+        gout = _f32c(gout)
+        g_sigma = torch.zeros(B, it, device=gout.device, dtype=torch.float32)
+        g_mu = torch.zeros_like(g_sigma)
+        g_state = torch.empty_like(gout)
+        den = ctx.solver.denoiser
+        with torch.cuda.device(gout.device):
+            _lib.check(_lib.lib().tfpnp_csmri_admm_backward(
+                den._grad_handle(gout.device), states.data_ptr(), y0.data_ptr(), m8.data_ptr(), sg.data_ptr(),
+                m.data_ptr(), it, 1, B, H, it, gout.data_ptr(), g_sigma.data_ptr(), g_mu.data_ptr(), g_state.data_ptr(),
+                torch.cuda.current_stream().cuda_stream), "tfpnp_csmri_admm_backward")
+
+        def widen(g, shape, dtype):          # parameters beyond iter_num did not take part: zero gradient
+            full = torch.zeros(B, max(1, math.prod(shape[1:])), device=g.device, dtype=torch.float32)
+            full[:, :it] = g
+            return full.reshape(shape).to(dtype)
+
+        return (None, None, g_state, None, None, widen(g_sigma, sshape, sdt), widen(g_mu, mshape, mdt), None)
 
 
 class _CSMRIVariant(PnPSolver):
