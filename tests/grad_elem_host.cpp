@@ -1,0 +1,277 @@
+// CPU emulation of UNetSimt::vjp (tfpnp_b200/csrc/unet_simt.cu) for tests/test_grad.py.  TEST INFRASTRUCTURE ONLY.
+// Runs the SAME layer sequence, workspace layout and per-element adjoint bodies as the CUDA engine
+// (grad_elem::unet_vjp_sequence / *_elem from tfpnp_b200/csrc/grad_elem.cuh), with plain loops standing in for the kernel
+// launches and a naive convolution standing in for conv3x3_simt.  Built by the test with g++ (no CUDA needed).
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include "../tfpnp_b200/csrc/grad_elem.cuh"
+
+using namespace tfpnp;
+
+namespace {
+
+// out[b,co,y,x] = act(bias[co] + sum w[co,ci,ky,kx] in[b,ci,y+ky-1,x+kx-1]), input = cat(src0, src1); w: [Cout][Cin][9]
+void conv3x3_host(const float* s0, int C0, const float* s1, int C1, const float* w, const float* bias, float* out, int Cout,
+                  int B, int H, int W, bool leaky) {
+  const int Cin = C0 + C1;
+  for (int b = 0; b < B; ++b)
+    for (int co = 0; co < Cout; ++co) {
+      float* o = out + ((size_t)b * Cout + co) * H * W;
+      for (int i = 0; i < H * W; ++i) o[i] = bias ? bias[co] : 0.f;
+      for (int c = 0; c < Cin; ++c) {
+        const float* in = c < C0 ? s0 + ((size_t)b * C0 + c) * H * W : s1 + ((size_t)b * C1 + (c - C0)) * H * W;
+        const float* wk = w + ((size_t)co * Cin + c) * 9;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const float wv = wk[ky * 3 + kx];
+            const int y_lo = ky == 0 ? 1 : 0, y_hi = ky == 2 ? H - 1 : H;
+            const int x_lo = kx == 0 ? 1 : 0, x_hi = kx == 2 ? W - 1 : W;
+            for (int y = y_lo; y < y_hi; ++y) {
+              const float* ir = in + (size_t)(y + ky - 1) * W + (kx - 1);
+              float* orow = o + (size_t)y * W;
+              for (int x = x_lo; x < x_hi; ++x) orow[x] += wv * ir[x];
+            }
+          }
+      }
+      if (leaky) for (int i = 0; i < H * W; ++i) o[i] = o[i] > 0.f ? o[i] : 0.2f * o[i];
+    }
+}
+
+struct HostOps {
+  const float* flat;                       // state_dict floats
+  size_t w_off[kNumUnetConv3], b_off[kNumUnetConv3], outc_w, outc_b;
+  std::vector<float> wt;                   // transposed + flipped weights
+  size_t wt_off[kNumUnetConv3];
+  int B, H, W;
+
+  void init() {
+    const ConvSpec* sp = unet_conv_specs();
+    size_t off = 0, total = 0;
+    for (int l = 0; l < kNumUnetConv3; ++l) {
+      w_off[l] = off; off += (size_t)sp[l].cout * sp[l].cin * 9;
+      b_off[l] = off; off += sp[l].cout;
+      wt_off[l] = total; total += (size_t)sp[l].cout * sp[l].cin * 9;
+    }
+    outc_w = off; outc_b = off + 32;
+    wt.resize(total);
+    for (int l = 0; l < kNumUnetConv3; ++l)
+      grad_elem::transpose_flip_weights(flat + w_off[l], wt.data() + wt_off[l], sp[l].cout, sp[l].cin);
+  }
+  int make_input(const float* x, const float* sigma, int64_t sstride, float* in2) {
+    const size_t HW = (size_t)H * W;
+    for (int b = 0; b < B; ++b)
+      for (size_t p = 0; p < HW; ++p) { in2[(size_t)b * 2 * HW + p] = x[b * HW + p]; in2[((size_t)b * 2 + 1) * HW + p] = sigma[b * sstride]; }
+    return 0;
+  }
+  int conv(int l, const float* s0, int C0, const float* s1, int C1, float* out, int h, int w) {
+    const ConvSpec& sp = unet_conv_specs()[l];
+    if (C0 + C1 != sp.cin) return -1;
+    conv3x3_host(s0, C0, s1, C1, flat + w_off[l], flat + b_off[l], out, sp.cout, B, h, w, true);
+    return 0;
+  }
+  int maxpool(const float* in, float* out, int C, int h, int w) {
+    for (size_t bc = 0; bc < (size_t)B * C; ++bc)
+      for (int y = 0; y < h / 2; ++y)
+        for (int x = 0; x < w / 2; ++x) {
+          const float* p = in + (bc * h + 2 * y) * w + 2 * x;
+          out[(bc * (h / 2) + y) * (w / 2) + x] = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[w], p[w + 1]));
+        }
+    return 0;
+  }
+  int upsample(const float* in, float* out, int C, int h, int w) {      // the expressions of upsample2_simt
+    const int Ho = 2 * h, Wo = 2 * w;
+    const float sy = (float)(h - 1) / (float)(Ho - 1), sx = (float)(w - 1) / (float)(Wo - 1);
+    for (size_t bc = 0; bc < (size_t)B * C; ++bc)
+      for (int y = 0; y < Ho; ++y)
+        for (int x = 0; x < Wo; ++x) {
+          const float fy = sy * y, fx = sx * x;
+          const int y0 = (int)fy, x0 = (int)fx;
+          const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+          const float ly = fy - y0, lx = fx - x0;
+          const float* p = in + bc * h * w;
+          const float top = (1.f - lx) * p[y0 * w + x0] + lx * p[y0 * w + x1];
+          const float bot = (1.f - lx) * p[y1 * w + x0] + lx * p[y1 * w + x1];
+          out[(bc * Ho + y) * Wo + x] = (1.f - ly) * top + ly * bot;
+        }
+    return 0;
+  }
+  int outc_pre(const float* a26, const float* x, float* r) {
+    const size_t HW = (size_t)H * W;
+    for (size_t i = 0; i < (size_t)B * HW; ++i) {
+      const size_t b = i / HW, p = i % HW;
+      float acc = flat[outc_b];
+      for (int c = 0; c < 32; ++c) acc = fmaf(flat[outc_w + c], a26[(b * 32 + c) * HW + p], acc);
+      r[i] = x[i] + acc;
+    }
+    return 0;
+  }
+  int outc_bwd(const float* gout, const float* r, const float* a26, float* gr, float* gpre) {
+    for (size_t i = 0; i < (size_t)B * H * W; ++i) grad_elem::outc_bwd_elem(i, gout, r, flat + outc_w, a26, gr, gpre, 32, H * W);
+    return 0;
+  }
+  int dgrad(int l, const float* gin, float* gout, int h, int w) {
+    const ConvSpec& sp = unet_conv_specs()[l];
+    conv3x3_host(gin, sp.cout, nullptr, 0, wt.data() + wt_off[l], nullptr, gout, sp.cin, B, h, w, false);
+    return 0;
+  }
+  int lrelu_bwd(float* g, const float* a, size_t n) {
+    for (size_t i = 0; i < n; ++i) g[i] *= grad_elem::lrelu_d(a[i]);
+    return 0;
+  }
+  int pool_bwd(const float* gpool, const float* a, const float* gskip, int Ccat, float* gpre, int C, int h, int w) {
+    for (size_t i = 0; i < (size_t)B * C * (h / 2) * (w / 2); ++i) grad_elem::pool_bwd_elem(i, gpool, a, gskip, Ccat, gpre, C, h, w);
+    return 0;
+  }
+  int up_bwd(const float* gcat, int Ccat, int coff, const float* a, float* gpre, int C, int h, int w) {
+    for (size_t i = 0; i < (size_t)B * C * h * w; ++i) grad_elem::up_bwd_elem(i, gcat, Ccat, coff, a, gpre, C, h, w);
+    return 0;
+  }
+  int first_finish(const float* gin2, const float* gr, float* gx, float* gsigma, int64_t gs_stride) {   // first_bwd_finish_simt
+    const size_t HW = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+      double s = 0;
+      for (size_t p = 0; p < HW; ++p) {
+        gx[b * HW + p] = gin2[(size_t)b * 2 * HW + p] + gr[b * HW + p];
+        s += gin2[((size_t)b * 2 + 1) * HW + p];
+      }
+      gsigma[b * gs_stride] = (float)s;
+    }
+    return 0;
+  }
+};
+
+// centred ortho 2-D DFT pair of tfpnp/utils/transforms.py:68-103 (fftshift(FFT(ifftshift(x))) for even N) by direct
+// summation: X[k] = 1/sqrt(N) sum_n x[n] exp(-+ 2 pi i (k - N/2)(n - N/2) / N) along both axes
+void dft2c_host(const cplx* in, cplx* out, int N, bool inverse) {
+  std::vector<double> cr((size_t)N * N), ci((size_t)N * N);
+  const double sgn = inverse ? 1.0 : -1.0, scale = 1.0 / std::sqrt((double)N);
+  for (int k = 0; k < N; ++k)
+    for (int n = 0; n < N; ++n) {
+      const double ang = sgn * 2.0 * M_PI * (double)((k - N / 2) * (n - N / 2) % N) / N;
+      cr[(size_t)k * N + n] = std::cos(ang) * scale; ci[(size_t)k * N + n] = std::sin(ang) * scale;
+    }
+  std::vector<double> tr((size_t)N * N), ti((size_t)N * N);
+  for (int r = 0; r < N; ++r)           // along columns (dim -2 of [H,W,2] is W; order is irrelevant for a separable DFT)
+    for (int k = 0; k < N; ++k) {
+      double ar = 0, ai = 0;
+      for (int n = 0; n < N; ++n) {
+        const double xr = in[(size_t)r * N + n].x, xi = in[(size_t)r * N + n].y;
+        ar += xr * cr[(size_t)k * N + n] - xi * ci[(size_t)k * N + n];
+        ai += xr * ci[(size_t)k * N + n] + xi * cr[(size_t)k * N + n];
+      }
+      tr[(size_t)r * N + k] = ar; ti[(size_t)r * N + k] = ai;
+    }
+  for (int c = 0; c < N; ++c)
+    for (int k = 0; k < N; ++k) {
+      double ar = 0, ai = 0;
+      for (int n = 0; n < N; ++n) {
+        const double xr = tr[(size_t)n * N + c], xi = ti[(size_t)n * N + c];
+        ar += xr * cr[(size_t)k * N + n] - xi * ci[(size_t)k * N + n];
+        ai += xr * ci[(size_t)k * N + n] + xi * cr[(size_t)k * N + n];
+      }
+      out[(size_t)k * N + c].x = (float)ar; out[(size_t)k * N + c].y = (float)ai;
+    }
+}
+
+struct HostAdmmOps {
+  const float* flat; const cplx* y0; const uint8_t* mask;   // y0 [B,N,N] complex, mask [B,N,N] in natural (centred) order
+  int B, N;
+  size_t n() const { return (size_t)B * N * N; }
+  int slot_get(const cplx* state, cplx* buf, int k) {
+    const size_t HW = (size_t)N * N;
+    for (size_t i = 0; i < n(); ++i) buf[i] = state[((i / HW) * 3 + k) * HW + i % HW];
+    return 0;
+  }
+  int slot_put(cplx* state, const cplx* buf, int k) {
+    const size_t HW = (size_t)N * N;
+    for (size_t i = 0; i < n(); ++i) state[((i / HW) * 3 + k) * HW + i % HW] = buf[i];
+    return 0;
+  }
+  int pre(const cplx* gz, const cplx* gu, const cplx* st_i, const cplx* st_n, cplx* A, cplx* IN) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::admm_pre_elem(i, gz, gu, st_i, st_n, A, IN, N * N);
+    return 0;
+  }
+  // the two modes of masked_fft_step (csmri_variants.cu): G = ifft2c(op(fft2c(in)))
+  int step(const cplx* in, cplx* out, const float* mu_i, bool blend, bool with_y0) {
+    const size_t HW = (size_t)N * N;
+    std::vector<cplx> Z(HW);
+    for (int b = 0; b < B; ++b) {
+      dft2c_host(in + b * HW, Z.data(), N, false);
+      for (size_t p = 0; p < HW; ++p) {
+        const bool on = mask[b * HW + p] != 0;
+        const cplx y = with_y0 ? y0[b * HW + p] : cplx{0.f, 0.f};
+        if (blend) {
+          if (on) { const float m = mu_i[b]; Z[p].x = (m * Z[p].x + y.x) / (1.f + m); Z[p].y = (m * Z[p].y + y.y) / (1.f + m); }
+        } else {
+          if (on) { Z[p].x -= y.x; Z[p].y -= y.y; } else { Z[p].x = 0.f; Z[p].y = 0.f; }
+        }
+      }
+      dft2c_host(Z.data(), out + b * HW, N, true);
+    }
+    return 0;
+  }
+  int blend(const cplx* A, const float* mu_i, cplx* Q) { return step(A, Q, mu_i, true, false); }
+  int residual(const cplx* IN, cplx* R) { return step(IN, R, nullptr, false, true); }
+  int mu_reduce(const cplx* A, const cplx* R, const float* mu_i, float* gmu, int64_t stride) {      // grad_mu_reduce
+    const size_t HW = (size_t)N * N;
+    for (int b = 0; b < B; ++b) {
+      double s = 0;
+      for (size_t p = 0; p < HW; ++p) s += (double)A[b * HW + p].x * R[b * HW + p].x + (double)A[b * HW + p].y * R[b * HW + p].y;
+      const float m = 1.f + mu_i[b];
+      gmu[b * stride] = (float)s / (m * m);
+    }
+    return 0;
+  }
+  int mid(const cplx* gx, cplx* gu, const cplx* Q, const cplx* st_i, float* gxt, float* v) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::admm_mid_elem(i, gx, gu, Q, st_i, gxt, v, N * N);
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg_i, const float* gxt, float* gv, float* gsig, int64_t stride);
+  int post(const float* gv, cplx* gx, cplx* gz, cplx* gu) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::admm_post_elem(i, gv, gx, gz, gu);
+    return 0;
+  }
+};
+
+int unet_vjp_host(const float* weights_flat, const float* x, const float* sigma, int64_t sstride, const float* gout, float* gx,
+                  float* gsigma, int64_t gs_stride, int B, int H, int W) {
+  HostOps ops;
+  ops.flat = weights_flat; ops.B = B; ops.H = H; ops.W = W;
+  ops.init();
+  std::vector<float> ws(grad_elem::unet_vjp_workspace_floats(B, H, W), 0.f);
+  return grad_elem::unet_vjp_sequence(ops, x, sigma, sstride, gout, gx, gsigma, gs_stride, ws.data(), B, H, W);
+}
+
+int HostAdmmOps::den_vjp(const float* v, const float* sg_i, const float* gxt, float* gv, float* gsig, int64_t stride) {
+  return unet_vjp_host(flat, v, sg_i, 1, gxt, gv, gsig, stride, B, N, N);
+}
+
+}  // namespace
+
+// states [iters+1][B,3,N,N,2]; y0 [B,1,N,N,2]; mask [B,1,N,N] u8; sigma_d, mu [B,iters] contiguous; outputs as
+// tfpnp_csmri_admm_backward (include/tfpnp_b200.h)
+extern "C" int emu_admm_backward(const float* weights_flat, const float* states, const float* y0, const uint8_t* mask,
+                                 const float* sigma_d, const float* mu, int B, int N, int iters, const float* grad_out,
+                                 float* g_sigma, float* g_mu, float* g_state_in) {
+  const size_t n = (size_t)B * N * N;
+  std::vector<float> P((size_t)2 * B * iters);                       // gather_params3: [sigma | mu][iters][B]
+  for (int i = 0; i < iters; ++i)
+    for (int b = 0; b < B; ++b) { P[(size_t)i * B + b] = sigma_d[b * iters + i]; P[(size_t)(iters + i) * B + b] = mu[b * iters + i]; }
+  std::vector<cplx> c[7];
+  for (auto& v : c) v.assign(n, cplx{0.f, 0.f});
+  std::vector<float> f[3];
+  for (auto& v : f) v.assign(n, 0.f);
+  HostAdmmOps ops{weights_flat, reinterpret_cast<const cplx*>(y0), mask, B, N};
+  grad_elem::AdmmGradBufs w{c[0].data(), c[1].data(), c[2].data(), c[3].data(), c[4].data(), c[5].data(), c[6].data(),
+                            f[0].data(), f[1].data(), f[2].data()};
+  return grad_elem::admm_backward_sequence(ops, reinterpret_cast<const cplx*>(states), P.data(), B, N * N, iters,
+                                           reinterpret_cast<const cplx*>(grad_out), g_sigma, g_mu,
+                                           reinterpret_cast<cplx*>(g_state_in), w);
+}
+
+extern "C" int emu_unet_vjp(const float* weights_flat, const float* x, const float* sigma, const float* gout, float* gx,
+                            float* gsigma, int B, int H, int W) {
+  return unet_vjp_host(weights_flat, x, sigma, 1, gout, gx, gsigma, 1, B, H, W);
+}

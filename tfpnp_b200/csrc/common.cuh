@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../include/tfpnp_b200.h"
+#include "grad_elem.cuh"
 
 namespace tfpnp {
 
@@ -101,26 +102,7 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-constexpr int kNumUnetConv3 = 27;
-constexpr size_t kUnetParamCount = 11773857;
-
-// UNet(2,1) 3x3 conv layer table in state_dict order (unet.py:37-46):
-// {cin, cout, level} with level = log2 downsampling of the layer's resolution.
-struct ConvSpec { int cin, cout, level; };
-inline const ConvSpec* unet_conv_specs() {
-  static const ConvSpec s[kNumUnetConv3] = {
-      {2, 32, 0},    {32, 32, 0},   {32, 32, 0},     // inc
-      {32, 64, 1},   {64, 64, 1},   {64, 64, 1},     // down1
-      {64, 128, 2},  {128, 128, 2}, {128, 128, 2},   // down2
-      {128, 256, 3}, {256, 256, 3}, {256, 256, 3},   // down3
-      {256, 512, 4}, {512, 512, 4}, {512, 512, 4},   // down4
-      {768, 256, 3}, {256, 256, 3}, {256, 256, 3},   // up1  (cat[skip 256, up 512])
-      {384, 128, 2}, {128, 128, 2}, {128, 128, 2},   // up2  (cat[skip 128, up 256])
-      {192, 64, 1},  {64, 64, 1},   {64, 64, 1},     // up3  (cat[skip 64,  up 128])
-      {96, 32, 0},   {32, 32, 0},   {32, 32, 0},     // up4  (cat[skip 32,  up 64])
-  };
-  return s;
-}
+// kNumUnetConv3, kUnetParamCount, ConvSpec, unet_conv_specs(): grad_elem.cuh (plain C++, shared with the CPU emulation)
 
 // abstract denoiser: d -> clamp(UNet(cat[d, sigma]), 0, 1)
 struct Denoiser {

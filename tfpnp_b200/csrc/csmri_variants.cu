@@ -311,23 +311,12 @@ struct VariantSolver {
 
 
 // ---- reverse mode of the ADMM solver (tfpnp/env/base.py:193-206 under autograd) ------------------------
-// Adjoint of one iteration (x', z', u') = step(z, u; sigma, mu) with incoming (gx', gz', gu'):
-//   gzt = gz' - gu';  q = ifft2c(B_mu fft2c(gzt))  (the k-space blend with y0 = 0 is self-adjoint);
-//   r = ifft2c(M (fft2c(x' + u) - y0));  g_mu = <gzt, r> / (1 + mu)^2;  gxt = Re(gx' + gu' + q);
-//   (gv, g_sigma) = J_D(Re(z - u), sigma)^T gxt;  gz = (gv, 0);  gu = gu' + q - (gv, 0);  gx = 0.
-// Checked on the CPU against autograd through the unmodified reference (oracle/grad_oracle.py, make_golden_grad.py).
-
-// A = gz' - gu';  IN = (Re x' , 0) + u   with x' = slot 0 of the next state, u = slot 2 of this state
+// The adjoint recursion, its per-element bodies and the iteration sequence live in grad_elem.cuh (host+device, run on the
+// CPU by tests/test_grad.py against autograd through the unmodified reference); here: the kernel wrappers and launches.
 __global__ void grad_pre(const float2* __restrict__ GZ, const float2* __restrict__ GU, const float2* __restrict__ st_i,
                          const float2* __restrict__ st_n, float2* __restrict__ A, float2* __restrict__ IN, int HW, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const size_t b = i / HW, p = i % HW;
-  const float2 gz = GZ[i], gu = GU[i];
-  A[i] = make_float2(gz.x - gu.x, gz.y - gu.y);
-  const float2 u = st_i[(b * 3 + 2) * HW + p];
-  const float xr = st_n[(b * 3 + 0) * HW + p].x;
-  IN[i] = make_float2(xr + u.x, u.y);
+  if (i < n) grad_elem::admm_pre_elem(i, GZ, GU, st_i, st_n, A, IN, HW);
 }
 // g_mu[b] = <A, R>_b / (1 + mu[b])^2 ; one CTA per image
 __global__ void __launch_bounds__(256)
@@ -347,29 +336,64 @@ grad_mu_reduce(const float2* __restrict__ A, const float2* __restrict__ R, const
   }
   if (threadIdx.x == 0) { const float m = 1.f + mu[b]; gmu[b * stride] = red[0] / (m * m); }
 }
-// gxt = Re(gx' + gu' + q);  GU += q;  v = Re(z - u) of this state (the denoiser input of the iteration)
 __global__ void grad_mid(const float2* __restrict__ GX, float2* __restrict__ GU, const float2* __restrict__ Q,
                          const float2* __restrict__ st_i, float* __restrict__ gxt, float* __restrict__ v, int HW, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const size_t b = i / HW, p = i % HW;
-  const float2 q = Q[i];
-  float2 gu = GU[i];
-  gxt[i] = GX[i].x + gu.x + q.x;
-  gu.x += q.x; gu.y += q.y;
-  GU[i] = gu;
-  v[i] = st_i[(b * 3 + 1) * HW + p].x - st_i[(b * 3 + 2) * HW + p].x;
+  if (i < n) grad_elem::admm_mid_elem(i, GX, GU, Q, st_i, gxt, v, HW);
 }
-// gz = (gv, 0);  gu -= (gv, 0);  gx = 0
 __global__ void grad_post(const float* __restrict__ gv, float2* __restrict__ GX, float2* __restrict__ GZ,
                           float2* __restrict__ GU, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float g = gv[i];
-  GX[i] = make_float2(0.f, 0.f);
-  GZ[i] = make_float2(g, 0.f);
-  GU[i].x -= g;
+  if (i < n) grad_elem::admm_post_elem(i, gv, GX, GZ, GU);
 }
+
+template <int R>
+struct AdmmGradOps {
+  static constexpr int N = 32 * R;
+  static constexpr int HW = N * N;
+  static constexpr int T256 = 256;
+  Denoiser* den; int B; cudaStream_t st;
+  float2 *T, *y0p, *zero; uint8_t* maskp;
+  size_t n() const { return (size_t)B * HW; }
+  unsigned nb() const { return (unsigned)((n() + T256 - 1) / T256); }
+  int slot_get(const float2* state, float2* buf, int k) {
+    slot_copy<<<nb(), T256, 0, st>>>(state, buf, nullptr, 3, k, HW, n(), 0);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int slot_put(float2* state, const float2* buf, int k) {
+    slot_copy<<<nb(), T256, 0, st>>>(state, const_cast<float2*>(buf), nullptr, 3, k, HW, n(), 1);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int pre(const float2* gz, const float2* gu, const float2* st_i, const float2* st_n, float2* A, float2* IN) {
+    grad_pre<<<nb(), T256, 0, st>>>(gz, gu, st_i, st_n, A, IN, HW, n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int blend(const float2* A, const float* mu_i, float2* Q) {
+    return masked_fft_step<R>(A, Q, T, zero, maskp, mu_i, MODE_BLEND, B, st);
+  }
+  int residual(const float2* IN, float2* Rr) { return masked_fft_step<R>(IN, Rr, T, y0p, maskp, nullptr, MODE_RESIDUAL, B, st); }
+  int mu_reduce(const float2* A, const float2* Rr, const float* mu_i, float* gmu, int64_t stride) {
+    grad_mu_reduce<<<B, 256, 0, st>>>(A, Rr, mu_i, gmu, stride, HW);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int mid(const float2* gx, float2* gu, const float2* Q, const float2* st_i, float* gxt, float* v) {
+    grad_mid<<<nb(), T256, 0, st>>>(gx, gu, Q, st_i, gxt, v, HW, n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg_i, const float* gxt, float* gv, float* gsig, int64_t stride) {
+    return den->vjp(v, sg_i, 1, gxt, gv, gsig, stride, B, N, N, st);
+  }
+  int post(const float* gv, float2* gx, float2* gz, float2* gu) {
+    grad_post<<<nb(), T256, 0, st>>>(gv, gx, gz, gu, n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+};
 
 template <int R>
 int admm_backward(Denoiser* den, const float* states, const float* y0, const uint8_t* mask, const float* sigma_d,
@@ -378,54 +402,27 @@ int admm_backward(Denoiser* den, const float* states, const float* y0, const uin
   constexpr int N = 32 * R;
   const int HW = N * N;
   const size_t n = (size_t)B * HW;
-  const int T256 = 256;
-  const unsigned nb = (unsigned)((n + T256 - 1) / T256);
   DevBuf gx, gz, gu, A, IN, Q, Rr, T, y0p, zero, gxt, v, gv, maskp, P;
-  int rc = 0;
   auto body = [&]() -> int {
     for (DevBuf* b : {&gx, &gz, &gu, &A, &IN, &Q, &Rr, &T, &y0p, &zero}) TFPNP_TRY(b->alloc(n * sizeof(float2)));
     for (DevBuf* b : {&gxt, &v, &gv}) TFPNP_TRY(b->alloc(n * sizeof(float)));
     TFPNP_TRY(maskp.alloc(n));
     TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float)));
     TFPNP_CUDA_OK(cudaMemsetAsync(zero.p, 0, n * sizeof(float2), st));
-    gather_params3<<<cdiv(B * iters, T256), T256, 0, st>>>(sigma_d, mu, nullptr, rs, cs, P.as<float>(), B, iters);
+    gather_params3<<<cdiv(B * iters, 256), 256, 0, st>>>(sigma_d, mu, nullptr, rs, cs, P.as<float>(), B, iters);
     TFPNP_COUNT_LAUNCH();
     TFPNP_TRY(csmri_prep(y0, mask, y0p.as<float2>(), maskp.as<uint8_t>(), B, N, st));
-    const size_t np = (size_t)B * iters;
-    const float2* go = reinterpret_cast<const float2*>(grad_out);
-#define VLAUNCH(kernel, ...) do { kernel<<<nb, T256, 0, st>>>(__VA_ARGS__); TFPNP_COUNT_LAUNCH(); } while (0)
-    VLAUNCH(slot_copy, go, gx.as<float2>(), nullptr, 3, 0, HW, n, 0);
-    VLAUNCH(slot_copy, go, gz.as<float2>(), nullptr, 3, 1, HW, n, 0);
-    VLAUNCH(slot_copy, go, gu.as<float2>(), nullptr, 3, 2, HW, n, 0);
-    const size_t state_elems = n * 3;     // float2 per recorded state
-    for (int i = iters - 1; i >= 0; --i) {
-      const float2* st_i = reinterpret_cast<const float2*>(states) + (size_t)i * state_elems;
-      const float2* st_n = st_i + state_elems;
-      const float* mu_i = P.as<float>() + np + (size_t)i * B;
-      const float* sg_i = P.as<float>() + (size_t)i * B;
-      VLAUNCH(grad_pre, gz.as<float2>(), gu.as<float2>(), st_i, st_n, A.as<float2>(), IN.as<float2>(), HW, n);
-      TFPNP_TRY(masked_fft_step<R>(A.as<float2>(), Q.as<float2>(), T.as<float2>(), zero.as<float2>(), maskp.as<uint8_t>(), mu_i,
-                                   MODE_BLEND, B, st));
-      TFPNP_TRY(masked_fft_step<R>(IN.as<float2>(), Rr.as<float2>(), T.as<float2>(), y0p.as<float2>(), maskp.as<uint8_t>(),
-                                   nullptr, MODE_RESIDUAL, B, st));
-      grad_mu_reduce<<<B, 256, 0, st>>>(A.as<float2>(), Rr.as<float2>(), mu_i, g_mu + i, iters, HW);
-      TFPNP_COUNT_LAUNCH();
-      VLAUNCH(grad_mid, gx.as<float2>(), gu.as<float2>(), Q.as<float2>(), st_i, gxt.as<float>(), v.as<float>(), HW, n);
-      TFPNP_TRY(den->vjp(v.as<float>(), sg_i, 1, gxt.as<float>(), gv.as<float>(), g_sigma + i, iters, B, N, N, st));
-      VLAUNCH(grad_post, gv.as<float>(), gx.as<float2>(), gz.as<float2>(), gu.as<float2>(), n);
-    }
-    if (g_state_in) {
-      float2* gs = reinterpret_cast<float2*>(g_state_in);
-      VLAUNCH(slot_copy, gs, gx.as<float2>(), nullptr, 3, 0, HW, n, 1);
-      VLAUNCH(slot_copy, gs, gz.as<float2>(), nullptr, 3, 1, HW, n, 1);
-      VLAUNCH(slot_copy, gs, gu.as<float2>(), nullptr, 3, 2, HW, n, 1);
-    }
-#undef VLAUNCH
+    AdmmGradOps<R> ops{den, B, st, T.as<float2>(), y0p.as<float2>(), zero.as<float2>(), maskp.as<uint8_t>()};
+    grad_elem::AdmmGradBufs w{gx.as<float2>(), gz.as<float2>(), gu.as<float2>(), A.as<float2>(), IN.as<float2>(),
+                              Q.as<float2>(), Rr.as<float2>(), gxt.as<float>(), v.as<float>(), gv.as<float>()};
+    TFPNP_TRY(grad_elem::admm_backward_sequence(ops, reinterpret_cast<const float2*>(states), P.as<float>(), B, HW, iters,
+                                                reinterpret_cast<const float2*>(grad_out), g_sigma, g_mu,
+                                                reinterpret_cast<float2*>(g_state_in), w));
     TFPNP_CUDA_OK(cudaGetLastError());
-    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers below are freed on return
+    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers are freed on return
     return 0;
   };
-  rc = body();
+  const int rc = body();
   for (DevBuf* b : {&gx, &gz, &gu, &A, &IN, &Q, &Rr, &T, &y0p, &zero, &gxt, &v, &gv, &maskp, &P}) b->release();
   return rc;
 }

@@ -1,0 +1,290 @@
+// Per-element bodies of the reverse-mode kernels of unet_simt.cu, written as host+device functions so the
+// index arithmetic can be exercised on the CPU: tests/test_grad.py compiles this header with g++ (tests/grad_elem_host.cpp)
+// and checks every function against PyTorch autograd.  The __global__ wrappers in unet_simt.cu only compute `i`.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cmath>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define TFPNP_HD __host__ __device__ __forceinline__
+namespace tfpnp { using cplx = float2; }
+#else
+#define TFPNP_HD inline
+namespace tfpnp { struct cplx { float x, y; }; }
+#endif
+
+namespace tfpnp {
+
+constexpr int kNumUnetConv3 = 27;
+constexpr size_t kUnetParamCount = 11773857;
+
+// UNet(2,1) 3x3 conv layer table in state_dict order (unet.py:37-46):
+// {cin, cout, level} with level = log2 downsampling of the layer's resolution.
+struct ConvSpec { int cin, cout, level; };
+inline const ConvSpec* unet_conv_specs() {
+  static const ConvSpec s[kNumUnetConv3] = {
+      {2, 32, 0},    {32, 32, 0},   {32, 32, 0},     // inc
+      {32, 64, 1},   {64, 64, 1},   {64, 64, 1},     // down1
+      {64, 128, 2},  {128, 128, 2}, {128, 128, 2},   // down2
+      {128, 256, 3}, {256, 256, 3}, {256, 256, 3},   // down3
+      {256, 512, 4}, {512, 512, 4}, {512, 512, 4},   // down4
+      {768, 256, 3}, {256, 256, 3}, {256, 256, 3},   // up1  (cat[skip 256, up 512])
+      {384, 128, 2}, {128, 128, 2}, {128, 128, 2},   // up2  (cat[skip 128, up 256])
+      {192, 64, 1},  {64, 64, 1},   {64, 64, 1},     // up3  (cat[skip 64,  up 128])
+      {96, 32, 0},   {32, 32, 0},   {32, 32, 0},     // up4  (cat[skip 32,  up 64])
+  };
+  return s;
+}
+
+namespace grad_elem {
+
+// d/dv LeakyReLU(0.2)(v) from the post-activation value (same sign as v; ATen uses the slope at v <= 0)
+TFPNP_HD float lrelu_d(float a) { return a > 0.f ? 1.f : 0.2f; }
+
+// g_r = gout * 1[0 <= r <= 1] (torch.clamp's backward);  gpre[b,c,p] = w[c] * g_r * lrelu'(a[b,c,p])
+TFPNP_HD void outc_bwd_elem(size_t i, const float* gout, const float* r, const float* w, const float* a, float* gr,
+                            float* gpre, int C, int HW) {
+  const size_t b = i / HW, p = i % HW;
+  const float rv = r[i];
+  const float g = (rv >= 0.f && rv <= 1.f) ? gout[i] : 0.f;
+  gr[i] = g;
+  for (int c = 0; c < C; ++c) {
+    const size_t j = (b * C + c) * HW + p;
+    gpre[j] = w[c] * g * lrelu_d(a[j]);
+  }
+}
+
+// Adjoint of MaxPool2d(2) (first maximum in scan order wins, as in ATen) + the skip-connection gradient + lrelu':
+//   gpre[b,c,Y,X] = ((argmax(b,c,Y/2,X/2) == (Y,X) ? gpool[b,c,Y/2,X/2] : 0) + gskip[b,c,Y,X]) * lrelu'(a[b,c,Y,X])
+// a, gpre: [B,C,H,W]; gpool: [B,C,H/2,W/2], i indexes it; gskip: channels [0,C) of a [B,Ccat,H,W] tensor (nullable)
+TFPNP_HD void pool_bwd_elem(size_t i, const float* gpool, const float* a, const float* gskip, int Ccat, float* gpre, int C,
+                            int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho);
+  const size_t bc = i / ((size_t)Wo * Ho);
+  const int c = (int)(bc % C);
+  const size_t b = bc / C;
+  const size_t base = (bc * H + 2 * y) * W + 2 * x;
+  const float v[4] = {a[base], a[base + 1], a[base + W], a[base + W + 1]};
+  int arg = 0;
+  float best = v[0];
+  for (int k = 1; k < 4; ++k)
+    if (v[k] > best) { best = v[k]; arg = k; }
+  const float gp = gpool[i];
+  const size_t sbase = ((b * Ccat + c) * H + 2 * y) * (size_t)W + 2 * x;
+  for (int k = 0; k < 4; ++k) {
+    const size_t off = (size_t)(k >> 1) * W + (k & 1);
+    const float g = (k == arg ? gp : 0.f) + (gskip ? gskip[sbase + off] : 0.f);
+    gpre[base + off] = g * lrelu_d(v[k]);
+  }
+}
+
+// weight of high-resolution index Y on low-resolution index i for bilinear x2 with align_corners=True (the float
+// expressions of upsample2_simt, so the adjoint is that of the forward kernel)
+TFPNP_HD float up_weight(int Y, int i, int h, float s) {
+  const float f = s * Y;
+  const int y0 = (int)f;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+  const float l = f - y0;
+  return (y0 == i ? 1.f - l : 0.f) + (y1 == i ? l : 0.f);
+}
+
+// Adjoint of the x2 bilinear up-sampling + lrelu' of the low-resolution source:
+//   gpre[b,c,i,j] = lrelu'(a[b,c,i,j]) * sum_{Y,X} wy(Y,i) wx(X,j) gup[b,coff+c,Y,X]
+// gup: channels [coff, coff+C) of a [B,Ccat,2h,2w] tensor; a, gpre: [B,C,h,w], i indexes them.
+// Rows Y in [2i-2, 2i+3] cover every Y with floor(sY) in {i-1, i} since 1/s = 2 + 1/(h-1).
+TFPNP_HD void up_bwd_elem(size_t i, const float* gcat, int Ccat, int coff, const float* a, float* gpre, int C, int h,
+                          int w) {
+  const int xj = (int)(i % w), yi = (int)((i / w) % h);
+  const size_t bc = i / ((size_t)w * h);
+  const int c = (int)(bc % C);
+  const size_t b = bc / C;
+  const int Ho = 2 * h, Wo = 2 * w;
+  const float sy = (float)(h - 1) / (float)(Ho - 1), sx = (float)(w - 1) / (float)(Wo - 1);
+  const float* g = gcat + (b * Ccat + coff + c) * (size_t)Ho * Wo;
+  float wx[6];
+  for (int k = 0; k < 6; ++k) {
+    const int X = 2 * xj - 2 + k;
+    wx[k] = (X >= 0 && X < Wo) ? up_weight(X, xj, w, sx) : 0.f;
+  }
+  float acc = 0.f;
+  for (int m = 0; m < 6; ++m) {
+    const int Y = 2 * yi - 2 + m;
+    if (Y < 0 || Y >= Ho) continue;
+    const float wy = up_weight(Y, yi, h, sy);
+    if (wy == 0.f) continue;
+    float row = 0.f;
+    for (int k = 0; k < 6; ++k) {
+      const int X = 2 * xj - 2 + k;
+      if (wx[k] != 0.f) row = fmaf(wx[k], g[(size_t)Y * Wo + X], row);
+    }
+    acc = fmaf(wy, row, acc);
+  }
+  gpre[i] = acc * lrelu_d(a[i]);
+}
+
+// weights of the input-gradient convolution: [Cout][Cin][3][3] -> [Cin][Cout][3][3] with the taps reversed
+inline void transpose_flip_weights(const float* w, float* t, int cout, int cin) {
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int k = 0; k < 9; ++k) t[((size_t)c * cout + o) * 9 + (8 - k)] = w[((size_t)o * cin + c) * 9 + k];
+}
+
+// ---- the layer sequence of the denoiser's VJP, shared by the CUDA engine (UNetSimt::vjp) and the CPU emulation -------
+// Workspace (floats, per image in units of HW): every layer's activation (366) | in2 2 | pooled 8 | upsampled 64 | r 1 |
+// g_r 1 | gA 32 | gB 32 | gcat[level 0..3] 96 + 48 + 24 + 12.
+inline size_t unet_vjp_workspace_floats(int B, int H, int W) {
+  const ConvSpec* sp = unet_conv_specs();
+  const size_t HW = (size_t)H * W;
+  size_t units = 0;
+  for (int l = 0; l < kNumUnetConv3; ++l) units += ((size_t)sp[l].cout * HW) >> (2 * sp[l].level);
+  units += (2 + 8 + 64 + 1 + 1 + 32 + 32 + 96 + 48 + 24 + 12) * HW;
+  return units * B;
+}
+
+// Ops: make_input, conv (forward layer: bias + LeakyReLU), maxpool, upsample, outc_pre, outc_bwd, dgrad (input gradient
+// of layer l), lrelu_bwd, pool_bwd, up_bwd, first_finish -- each returns 0 on success.  Tensors are NCHW fp32.
+template <class Ops>
+int unet_vjp_sequence(Ops& ops, const float* x, const float* sigma, int64_t sstride, const float* gout, float* gx,
+                      float* gsigma, int64_t gs_stride, float* base, int B, int H, int W) {
+  const ConvSpec* sp = unet_conv_specs();
+  const size_t HW = (size_t)H * W;
+  float* a[kNumUnetConv3];
+  size_t off = 0;
+  auto carve = [&](size_t floats_per_image) { float* p = base + off; off += floats_per_image * B; return p; };
+  for (int l = 0; l < kNumUnetConv3; ++l) a[l] = carve(((size_t)sp[l].cout * HW) >> (2 * sp[l].level));
+  float* in2 = carve(2 * HW);
+  float* pooled = carve(8 * HW);
+  float* upbuf = carve(64 * HW);
+  float* r = carve(HW);
+  float* gr = carve(HW);
+  float* gA = carve(32 * HW);
+  float* gB = carve(32 * HW);
+  float* gcat[4] = {carve(96 * HW), carve(48 * HW), carve(24 * HW), carve(12 * HW)};
+  const int ch[5] = {32, 64, 128, 256, 512};
+#define TFPNP_SEQ(expr) do { int _s = (expr); if (_s != 0) return _s; } while (0)
+  // forward, every activation kept
+  TFPNP_SEQ(ops.make_input(x, sigma, sstride, in2));
+  TFPNP_SEQ(ops.conv(0, in2, 2, nullptr, 0, a[0], H, W));
+  TFPNP_SEQ(ops.conv(1, a[0], 32, nullptr, 0, a[1], H, W));
+  TFPNP_SEQ(ops.conv(2, a[1], 32, nullptr, 0, a[2], H, W));
+  for (int lv = 1; lv <= 4; ++lv) {
+    const int h = H >> lv, w = W >> lv, l0 = 3 * lv;
+    TFPNP_SEQ(ops.maxpool(a[l0 - 1], pooled, ch[lv - 1], 2 * h, 2 * w));
+    TFPNP_SEQ(ops.conv(l0, pooled, ch[lv - 1], nullptr, 0, a[l0], h, w));
+    TFPNP_SEQ(ops.conv(l0 + 1, a[l0], ch[lv], nullptr, 0, a[l0 + 1], h, w));
+    TFPNP_SEQ(ops.conv(l0 + 2, a[l0 + 1], ch[lv], nullptr, 0, a[l0 + 2], h, w));
+  }
+  for (int k = 0; k < 4; ++k) {
+    const int lv = 3 - k, h = H >> lv, w = W >> lv, l0 = 15 + 3 * k;
+    TFPNP_SEQ(ops.upsample(a[l0 - 1], upbuf, ch[lv + 1], h / 2, w / 2));
+    TFPNP_SEQ(ops.conv(l0, a[3 * lv + 2], ch[lv], upbuf, ch[lv + 1], a[l0], h, w));      // cat[skip, up]  (unet.py:119)
+    TFPNP_SEQ(ops.conv(l0 + 1, a[l0], ch[lv], nullptr, 0, a[l0 + 1], h, w));
+    TFPNP_SEQ(ops.conv(l0 + 2, a[l0 + 1], ch[lv], nullptr, 0, a[l0 + 2], h, w));
+  }
+  TFPNP_SEQ(ops.outc_pre(a[26], x, r));
+  // backward: `cur` = gradient w.r.t. the pre-activation output of layer l
+  float* cur = gA;
+  float* oth = gB;
+  TFPNP_SEQ(ops.outc_bwd(gout, r, a[26], gr, cur));
+  for (int l = 26; l >= 1; --l) {
+    const int lv = sp[l].level, h = H >> lv, w = W >> lv;
+    if (l >= 15 && (l - 15) % 3 == 0) {
+      // decoder block head: input = cat[skip(level lv), up(a[l-1])]  (unet.py:99-121)
+      TFPNP_SEQ(ops.dgrad(l, cur, gcat[lv], h, w));
+      TFPNP_SEQ(ops.up_bwd(gcat[lv], sp[l].cin, ch[lv], a[l - 1], cur, ch[lv + 1], h / 2, w / 2));
+    } else if (l <= 12 && l % 3 == 0) {
+      // encoder block head: input = maxpool(a[l-1]); a[l-1] is also the skip of level lv-1  (unet.py:80-90)
+      TFPNP_SEQ(ops.dgrad(l, cur, oth, h, w));
+      TFPNP_SEQ(ops.pool_bwd(oth, a[l - 1], gcat[lv - 1], ch[lv - 1] + ch[lv], cur, ch[lv - 1], 2 * h, 2 * w));
+    } else {
+      TFPNP_SEQ(ops.dgrad(l, cur, oth, h, w));
+      TFPNP_SEQ(ops.lrelu_bwd(oth, a[l - 1], (size_t)B * sp[l].cin * h * w));
+      float* t = cur; cur = oth; oth = t;
+    }
+  }
+  TFPNP_SEQ(ops.dgrad(0, cur, oth, H, W));      // [B,2,H,W]: d/dx through the network, d/d(noise map)
+  TFPNP_SEQ(ops.first_finish(oth, gr, gx, gsigma, gs_stride));
+#undef TFPNP_SEQ
+  return 0;
+}
+
+// ---- reverse mode of ADMMSolver_CSMRI.forward (csmri_variants.cu: admm_backward) -----------------------------------
+// Adjoint of one iteration (x', z', u') = step(z, u; sigma, mu) with incoming (gx', gz', gu'):
+//   gzt = gz' - gu';  q = ifft2c(B_mu fft2c(gzt))  (the k-space blend with y0 = 0 is self-adjoint);
+//   r = ifft2c(M (fft2c(x' + u) - y0));  g_mu = <gzt, r> / (1 + mu)^2;  gxt = Re(gx' + gu' + q);
+//   (gv, g_sigma) = J_D(Re(z - u), sigma)^T gxt;  gz = (gv, 0);  gu = gu' + q - (gv, 0);  gx = 0.
+// States are [B,3,HW] complex (x, z, u).
+
+// A = gz' - gu';  IN = (Re x', 0) + u   with x' = slot 0 of the next state, u = slot 2 of this state
+TFPNP_HD void admm_pre_elem(size_t i, const cplx* GZ, const cplx* GU, const cplx* st_i, const cplx* st_n, cplx* A, cplx* IN,
+                            int HW) {
+  const size_t b = i / HW, p = i % HW;
+  const cplx gz = GZ[i], gu = GU[i];
+  A[i].x = gz.x - gu.x; A[i].y = gz.y - gu.y;
+  const cplx u = st_i[(b * 3 + 2) * HW + p];
+  const float xr = st_n[(b * 3 + 0) * HW + p].x;
+  IN[i].x = xr + u.x; IN[i].y = u.y;
+}
+// gxt = Re(gx' + gu' + q);  GU += q;  v = Re(z - u) of this state (the denoiser input of the iteration)
+TFPNP_HD void admm_mid_elem(size_t i, const cplx* GX, cplx* GU, const cplx* Q, const cplx* st_i, float* gxt, float* v,
+                            int HW) {
+  const size_t b = i / HW, p = i % HW;
+  const cplx q = Q[i];
+  cplx gu = GU[i];
+  gxt[i] = GX[i].x + gu.x + q.x;
+  gu.x += q.x; gu.y += q.y;
+  GU[i] = gu;
+  v[i] = st_i[(b * 3 + 1) * HW + p].x - st_i[(b * 3 + 2) * HW + p].x;
+}
+// gz = (gv, 0);  gu -= (gv, 0);  gx = 0
+TFPNP_HD void admm_post_elem(size_t i, const float* gv, cplx* GX, cplx* GZ, cplx* GU) {
+  const float g = gv[i];
+  GX[i].x = 0.f; GX[i].y = 0.f;
+  GZ[i].x = g; GZ[i].y = 0.f;
+  GU[i].x -= g;
+}
+
+struct AdmmGradBufs {      // [B,HW] each
+  cplx *gx, *gz, *gu, *A, *IN, *Q, *R;
+  float *gxt, *v, *gv;
+};
+
+// Ops: slot_get / slot_put (slot k of a [B,3,HW] state <-> [B,HW]), pre, blend (Q = ifft2c(B_mu fft2c(A))), residual
+// (R = ifft2c(M (fft2c(IN) - y0))), mu_reduce, mid, den_vjp, post -- each returns 0 on success.
+// P: hyper-parameters transposed, sigma_d at P[i*B + b], mu at P[(iters + i)*B + b].  g_sigma / g_mu: [B,iters] contiguous.
+template <class Ops>
+int admm_backward_sequence(Ops& ops, const cplx* states, const float* P, int B, int HW, int iters, const cplx* grad_out,
+                           float* g_sigma, float* g_mu, cplx* g_state_in, const AdmmGradBufs& w) {
+#define TFPNP_SEQ(expr) do { int _s = (expr); if (_s != 0) return _s; } while (0)
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gx, 0));
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gz, 1));
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gu, 2));
+  const size_t state_elems = (size_t)B * HW * 3;
+  const size_t np = (size_t)B * iters;
+  for (int i = iters - 1; i >= 0; --i) {
+    const cplx* st_i = states + (size_t)i * state_elems;
+    const cplx* st_n = st_i + state_elems;
+    const float* sg_i = P + (size_t)i * B;
+    const float* mu_i = P + np + (size_t)i * B;
+    TFPNP_SEQ(ops.pre(w.gz, w.gu, st_i, st_n, w.A, w.IN));
+    TFPNP_SEQ(ops.blend(w.A, mu_i, w.Q));
+    TFPNP_SEQ(ops.residual(w.IN, w.R));
+    TFPNP_SEQ(ops.mu_reduce(w.A, w.R, mu_i, g_mu + i, iters));
+    TFPNP_SEQ(ops.mid(w.gx, w.gu, w.Q, st_i, w.gxt, w.v));
+    TFPNP_SEQ(ops.den_vjp(w.v, sg_i, w.gxt, w.gv, g_sigma + i, iters));
+    TFPNP_SEQ(ops.post(w.gv, w.gx, w.gz, w.gu));
+  }
+  if (g_state_in) {
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gx, 0));
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gz, 1));
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gu, 2));
+  }
+#undef TFPNP_SEQ
+  return 0;
+}
+
+}  // namespace grad_elem
+}  // namespace tfpnp

@@ -5,6 +5,7 @@
 // on the GPU against an fp32 result that shares nothing with it but the weights.
 // NCHW fp32 activations, direct 3x3 convolution with shared-memory halo tiles.
 #include "common.cuh"
+#include "grad_elem.cuh"
 #include <vector>
 
 namespace tfpnp {
@@ -149,102 +150,32 @@ __global__ void outc_pre_simt(const float* __restrict__ feat, const float* __res
   r[i] = x[i] + acc;
 }
 
-// g_r = gout * 1[0 <= r <= 1] (torch.clamp's backward);  gpre[b,c,p] = w[c] * g_r * lrelu'(a[b,c,p])
+// element bodies: grad_elem.cuh (host+device, exercised on the CPU by tests/test_grad.py)
 __global__ void outc_bwd_simt(const float* __restrict__ gout, const float* __restrict__ r, const float* __restrict__ w,
                               const float* __restrict__ a, float* __restrict__ gr, float* __restrict__ gpre, int C, int HW,
                               int B) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * HW) return;
-  int b = i / HW, p = i % HW;
-  const float rv = r[i];
-  const float g = (rv >= 0.f && rv <= 1.f) ? gout[i] : 0.f;
-  gr[i] = g;
-  for (int c = 0; c < C; ++c) {
-    const size_t j = ((size_t)b * C + c) * HW + p;
-    gpre[j] = w[c] * g * (a[j] > 0.f ? 1.f : 0.2f);
-  }
+  if (i < (size_t)B * HW) grad_elem::outc_bwd_elem(i, gout, r, w, a, gr, gpre, C, HW);
 }
 
 // g *= lrelu'(a): a is the layer's post-activation output (same sign as the pre-activation)
 __global__ void lrelu_bwd_simt(float* __restrict__ g, const float* __restrict__ a, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) g[i] *= (a[i] > 0.f ? 1.f : 0.2f);
+  if (i < n) g[i] *= grad_elem::lrelu_d(a[i]);
 }
 
-// Adjoint of MaxPool2d(2) (first maximum in scan order wins, as in ATen) + the skip-connection gradient + lrelu':
-//   gpre[b,c,Y,X] = (argmax(b,c,Y/2,X/2) == (Y,X) ? gpool[b,c,Y/2,X/2] : 0) + gskip[b,c,Y,X]) * lrelu'(a[b,c,Y,X])
-// a, gpre: [B,C,H,W]; gpool: [B,C,H/2,W/2]; gskip: channels [0,C) of a [B,Ccat,H,W] tensor (nullable)
+// adjoint of MaxPool2d(2) + skip-connection gradient + lrelu'; one thread per pooled element
 __global__ void pool_bwd_simt(const float* __restrict__ gpool, const float* __restrict__ a, const float* __restrict__ gskip,
                               int Ccat, float* __restrict__ gpre, int C, int H, int W, int B) {
-  const int Ho = H / 2, Wo = W / 2;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * C * Ho * Wo) return;
-  const int x = i % Wo, y = (i / Wo) % Ho;
-  const size_t bc = i / ((size_t)Wo * Ho);
-  const int c = (int)(bc % C);
-  const size_t b = bc / C;
-  const size_t base = (bc * H + 2 * y) * W + 2 * x;
-  const float v[4] = {a[base], a[base + 1], a[base + W], a[base + W + 1]};
-  int arg = 0;
-  float best = v[0];
-#pragma unroll
-  for (int k = 1; k < 4; ++k) if (v[k] > best) { best = v[k]; arg = k; }
-  const float gp = gpool[i];
-  const size_t sbase = ((b * Ccat + c) * H + 2 * y) * (size_t)W + 2 * x;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const size_t off = (size_t)(k >> 1) * W + (k & 1);
-    float g = (k == arg ? gp : 0.f) + (gskip ? gskip[sbase + off] : 0.f);
-    gpre[base + off] = g * (v[k] > 0.f ? 1.f : 0.2f);
-  }
+  if (i < (size_t)B * C * (H / 2) * (W / 2)) grad_elem::pool_bwd_elem(i, gpool, a, gskip, Ccat, gpre, C, H, W);
 }
 
-// weight of high-resolution index Y on low-resolution index i for bilinear x2 with align_corners=True (the float
-// expressions of upsample2_simt, so the adjoint is that of the forward kernel)
-__device__ __forceinline__ float up_weight(int Y, int i, int h, float s) {
-  const float f = s * Y;
-  const int y0 = (int)f;
-  const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-  const float l = f - y0;
-  return (y0 == i ? 1.f - l : 0.f) + (y1 == i ? l : 0.f);
-}
-
-// Adjoint of the x2 bilinear up-sampling + lrelu' of the low-resolution source:
-//   gpre[b,c,i,j] = lrelu'(a[b,c,i,j]) * sum_{Y,X} wy(Y,i) wx(X,j) gup[b,coff+c,Y,X]
-// gup: channels [coff, coff+C) of a [B,Ccat,2h,2w] tensor; a, gpre: [B,C,h,w]
+// adjoint of the x2 bilinear up-sampling + lrelu' of its low-resolution source; one thread per low-resolution element
 __global__ void up_bwd_simt(const float* __restrict__ gcat, int Ccat, int coff, const float* __restrict__ a,
                             float* __restrict__ gpre, int C, int h, int w, int B) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * C * h * w) return;
-  const int xj = i % w, yi = (i / w) % h;
-  const size_t bc = i / ((size_t)w * h);
-  const int c = (int)(bc % C);
-  const size_t b = bc / C;
-  const int Ho = 2 * h, Wo = 2 * w;
-  const float sy = (float)(h - 1) / (float)(Ho - 1), sx = (float)(w - 1) / (float)(Wo - 1);
-  const float* g = gcat + (b * Ccat + coff + c) * (size_t)Ho * Wo;
-  float wx[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const int X = 2 * xj - 2 + k;
-    wx[k] = (X >= 0 && X < Wo) ? up_weight(X, xj, w, sx) : 0.f;
-  }
-  float acc = 0.f;
-#pragma unroll
-  for (int m = 0; m < 6; ++m) {
-    const int Y = 2 * yi - 2 + m;
-    if (Y < 0 || Y >= Ho) continue;
-    const float wy = up_weight(Y, yi, h, sy);
-    if (wy == 0.f) continue;
-    float row = 0.f;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int X = 2 * xj - 2 + k;
-      if (wx[k] != 0.f) row = fmaf(wx[k], g[(size_t)Y * Wo + X], row);
-    }
-    acc = fmaf(wy, row, acc);
-  }
-  gpre[i] = acc * (a[i] > 0.f ? 1.f : 0.2f);
+  if (i < (size_t)B * C * h * w) grad_elem::up_bwd_elem(i, gcat, Ccat, coff, a, gpre, C, h, w);
 }
 
 // gx = d/d(x) = gin2[:,0] + g_r (the residual connection);  gsigma[b] = sum_p gin2[b,1,p] (the noise map is sigma[b] everywhere)
@@ -387,9 +318,7 @@ struct UNetSimt : Denoiser {
       const int ci = sp[l].cin, co = sp[l].cout;
       const float* w = host_w.data() + w_off[l];
       float* t = h.data() + wt_off[l];
-      for (int o = 0; o < co; ++o)
-        for (int c = 0; c < ci; ++c)
-          for (int k = 0; k < 9; ++k) t[((size_t)c * co + o) * 9 + (8 - k)] = w[((size_t)o * ci + c) * 9 + k];
+      grad_elem::transpose_flip_weights(w, t, co, ci);
     }
     TFPNP_TRY(wt.alloc(total * sizeof(float)));
     TFPNP_CUDA_OK(cudaMemcpy(wt.p, h.data(), total * sizeof(float), cudaMemcpyHostToDevice));
@@ -409,99 +338,72 @@ struct UNetSimt : Denoiser {
   }
 
   // (gx, gsigma) = J(x, sigma)^T gout for out = clamp(x + UNet(cat[x, sigma]), 0, 1): recomputes the forward pass keeping
-  // every layer's activation (fp32 NCHW, 366 HW floats per image), then walks the layers backwards.
+  // every layer's activation (fp32 NCHW, 366 HW floats per image), then walks the layers backwards.  The layer sequence
+  // and the workspace layout are grad_elem::unet_vjp_sequence (shared with the CPU emulation of tests/test_grad.py).
+  struct GradOps {
+    UNetSimt* u; int B, H, W; cudaStream_t st;
+    static constexpr int T = 256;
+    unsigned blocks(size_t n) const { return (unsigned)((n + T - 1) / T); }
+    int make_input(const float* x, const float* sigma, int64_t sstride, float* in2) {
+      make_input_simt<<<blocks((size_t)B * H * W), T, 0, st>>>(x, sigma, sstride, in2, H * W, B);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+    int conv(int l, const float* s0, int C0, const float* s1, int C1, float* out, int h, int w) {
+      return u->conv(l, s0, C0, s1, C1, out, B, h, w, st);
+    }
+    int maxpool(const float* in, float* out, int C, int h, int w) {
+      maxpool2_simt<<<blocks((size_t)B * C * (h / 2) * (w / 2)), T, 0, st>>>(in, out, B * C, h, w);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+    int upsample(const float* in, float* out, int C, int h, int w) {
+      upsample2_simt<<<blocks((size_t)B * C * 4 * h * w), T, 0, st>>>(in, out, B * C, h, w);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+    int outc_pre(const float* a26, const float* x, float* r) {
+      const float* wp = u->weights.as<float>();
+      outc_pre_simt<<<blocks((size_t)B * H * W), T, 0, st>>>(a26, wp + u->outc_w, wp + u->outc_b, x, r, 32, H * W, B);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+    int outc_bwd(const float* gout, const float* r, const float* a26, float* gr, float* gpre) {
+      outc_bwd_simt<<<blocks((size_t)B * H * W), T, 0, st>>>(gout, r, u->weights.as<float>() + u->outc_w, a26, gr, gpre, 32,
+                                                              H * W, B);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+    int dgrad(int l, const float* gin, float* gout, int h, int w) { return u->dgrad(l, gin, gout, B, h, w, st); }
+    int lrelu_bwd(float* g, const float* a, size_t n) {
+      lrelu_bwd_simt<<<blocks(n), T, 0, st>>>(g, a, n);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+    int pool_bwd(const float* gpool, const float* a, const float* gskip, int Ccat, float* gpre, int C, int h, int w) {
+      pool_bwd_simt<<<blocks((size_t)B * C * (h / 2) * (w / 2)), T, 0, st>>>(gpool, a, gskip, Ccat, gpre, C, h, w, B);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+    int up_bwd(const float* gcat, int Ccat, int coff, const float* a, float* gpre, int C, int h, int w) {
+      up_bwd_simt<<<blocks((size_t)B * C * h * w), T, 0, st>>>(gcat, Ccat, coff, a, gpre, C, h, w, B);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+    int first_finish(const float* gin2, const float* gr, float* gx, float* gsigma, int64_t gs_stride) {
+      first_bwd_finish_simt<<<B, 256, 0, st>>>(gin2, gr, gx, gsigma, gs_stride, H * W);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+  };
+
   int vjp(const float* x, const float* sigma, int64_t sstride, const float* gout, float* gx, float* gsigma,
           int64_t gs_stride, int B, int H, int W, cudaStream_t st) override {
     TFPNP_CHECK(H % 16 == 0 && W % 16 == 0 && H >= 16 && W >= 16, "UNet needs H,W multiples of 16, got %dx%d", H, W);
     TFPNP_TRY(ensure_grad_weights());
-    const ConvSpec* sp = unet_conv_specs();
-    const size_t HW = (size_t)H * W;
-    // workspace, in units of HW floats per image
-    size_t act_units = 0;
-    size_t a_off[kNumUnetConv3];
-    for (int l = 0; l < kNumUnetConv3; ++l) { a_off[l] = act_units; act_units += (size_t)sp[l].cout * HW >> (2 * sp[l].level); }
-    // (sizes in floats per image from here on)
-    const size_t in2_off = act_units, pool_off = in2_off + 2 * HW, up_off = pool_off + 8 * HW, r_off = up_off + 64 * HW,
-                 gr_off = r_off + HW, gA_off = gr_off + HW, gB_off = gA_off + 32 * HW, gcat_off = gB_off + 32 * HW;
-    const size_t gcat_sz[4] = {96 * HW, 48 * HW, 24 * HW, 12 * HW};   // level 0..3: (skip + up) channels at that level
-    const size_t per_img = gcat_off + gcat_sz[0] + gcat_sz[1] + gcat_sz[2] + gcat_sz[3];
-    TFPNP_TRY(gws.alloc(per_img * B * sizeof(float)));
-    float* base = gws.as<float>();
-    float* a[kNumUnetConv3];
-    for (int l = 0; l < kNumUnetConv3; ++l) a[l] = base + a_off[l] * B;
-    float* in2 = base + in2_off * B;
-    float* pooled = base + pool_off * B;
-    float* upbuf = base + up_off * B;
-    float* r = base + r_off * B;
-    float* gr = base + gr_off * B;
-    float* gA = base + gA_off * B;
-    float* gB = base + gB_off * B;
-    float* gcat[4];
-    gcat[0] = base + gcat_off * B;
-    for (int lv = 1; lv < 4; ++lv) gcat[lv] = gcat[lv - 1] + gcat_sz[lv - 1] * B;
-    const int ch[5] = {32, 64, 128, 256, 512};
-    const int T = 256;
-    const float* wp = weights.as<float>();
-
-    // forward, every activation kept
-    make_input_simt<<<cdiv((int)(B * HW), T), T, 0, st>>>(x, sigma, sstride, in2, (int)HW, B);
-    TFPNP_COUNT_LAUNCH();
-    TFPNP_TRY(conv(0, in2, 2, nullptr, 0, a[0], B, H, W, st));
-    TFPNP_TRY(conv(1, a[0], 32, nullptr, 0, a[1], B, H, W, st));
-    TFPNP_TRY(conv(2, a[1], 32, nullptr, 0, a[2], B, H, W, st));
-    for (int lv = 1; lv <= 4; ++lv) {
-      const int h = H >> lv, w = W >> lv, l0 = 3 * lv;
-      const size_t n = (size_t)B * ch[lv - 1] * h * w;
-      maxpool2_simt<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(a[l0 - 1], pooled, B * ch[lv - 1], h * 2, w * 2);
-      TFPNP_COUNT_LAUNCH();
-      TFPNP_TRY(conv(l0, pooled, ch[lv - 1], nullptr, 0, a[l0], B, h, w, st));
-      TFPNP_TRY(conv(l0 + 1, a[l0], ch[lv], nullptr, 0, a[l0 + 1], B, h, w, st));
-      TFPNP_TRY(conv(l0 + 2, a[l0 + 1], ch[lv], nullptr, 0, a[l0 + 2], B, h, w, st));
-    }
-    for (int k = 0; k < 4; ++k) {
-      const int lv = 3 - k, h = H >> lv, w = W >> lv, l0 = 15 + 3 * k;
-      const size_t n = (size_t)B * ch[lv + 1] * h * w;
-      upsample2_simt<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(a[l0 - 1], upbuf, B * ch[lv + 1], h / 2, w / 2);
-      TFPNP_COUNT_LAUNCH();
-      TFPNP_TRY(conv(l0, a[3 * lv + 2], ch[lv], upbuf, ch[lv + 1], a[l0], B, h, w, st));
-      TFPNP_TRY(conv(l0 + 1, a[l0], ch[lv], nullptr, 0, a[l0 + 1], B, h, w, st));
-      TFPNP_TRY(conv(l0 + 2, a[l0 + 1], ch[lv], nullptr, 0, a[l0 + 2], B, h, w, st));
-    }
-    outc_pre_simt<<<cdiv((int)(B * HW), T), T, 0, st>>>(a[26], wp + outc_w, wp + outc_b, x, r, 32, (int)HW, B);
-    TFPNP_COUNT_LAUNCH();
-
-    // backward
-    float* cur = gA;      // gradient w.r.t. the pre-activation output of layer l
-    float* oth = gB;
-    outc_bwd_simt<<<cdiv((int)(B * HW), T), T, 0, st>>>(gout, r, wp + outc_w, a[26], gr, cur, 32, (int)HW, B);
-    TFPNP_COUNT_LAUNCH();
-    for (int l = 26; l >= 1; --l) {
-      const int lv = sp[l].level, h = H >> lv, w = W >> lv;
-      if (l >= 15 && (l - 15) % 3 == 0) {
-        // decoder block head: input = cat[skip(level lv), up(a[l-1])]  (unet.py:99-121)
-        TFPNP_TRY(dgrad(l, cur, gcat[lv], B, h, w, st));
-        const size_t n = (size_t)B * ch[lv + 1] * (h / 2) * (w / 2);
-        up_bwd_simt<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(gcat[lv], sp[l].cin, ch[lv], a[l - 1], cur, ch[lv + 1], h / 2,
-                                                               w / 2, B);
-        TFPNP_COUNT_LAUNCH();
-      } else if (l <= 12 && l % 3 == 0) {
-        // encoder block head: input = maxpool(a[l-1]); a[l-1] is also the skip of level lv-1  (unet.py:80-90)
-        TFPNP_TRY(dgrad(l, cur, oth, B, h, w, st));
-        const size_t n = (size_t)B * ch[lv - 1] * h * w;
-        pool_bwd_simt<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(oth, a[l - 1], gcat[lv - 1], ch[lv - 1] + ch[lv], cur,
-                                                                 ch[lv - 1], 2 * h, 2 * w, B);
-        TFPNP_COUNT_LAUNCH();
-      } else {
-        TFPNP_TRY(dgrad(l, cur, oth, B, h, w, st));
-        const size_t n = (size_t)B * sp[l].cin * h * w;
-        lrelu_bwd_simt<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(oth, a[l - 1], n);
-        TFPNP_COUNT_LAUNCH();
-        float* t = cur; cur = oth; oth = t;
-      }
-    }
-    TFPNP_TRY(dgrad(0, cur, oth, B, H, W, st));      // [B,2,H,W]: d/dx through the network, d/d(noise map)
-    first_bwd_finish_simt<<<B, 256, 0, st>>>(oth, gr, gx, gsigma, gs_stride, (int)HW);
-    TFPNP_COUNT_LAUNCH();
+    TFPNP_TRY(gws.alloc(grad_elem::unet_vjp_workspace_floats(B, H, W) * sizeof(float)));
+    GradOps ops{this, B, H, W, st};
+    TFPNP_TRY(grad_elem::unet_vjp_sequence(ops, x, sigma, sstride, gout, gx, gsigma, gs_stride, gws.as<float>(), B, H, W));
     TFPNP_CUDA_OK(cudaGetLastError());
     return 0;
   }
