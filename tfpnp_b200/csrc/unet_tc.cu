@@ -1425,7 +1425,7 @@ struct UNetTc : Denoiser {
   std::vector<ConvParams> convs; // layers 1..26 -> convs[l]
   std::vector<int> conv_bn;
   std::vector<Conv2Plan> convs2; // v2 (halo-tile) plans; grid == 0 -> layer uses v1
-  std::vector<ConvPairPlan> convsp; // CTA-pair plans (opt-in); grid == 0 -> layer uses v2 / v1
+  std::vector<ConvPairPlan> convsp; // CTA-pair plans (default where eligible); grid == 0 -> layer uses v2 / v1
 
   int init(const float* host) {
     const ConvSpec* sp = unet_conv_specs();
