@@ -39,7 +39,50 @@ void conv3x3_host(const float* s0, int C0, const float* s1, int C1, const float*
     }
 }
 
+// stand-in for the tcgen05 kernel (conv_v1_*): NHWC fp16 in/out, weights [tap][rows][K] fp16, fp32 accumulate,
+// out = max(v, slope v) rounded to fp16
+// With residual planes (FP16X3): the three products x_hi w_hi + x_lo w_hi + x_hi w_lo, and Y split into hi + residual.
+void conv3x3_tc_host(const uint16_t* X, const uint16_t* Xlo, int K, const uint16_t* Wt, const uint16_t* Wlo, const float* bias,
+                     float slope, uint16_t* Y, uint16_t* Ylo, int rows, int B, int H, int W) {
+  std::vector<float> xf((size_t)B * H * W * K), wf((size_t)9 * rows * K), xl, wl;
+  for (size_t i = 0; i < xf.size(); ++i) xf[i] = grad_elem::h2f_bits(X[i]);
+  for (size_t i = 0; i < wf.size(); ++i) wf[i] = grad_elem::h2f_bits(Wt[i]);
+  if (Xlo) {
+    xl.resize(xf.size()); wl.resize(wf.size());
+    for (size_t i = 0; i < xf.size(); ++i) xl[i] = grad_elem::h2f_bits(Xlo[i]);
+    for (size_t i = 0; i < wf.size(); ++i) wl[i] = grad_elem::h2f_bits(Wlo[i]);
+  }
+  for (int b = 0; b < B; ++b)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x)
+        for (int r = 0; r < rows; ++r) {
+          float acc = bias ? bias[r] : 0.f;
+          for (int t = 0; t < 9; ++t) {
+            const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float* xp = xf.data() + (((size_t)b * H + yy) * W + xx) * K;
+            const float* wp = wf.data() + ((size_t)t * rows + r) * K;
+            float s = 0.f;
+            for (int k = 0; k < K; ++k) s += xp[k] * wp[k];
+            if (Xlo) {
+              const float* xlp = xl.data() + (xp - xf.data());
+              const float* wlp = wl.data() + (wp - wf.data());
+              for (int k = 0; k < K; ++k) s += xlp[k] * wp[k] + xp[k] * wlp[k];
+            }
+            acc += s;
+          }
+          const float v = acc > slope * acc ? acc : slope * acc;
+          const size_t o = (((size_t)b * H + y) * W + x) * rows + r;
+          Y[o] = grad_elem::f2h_bits(v);
+          if (Ylo) Ylo[o] = grad_elem::f2h_bits(v - grad_elem::h2f_bits(Y[o]));
+        }
+}
+
 struct HostOps {
+  int tc = 0;                              // convolutions through the fp16 (1) / split-fp16 (2) NHWC path (TFPNP_GRAD_TC)
+  std::vector<uint16_t> X, Y, Xlo, Ylo;
+  uint16_t* lo(std::vector<uint16_t>& v) { return tc == 2 ? v.data() : nullptr; }
+  std::vector<float> scale;
   const float* flat;                       // state_dict floats
   size_t w_off[kNumUnetConv3], b_off[kNumUnetConv3], outc_w, outc_b;
   std::vector<float> wt;                   // transposed + flipped weights
@@ -65,9 +108,30 @@ struct HostOps {
       for (size_t p = 0; p < HW; ++p) { in2[(size_t)b * 2 * HW + p] = x[b * HW + p]; in2[((size_t)b * 2 + 1) * HW + p] = sigma[b * sstride]; }
     return 0;
   }
+  void to_half(const float* src, int C, int Ctot, int coff, int hw, const float* sc) {
+    for (size_t i = 0; i < (size_t)B * C * hw; ++i) grad_elem::to_half_nhwc_elem(i, src, X.data(), lo(Xlo), C, Ctot, coff, hw, sc);
+  }
+  void from_half(size_t yoff, float* dst, int C, int Ctot, int coff, int hw, const float* sc) {
+    for (size_t i = 0; i < (size_t)B * C * hw; ++i)
+      grad_elem::from_half_nhwc_elem(i, Y.data() + yoff, tc == 2 ? Ylo.data() + yoff : nullptr, dst, C, Ctot, coff, hw, sc);
+  }
+  void reset_xy() {
+    const size_t n = (size_t)96 * H * W * B;
+    X.assign(n, 0); Y.assign(n, 0); Xlo.assign(n, 0); Ylo.assign(n, 0);
+  }
   int conv(int l, const float* s0, int C0, const float* s1, int C1, float* out, int h, int w) {
     const ConvSpec& sp = unet_conv_specs()[l];
     if (C0 + C1 != sp.cin) return -1;
+    if (tc && l >= 1) {                    // UNetSimt::GradOps::conv, tensor-core branch
+      reset_xy();
+      to_half(s0, C0, C0 + C1, 0, h * w, nullptr);
+      if (s1) to_half(s1, C1, C0 + C1, C0, h * w, nullptr);
+      std::vector<uint16_t> wt16((size_t)9 * sp.cout * sp.cin), wl16(wt16.size());
+      grad_elem::build_tc_weights(flat + w_off[l], sp.cout, sp.cin, false, 0, sp.cout, wt16.data(), lo(wl16));
+      conv3x3_tc_host(X.data(), lo(Xlo), sp.cin, wt16.data(), lo(wl16), flat + b_off[l], 0.2f, Y.data(), lo(Ylo), sp.cout, B, h, w);
+      from_half(0, out, sp.cout, sp.cout, 0, h * w, nullptr);
+      return 0;
+    }
     conv3x3_host(s0, C0, s1, C1, flat + w_off[l], flat + b_off[l], out, sp.cout, B, h, w, true);
     return 0;
   }
@@ -113,6 +177,29 @@ struct HostOps {
   }
   int dgrad(int l, const float* gin, float* gout, int h, int w) {
     const ConvSpec& sp = unet_conv_specs()[l];
+    if (tc && l >= 1) {                    // UNetSimt::GradOps::dgrad, tensor-core branch
+      reset_xy();
+      scale.assign(B, 1.f);
+      const size_t per = (size_t)sp.cout * h * w;
+      for (int b = 0; b < B; ++b) {        // absmax_scale_simt
+        float m = 0.f;
+        for (size_t i = 0; i < per; ++i) m = fmaxf(m, fabsf(gin[b * per + i]));
+        scale[b] = grad_elem::pow2_scale(m);
+      }
+      to_half(gin, sp.cout, sp.cout, 0, h * w, scale.data());
+      int rows[2];
+      const int np = grad_elem::dgrad_parts(l, rows);
+      size_t yoff = 0;
+      for (int p = 0, coff = 0, r0 = 0; p < np; coff += rows[p], r0 += rows[p], ++p) {
+        std::vector<uint16_t> wt16((size_t)9 * rows[p] * sp.cout), wl16(wt16.size());
+        grad_elem::build_tc_weights(flat + w_off[l], sp.cout, sp.cin, true, r0, rows[p], wt16.data(), lo(wl16));
+        conv3x3_tc_host(X.data(), lo(Xlo), sp.cout, wt16.data(), lo(wl16), nullptr, 1.0f, Y.data() + yoff,
+                        tc == 2 ? Ylo.data() + yoff : nullptr, rows[p], B, h, w);
+        from_half(yoff, gout, rows[p], sp.cin, coff, h * w, scale.data());
+        yoff += (size_t)B * h * w * rows[p];
+      }
+      return 0;
+    }
     conv3x3_host(gin, sp.cout, nullptr, 0, wt.data() + wt_off[l], nullptr, gout, sp.cin, B, h, w, false);
     return 0;
   }
@@ -236,8 +323,9 @@ struct HostAdmmOps {
 };
 
 int unet_vjp_host(const float* weights_flat, const float* x, const float* sigma, int64_t sstride, const float* gout, float* gx,
-                  float* gsigma, int64_t gs_stride, int B, int H, int W) {
+                  float* gsigma, int64_t gs_stride, int B, int H, int W, int tc = 0) {
   HostOps ops;
+  ops.tc = tc;
   ops.flat = weights_flat; ops.B = B; ops.H = H; ops.W = W;
   ops.init();
   std::vector<float> ws(grad_elem::unet_vjp_workspace_floats(B, H, W), 0.f);
@@ -274,4 +362,10 @@ extern "C" int emu_admm_backward(const float* weights_flat, const float* states,
 extern "C" int emu_unet_vjp(const float* weights_flat, const float* x, const float* sigma, const float* gout, float* gx,
                             float* gsigma, int B, int H, int W) {
   return unet_vjp_host(weights_flat, x, sigma, 1, gout, gx, gsigma, 1, B, H, W);
+}
+
+// the same sequence with every convolution through the fp16 NHWC (tensor-core) branch
+extern "C" int emu_unet_vjp_tc(const float* weights_flat, const float* x, const float* sigma, const float* gout, float* gx,
+                               float* gsigma, int B, int H, int W, int mode) {
+  return unet_vjp_host(weights_flat, x, sigma, 1, gout, gx, gsigma, 1, B, H, W, mode);
 }

@@ -88,6 +88,23 @@ def test_cuda_vjp_sequence_on_cpu(emu):
     assert rel_err(gx, g["den_gx"])[1] <= 1e-5 and rel_err(gs, g["den_gsigma"])[1] <= 1e-5
 
 
+@pytest.mark.parametrize("mode,tol_x,tol_s", [(1, 5e-3, 1e-1), (2, 1e-5, 1e-4)])
+def test_cuda_vjp_sequence_tensor_core_branch_on_cpu(emu, mode, tol_x, tol_s):
+    """TFPNP_GRAD_TC=1/2: the same sequence with every convolution on NHWC fp16 (mode 1) / split-fp16 (mode 2) copies --
+    per-image power-of-two gradient scale, channel-range scatter of the two parts of a decoder head's input gradient,
+    transposed + flipped fp16 weights -- with a loop convolution standing in for the tcgen05 kernel.  d/dsigma is a sum of
+    signed per-pixel terms that mostly cancel, so plain fp16 operands leave it at the 1e-1 level; the split-fp16 mode is
+    the accurate one."""
+    from tfpnp_b200.denoiser import flatten_state_dict
+    g = load_golden("grad_csmri_small")
+    flat = flatten_state_dict(weights("he"))
+    x, s, go = g["den_x"].contiguous(), g["den_sigma"].contiguous(), g["den_gout"].contiguous()
+    gx, gs = torch.zeros_like(x), torch.zeros(2)
+    assert emu.emu_unet_vjp_tc(_ptr(flat), _ptr(x), _ptr(s), _ptr(go), _ptr(gx), _ptr(gs), 2, 32, 32, mode) == 0
+    assert rel_err(gx, g["den_gx"])[0] <= tol_x, rel_err(gx, g["den_gx"])
+    assert rel_err(gs, g["den_gsigma"])[1] <= tol_s, rel_err(gs, g["den_gsigma"])
+
+
 def test_cuda_admm_backward_sequence_on_cpu(emu):
     """admm_backward_sequence + pre/mid/post element bodies over a recorded trajectory.  Tolerance: the gradient is
     piecewise smooth (LeakyReLU / max-pool / clamp switches); a convolution that rounds differently from ATen's flips a
@@ -139,6 +156,29 @@ def test_native_denoiser_vjp_matches_reference_gradients(dev):
     out = den16(x, s)
     ax, as_ = torch.autograd.grad(out, (x, s), g["den_gout"].to(dev))
     assert rel_err(ax, g["den_gx"])[0] <= 1e-3 and rel_err(as_, g["den_gsigma"])[0] <= 1e-3
+
+
+@pytest.mark.gpu
+@needs_grad_flag
+@pytest.mark.parametrize("mode,tol_x,tol_s", [("1", 5e-3, 1e-1), ("2", 1e-3, 1e-3)])
+def test_native_denoiser_vjp_tensor_core_branch(dev, monkeypatch, mode, tol_x, tol_s):
+    """TFPNP_GRAD_TC: the convolutions of the reverse-mode sequences on the tcgen05 kernel (fp16 / split-fp16)."""
+    import tfpnp_b200 as T
+    monkeypatch.setenv("TFPNP_GRAD_TC", mode)
+    g = load_golden("grad_csmri_small")
+    den = T.UNetDenoiser2D(state_dict=weights("he"), precision="fp32_simt")
+    gx, gs = den.vjp(g["den_x"].to(dev), g["den_sigma"].to(dev), g["den_gout"].to(dev))
+    assert rel_err(gx, g["den_gx"])[0] <= tol_x, rel_err(gx, g["den_gx"])
+    assert rel_err(gs, g["den_gsigma"])[1] <= tol_s, rel_err(gs, g["den_gsigma"])
+    # a second shape re-plans the tensor maps; B = 3 is not a multiple of the tile batch
+    x = g["den_x"].to(dev)[:1].repeat(3, 1, 2, 2).contiguous()
+    s3 = g["den_sigma"].to(dev)[:1].repeat(3)
+    go = g["den_gout"].to(dev)[:1].repeat(3, 1, 2, 2).contiguous()
+    monkeypatch.setenv("TFPNP_GRAD_TC", "0")
+    rx, rs = den.vjp(x, s3, go)
+    monkeypatch.setenv("TFPNP_GRAD_TC", mode)
+    gx, gs = den.vjp(x, s3, go)
+    assert rel_err(gx, rx)[0] <= tol_x and rel_err(gs, rs)[1] <= tol_s
 
 
 @pytest.mark.gpu

@@ -5,9 +5,11 @@
 #include <cstddef>
 #include <cstdint>
 #include <cmath>
+#include <cstring>
 
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #define TFPNP_HD __host__ __device__ __forceinline__
 namespace tfpnp { using cplx = float2; }
 #else
@@ -209,6 +211,115 @@ int unet_vjp_sequence(Ops& ops, const float* x, const float* sigma, int64_t sstr
   TFPNP_SEQ(ops.first_finish(oth, gr, gx, gsigma, gs_stride));
 #undef TFPNP_SEQ
   return 0;
+}
+
+// ---- tensor-core variant of the convolutions in the sequences above (TFPNP_GRAD_TC=1) ----------------------------------
+// Activations / gradients stay fp32 NCHW (the element-wise adjoints above are unchanged); every 3x3 convolution -- forward
+// recompute and input gradient -- runs on the tcgen05 kernel (unet_tc.cu: conv_v1_*) on NHWC fp16 copies:
+//   fp32 NCHW --(x scale[b], round to fp16, NHWC)--> X --conv--> Y --(fp32, / scale[b], NCHW channel range)--> result
+// scale[b] is a per-image power of two that puts max|g| into [512, 1024): the backward pass is linear in the cotangent, so
+// the scale is exact and only guards the fp16 range.  Forward activations use scale 1.
+
+// fp32 <-> IEEE binary16 bits, round to nearest even (device: the hardware conversion; host: the same rounding in software)
+TFPNP_HD uint16_t f2h_bits(float f) {
+#ifdef __CUDA_ARCH__
+  return __half_as_ushort(__float2half_rn(f));
+#else
+  uint32_t x; memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7fffffffu;
+  if (x >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0u));   // inf / nan
+  if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                                      // rounds to inf (>= 65520)
+  if (x < 0x33000001u) return (uint16_t)sign;                                                   // rounds to zero (<= 2^-25)
+  int e = (int)(x >> 23) - 127;
+  uint32_t m = (x & 0x7fffffu) | 0x800000u;
+  int shift = e < -14 ? 13 + (-14 - e) : 13;            // subnormal halves lose more bits
+  uint32_t half_m = m >> shift;
+  const uint32_t rem = m & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (half_m & 1u))) ++half_m;
+  if (e < -14) return (uint16_t)(sign | half_m);        // subnormal (a carry into the exponent field is the right answer)
+  return (uint16_t)(sign | (((uint32_t)(e + 15) << 10) + (half_m - 0x400u)));
+#endif
+}
+TFPNP_HD float h2f_bits(uint16_t h) {
+#ifdef __CUDA_ARCH__
+  return __half2float(__ushort_as_half(h));
+#else
+  const uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
+  uint32_t e = (h >> 10) & 0x1fu, m = h & 0x3ffu, x;
+  if (e == 0) {
+    if (m == 0) x = sign;
+    else { int k = 0; while (!(m & 0x400u)) { m <<= 1; ++k; } x = sign | ((uint32_t)(113 - k) << 23) | ((m & 0x3ffu) << 13); }
+  } else if (e == 31) x = sign | 0x7f800000u | (m << 13);
+  else x = sign | ((e + 112) << 23) | (m << 13);
+  float f; memcpy(&f, &x, 4);
+  return f;
+#endif
+}
+
+// power-of-two scale that puts maxabs into [512, 1024); 1 for zero / non-finite input
+TFPNP_HD float pow2_scale(float maxabs) {
+  if (!(maxabs > 0.f) || !(maxabs < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(maxabs, &e);                 // maxabs = m 2^e, m in [0.5, 1)
+  const int k = 10 - e;
+  return ldexpf(1.f, k > 100 ? 100 : k);
+}
+
+// src [B,C,HW] fp32 -> channels [coff, coff+C) of dst [B,HW,Ctot] fp16 bits, times scale[b] (nullable); i over B*C*HW.
+// dst_lo (nullable): the fp16 residual plane of the split-fp16 (FP16X3) mode, v = hi + lo to ~22 bits.
+TFPNP_HD void to_half_nhwc_elem(size_t i, const float* src, uint16_t* dst, uint16_t* dst_lo, int C, int Ctot, int coff, int HW,
+                                const float* scale) {
+  const size_t p = i % HW, bc = i / HW;
+  const int c = (int)(bc % C);
+  const size_t b = bc / C;
+  const float v = src[i] * (scale ? scale[b] : 1.f);
+  const size_t o = (b * HW + p) * Ctot + coff + c;
+  const uint16_t hi = f2h_bits(v);
+  dst[o] = hi;
+  if (dst_lo) dst_lo[o] = f2h_bits(v - h2f_bits(hi));
+}
+// src [B,HW,C] fp16 bits (+ residual plane) -> channels [coff, coff+C) of dst [B,Ctot,HW] fp32, divided by scale[b] (nullable)
+TFPNP_HD void from_half_nhwc_elem(size_t i, const uint16_t* src, const uint16_t* src_lo, float* dst, int C, int Ctot, int coff,
+                                  int HW, const float* scale) {
+  const size_t p = i % HW, bc = i / HW;
+  const int c = (int)(bc % C);
+  const size_t b = bc / C;
+  const float inv = scale ? 1.f / scale[b] : 1.f;      // a power of two: exact
+  const size_t o = (b * HW + p) * C + c;
+  const float v = h2f_bits(src[o]) + (src_lo ? h2f_bits(src_lo[o]) : 0.f);
+  dst[(b * Ctot + coff + c) * HW + p] = v * inv;
+}
+
+// fp16 weights [tap][rows][K] of the tcgen05 convolution kernels from the state_dict tensor w [cout][cin][3][3]:
+//   forward  (transpose_flip = false): rows = output channels [row0, row0+rows), K = cin
+//   backward (transpose_flip = true):  rows = INPUT channels  [row0, row0+rows), K = cout, taps reversed
+// out_lo (nullable): the fp16 residual plane of the split-fp16 mode
+inline void build_tc_weights(const float* w, int cout, int cin, bool transpose_flip, int row0, int rows, uint16_t* out,
+                             uint16_t* out_lo = nullptr) {
+  for (int t = 0; t < 9; ++t)
+    for (int r = 0; r < rows; ++r) {
+      const int K = transpose_flip ? cout : cin;
+      for (int k = 0; k < K; ++k) {
+        const float v = transpose_flip ? w[((size_t)k * cin + (row0 + r)) * 9 + (8 - t)] : w[((size_t)(row0 + r) * cin + k) * 9 + t];
+        const size_t o = ((size_t)t * rows + r) * K + k;
+        out[o] = f2h_bits(v);
+        if (out_lo) out_lo[o] = f2h_bits(v - h2f_bits(out[o]));
+      }
+    }
+}
+
+// the output-channel parts an input-gradient convolution of layer l is split into (the tcgen05 kernel takes 32, 64 or
+// multiples of 128 output channels): decoder heads split at the concatenation boundary (skip | up-sampled)
+inline int dgrad_parts(int l, int rows[2]) {
+  const ConvSpec& sp = unet_conv_specs()[l];
+  if (l >= 15 && (l - 15) % 3 == 0) {
+    const int ch[5] = {32, 64, 128, 256, 512};
+    rows[0] = ch[sp.level]; rows[1] = sp.cin - rows[0];
+    return 2;
+  }
+  rows[0] = sp.cin; rows[1] = 0;
+  return 1;
 }
 
 // ---- reverse mode of ADMMSolver_CSMRI.forward (csmri_variants.cu: admm_backward) -----------------------------------

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "grad_elem.cuh"
 #include <vector>
+#include <cstdlib>
 
 namespace tfpnp {
 namespace {
@@ -200,6 +201,33 @@ first_bwd_finish_simt(const float* __restrict__ gin2, const float* __restrict__ 
   if (threadIdx.x == 0) gsigma[b * gs_stride] = red[0];
 }
 
+// ---- tensor-core convolutions inside the reverse-mode sequences (TFPNP_GRAD_TC=1; grad_elem.cuh) -------------------------
+// scale[b] = power of two that puts max|g[b]| into [512, 1024); one CTA per image
+__global__ void __launch_bounds__(256)
+absmax_scale_simt(const float* __restrict__ g, float* __restrict__ scale, size_t per_image) {
+  __shared__ float red[256];
+  const float* p = g + (size_t)blockIdx.x * per_image;
+  float m = 0.f;
+  for (size_t i = threadIdx.x; i < per_image; i += 256) m = fmaxf(m, fabsf(p[i]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + k]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) scale[blockIdx.x] = grad_elem::pow2_scale(red[0]);
+}
+__global__ void to_half_nhwc_simt(const float* __restrict__ src, uint16_t* __restrict__ dst, uint16_t* __restrict__ dst_lo, int C,
+                                  int Ctot, int coff, int HW, const float* __restrict__ scale, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::to_half_nhwc_elem(i, src, dst, dst_lo, C, Ctot, coff, HW, scale);
+}
+__global__ void from_half_nhwc_simt(const uint16_t* __restrict__ src, const uint16_t* __restrict__ src_lo, float* __restrict__ dst,
+                                    int C, int Ctot, int coff, int HW, const float* __restrict__ scale, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::from_half_nhwc_elem(i, src, src_lo, dst, C, Ctot, coff, HW, scale);
+}
+
 struct UNetSimt : Denoiser {
   DevBuf weights;   // raw state_dict floats
   size_t w_off[kNumUnetConv3], b_off[kNumUnetConv3], outc_w, outc_b;
@@ -308,6 +336,88 @@ struct UNetSimt : Denoiser {
   size_t wt_off[kNumUnetConv3];
   std::vector<float> host_w;   // state_dict floats kept for the lazy build of `wt`
 
+
+  // tensor-core convolutions for the reverse-mode sequences (opt-in: TFPNP_GRAD_TC=1)
+  int grad_tc = 0;              // 0: fp32 CUDA cores; 1: tcgen05 fp16; 2: tcgen05 split-fp16 (FP16X3: hi + residual planes)
+  int tc_mode_built = 0;
+  DevBuf tc_w, tc_wlo, tc_x, tc_xlo, tc_y, tc_ylo, tc_scale;
+  size_t tcw_f[kNumUnetConv3], tcw_b[kNumUnetConv3][2];
+  ConvV1Layer* tc_fwd[kNumUnetConv3] = {};
+  ConvV1Layer* tc_bwd[kNumUnetConv3][2] = {};
+  int tcB = 0, tcH = 0, tcW = 0;
+
+  void free_tc_plans() {
+    for (int l = 0; l < kNumUnetConv3; ++l) {
+      if (tc_fwd[l]) conv_v1_free(tc_fwd[l]);
+      tc_fwd[l] = nullptr;
+      for (int p = 0; p < 2; ++p) { if (tc_bwd[l][p]) conv_v1_free(tc_bwd[l][p]); tc_bwd[l][p] = nullptr; }
+    }
+    tcB = tcH = tcW = 0;
+  }
+
+  int ensure_tc(int B, int H, int W) {
+    const ConvSpec* sp = unet_conv_specs();
+    const bool x3 = grad_tc == 2;
+    if (tc_mode_built != grad_tc) { free_tc_plans(); tc_w.release(); tc_wlo.release(); tc_mode_built = grad_tc; }
+    if (!tc_w.p) {
+      size_t total = 0;
+      for (int l = 1; l < kNumUnetConv3; ++l) {
+        tcw_f[l] = total; total += (size_t)9 * sp[l].cout * sp[l].cin;
+        int rows[2];
+        const int np = grad_elem::dgrad_parts(l, rows);
+        for (int p = 0; p < np; ++p) { tcw_b[l][p] = total; total += (size_t)9 * rows[p] * sp[l].cout; }
+      }
+      std::vector<uint16_t> h(total), hl(x3 ? total : 0);
+      for (int l = 1; l < kNumUnetConv3; ++l) {
+        const float* w = host_w.data() + w_off[l];
+        grad_elem::build_tc_weights(w, sp[l].cout, sp[l].cin, false, 0, sp[l].cout, h.data() + tcw_f[l],
+                                    x3 ? hl.data() + tcw_f[l] : nullptr);
+        int rows[2];
+        const int np = grad_elem::dgrad_parts(l, rows);
+        for (int p = 0, r0 = 0; p < np; r0 += rows[p], ++p)
+          grad_elem::build_tc_weights(w, sp[l].cout, sp[l].cin, true, r0, rows[p], h.data() + tcw_b[l][p],
+                                      x3 ? hl.data() + tcw_b[l][p] : nullptr);
+      }
+      TFPNP_TRY(tc_w.alloc(total * sizeof(uint16_t)));
+      TFPNP_CUDA_OK(cudaMemcpy(tc_w.p, h.data(), total * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      if (x3) {
+        TFPNP_TRY(tc_wlo.alloc(total * sizeof(uint16_t)));
+        TFPNP_CUDA_OK(cudaMemcpy(tc_wlo.p, hl.data(), total * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      }
+    }
+    if (B == tcB && H == tcH && W == tcW) return 0;
+    free_tc_plans();
+    const size_t HW = (size_t)H * W;
+    TFPNP_TRY(tc_x.alloc(96 * HW * B * sizeof(uint16_t)));     // widest operand: cat[skip 32, up 64] at full resolution
+    TFPNP_TRY(tc_y.alloc(96 * HW * B * sizeof(uint16_t)));     // widest result: its input gradient, in two parts
+    TFPNP_TRY(tc_scale.alloc(B * sizeof(float)));
+    if (x3) {
+      TFPNP_TRY(tc_xlo.alloc(96 * HW * B * sizeof(uint16_t)));
+      TFPNP_TRY(tc_ylo.alloc(96 * HW * B * sizeof(uint16_t)));
+    }
+    const __half* W16 = tc_w.as<__half>();
+    const __half* W16lo = x3 ? tc_wlo.as<__half>() : nullptr;
+    const __half* Xlo = x3 ? tc_xlo.as<__half>() : nullptr;
+    __half* Ylo = x3 ? tc_ylo.as<__half>() : nullptr;
+    const float* biases = weights.as<float>();
+    for (int l = 1; l < kNumUnetConv3; ++l) {
+      const int h = H >> sp[l].level, w = W >> sp[l].level;
+      TFPNP_TRY(conv_v1_plan(&tc_fwd[l], tc_x.as<__half>(), Xlo, sp[l].cin, W16 + tcw_f[l], x3 ? W16lo + tcw_f[l] : nullptr,
+                             biases + b_off[l], tc_y.as<__half>(), Ylo, B, h, w, sp[l].cout, 1, 0.2f));
+      int rows[2];
+      const int np = grad_elem::dgrad_parts(l, rows);
+      size_t yoff = 0;
+      for (int p = 0; p < np; ++p) {
+        TFPNP_TRY(conv_v1_plan(&tc_bwd[l][p], tc_x.as<__half>(), Xlo, sp[l].cout, W16 + tcw_b[l][p],
+                               x3 ? W16lo + tcw_b[l][p] : nullptr, zero_bias.as<float>(), tc_y.as<__half>() + yoff,
+                               x3 ? Ylo + yoff : nullptr, B, h, w, rows[p], 1, 1.0f));
+        yoff += (size_t)B * h * w * rows[p];
+      }
+    }
+    tcB = B; tcH = H; tcW = W;
+    return 0;
+  }
+
   int ensure_grad_weights() {
     if (wt.p) return 0;
     const ConvSpec* sp = unet_conv_specs();
@@ -349,8 +459,29 @@ struct UNetSimt : Denoiser {
       TFPNP_COUNT_LAUNCH();
       return 0;
     }
+    int to_half(const float* src, int C, int Ctot, int coff, int hw, const float* scale) {
+      const size_t n = (size_t)B * C * hw;
+      to_half_nhwc_simt<<<blocks(n), T, 0, st>>>(src, u->tc_x.as<uint16_t>(), u->grad_tc == 2 ? u->tc_xlo.as<uint16_t>() : nullptr,
+                                                 C, Ctot, coff, hw, scale, n);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
+    int from_half(size_t yoff, float* dst, int C, int Ctot, int coff, int hw, const float* scale) {
+      const size_t n = (size_t)B * C * hw;
+      from_half_nhwc_simt<<<blocks(n), T, 0, st>>>(u->tc_y.as<uint16_t>() + yoff,
+                                                   u->grad_tc == 2 ? u->tc_ylo.as<uint16_t>() + yoff : nullptr, dst, C, Ctot, coff,
+                                                   hw, scale, n);
+      TFPNP_COUNT_LAUNCH();
+      return 0;
+    }
     int conv(int l, const float* s0, int C0, const float* s1, int C1, float* out, int h, int w) {
-      return u->conv(l, s0, C0, s1, C1, out, B, h, w, st);
+      if (!u->grad_tc || l == 0) return u->conv(l, s0, C0, s1, C1, out, B, h, w, st);
+      // tcgen05 path: cat[s0, s1] -> NHWC fp16 -> conv + bias + LeakyReLU -> fp32 NCHW
+      TFPNP_TRY(to_half(s0, C0, C0 + C1, 0, h * w, nullptr));
+      if (s1) TFPNP_TRY(to_half(s1, C1, C0 + C1, C0, h * w, nullptr));
+      TFPNP_TRY(conv_v1_launch(u->tc_fwd[l], st));
+      const int cout = unet_conv_specs()[l].cout;
+      return from_half(0, out, cout, cout, 0, h * w, nullptr);
     }
     int maxpool(const float* in, float* out, int C, int h, int w) {
       maxpool2_simt<<<blocks((size_t)B * C * (h / 2) * (w / 2)), T, 0, st>>>(in, out, B * C, h, w);
@@ -374,7 +505,25 @@ struct UNetSimt : Denoiser {
       TFPNP_COUNT_LAUNCH();
       return 0;
     }
-    int dgrad(int l, const float* gin, float* gout, int h, int w) { return u->dgrad(l, gin, gout, B, h, w, st); }
+    int dgrad(int l, const float* gin, float* gout, int h, int w) {
+      if (!u->grad_tc || l == 0) return u->dgrad(l, gin, gout, B, h, w, st);
+      // tcgen05 path: per-image power-of-two scale -> NHWC fp16 -> conv with transposed, flipped weights (one launch per
+      // output-channel part) -> fp32 NCHW channel ranges, un-scaled
+      const ConvSpec& sp = unet_conv_specs()[l];
+      float* scale = u->tc_scale.as<float>();
+      absmax_scale_simt<<<B, 256, 0, st>>>(gin, scale, (size_t)sp.cout * h * w);
+      TFPNP_COUNT_LAUNCH();
+      TFPNP_TRY(to_half(gin, sp.cout, sp.cout, 0, h * w, scale));
+      int rows[2];
+      const int np = grad_elem::dgrad_parts(l, rows);
+      size_t yoff = 0;
+      for (int p = 0, coff = 0; p < np; coff += rows[p], ++p) {
+        TFPNP_TRY(conv_v1_launch(u->tc_bwd[l][p], st));
+        TFPNP_TRY(from_half(yoff, gout, rows[p], sp.cin, coff, h * w, scale));
+        yoff += (size_t)B * h * w * rows[p];
+      }
+      return 0;
+    }
     int lrelu_bwd(float* g, const float* a, size_t n) {
       lrelu_bwd_simt<<<blocks(n), T, 0, st>>>(g, a, n);
       TFPNP_COUNT_LAUNCH();
@@ -402,12 +551,21 @@ struct UNetSimt : Denoiser {
     TFPNP_CHECK(H % 16 == 0 && W % 16 == 0 && H >= 16 && W >= 16, "UNet needs H,W multiples of 16, got %dx%d", H, W);
     TFPNP_TRY(ensure_grad_weights());
     TFPNP_TRY(gws.alloc(grad_elem::unet_vjp_workspace_floats(B, H, W) * sizeof(float)));
+    {
+      const char* e = getenv("TFPNP_GRAD_TC");          // tensor-core convolutions: opt-in until validated on a GPU
+      grad_tc = e ? atoi(e) : 0;                        // 1: fp16 operands, 2: split-fp16 (FP16X3)
+      if (grad_tc < 0 || grad_tc > 2) grad_tc = 0;
+    }
+    if (grad_tc) TFPNP_TRY(ensure_tc(B, H, W));
     GradOps ops{this, B, H, W, st};
     TFPNP_TRY(grad_elem::unet_vjp_sequence(ops, x, sigma, sstride, gout, gx, gsigma, gs_stride, gws.as<float>(), B, H, W));
     TFPNP_CUDA_OK(cudaGetLastError());
     return 0;
   }
-  ~UNetSimt() override { weights.release(); ws.release(); wt.release(); zero_bias.release(); gws.release(); }
+  ~UNetSimt() override {
+    free_tc_plans();
+    for (DevBuf* b : {&weights, &ws, &wt, &zero_bias, &gws, &tc_w, &tc_wlo, &tc_x, &tc_xlo, &tc_y, &tc_ylo, &tc_scale}) b->release();
+  }
 };
 
 }  // namespace
