@@ -180,6 +180,10 @@ int tfpnp_fft2(const float* in, float* out, float* workspace, int n_imgs, int N,
 /* ---- reward metric: torch_psnr (tfpnp/env/base.py:237-242) ------------------
  * psnr[b] = 10 log10(1 / mean((clamp(out[b],0,1) - gt[b])^2)); out, gt: [B,HW] */
 int tfpnp_psnr(const float* out, const float* gt, float* psnr, int B, int64_t HW, void* stream);
+/* Reverse mode of tfpnp_psnr (the reward is part of the actor loss, tfpnp/trainer/mddpg/trainer.py:189):
+ * grad_out[b,p] = grad_psnr[b] * d psnr[b] / d out[b,p]; `psnr` is the forward result.  ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+int tfpnp_psnr_backward(const float* out, const float* gt, const float* psnr, const float* grad_psnr, float* grad_out, int B,
+                        int64_t HW, void* stream);
 
 /* ---- environment bookkeeping: PnPEnv.step (tfpnp/env/base.py:157-191) ----------
  * The caller side of the solver on every episode step.  `idx` is a DEVICE vector of int64 row

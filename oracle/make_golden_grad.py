@@ -60,6 +60,30 @@ def main():
          gout=gstate.numpy(), g_sigma_d=ref_gs.numpy(), g_mu=ref_gm.numpy(), g_state=ref_gst.numpy(),
          wsum=weight_checksum(sd), init="he", seed=0)
 
+    # 3. the call the trainer differentiates: ob2, reward = env.forward(ob, action) (tfpnp/env/base.py:193-206), loss through the
+    #    next observation the critic reads (get_eval_ob) and through the PSNR reward (trainer.py:173-189)
+    from . import env_oracle as E
+    from .make_golden import _load_ref_env
+    B, n, pack = 3, 32, 2
+    d = synth.csmri_batch(B, n, pack)
+    data = E.env_data("csmri", d)
+    env = _load_ref_env("csmri")(None, refshim.reference_solver("csmri", sd), 3)
+    ob = env.reset(data={k: v.clone() for k, v in data.items()})
+    g = torch.Generator().manual_seed(17)
+    sg = (d["sigma_d"][:, :pack].clone()).requires_grad_(True)
+    mu = (d["mu"][:, :pack].clone()).requires_grad_(True)
+    action = {"sigma_d": sg, "mu": mu, "idx_stop": torch.zeros(B, dtype=torch.long)}
+    ob2, reward = env.forward(ob, action)
+    eval2 = env.get_eval_ob(ob2)
+    G1 = torch.randn(eval2.shape, generator=g)
+    G2 = torch.randn(reward.shape, generator=g)
+    loss = (eval2 * G1).sum() + (reward * G2).sum()
+    e_gs, e_gm = torch.autograd.grad(loss, (sg, mu))
+    print(f"  env.forward: reward {reward.detach().flatten().tolist()}, |d loss/d sigma_d| {e_gs.abs().max():.3e}, |d loss/d mu| {e_gm.abs().max():.3e}")
+    save("grad_env_csmri", **{"data_" + k: v.numpy() for k, v in data.items()}, sigma_d=sg.detach().numpy(), mu=mu.detach().numpy(),
+         G1=G1.numpy(), G2=G2.numpy(), eval_ob2=eval2.detach().numpy(), reward=reward.detach().numpy(), g_sigma_d=e_gs.numpy(),
+         g_mu=e_gm.numpy(), wsum=weight_checksum(sd), init="he", seed=0, max_episode_step=3)
+
 
 if __name__ == "__main__":
     main()

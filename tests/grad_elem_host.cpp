@@ -369,3 +369,9 @@ extern "C" int emu_unet_vjp_tc(const float* weights_flat, const float* x, const 
                                float* gsigma, int B, int H, int W, int mode) {
   return unet_vjp_host(weights_flat, x, sigma, 1, gout, gx, gsigma, 1, B, H, W, mode);
 }
+
+// psnr_bwd_kernel (misc.cu)
+extern "C" int emu_psnr_bwd(const float* out, const float* gt, const float* psnr, const float* gpsnr, float* gout, int B, int64_t HW) {
+  for (size_t i = 0; i < (size_t)B * HW; ++i) grad_elem::psnr_bwd_elem(i, out, gt, psnr, gpsnr, gout, (size_t)HW);
+  return 0;
+}

@@ -126,6 +126,39 @@ def test_cuda_admm_backward_sequence_on_cpu(emu):
     assert torch.count_nonzero(gst[:, 0]) == 0
 
 
+def test_psnr_backward_element_body_on_cpu(emu):
+    """psnr_bwd_elem (the reward's gradient, tfpnp/env/base.py:237-242 under autograd) against autograd."""
+    from oracle import pnp_oracle as O
+    g = torch.Generator().manual_seed(3)
+    out = (torch.rand(3, 1, 16, 16, generator=g) * 1.4 - 0.2).requires_grad_(True)      # some pixels outside [0, 1]
+    gt = torch.rand(3, 1, 16, 16, generator=g)
+    ps = O.psnr(out, gt)
+    gp = torch.randn(ps.shape, generator=g)
+    ref, = torch.autograd.grad(ps, out, gp)
+    mine = torch.zeros_like(ref)
+    o2, g2, p2, gp2 = out.detach().contiguous(), gt.contiguous(), ps.detach().reshape(-1).contiguous(), gp.reshape(-1).contiguous()
+    assert emu.emu_psnr_bwd(_ptr(o2), _ptr(g2), _ptr(p2), _ptr(gp2), _ptr(mine), 3, 256) == 0
+    assert rel_err(mine, ref)[1] <= 1e-5
+    assert torch.count_nonzero(mine[(out.detach() < 0) | (out.detach() > 1)]) == 0
+
+
+def test_policy_ob_routes_gradient_to_the_variables():
+    """_PackObFn: d/d(variables) of get_policy_ob is the leading channels' gradient (real part for complex states)."""
+    from tfpnp_b200.env import _PackObFn
+    g = torch.Generator().manual_seed(5)
+    v = torch.randn(2, 3, 8, 8, 2, generator=g, requires_grad=True)
+    rest = torch.randn(2, 4, 8, 8, generator=g)
+    packed = torch.cat([v.detach()[..., 0], rest], dim=1)
+    G1 = torch.randn(packed.shape, generator=g)
+    mine, = torch.autograd.grad(_PackObFn.apply(v, packed, 3, True), v, G1)
+    ref, = torch.autograd.grad(torch.cat([v[..., 0], rest], dim=1), v, G1)
+    assert torch.equal(mine, ref)
+    vr = torch.randn(2, 3, 8, 8, generator=g, requires_grad=True)
+    packed = torch.cat([vr.detach(), rest], dim=1)
+    mine, = torch.autograd.grad(_PackObFn.apply(vr, packed, 3, False), vr, G1)
+    assert torch.equal(mine, G1[:, :3])
+
+
 def test_reverse_mode_is_opt_in():
     import tfpnp_b200 as T
     assert T.ADMMSolver_CSMRI.differentiable is False and T.ADMMSolver_CSMRI._has_backward is True
@@ -212,3 +245,30 @@ def test_reverse_mode_off_by_default(dev):
     s = T.ADMMSolver_CSMRI(T.UNetDenoiser2D(state_dict=weights("he"), precision="fp16"))
     with pytest.raises(NotImplementedError):
         s((g["state"].to(dev), (g["y0"].to(dev), g["mask"].to(dev))), (g["sigma_d"].to(dev).requires_grad_(True), g["mu"].to(dev)))
+
+
+@pytest.mark.gpu
+@needs_grad_flag
+@pytest.mark.parametrize("prec,tol", [("fp32_simt", 2e-3), ("fp16", 3e-2)])
+def test_env_forward_under_autograd_matches_reference(dev, prec, tol):
+    """ob2, reward = env.forward(ob, action) differentiated w.r.t. the action as the actor update does
+    (tfpnp/trainer/mddpg/trainer.py:173-189): through the next observation (get_eval_ob) and the PSNR reward.
+    Fixture: the unmodified reference CSMRIEnv + solver under autograd (oracle/make_golden_grad.py)."""
+    import tfpnp_b200 as T
+    g = load_golden("grad_env_csmri")
+    solver = T.ADMMSolver_CSMRI(T.UNetDenoiser2D(state_dict=weights("he"), precision=prec))
+    solver.differentiable = True
+    env = T.CSMRIEnv(None, solver, int(g["max_episode_step"])).to(dev)
+    data = {k[5:]: v.to(dev) for k, v in g.items() if k.startswith("data_")}
+    ob = env.reset(data=data)
+    sg = g["sigma_d"].to(dev).requires_grad_(True)
+    mu = g["mu"].to(dev).requires_grad_(True)
+    B = sg.shape[0]
+    ob2, reward = env.forward(ob, {"sigma_d": sg, "mu": mu, "idx_stop": torch.zeros(B, dtype=torch.long, device=dev)})
+    eval2 = env.get_eval_ob(ob2)
+    assert rel_err(eval2, g["eval_ob2"])[0] <= (1e-4 if prec == "fp32_simt" else 5e-3)
+    assert (reward.detach().cpu() - g["reward"]).abs().max() <= (1e-3 if prec == "fp32_simt" else 5e-2)
+    loss = (eval2 * g["G1"].to(dev)).sum() + (reward * g["G2"].to(dev)).sum()
+    gs, gm = torch.autograd.grad(loss, (sg, mu))
+    assert rel_err(gs, g["g_sigma_d"])[0] <= tol, rel_err(gs, g["g_sigma_d"])
+    assert rel_err(gm, g["g_mu"])[0] <= tol, rel_err(gm, g["g_mu"])

@@ -66,6 +66,7 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p]),
     "tfpnp_fft2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tfpnp_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "tfpnp_psnr_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "tfpnp_env_gather": (C.c_int, [C.POINTER(GatherItem), C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "tfpnp_env_scatter_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_int, C.c_void_p]),

@@ -7,6 +7,10 @@
 #include <cmath>
 #include <cstring>
 
+#ifndef __CUDACC__
+inline float exp10f_portable(float x) { return powf(10.f, x); }
+#define exp10f exp10f_portable
+#endif
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -320,6 +324,18 @@ inline int dgrad_parts(int l, int rows[2]) {
   }
   rows[0] = sp.cin; rows[1] = 0;
   return 1;
+}
+
+// ---- reverse mode of torch_psnr (tfpnp/env/base.py:237-242): psnr = 10 log10(1 / mean((clamp(out,0,1) - gt)^2)) ---------
+//   d psnr / d out[p] = -(10 / ln 10) (2 / HW) (clamp(out[p]) - gt[p]) 1[0 <= out[p] <= 1] / mse,   mse = 10^(-psnr / 10)
+TFPNP_HD void psnr_bwd_elem(size_t i, const float* out, const float* gt, const float* psnr, const float* gpsnr, float* gout,
+                            size_t HW) {
+  const size_t b = i / HW;
+  const float o = out[i];
+  const bool inside = o >= 0.f && o <= 1.f;
+  const float mse = exp10f(-0.1f * psnr[b]);
+  const float k = -4.342944819032518f * 2.f / (float)HW / mse;      // -(10 / ln 10) (2 / HW) / mse
+  gout[i] = inside ? gpsnr[b] * k * (o - gt[i]) : 0.f;
 }
 
 // ---- reverse mode of ADMMSolver_CSMRI.forward (csmri_variants.cu: admm_backward) -----------------------------------

@@ -30,6 +30,13 @@ psnr_kernel(const float* __restrict__ out, const float* __restrict__ gt, float* 
   }
 }
 
+// d psnr / d out (grad_elem.cuh: psnr_bwd_elem)
+__global__ void psnr_bwd_kernel(const float* __restrict__ out, const float* __restrict__ gt, const float* __restrict__ psnr,
+                                const float* __restrict__ gpsnr, float* __restrict__ gout, size_t HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::psnr_bwd_elem(i, out, gt, psnr, gpsnr, gout, HW);
+}
+
 struct GeomCache {
   std::map<std::pair<int, int>, std::unique_ptr<CtGeom>> m;
   CtGeom* get(int N, int views, const float* c, const float* s) {
@@ -56,6 +63,17 @@ extern "C" {
 int tfpnp_psnr(const float* out, const float* gt, float* psnr, int B, int64_t HW, void* stream) {
   TFPNP_CHECK(out && gt && psnr && B > 0 && HW > 0, "bad argument");
   psnr_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, gt, psnr, HW);
+  TFPNP_COUNT_LAUNCH();
+  TFPNP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int tfpnp_psnr_backward(const float* out, const float* gt, const float* psnr, const float* grad_psnr, float* grad_out, int B,
+                        int64_t HW, void* stream) {
+  TFPNP_CHECK(out && gt && psnr && grad_psnr && grad_out && B > 0 && HW > 0, "bad argument");
+  const size_t n = (size_t)B * HW;
+  psnr_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, gt, psnr, grad_psnr, grad_out,
+                                                                                            (size_t)HW, n);
   TFPNP_COUNT_LAUNCH();
   TFPNP_CUDA_OK(cudaGetLastError());
   return 0;

@@ -207,7 +207,7 @@ class PnPEnv(DifferentiableEnv):
         gt = self._get_attribute(ob, 'gt')
         inputs = self._get_attribute(ob, 'solver_input')
         parameters = self.solver.filter_hyperparameter(action)
-        solver_state = self.solver(inputs, parameters)    # raises NotImplementedError under autograd
+        solver_state = self.solver(inputs, parameters)    # under autograd: opt-in, solver.differentiable = True
         output2 = self.solver.get_output(solver_state)
         reward = self.metric_fn(output2, gt) - self.metric_fn(output, gt)
         return self._build_next_ob(ob, solver_state), reward
@@ -297,7 +297,35 @@ class PnPEnv(DifferentiableEnv):
             with torch.cuda.device(first.device):
                 _lib.check(_lib.lib().tfpnp_env_policy_ob(arr, len(chans), None, B, H * W, dst.data_ptr(),
                                                           _stream(first.device)), "tfpnp_env_policy_ob")
+        v = ob['variables']
+        if torch.is_grad_enabled() and v.requires_grad:
+            # env.forward under autograd (trainer.py:173-187): the critic reads the solver variables of the next
+            # observation through these channels, so they must carry a gradient.  The variables are the leading
+            # channels ('variables' is first in every _policy_channels); the values are the kernel's.
+            key, kind = self._policy_channels[0]
+            assert key == 'variables'
+            nv = v.shape[1]
+            return _PackObFn.apply(v, dst, nv, kind == 'c2real')
         return dst
+
+
+class _PackObFn(torch.autograd.Function):
+    """Identity on the packed observation that routes d/d(ob[:, :nv]) back to the solver variables (pure data movement:
+    'c2real' takes the real part of a complex variable, tfpnp/utils/transforms.py:16-17)."""
+
+    @staticmethod
+    def forward(ctx, variables, packed, nv, complex_state):
+        ctx.nv, ctx.complex_state, ctx.vshape = nv, complex_state, variables.shape
+        return packed.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        gv = torch.zeros(ctx.vshape, device=g.device, dtype=g.dtype)
+        if ctx.complex_state:
+            gv[..., 0] = g[:, :ctx.nv]
+        else:
+            gv.copy_(g[:, :ctx.nv])
+        return gv, None, None, None
 
 
 class CSMRIEnv(PnPEnv):

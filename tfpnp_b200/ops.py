@@ -46,17 +46,46 @@ def radon_backward(sino: torch.Tensor, resolution: int, views: int) -> torch.Ten
     return out
 
 
-def torch_psnr(output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
-    """Per-image PSNR [B,1], tfpnp/env/base.py:237-242, one fused kernel."""
-    assert output.is_cuda and gt.is_cuda
-    N = output.shape[0]
-    o = output.contiguous().float().reshape(N, -1)
-    g = gt.contiguous().float().reshape(N, -1)
+def _psnr_native(o: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    N = o.shape[0]
     res = torch.empty(N, device=o.device, dtype=torch.float32)
     with torch.cuda.device(o.device):
         _lib.check(_lib.lib().tfpnp_psnr(o.data_ptr(), g.data_ptr(), res.data_ptr(), N, o.shape[1],
                                          torch.cuda.current_stream().cuda_stream), "tfpnp_psnr")
-    return res.unsqueeze(1)
+    return res
+
+
+class _PsnrFn(torch.autograd.Function):
+    """torch_psnr under autograd (the reward enters the actor loss, tfpnp/trainer/mddpg/trainer.py:189): native forward,
+    tfpnp_psnr_backward.  Reverse mode is round-1 code that has not run on a GPU yet."""
+
+    @staticmethod
+    def forward(ctx, o, g):
+        res = _psnr_native(o, g)
+        ctx.save_for_backward(o, g, res)
+        return res
+
+    @staticmethod
+    def backward(ctx, gres):
+        o, g, res = ctx.saved_tensors
+        go = torch.empty_like(o)
+        gres = gres.contiguous().float()
+        with torch.cuda.device(o.device):
+            _lib.check(_lib.lib().tfpnp_psnr_backward(o.data_ptr(), g.data_ptr(), res.data_ptr(), gres.data_ptr(), go.data_ptr(),
+                                                      o.shape[0], o.shape[1], torch.cuda.current_stream().cuda_stream),
+                       "tfpnp_psnr_backward")
+        return go, None
+
+
+def torch_psnr(output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """Per-image PSNR [B,1], tfpnp/env/base.py:237-242, one fused kernel (differentiable w.r.t. ``output``)."""
+    assert output.is_cuda and gt.is_cuda
+    N = output.shape[0]
+    o = output.contiguous().float().reshape(N, -1)
+    g = gt.detach().contiguous().float().reshape(N, -1)
+    if torch.is_grad_enabled() and o.requires_grad:
+        return _PsnrFn.apply(o, g).unsqueeze(1)
+    return _psnr_native(o, g).unsqueeze(1)
 
 
 def conv3x3_lrelu_nhwc(x0: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, x1: torch.Tensor = None):
