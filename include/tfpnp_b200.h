@@ -159,6 +159,15 @@ int tfpnp_csmri_admm_backward(void* denoiser, const float* states, const float* 
                               int N, int iters, const float* grad_out, float* grad_sigma_d, float* grad_mu,
                               float* grad_state_in, void* stream);
 
+/* Reverse mode of ADMMSolver_SPI.forward (tasks/spi/solver.py:17-51), same conventions: states [iters+1][B,3,H,W] real,
+ * x0 [B,1,H,W], K [B] with element stride K_stride (the reference's K tensor, i.e. K/10).  Only the closed-form branch of
+ * spi_inverse (K1 == 0, transforms.py:415) carries a gradient: the reference's bisection iterates are constants under
+ * autograd.  ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+int tfpnp_spi_admm_backward(void* denoiser, const float* states, const float* x0, const float* K, int64_t K_stride,
+                            const float* sigma_d, const float* mu, int64_t row_stride, int64_t col_stride, int B, int H,
+                            int W, int iters, const float* grad_out, float* grad_sigma_d, float* grad_mu,
+                            float* grad_state_in, void* stream);
+
 /* ---- CT operators (own discretisation of the reference geometry,
  *      tfpnp/utils/transforms.py:465-491) ------------------------------------- */
 /* img [B,1,N,N] <-> sino [B,1,views,ceil(sqrt(2)N)]; cos/sin: optional HOST tables as above */

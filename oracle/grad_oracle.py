@@ -186,3 +186,52 @@ def denoise_vjp_manual(sd, x: Tensor, sigma: Tensor, gout: Tensor) -> Tuple[Tens
                 cur = dgrad(l, cur) * _lrelu_d(a[l - 1])
         gin2 = dgrad(0, cur)
         return gin2[:, :1] + gr, gin2[:, 1].reshape(B, -1).sum(1)
+
+
+# ----------------------------------------------------------------------------
+# SPI (tasks/spi/solver.py:17-51): only the closed-form branch of spi_inverse carries a gradient
+# ----------------------------------------------------------------------------
+
+def admm_spi_vjp_autograd(sd, state, x0, K, sigma_d, mu, gout):
+    state = state.detach().clone().requires_grad_(True)
+    sigma_d = sigma_d.detach().clone().requires_grad_(True)
+    mu = mu.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        out = O.admm_spi(sd, state, x0, K, sigma_d, mu)
+        gs, gm, gst = torch.autograd.grad(out, (sigma_d, mu, state), gout)
+    return gs, gm, gst
+
+
+def admm_spi_trajectory(sd, state, x0, K, sigma_d, mu):
+    states = [state]
+    with torch.no_grad():
+        for i in range(sigma_d.shape[-1]):
+            states.append(O.admm_spi(sd, states[-1], x0, K, sigma_d[:, i:i + 1], mu[:, i:i + 1]))
+    return states
+
+
+def admm_spi_vjp_manual(sd, states, x0, K, sigma_d, mu, gout, denoise_vjp=denoise_vjp_autograd):
+    """The recursion of grad_elem.cuh: spi_backward_sequence / spi_step_elem."""
+    B, it = sigma_d.shape
+    gx, gz, gu = (t.clone() for t in O._split3(gout))
+    g_sigma, g_mu = torch.zeros(B, it), torch.zeros(B, it)
+    Kv = K[:, 0, 0, 0].reshape(B, 1, 1, 1) * 10
+    Ksq = Kv ** 2
+    K1 = x0 * Ksq
+    for i in reversed(range(it)):
+        x, _, u = O._split3(states[i])
+        _, zn, un = O._split3(states[i + 1])
+        m = mu[:, i].reshape(B, 1, 1, 1)
+        gv, gs = denoise_vjp(sd, zn - un, sigma_d[:, i], gx)
+        g_sigma[:, i] = gs
+        gut = gu - gv
+        gzt = gz + gv - gut
+        K0 = Ksq - K1
+        zpre = (x + u) - K0 / m
+        live = (K1 == 0) & (zpre >= 0) & (zpre <= 1)
+        gt = torch.where(live, gzt, torch.zeros_like(gzt))
+        g_mu[:, i] = (gt * K0 / (m * m)).reshape(B, -1).sum(1)
+        gx = gut + gt
+        gu = gut + gt
+        gz = torch.zeros_like(gz)
+    return g_sigma, g_mu, torch.cat((gx, gz, gu), dim=1)

@@ -60,6 +60,30 @@ def main():
          gout=gstate.numpy(), g_sigma_d=ref_gs.numpy(), g_mu=ref_gm.numpy(), g_state=ref_gst.numpy(),
          wsum=weight_checksum(sd), init="he", seed=0)
 
+    # 2b. SPI (tasks/spi/solver.py:17-51): the "differentiable binary search" of spi_inverse is a constant under autograd
+    d = synth.spi_batch(3, 32, 3)
+    g = torch.Generator().manual_seed(19)
+    # a mid-episode state (x, z, u) instead of reset(): after reset the closed-form pixels (x0 == 0) sit below the clamp
+    # (x + u - K0/mu < 0) and d/dmu would be identically zero
+    d["state"] = torch.cat([torch.rand(3, 1, 32, 32, generator=g) * 1.2, torch.rand(3, 1, 32, 32, generator=g),
+                            torch.rand(3, 1, 32, 32, generator=g) * 0.6], dim=1)
+    gstate = torch.randn(d["state"].shape, generator=g)
+    sol = refshim.reference_solver("spi", sd)
+    st = d["state"].clone().requires_grad_(True)
+    sg = d["sigma_d"].clone().requires_grad_(True)
+    mu = d["mu"].clone().requires_grad_(True)
+    out = sol((st, (d["x0"], d["K"])), (sg, mu))
+    s_gs, s_gm, s_gst = torch.autograd.grad(out, (sg, mu, st), gstate)
+    a = G.admm_spi_vjp_autograd(sd, d["state"], d["x0"], d["K"], d["sigma_d"], d["mu"], gstate)
+    print(f"  SPI vjp (autograd through the oracle) vs reference: sigma_d {close(a[0], s_gs, 1e-5):.2e}  mu {close(a[1], s_gm, 1e-5):.2e}  "
+          f"state {close(a[2], s_gst, 1e-5):.2e}")
+    states = G.admm_spi_trajectory(sd, d["state"], d["x0"], d["K"], d["sigma_d"], d["mu"])
+    m_ = G.admm_spi_vjp_manual(sd, states, d["x0"], d["K"], d["sigma_d"], d["mu"], gstate)
+    print(f"  SPI vjp (adjoint recursion) vs reference:           sigma_d {close(m_[0], s_gs, 1e-4):.2e}  mu {close(m_[1], s_gm, 1e-4):.2e}  "
+          f"state {close(m_[2], s_gst, 1e-4):.2e}   (closed-form pixels: {(d['x0'] == 0).float().mean():.3f})")
+    save("grad_spi_small", **np_({k: d[k] for k in ("state", "x0", "K", "sigma_d", "mu")}), gout=gstate.numpy(),
+         g_sigma_d=s_gs.numpy(), g_mu=s_gm.numpy(), g_state=s_gst.numpy(), wsum=weight_checksum(sd), init="he", seed=0)
+
     # 3. the call the trainer differentiates: ob2, reward = env.forward(ob, action) (tfpnp/env/base.py:193-206), loss through the
     #    next observation the critic reads (get_eval_ob) and through the PSNR reward (trainer.py:173-189)
     from . import env_oracle as E

@@ -375,3 +375,55 @@ extern "C" int emu_psnr_bwd(const float* out, const float* gt, const float* psnr
   for (size_t i = 0; i < (size_t)B * HW; ++i) grad_elem::psnr_bwd_elem(i, out, gt, psnr, gpsnr, gout, (size_t)HW);
   return 0;
 }
+
+// spi_backward (spi.cu): the shared sequence + element bodies with loops for the launches
+namespace {
+struct HostSpiOps {
+  const float* flat; const float* x0; const float* K; int64_t K_stride; int B, H, W;
+  size_t n() const { return (size_t)B * H * W; }
+  int slot_get(const float* state, float* buf, int k) {
+    const size_t HW = (size_t)H * W;
+    for (size_t i = 0; i < n(); ++i) buf[i] = state[((i / HW) * 3 + k) * HW + i % HW];
+    return 0;
+  }
+  int slot_put(float* state, float* buf, int k) {
+    const size_t HW = (size_t)H * W;
+    for (size_t i = 0; i < n(); ++i) state[((i / HW) * 3 + k) * HW + i % HW] = buf[i];
+    return 0;
+  }
+  int make_v(const float* st_n, float* v) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::spi_v_elem(i, st_n, v, H * W);
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg_i, const float* gx, float* gv, float* gsig, int64_t stride) {
+    return unet_vjp_host(flat, v, sg_i, 1, gx, gv, gsig, stride, B, H, W);
+  }
+  int step(const float* st_i, const float* mu_i, const float* gv, float* gx, float* gz, float* gu, float* term) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::spi_step_elem(i, st_i, x0, K, K_stride, mu_i, gv, gx, gz, gu, term, H * W);
+    return 0;
+  }
+  int reduce(const float* term, float* out, int64_t stride) {      // image_sum_kernel
+    const size_t HW = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+      double s = 0;
+      for (size_t p = 0; p < HW; ++p) s += term[b * HW + p];
+      out[b * stride] = (float)s;
+    }
+    return 0;
+  }
+};
+}  // namespace
+
+extern "C" int emu_spi_backward(const float* weights_flat, const float* states, const float* x0, const float* K, int64_t K_stride,
+                                const float* sigma_d, const float* mu, int B, int H, int W, int iters, const float* grad_out,
+                                float* g_sigma, float* g_mu, float* g_state_in) {
+  const size_t n = (size_t)B * H * W;
+  std::vector<float> P((size_t)2 * B * iters);                       // spi_gather_params
+  for (int i = 0; i < iters; ++i)
+    for (int b = 0; b < B; ++b) { P[(size_t)i * B + b] = sigma_d[b * iters + i]; P[(size_t)(iters + i) * B + b] = mu[b * iters + i]; }
+  std::vector<float> f[6];
+  for (auto& v : f) v.assign(n, 0.f);
+  HostSpiOps ops{weights_flat, x0, K, K_stride, B, H, W};
+  grad_elem::SpiGradBufs w{f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data()};
+  return grad_elem::spi_backward_sequence(ops, states, P.data(), B, H * W, iters, grad_out, g_sigma, g_mu, g_state_in, w);
+}

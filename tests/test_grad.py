@@ -126,6 +126,34 @@ def test_cuda_admm_backward_sequence_on_cpu(emu):
     assert torch.count_nonzero(gst[:, 0]) == 0
 
 
+def test_spi_gradients_oracle_and_cuda_sequence_on_cpu(emu):
+    """SPI (tasks/spi/solver.py:17-51): the fixture is autograd through the unmodified reference (a mid-episode state, so
+    the closed-form branch of spi_inverse is live inside the clamp and d/dmu is not identically zero); checked against it:
+    autograd through the oracle, the hand-derived recursion, and the CUDA sequence + element bodies run on the host."""
+    from tfpnp_b200.denoiser import flatten_state_dict
+    g = load_golden("grad_spi_small")
+    sd = weights("he")
+    assert g["g_mu"].abs().max() > 1e-3
+    a = G.admm_spi_vjp_autograd(sd, g["state"], g["x0"], g["K"], g["sigma_d"], g["mu"], g["gout"])
+    for mine, key in zip(a, ("g_sigma_d", "g_mu", "g_state")):
+        assert rel_err(mine, g[key])[1] <= 1e-5
+    states = G.admm_spi_trajectory(sd, g["state"], g["x0"], g["K"], g["sigma_d"], g["mu"])
+    m = G.admm_spi_vjp_manual(sd, states, g["x0"], g["K"], g["sigma_d"], g["mu"], g["gout"], denoise_vjp=G.denoise_vjp_manual)
+    for mine, key in zip(m, ("g_sigma_d", "g_mu", "g_state")):
+        assert rel_err(mine, g[key])[1] <= 1e-4
+    flat = flatten_state_dict(sd)
+    B, it = g["sigma_d"].shape
+    st = torch.stack(states).contiguous()
+    Kv = g["K"][:, 0, 0, 0].contiguous()
+    gs, gm, gst = torch.zeros(B, it), torch.zeros(B, it), torch.zeros_like(g["gout"])
+    rc = emu.emu_spi_backward(_ptr(flat), _ptr(st), _ptr(g["x0"].contiguous()), _ptr(Kv), 1, _ptr(g["sigma_d"].contiguous()),
+                              _ptr(g["mu"].contiguous()), B, 32, 32, it, _ptr(g["gout"].contiguous()), _ptr(gs), _ptr(gm), _ptr(gst))
+    assert rc == 0
+    for mine, key in ((gs, "g_sigma_d"), (gm, "g_mu"), (gst, "g_state")):
+        assert rel_err(mine, g[key])[0] <= 1e-3, (key, rel_err(mine, g[key]))
+    assert torch.count_nonzero(gst[:, 1]) == 0       # z of the input state is never read
+
+
 def test_psnr_backward_element_body_on_cpu(emu):
     """psnr_bwd_elem (the reward's gradient, tfpnp/env/base.py:237-242 under autograd) against autograd."""
     from oracle import pnp_oracle as O
@@ -162,7 +190,9 @@ def test_policy_ob_routes_gradient_to_the_variables():
 def test_reverse_mode_is_opt_in():
     import tfpnp_b200 as T
     assert T.ADMMSolver_CSMRI.differentiable is False and T.ADMMSolver_CSMRI._has_backward is True
-    assert T.IADMMSolver_PR._has_backward is False and T.UNetDenoiser2D.differentiable is False
+    assert T.ADMMSolver_SPI.differentiable is False and T.ADMMSolver_SPI._has_backward is True
+    assert T.IADMMSolver_PR._has_backward is False and T.IADMMSolver_CT._has_backward is False
+    assert T.UNetDenoiser2D.differentiable is False
 
 
 @pytest.fixture(scope="module")
@@ -272,3 +302,20 @@ def test_env_forward_under_autograd_matches_reference(dev, prec, tol):
     gs, gm = torch.autograd.grad(loss, (sg, mu))
     assert rel_err(gs, g["g_sigma_d"])[0] <= tol, rel_err(gs, g["g_sigma_d"])
     assert rel_err(gm, g["g_mu"])[0] <= tol, rel_err(gm, g["g_mu"])
+
+
+@pytest.mark.gpu
+@needs_grad_flag
+@pytest.mark.parametrize("prec,tol", [("fp32_simt", 2e-3), ("fp16", 3e-2)])
+def test_native_spi_backward_matches_reference_gradients(dev, prec, tol):
+    import tfpnp_b200 as T
+    g = load_golden("grad_spi_small")
+    s = T.ADMMSolver_SPI(T.UNetDenoiser2D(state_dict=weights("he"), precision=prec))
+    s.differentiable = True
+    state = g["state"].to(dev).requires_grad_(True)
+    sg = g["sigma_d"].to(dev).requires_grad_(True)
+    mu = g["mu"].to(dev).requires_grad_(True)
+    out = s((state, (g["x0"].to(dev), g["K"].to(dev))), (sg, mu))
+    g_s, g_m, g_st = torch.autograd.grad(out, (sg, mu, state), g["gout"].to(dev))
+    for mine, key in ((g_s, "g_sigma_d"), (g_m, "g_mu"), (g_st, "g_state")):
+        assert rel_err(mine, g[key])[0] <= tol, (prec, key, rel_err(mine, g[key]))

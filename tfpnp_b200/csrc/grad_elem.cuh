@@ -413,5 +413,72 @@ int admm_backward_sequence(Ops& ops, const cplx* states, const float* P, int B, 
   return 0;
 }
 
+// ---- reverse mode of ADMMSolver_SPI.forward (tasks/spi/solver.py:17-51; spi.cu: spi_backward) ---------------------------
+// One iteration: z' = clamp(prox(x + u)), u' = u + x - z', x' = D(z' - u', sigma).  Under autograd the reference's
+// "differentiable binary search" (transforms.py:419-437) is a constant: its iterates are midpoints of a fixed interval, so
+// only the closed-form branch K1 == 0, z = (x + u) - K0 / mu, carries a gradient (through the clamp).  With incoming
+// (gx', gz', gu'):   (gv, g_sigma) = J_D(z' - u', sigma)^T gx';  gzt = gz' + gv;  gut = gu' - gv;  gzt -= gut;
+//   g_t = gzt 1[K1 == 0] 1[0 <= (x + u) - K0/mu <= 1];  gx = gut + g_t;  gu = gut + g_t;  gz = 0;  g_mu = sum g_t K0 / mu^2.
+// States are [B,3,HW] real (x, z, u).
+
+// v = z' - u' (the denoiser input of the iteration) from the NEXT state
+TFPNP_HD void spi_v_elem(size_t i, const float* st_n, float* v, int HW) {
+  const size_t b = i / HW, p = i % HW;
+  v[i] = st_n[(b * 3 + 1) * HW + p] - st_n[(b * 3 + 2) * HW + p];
+}
+// in place on (GX, GZ, GU); term[i] = this pixel's contribution to g_mu
+TFPNP_HD void spi_step_elem(size_t i, const float* st_i, const float* x0, const float* K, int64_t K_stride, const float* mu,
+                            const float* gv, float* GX, float* GZ, float* GU, float* term, int HW) {
+  const size_t b = i / HW, p = i % HW;
+  const float K10 = K[b * K_stride] * 10.f;                // solver.py:32
+  const float Ksq = K10 * K10;
+  const float K1 = x0[i] * Ksq;                            // solver.py:33
+  const float m = mu[b];
+  const float g = gv[i];
+  const float gut = GU[i] - g;
+  const float gzt = GZ[i] + g - gut;
+  float gt = 0.f, t = 0.f;
+  if (K1 == 0.f) {
+    const float K0 = Ksq - K1;
+    const float zpre = (st_i[(b * 3 + 0) * HW + p] + st_i[(b * 3 + 2) * HW + p]) - K0 / m;
+    if (zpre >= 0.f && zpre <= 1.f) { gt = gzt; t = gzt * K0 / (m * m); }
+  }
+  GX[i] = gut + gt;
+  GU[i] = gut + gt;
+  GZ[i] = 0.f;
+  term[i] = t;
+}
+
+struct SpiGradBufs { float *gx, *gz, *gu, *v, *gv, *term; };   // [B,HW] each
+
+// Ops: slot_get / slot_put, make_v, den_vjp(v, sigma_i, gx', gv, g_sigma ptr, stride), step, reduce(term, g_mu ptr, stride)
+template <class Ops>
+int spi_backward_sequence(Ops& ops, const float* states, const float* P, int B, int HW, int iters, const float* grad_out,
+                          float* g_sigma, float* g_mu, float* g_state_in, const SpiGradBufs& w) {
+#define TFPNP_SEQ(expr) do { int _s = (expr); if (_s != 0) return _s; } while (0)
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gx, 0));
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gz, 1));
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gu, 2));
+  const size_t state_elems = (size_t)B * HW * 3;
+  const size_t np = (size_t)B * iters;
+  for (int i = iters - 1; i >= 0; --i) {
+    const float* st_i = states + (size_t)i * state_elems;
+    const float* st_n = st_i + state_elems;
+    const float* sg_i = P + (size_t)i * B;
+    const float* mu_i = P + np + (size_t)i * B;
+    TFPNP_SEQ(ops.make_v(st_n, w.v));
+    TFPNP_SEQ(ops.den_vjp(w.v, sg_i, w.gx, w.gv, g_sigma + i, iters));
+    TFPNP_SEQ(ops.step(st_i, mu_i, w.gv, w.gx, w.gz, w.gu, w.term));
+    TFPNP_SEQ(ops.reduce(w.term, g_mu + i, iters));
+  }
+  if (g_state_in) {
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gx, 0));
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gz, 1));
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gu, 2));
+  }
+#undef TFPNP_SEQ
+  return 0;
+}
+
 }  // namespace grad_elem
 }  // namespace tfpnp

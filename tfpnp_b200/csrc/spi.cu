@@ -78,4 +78,125 @@ int spi_update(const float* x, float* z, float* u, float* d, const float* x0, co
   return 0;
 }
 
+// ---- reverse mode: sequence and element bodies in grad_elem.cuh -----------------------------------------
+namespace {
+
+__global__ void spi_slot_copy(const float* __restrict__ state, float* __restrict__ buf, int k, int HW, size_t n, int to_state) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* s = const_cast<float*>(state) + ((i / HW) * 3 + k) * HW + i % HW;
+  if (to_state) *s = buf[i]; else buf[i] = *s;
+}
+__global__ void spi_v_kernel(const float* __restrict__ st_n, float* __restrict__ v, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::spi_v_elem(i, st_n, v, HW);
+}
+__global__ void spi_step_bwd_kernel(const float* __restrict__ st_i, const float* __restrict__ x0, const float* __restrict__ K,
+                                    int64_t K_stride, const float* __restrict__ mu, const float* __restrict__ gv,
+                                    float* __restrict__ GX, float* __restrict__ GZ, float* __restrict__ GU,
+                                    float* __restrict__ term, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::spi_step_elem(i, st_i, x0, K, K_stride, mu, gv, GX, GZ, GU, term, HW);
+}
+// out[b * stride] = sum_p term[b, p]; one CTA per image
+__global__ void __launch_bounds__(256)
+image_sum_kernel(const float* __restrict__ term, float* __restrict__ out, int64_t stride, int HW) {
+  __shared__ float red[256];
+  const float* t = term + (size_t)blockIdx.x * HW;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) s += t[p];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x * stride] = red[0];
+}
+// hyper-parameters transposed: P[i*B + b] = sigma_d[b, i], P[(iters + i)*B + b] = mu[b, i]
+__global__ void spi_gather_params(const float* __restrict__ sg, const float* __restrict__ mu, int64_t rs, int64_t cs,
+                                  float* __restrict__ P, int B, int iters) {
+  const int n = B * iters;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = t / B, b = t % B;
+    P[t] = sg[b * rs + i * cs];
+    P[n + t] = mu[b * rs + i * cs];
+  }
+}
+
+struct SpiGradOps {
+  Denoiser* den; int B, H, W; cudaStream_t st;
+  const float* x0; const float* K; int64_t K_stride;
+  static constexpr int T = 256;
+  int HW() const { return H * W; }
+  size_t n() const { return (size_t)B * H * W; }
+  unsigned nb() const { return (unsigned)((n() + T - 1) / T); }
+  int slot_get(const float* state, float* buf, int k) {
+    spi_slot_copy<<<nb(), T, 0, st>>>(state, buf, k, HW(), n(), 0);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int slot_put(float* state, float* buf, int k) {
+    spi_slot_copy<<<nb(), T, 0, st>>>(state, buf, k, HW(), n(), 1);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int make_v(const float* st_n, float* v) {
+    spi_v_kernel<<<nb(), T, 0, st>>>(st_n, v, HW(), n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg_i, const float* gx, float* gv, float* gsig, int64_t stride) {
+    return den->vjp(v, sg_i, 1, gx, gv, gsig, stride, B, H, W, st);
+  }
+  int step(const float* st_i, const float* mu_i, const float* gv, float* gx, float* gz, float* gu, float* term) {
+    spi_step_bwd_kernel<<<nb(), T, 0, st>>>(st_i, x0, K, K_stride, mu_i, gv, gx, gz, gu, term, HW(), n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int reduce(const float* term, float* out, int64_t stride) {
+    image_sum_kernel<<<B, 256, 0, st>>>(term, out, stride, HW());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+};
+
+}  // namespace
+
+int spi_backward(Denoiser* den, const float* states, const float* x0, const float* K, int64_t K_stride, const float* sigma_d,
+                 const float* mu, int64_t rs, int64_t cs, int B, int H, int W, int iters, const float* grad_out, float* g_sigma,
+                 float* g_mu, float* g_state_in, cudaStream_t st) {
+  const size_t n = (size_t)B * H * W;
+  DevBuf bufs[6], P;
+  auto body = [&]() -> int {
+    for (DevBuf& b : bufs) TFPNP_TRY(b.alloc(n * sizeof(float)));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 2 * sizeof(float)));
+    spi_gather_params<<<cdiv(B * iters, 256), 256, 0, st>>>(sigma_d, mu, rs, cs, P.as<float>(), B, iters);
+    TFPNP_COUNT_LAUNCH();
+    SpiGradOps ops{den, B, H, W, st, x0, K, K_stride};
+    grad_elem::SpiGradBufs w{bufs[0].as<float>(), bufs[1].as<float>(), bufs[2].as<float>(), bufs[3].as<float>(),
+                             bufs[4].as<float>(), bufs[5].as<float>()};
+    TFPNP_TRY(grad_elem::spi_backward_sequence(ops, states, P.as<float>(), B, H * W, iters, grad_out, g_sigma, g_mu, g_state_in, w));
+    TFPNP_CUDA_OK(cudaGetLastError());
+    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers are freed on return
+    return 0;
+  };
+  const int rc = body();
+  for (DevBuf& b : bufs) b.release();
+  P.release();
+  return rc;
+}
+
 }  // namespace tfpnp
+
+extern "C" int tfpnp_spi_admm_backward(void* denoiser, const float* states, const float* x0, const float* K, int64_t K_stride,
+                                       const float* sigma_d, const float* mu, int64_t row_stride, int64_t col_stride, int B,
+                                       int H, int W, int iters, const float* grad_out, float* grad_sigma_d, float* grad_mu,
+                                       float* grad_state_in, void* stream) {
+  using namespace tfpnp;
+  TFPNP_CHECK(denoiser && states && x0 && K && sigma_d && mu && grad_out && grad_sigma_d && grad_mu && B > 0 && iters > 0,
+              "bad argument");
+  g_launch_count = 0;
+  return spi_backward(static_cast<Denoiser*>(denoiser), states, x0, K, K_stride, sigma_d, mu, row_stride, col_stride, B, H, W,
+                      iters, grad_out, grad_sigma_d, grad_mu, grad_state_in, static_cast<cudaStream_t>(stream));
+}

@@ -10,8 +10,9 @@ unchanged.  ``forward`` marshals raw device pointers into ``tfpnp_solver_forward
 
 There is no PyTorch/CPU fallback.  The differentiable use (``PnPEnv.forward`` under
 autograd, tfpnp/env/base.py:193-206) is opt-in and exists for ``ADMMSolver_CSMRI``
-only (``solver.differentiable = True``: gradients w.r.t. sigma_d / mu / the input state through
-``tfpnp_csmri_admm_backward``); everything else raises NotImplementedError under autograd.
+and ``ADMMSolver_SPI`` (``solver.differentiable = True``: gradients w.r.t. sigma_d / mu / the input
+state through ``tfpnp_csmri_admm_backward`` / ``tfpnp_spi_admm_backward``); everything else raises
+NotImplementedError under autograd.
 """
 from __future__ import annotations
 
@@ -121,7 +122,7 @@ class _NativeADMM(PnPSolver):
         if self._wants_grad(variables, parameters) and not (self.differentiable and self._has_backward):
             raise NotImplementedError(
                 "the differentiable solver path (PnPEnv.forward under autograd, SURVEY 8f N4) is opt-in and built for "
-                "ADMMSolver_CSMRI only: set solver.differentiable = True")
+                "ADMMSolver_CSMRI / ADMMSolver_SPI only: set solver.differentiable = True")
 
     def _run(self, handle, variables, aux0, aux1, aux1_stride, params, iter_num):
         B = variables.shape[0]
@@ -479,6 +480,7 @@ class PGSolver_CT(PnPSolver):
 class ADMMSolver_SPI(ADMMSolver):
     """tasks/spi/solver.py:8-51."""
     _task = _lib.TASK_SPI
+    _has_backward = True
 
     def filter_aux_inputs(self, state):     # solver.py:9-10
         return (state['x0'], state['K'])
@@ -492,7 +494,54 @@ class ADMMSolver_SPI(ADMMSolver):
         Kf = K if K.dtype == torch.float32 else K.float()
         Kv = Kf[:, 0, 0, 0]                                   # solver.py:32 (the *10 happens on device)
         h = self._solver_handle(variables.device, H, W)
+        if self._wants_grad(variables, (sigma_d, mu)):
+            if iter_num is None:
+                iter_num = sigma_d.shape[-1]
+            return _SPIAdmmFn.apply(self, h, variables, _f32c(x0), Kv.contiguous(), sigma_d, mu, int(iter_num))
         return self._run(h, variables, _f32c(x0), Kv, Kv.stride(0), (sigma_d, mu), iter_num)
+
+
+class _SPIAdmmFn(torch.autograd.Function):
+    """autograd node for ADMMSolver_SPI.forward: trajectory with the native forward, tfpnp_spi_admm_backward (spi.cu).
+    Only the closed-form branch of spi_inverse carries a gradient, as under autograd in the reference."""
+
+    @staticmethod
+    def forward(ctx, solver, handle, variables, x0, Kv, sigma_d, mu, iter_num):
+        B = variables.shape[0]
+        sg = sigma_d.detach().float().reshape(B, -1)[:, :iter_num].contiguous()
+        m = mu.detach().float().reshape(B, -1)[:, :iter_num].contiguous()
+        if sg.shape[1] < iter_num or m.shape[1] < iter_num:
+            raise IndexError(f"iter_num={iter_num} exceeds the hyper-parameter width")
+        states = [_f32c(variables.detach())]
+        with torch.no_grad():
+            for i in range(iter_num):
+                states.append(solver._run(handle, states[-1], x0, Kv, 1, (sg[:, i:i + 1], m[:, i:i + 1]), 1))
+        ctx.solver = solver
+        ctx.meta = (sigma_d.shape, mu.shape, sigma_d.dtype, mu.dtype, iter_num)
+        ctx.save_for_backward(torch.stack(states), x0, Kv, sg, m)
+        return states[-1].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        states, x0, Kv, sg, m = ctx.saved_tensors
+        sshape, mshape, sdt, mdt, it = ctx.meta
+        B, _, H, W = gout.shape
+        gout = _f32c(gout)
+        g_sigma = torch.zeros(B, it, device=gout.device, dtype=torch.float32)
+        g_mu = torch.zeros_like(g_sigma)
+        g_state = torch.empty_like(gout)
+        with torch.cuda.device(gout.device):
+            _lib.check(_lib.lib().tfpnp_spi_admm_backward(
+                ctx.solver.denoiser._grad_handle(gout.device), states.data_ptr(), x0.data_ptr(), Kv.data_ptr(), 1,
+                sg.data_ptr(), m.data_ptr(), it, 1, B, H, W, it, gout.data_ptr(), g_sigma.data_ptr(), g_mu.data_ptr(),
+                g_state.data_ptr(), torch.cuda.current_stream().cuda_stream), "tfpnp_spi_admm_backward")
+
+        def widen(g, shape, dtype):
+            full = torch.zeros(B, max(1, math.prod(shape[1:])), device=g.device, dtype=torch.float32)
+            full[:, :it] = g
+            return full.reshape(shape).to(dtype)
+
+        return (None, None, g_state, None, None, widen(g_sigma, sshape, sdt), widen(g_mu, mshape, mdt), None)
 
 
 # ---- factories, same names / error behaviour as the reference ---------------------------------
