@@ -168,6 +168,16 @@ int tfpnp_spi_admm_backward(void* denoiser, const float* states, const float* x0
                             int W, int iters, const float* grad_out, float* grad_sigma_d, float* grad_mu,
                             float* grad_state_in, void* stream);
 
+/* Reverse mode of IADMMSolver_CT.forward (tasks/ct/solver.py:17-53), same conventions: states [iters+1][B,3,N,N] real,
+ * y0 [B,1,views,ceil(sqrt(2)N)], the geometry arguments of tfpnp_radon_forward, opnorm as given to the solver;
+ * additionally grad_tau [B,iters].  Uses A^T A = (A^T A)^T (the backprojector is the exact transpose of the projector).
+ * ROUND-1 STATUS: as tfpnp_denoiser_vjp; like the CT forward path, pinned to this build's own Radon pair only. */
+int tfpnp_ct_iadmm_backward(void* denoiser, const float* states, const float* y0, int views, float opnorm,
+                            const float* cos_host, const float* sin_host, const float* sigma_d, const float* mu,
+                            const float* tau, int64_t row_stride, int64_t col_stride, int B, int N, int iters,
+                            const float* grad_out, float* grad_sigma_d, float* grad_mu, float* grad_tau,
+                            float* grad_state_in, void* stream);
+
 /* ---- CT operators (own discretisation of the reference geometry,
  *      tfpnp/utils/transforms.py:465-491) ------------------------------------- */
 /* img [B,1,N,N] <-> sino [B,1,views,ceil(sqrt(2)N)]; cos/sin: optional HOST tables as above */

@@ -235,3 +235,25 @@ def admm_spi_vjp_manual(sd, states, x0, K, sigma_d, mu, gout, denoise_vjp=denois
         gu = gut + gt
         gz = torch.zeros_like(gz)
     return g_sigma, g_mu, torch.cat((gx, gz, gu), dim=1)
+
+
+# ----------------------------------------------------------------------------
+# CT (tasks/ct/solver.py:17-53) on the build's own Radon pair: parity unpinned like the forward path, so the gradients
+# are checked against autograd through the oracle only
+# ----------------------------------------------------------------------------
+
+def iadmm_ct_vjp_autograd(sd, state, y0, views, opnorm, sigma_d, mu, tau, gout):
+    state = state.detach().clone().requires_grad_(True)
+    ps = [p.detach().clone().requires_grad_(True) for p in (sigma_d, mu, tau)]
+    with torch.enable_grad():
+        out = O.iadmm_ct(sd, state, y0, views, opnorm, *ps)
+        gs, gm, gt, gst = torch.autograd.grad(out, (*ps, state), gout)
+    return gs, gm, gt, gst
+
+
+def iadmm_ct_trajectory(sd, state, y0, views, opnorm, sigma_d, mu, tau):
+    states = [state]
+    with torch.no_grad():
+        for i in range(sigma_d.shape[-1]):
+            states.append(O.iadmm_ct(sd, states[-1], y0, views, opnorm, sigma_d[:, i:i + 1], mu[:, i:i + 1], tau[:, i:i + 1]))
+    return states

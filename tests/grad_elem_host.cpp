@@ -427,3 +427,67 @@ extern "C" int emu_spi_backward(const float* weights_flat, const float* states, 
   grad_elem::SpiGradBufs w{f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data()};
   return grad_elem::spi_backward_sequence(ops, states, P.data(), B, H * W, iters, grad_out, g_sigma, g_mu, g_state_in, w);
 }
+
+// ct backward (misc.cu: tfpnp_ct_iadmm_backward): shared sequence + element bodies; the projector pair A^T(A . [- y0]) is a
+// callback into the test (the oracle's Radon pair), everything else loops
+namespace {
+typedef int (*ata_fn)(const float* img, int with_y0, float* out);
+struct HostCtOps {
+  const float* flat; ata_fn cb; float inv_opnorm2; int B, N;
+  int HW() const { return N * N; }
+  size_t n() const { return (size_t)B * N * N; }
+  int slot_get(const float* state, float* buf, int k) {
+    for (size_t i = 0; i < n(); ++i) buf[i] = state[((i / HW()) * 3 + k) * HW() + i % HW()];
+    return 0;
+  }
+  int slot_put(float* state, float* buf, int k) {
+    for (size_t i = 0; i < n(); ++i) state[((i / HW()) * 3 + k) * HW() + i % HW()] = buf[i];
+    return 0;
+  }
+  int pre(const float* gz, const float* gu, const float* st_i, float* gzt, float* z) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::ct_pre_elem(i, gz, gu, st_i, gzt, z, HW());
+    return 0;
+  }
+  int ata(const float* img, bool with_y0, float* out) { return cb(img, with_y0 ? 1 : 0, out); }
+  int mid(const float* st_i, const float* st_n, const float* gzt, const float* w1, const float* w2, const float* mu_i,
+          const float* tau_i, float* gx, float* gz, float* gu, float* v, float* t_tau, float* t_mu) {
+    for (size_t i = 0; i < n(); ++i)
+      grad_elem::ct_mid_elem(i, st_i, st_n, gzt, w1, w2, mu_i, tau_i, inv_opnorm2, gx, gz, gu, v, t_tau, t_mu, HW());
+    return 0;
+  }
+  int reduce(const float* term, float* out, int64_t stride) {
+    for (int b = 0; b < B; ++b) {
+      double s = 0;
+      for (int p = 0; p < HW(); ++p) s += term[(size_t)b * HW() + p];
+      out[b * stride] = (float)s;
+    }
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg_i, const float* gxt, float* gv, float* gsig, int64_t stride) {
+    return unet_vjp_host(flat, v, sg_i, 1, gxt, gv, gsig, stride, B, N, N);
+  }
+  int post(const float* gv, float* gx, float* gz, float* gu) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::ct_post_elem(i, gv, gx, gz, gu);
+    return 0;
+  }
+};
+}  // namespace
+
+extern "C" int emu_ct_backward(const float* weights_flat, const float* states, ata_fn cb, float opnorm, const float* sigma_d,
+                               const float* mu, const float* tau, int B, int N, int iters, const float* grad_out, float* g_sigma,
+                               float* g_mu, float* g_tau, float* g_state_in) {
+  const size_t n = (size_t)B * N * N;
+  std::vector<float> P((size_t)3 * B * iters);                       // gather_params_t3
+  for (int i = 0; i < iters; ++i)
+    for (int b = 0; b < B; ++b) {
+      P[(size_t)i * B + b] = sigma_d[b * iters + i];
+      P[(size_t)(iters + i) * B + b] = mu[b * iters + i];
+      P[(size_t)(2 * iters + i) * B + b] = tau[b * iters + i];
+    }
+  std::vector<float> f[11];
+  for (auto& v : f) v.assign(n, 0.f);
+  HostCtOps ops{weights_flat, cb, 1.0f / (opnorm * opnorm), B, N};
+  grad_elem::CtGradBufs w{f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(), f[6].data(), f[7].data(),
+                          f[8].data(), f[9].data(), f[10].data()};
+  return grad_elem::ct_backward_sequence(ops, states, P.data(), B, N * N, iters, grad_out, g_sigma, g_mu, g_tau, g_state_in, w);
+}

@@ -154,6 +154,47 @@ def test_spi_gradients_oracle_and_cuda_sequence_on_cpu(emu):
     assert torch.count_nonzero(gst[:, 1]) == 0       # z of the input state is never read
 
 
+def test_ct_gradients_cuda_sequence_on_cpu(emu):
+    """CT (tasks/ct/solver.py:17-53): the CUDA sequence + element bodies on the host, with the oracle's Radon pair standing
+    in for the projector kernels, against autograd through the oracle (CT has no reference to pin to: torch_radon is
+    absent)."""
+    import ctypes as C
+    import numpy as np
+    from oracle import pnp_oracle as O, synth
+    from tfpnp_b200.denoiser import flatten_state_dict
+    sd = weights("he")
+    B, N, views, it = 2, 32, 12, 2
+    d = synth.ct_batch(B, N, views, it)
+    opnorm = float(d["opnorm"])
+    g = torch.Generator().manual_seed(23)
+    state = torch.cat([torch.rand(B, 1, N, N, generator=g), torch.rand(B, 1, N, N, generator=g),
+                       torch.rand(B, 1, N, N, generator=g) * 0.3], dim=1)
+    gout = torch.randn(state.shape, generator=g)
+    ref = G.iadmm_ct_vjp_autograd(sd, state, d["y0"], views, opnorm, d["sigma_d"], d["mu"], d["tau"], gout)
+    states = torch.stack(G.iadmm_ct_trajectory(sd, state, d["y0"], views, opnorm, d["sigma_d"], d["mu"], d["tau"])).contiguous()
+    cs, sn, det = O.ct_geometry(N, views)
+
+    @C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
+    def ata(img_p, with_y0, out_p):
+        img = torch.from_numpy(np.ctypeslib.as_array(C.cast(img_p, C.POINTER(C.c_float)), shape=(B, 1, N, N)).copy())
+        s = O.radon_forward(img, cs, sn, det)
+        if with_y0:
+            s = s - d["y0"]
+        w = O.radon_backward(s, cs, sn, N).contiguous().float()
+        C.memmove(out_p, w.data_ptr(), w.numel() * 4)
+        return 0
+
+    flat = flatten_state_dict(sd)
+    outs = [torch.zeros(B, it) for _ in range(3)] + [torch.zeros_like(gout)]
+    rc = emu.emu_ct_backward(_ptr(flat), _ptr(states), ata, C.c_float(opnorm), _ptr(d["sigma_d"].contiguous()),
+                             _ptr(d["mu"].contiguous()), _ptr(d["tau"].contiguous()), B, N, it, _ptr(gout.contiguous()),
+                             *[_ptr(o) for o in outs])
+    assert rc == 0
+    for mine, r, name in zip(outs, ref, ("sigma_d", "mu", "tau", "state")):
+        assert r.abs().max() > 0, name
+        assert rel_err(mine, r)[0] <= 1e-3, (name, rel_err(mine, r))
+
+
 def test_psnr_backward_element_body_on_cpu(emu):
     """psnr_bwd_elem (the reward's gradient, tfpnp/env/base.py:237-242 under autograd) against autograd."""
     from oracle import pnp_oracle as O
@@ -191,7 +232,7 @@ def test_reverse_mode_is_opt_in():
     import tfpnp_b200 as T
     assert T.ADMMSolver_CSMRI.differentiable is False and T.ADMMSolver_CSMRI._has_backward is True
     assert T.ADMMSolver_SPI.differentiable is False and T.ADMMSolver_SPI._has_backward is True
-    assert T.IADMMSolver_PR._has_backward is False and T.IADMMSolver_CT._has_backward is False
+    assert T.IADMMSolver_PR._has_backward is False and T.IADMMSolver_CT._has_backward is True
     assert T.UNetDenoiser2D.differentiable is False
 
 
@@ -319,3 +360,30 @@ def test_native_spi_backward_matches_reference_gradients(dev, prec, tol):
     g_s, g_m, g_st = torch.autograd.grad(out, (sg, mu, state), g["gout"].to(dev))
     for mine, key in ((g_s, "g_sigma_d"), (g_m, "g_mu"), (g_st, "g_state")):
         assert rel_err(mine, g[key])[0] <= tol, (prec, key, rel_err(mine, g[key]))
+
+
+@pytest.mark.gpu
+@needs_grad_flag
+def test_native_ct_backward_matches_oracle_gradients(dev):
+    """CT has no reference to pin to (torch_radon absent): native backward vs autograd through the oracle on the same
+    discretisation, opnorm passed explicitly as in the forward parity tests."""
+    import tfpnp_b200 as T
+    from oracle import synth
+    sd = weights("he")
+    B, N, views, it = 2, 32, 30, 2
+    d = synth.ct_batch(B, N, views, it)
+    opnorm = float(d["opnorm"])
+    g = torch.Generator().manual_seed(23)
+    state = torch.cat([torch.rand(B, 1, N, N, generator=g), torch.rand(B, 1, N, N, generator=g),
+                       torch.rand(B, 1, N, N, generator=g) * 0.3], dim=1)
+    gout = torch.randn(state.shape, generator=g)
+    ref = G.iadmm_ct_vjp_autograd(sd, state, d["y0"], views, opnorm, d["sigma_d"], d["mu"], d["tau"], gout)
+    s = T.IADMMSolver_CT(T.UNetDenoiser2D(state_dict=sd, precision="fp32_simt"))
+    s.differentiable = True
+    s.opnorm_override = opnorm
+    st = state.to(dev).requires_grad_(True)
+    ps = [d[k].to(dev).requires_grad_(True) for k in ("sigma_d", "mu", "tau")]
+    out = s((st, (d["y0"].to(dev), d["view"].to(dev))), tuple(ps))
+    mine = torch.autograd.grad(out, (*ps, st), gout.to(dev))
+    for a, r, name in zip(mine, ref, ("sigma_d", "mu", "tau", "state")):
+        assert rel_err(a, r)[0] <= 2e-3, (name, rel_err(a, r))

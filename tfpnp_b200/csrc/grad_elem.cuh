@@ -480,5 +480,81 @@ int spi_backward_sequence(Ops& ops, const float* states, const float* P, int B, 
   return 0;
 }
 
+// ---- reverse mode of IADMMSolver_CT.forward (tasks/ct/solver.py:17-53; misc.cu: ct_backward) ----------------------------
+// One iteration: x' = D(z - u, sigma);  z' = z - tau (bp(z) + mu r),  bp(z) = A^T(A z - y0)/opnorm^2,  r = z - x' - u;
+// u' = u + x' - z'.  With incoming (gx', gz', gu'):  gxt = gx' + gu';  gzt = gz' - gu';
+//   gz = gzt - tau (A^T A gzt / opnorm^2 + mu gzt);  gxt += tau mu gzt;  gu = gu' + tau mu gzt;
+//   g_tau = -<gzt, bp(z) + mu r>;  g_mu = -tau <gzt, r>;  (gv, g_sigma) = J_D(z - u, sigma)^T gxt;  gz += gv;  gu -= gv;  gx = 0.
+// A^T A is symmetric because the backprojector is the exact transpose of the projector.  States are [B,3,HW] real.
+
+// gzt = gz' - gu' -> GZT;  z of this state -> Z (contiguous operands for the projector)
+TFPNP_HD void ct_pre_elem(size_t i, const float* GZ, const float* GU, const float* st_i, float* GZT, float* Z, int HW) {
+  const size_t b = i / HW, p = i % HW;
+  GZT[i] = GZ[i] - GU[i];
+  Z[i] = st_i[(b * 3 + 1) * HW + p];
+}
+// W1 = A^T A gzt, W2 = A^T (A z - y0) (both un-normalised).  In place on (GX -> gxt, GZ, GU); v = z - u;
+// term_tau / term_mu: this pixel's contributions to g_tau / g_mu
+TFPNP_HD void ct_mid_elem(size_t i, const float* st_i, const float* st_n, const float* GZT, const float* W1, const float* W2,
+                          const float* mu, const float* tau, float inv_opnorm2, float* GX, float* GZ, float* GU, float* v,
+                          float* term_tau, float* term_mu, int HW) {
+  const size_t b = i / HW, p = i % HW;
+  const float m = mu[b], t = tau[b];
+  const float z = st_i[(b * 3 + 1) * HW + p], u = st_i[(b * 3 + 2) * HW + p], xn = st_n[(b * 3 + 0) * HW + p];
+  const float r = z - xn - u;
+  const float gzt = GZT[i];
+  const float gu_in = GU[i];
+  GZ[i] = gzt - t * (W1[i] * inv_opnorm2 + m * gzt);
+  GX[i] = GX[i] + gu_in + t * m * gzt;          // gxt
+  GU[i] = gu_in + t * m * gzt;
+  term_tau[i] = -gzt * (W2[i] * inv_opnorm2 + m * r);
+  term_mu[i] = -t * gzt * r;
+  v[i] = z - u;
+}
+// gz += gv;  gu -= gv;  gx = 0
+TFPNP_HD void ct_post_elem(size_t i, const float* gv, float* GX, float* GZ, float* GU) {
+  const float g = gv[i];
+  GX[i] = 0.f;
+  GZ[i] += g;
+  GU[i] -= g;
+}
+
+struct CtGradBufs { float *gx, *gz, *gu, *gzt, *z, *w1, *w2, *v, *gv, *t_tau, *t_mu; };   // [B,HW] each
+
+// Ops: slot_get / slot_put, pre, ata (W = A^T (A img - y0?) un-normalised; with_y0 selects the residual form), mid, reduce
+// (per-image sum -> strided output), den_vjp, post.  P: [sigma | mu | tau][iters][B].
+template <class Ops>
+int ct_backward_sequence(Ops& ops, const float* states, const float* P, int B, int HW, int iters, const float* grad_out,
+                         float* g_sigma, float* g_mu, float* g_tau, float* g_state_in, const CtGradBufs& w) {
+#define TFPNP_SEQ(expr) do { int _s = (expr); if (_s != 0) return _s; } while (0)
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gx, 0));
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gz, 1));
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gu, 2));
+  const size_t state_elems = (size_t)B * HW * 3;
+  const size_t np = (size_t)B * iters;
+  for (int i = iters - 1; i >= 0; --i) {
+    const float* st_i = states + (size_t)i * state_elems;
+    const float* st_n = st_i + state_elems;
+    const float* sg_i = P + (size_t)i * B;
+    const float* mu_i = P + np + (size_t)i * B;
+    const float* tau_i = P + 2 * np + (size_t)i * B;
+    TFPNP_SEQ(ops.pre(w.gz, w.gu, st_i, w.gzt, w.z));
+    TFPNP_SEQ(ops.ata(w.gzt, false, w.w1));
+    TFPNP_SEQ(ops.ata(w.z, true, w.w2));
+    TFPNP_SEQ(ops.mid(st_i, st_n, w.gzt, w.w1, w.w2, mu_i, tau_i, w.gx, w.gz, w.gu, w.v, w.t_tau, w.t_mu));
+    TFPNP_SEQ(ops.reduce(w.t_tau, g_tau + i, iters));
+    TFPNP_SEQ(ops.reduce(w.t_mu, g_mu + i, iters));
+    TFPNP_SEQ(ops.den_vjp(w.v, sg_i, w.gx, w.gv, g_sigma + i, iters));
+    TFPNP_SEQ(ops.post(w.gv, w.gx, w.gz, w.gu));
+  }
+  if (g_state_in) {
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gx, 0));
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gz, 1));
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gu, 2));
+  }
+#undef TFPNP_SEQ
+  return 0;
+}
+
 }  // namespace grad_elem
 }  // namespace tfpnp

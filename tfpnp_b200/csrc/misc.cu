@@ -37,6 +37,101 @@ __global__ void psnr_bwd_kernel(const float* __restrict__ out, const float* __re
   if (i < n) grad_elem::psnr_bwd_elem(i, out, gt, psnr, gpsnr, gout, HW);
 }
 
+// ---- reverse mode of the CT solver: sequence and element bodies in grad_elem.cuh --------------------------
+__global__ void real_slot_copy(const float* __restrict__ state, float* __restrict__ buf, int k, int HW, size_t n, int to_state) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* s = const_cast<float*>(state) + ((i / HW) * 3 + k) * HW + i % HW;
+  if (to_state) *s = buf[i]; else buf[i] = *s;
+}
+__global__ void ct_pre_kernel(const float* __restrict__ GZ, const float* __restrict__ GU, const float* __restrict__ st_i,
+                              float* __restrict__ GZT, float* __restrict__ Z, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::ct_pre_elem(i, GZ, GU, st_i, GZT, Z, HW);
+}
+__global__ void ct_mid_kernel(const float* __restrict__ st_i, const float* __restrict__ st_n, const float* __restrict__ GZT,
+                              const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ mu,
+                              const float* __restrict__ tau, float inv_opnorm2, float* __restrict__ GX, float* __restrict__ GZ,
+                              float* __restrict__ GU, float* __restrict__ v, float* __restrict__ t_tau,
+                              float* __restrict__ t_mu, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::ct_mid_elem(i, st_i, st_n, GZT, W1, W2, mu, tau, inv_opnorm2, GX, GZ, GU, v, t_tau, t_mu, HW);
+}
+__global__ void ct_post_kernel(const float* __restrict__ gv, float* __restrict__ GX, float* __restrict__ GZ,
+                               float* __restrict__ GU, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::ct_post_elem(i, gv, GX, GZ, GU);
+}
+__global__ void __launch_bounds__(256)
+image_sum(const float* __restrict__ term, float* __restrict__ out, int64_t stride, int HW) {
+  __shared__ float red[256];
+  const float* t = term + (size_t)blockIdx.x * HW;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) s += t[p];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x * stride] = red[0];
+}
+__global__ void gather_params_t3(const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2,
+                                 int64_t rs, int64_t cs, float* __restrict__ P, int B, int iters) {
+  const int n = B * iters;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = t / B, b = t % B;
+    const int64_t src = b * rs + i * cs;
+    P[t] = p0[src]; P[n + t] = p1[src]; P[2 * n + t] = p2[src];
+  }
+}
+
+struct CtGradOps {
+  Denoiser* den; const CtGeom* g; const float* y0; float* sino; float inv_opnorm2; int B; cudaStream_t st;
+  static constexpr int T = 256;
+  int HW() const { return g->N * g->N; }
+  size_t n() const { return (size_t)B * HW(); }
+  unsigned nb() const { return (unsigned)((n() + T - 1) / T); }
+  int slot_get(const float* state, float* buf, int k) {
+    real_slot_copy<<<nb(), T, 0, st>>>(state, buf, k, HW(), n(), 0);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int slot_put(float* state, float* buf, int k) {
+    real_slot_copy<<<nb(), T, 0, st>>>(state, buf, k, HW(), n(), 1);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int pre(const float* gz, const float* gu, const float* st_i, float* gzt, float* z) {
+    ct_pre_kernel<<<nb(), T, 0, st>>>(gz, gu, st_i, gzt, z, HW(), n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int ata(const float* img, bool with_y0, float* out) {      // out = A^T (A img [- y0])
+    TFPNP_TRY(radon_forward(*g, img, with_y0 ? y0 : nullptr, sino, B, st));
+    return radon_backward(*g, sino, out, B, st);
+  }
+  int mid(const float* st_i, const float* st_n, const float* gzt, const float* w1, const float* w2, const float* mu_i,
+          const float* tau_i, float* gx, float* gz, float* gu, float* v, float* t_tau, float* t_mu) {
+    ct_mid_kernel<<<nb(), T, 0, st>>>(st_i, st_n, gzt, w1, w2, mu_i, tau_i, inv_opnorm2, gx, gz, gu, v, t_tau, t_mu, HW(), n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int reduce(const float* term, float* out, int64_t stride) {
+    image_sum<<<B, 256, 0, st>>>(term, out, stride, HW());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg_i, const float* gxt, float* gv, float* gsig, int64_t stride) {
+    return den->vjp(v, sg_i, 1, gxt, gv, gsig, stride, B, g->N, g->N, st);
+  }
+  int post(const float* gv, float* gx, float* gz, float* gu) {
+    ct_post_kernel<<<nb(), T, 0, st>>>(gv, gx, gz, gu, n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+};
+
 struct GeomCache {
   std::map<std::pair<int, int>, std::unique_ptr<CtGeom>> m;
   CtGeom* get(int N, int views, const float* c, const float* s) {
@@ -100,6 +195,42 @@ int tfpnp_radon_backward(const float* sino, float* img, int B, int N, int views,
   CtGeom* g = geom_cache().get(N, views, cos_host, sin_host);
   if (!g) return TFPNP_ERR_CUDA;
   return radon_backward(*g, sino, img, B, static_cast<cudaStream_t>(stream));
+}
+
+int tfpnp_ct_iadmm_backward(void* denoiser, const float* states, const float* y0, int views, float opnorm,
+                            const float* cos_host, const float* sin_host, const float* sigma_d, const float* mu,
+                            const float* tau, int64_t row_stride, int64_t col_stride, int B, int N, int iters,
+                            const float* grad_out, float* grad_sigma_d, float* grad_mu, float* grad_tau, float* grad_state_in,
+                            void* stream) {
+  TFPNP_CHECK(denoiser && states && y0 && sigma_d && mu && tau && grad_out && grad_sigma_d && grad_mu && grad_tau && B > 0 &&
+                  iters > 0 && views > 0 && opnorm > 0.f, "bad argument");
+  g_launch_count = 0;
+  CtGeom* g = geom_cache().get(N, views, cos_host, sin_host);
+  if (!g) return TFPNP_ERR_CUDA;
+  TFPNP_TRY(g->reserve(B));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)B * N * N;
+  DevBuf bufs[11], sino, P;
+  auto body = [&]() -> int {
+    for (DevBuf& b : bufs) TFPNP_TRY(b.alloc(n * sizeof(float)));
+    TFPNP_TRY(sino.alloc((size_t)B * g->views * g->det * sizeof(float)));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float)));
+    gather_params_t3<<<cdiv(B * iters, 256), 256, 0, st>>>(sigma_d, mu, tau, row_stride, col_stride, P.as<float>(), B, iters);
+    TFPNP_COUNT_LAUNCH();
+    CtGradOps ops{static_cast<Denoiser*>(denoiser), g, y0, sino.as<float>(), 1.0f / (opnorm * opnorm), B, st};
+    float* f[11];
+    for (int k = 0; k < 11; ++k) f[k] = bufs[k].as<float>();
+    grad_elem::CtGradBufs w{f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], f[9], f[10]};
+    TFPNP_TRY(grad_elem::ct_backward_sequence(ops, states, P.as<float>(), B, N * N, iters, grad_out, grad_sigma_d, grad_mu,
+                                              grad_tau, grad_state_in, w));
+    TFPNP_CUDA_OK(cudaGetLastError());
+    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers are freed on return
+    return 0;
+  };
+  const int rc = body();
+  for (DevBuf& b : bufs) b.release();
+  sino.release(); P.release();
+  return rc;
 }
 
 }  // extern "C"

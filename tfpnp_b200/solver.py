@@ -10,9 +10,9 @@ unchanged.  ``forward`` marshals raw device pointers into ``tfpnp_solver_forward
 
 There is no PyTorch/CPU fallback.  The differentiable use (``PnPEnv.forward`` under
 autograd, tfpnp/env/base.py:193-206) is opt-in and exists for ``ADMMSolver_CSMRI``
-and ``ADMMSolver_SPI`` (``solver.differentiable = True``: gradients w.r.t. sigma_d / mu / the input
-state through ``tfpnp_csmri_admm_backward`` / ``tfpnp_spi_admm_backward``); everything else raises
-NotImplementedError under autograd.
+``ADMMSolver_SPI`` and ``IADMMSolver_CT`` (``solver.differentiable = True``: gradients w.r.t. the
+hyper-parameters and the input state through ``tfpnp_{csmri_admm,spi_admm,ct_iadmm}_backward``);
+everything else raises NotImplementedError under autograd.
 """
 from __future__ import annotations
 
@@ -122,7 +122,7 @@ class _NativeADMM(PnPSolver):
         if self._wants_grad(variables, parameters) and not (self.differentiable and self._has_backward):
             raise NotImplementedError(
                 "the differentiable solver path (PnPEnv.forward under autograd, SURVEY 8f N4) is opt-in and built for "
-                "ADMMSolver_CSMRI / ADMMSolver_SPI only: set solver.differentiable = True")
+                "the CS-MRI / SPI / CT ADMM solvers only: set solver.differentiable = True")
 
     def _run(self, handle, variables, aux0, aux1, aux1_stride, params, iter_num):
         B = variables.shape[0]
@@ -404,6 +404,7 @@ class IADMMSolver_CT(IADMMSolver):
     """tasks/ct/solver.py:7-53 (Radon pair: this build's own discretisation, parity unpinned
     w.r.t. the absent torch_radon)."""
     _task = _lib.TASK_CT
+    _has_backward = True
 
     def __init__(self, denoiser):
         super().__init__(denoiser)
@@ -423,7 +424,53 @@ class IADMMSolver_CT(IADMMSolver):
         opnorm = self.opnorm_override or self.radon_generator(W, views, variables.device)
         cos, sin = RadonGenerator.tables(views)
         h = self._solver_handle(variables.device, H, W, views=views, opnorm=opnorm, cos=cos, sin=sin)
+        if self._wants_grad(variables, (sigma_d, mu, tau)):
+            if iter_num is None:
+                iter_num = sigma_d.shape[-1]
+            return _CTIadmmFn.apply(self, h, variables, _f32c(y0), sigma_d, mu, tau, int(iter_num), views, float(opnorm), cos, sin)
         return self._run(h, variables, _f32c(y0), None, 0, (sigma_d, mu, tau), iter_num)
+
+
+class _CTIadmmFn(torch.autograd.Function):
+    """autograd node for IADMMSolver_CT.forward: trajectory with the native forward, tfpnp_ct_iadmm_backward (misc.cu)."""
+
+    @staticmethod
+    def forward(ctx, solver, handle, variables, y0, sigma_d, mu, tau, iter_num, views, opnorm, cos, sin):
+        B = variables.shape[0]
+        ps = [p.detach().float().reshape(B, -1)[:, :iter_num].contiguous() for p in (sigma_d, mu, tau)]
+        if any(p.shape[1] < iter_num for p in ps):
+            raise IndexError(f"iter_num={iter_num} exceeds the hyper-parameter width")
+        states = [_f32c(variables.detach())]
+        with torch.no_grad():
+            for i in range(iter_num):
+                states.append(solver._run(handle, states[-1], y0, None, 0, tuple(p[:, i:i + 1] for p in ps), 1))
+        ctx.solver = solver
+        ctx.meta = ([p.shape for p in (sigma_d, mu, tau)], [p.dtype for p in (sigma_d, mu, tau)], iter_num, views, opnorm, cos, sin)
+        ctx.save_for_backward(torch.stack(states), y0, *ps)
+        return states[-1].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        states, y0, sg, m, t = ctx.saved_tensors
+        shapes, dtypes, it, views, opnorm, cos, sin = ctx.meta
+        B, _, H, W = gout.shape
+        gout = _f32c(gout)
+        grads = [torch.zeros(B, it, device=gout.device, dtype=torch.float32) for _ in range(3)]
+        g_state = torch.empty_like(gout)
+        with torch.cuda.device(gout.device):
+            _lib.check(_lib.lib().tfpnp_ct_iadmm_backward(
+                ctx.solver.denoiser._grad_handle(gout.device), states.data_ptr(), y0.data_ptr(), views, opnorm,
+                cos.data_ptr(), sin.data_ptr(), sg.data_ptr(), m.data_ptr(), t.data_ptr(), it, 1, B, W, it, gout.data_ptr(),
+                grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), g_state.data_ptr(),
+                torch.cuda.current_stream().cuda_stream), "tfpnp_ct_iadmm_backward")
+
+        def widen(g, shape, dtype):
+            full = torch.zeros(B, max(1, math.prod(shape[1:])), device=g.device, dtype=torch.float32)
+            full[:, :it] = g
+            return full.reshape(shape).to(dtype)
+
+        gs, gm, gt = (widen(g, sh, dt) for g, sh, dt in zip(grads, shapes, dtypes))
+        return (None, None, g_state, None, gs, gm, gt, None, None, None, None, None)
 
 
 class PGSolver_CT(PnPSolver):
