@@ -178,6 +178,15 @@ int tfpnp_ct_iadmm_backward(void* denoiser, const float* states, const float* y0
                             const float* grad_out, float* grad_sigma_d, float* grad_mu, float* grad_tau,
                             float* grad_state_in, void* stream);
 
+/* Reverse mode of IADMMSolver_PR.forward (tasks/pr/solver.py:37-76), same conventions: states [iters+1][B,3,N,N,2],
+ * y0 [B,M,N,N] f32, mask [B,M,N,N,2] f32 (unit-modulus CDP masks), M = n_masks.  The magnitude projection
+ * h(w) = (1 - y0/|w|) w has a symmetric real Jacobian, so the adjoint of the gradient operator is the operator itself with h
+ * replaced by that Jacobian (pr.cu).  FFTs through tfpnp_fft2.  ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+int tfpnp_pr_iadmm_backward(void* denoiser, const float* states, const float* y0, const float* mask, int n_masks,
+                            const float* sigma_d, const float* mu, const float* tau, int64_t row_stride,
+                            int64_t col_stride, int B, int N, int iters, const float* grad_out, float* grad_sigma_d,
+                            float* grad_mu, float* grad_tau, float* grad_state_in, void* stream);
+
 /* ---- CT operators (own discretisation of the reference geometry,
  *      tfpnp/utils/transforms.py:465-491) ------------------------------------- */
 /* img [B,1,N,N] <-> sino [B,1,views,ceil(sqrt(2)N)]; cos/sin: optional HOST tables as above */

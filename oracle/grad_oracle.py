@@ -257,3 +257,24 @@ def iadmm_ct_trajectory(sd, state, y0, views, opnorm, sigma_d, mu, tau):
         for i in range(sigma_d.shape[-1]):
             states.append(O.iadmm_ct(sd, states[-1], y0, views, opnorm, sigma_d[:, i:i + 1], mu[:, i:i + 1], tau[:, i:i + 1]))
     return states
+
+
+# ----------------------------------------------------------------------------
+# PR (tasks/pr/solver.py:37-76)
+# ----------------------------------------------------------------------------
+
+def iadmm_pr_vjp_autograd(sd, state, y0, mask, sigma_d, mu, tau, gout):
+    state = state.detach().clone().requires_grad_(True)
+    ps = [p.detach().clone().requires_grad_(True) for p in (sigma_d, mu, tau)]
+    with torch.enable_grad():
+        out = O.iadmm_pr(sd, state, y0, mask, *ps)
+        gs, gm, gt, gst = torch.autograd.grad(out, (*ps, state), gout)
+    return gs, gm, gt, gst
+
+
+def iadmm_pr_trajectory(sd, state, y0, mask, sigma_d, mu, tau):
+    states = [state]
+    with torch.no_grad():
+        for i in range(sigma_d.shape[-1]):
+            states.append(O.iadmm_pr(sd, states[-1], y0, mask, sigma_d[:, i:i + 1], mu[:, i:i + 1], tau[:, i:i + 1]))
+    return states

@@ -84,6 +84,22 @@ def main():
     save("grad_spi_small", **np_({k: d[k] for k in ("state", "x0", "K", "sigma_d", "mu")}), gout=gstate.numpy(),
          g_sigma_d=s_gs.numpy(), g_mu=s_gm.numpy(), g_state=s_gst.numpy(), wsum=weight_checksum(sd), init="he", seed=0)
 
+    # 2c. PR (tasks/pr/solver.py:37-76)
+    d = synth.pr_batch(2, 32, 3)
+    g = torch.Generator().manual_seed(29)
+    gstate = torch.randn(d["state"].shape, generator=g)
+    sol = refshim.reference_solver("pr", sd)
+    st = d["state"].clone().requires_grad_(True)
+    ps = [d[k].clone().requires_grad_(True) for k in ("sigma_d", "mu", "tau")]
+    out = sol((st, (d["y0"], d["mask"])), tuple(ps))
+    p_ref = torch.autograd.grad(out, (*ps, st), gstate)
+    a = G.iadmm_pr_vjp_autograd(sd, d["state"], d["y0"], d["mask"], d["sigma_d"], d["mu"], d["tau"], gstate)
+    print("  PR vjp (autograd through the oracle) vs reference: " + "  ".join(f"{n} {close(x, r, 1e-5):.2e}" for n, x, r in
+          zip(("sigma_d", "mu", "tau", "state"), a, p_ref)))
+    save("grad_pr_small", **np_({k: d[k] for k in ("state", "y0", "mask", "sigma_d", "mu", "tau")}), gout=gstate.numpy(),
+         g_sigma_d=p_ref[0].numpy(), g_mu=p_ref[1].numpy(), g_tau=p_ref[2].numpy(), g_state=p_ref[3].numpy(),
+         wsum=weight_checksum(sd), init="he", seed=0)
+
     # 3. the call the trainer differentiates: ob2, reward = env.forward(ob, action) (tfpnp/env/base.py:193-206), loss through the
     #    next observation the critic reads (get_eval_ob) and through the PSNR reward (trainer.py:173-189)
     from . import env_oracle as E

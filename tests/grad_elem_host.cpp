@@ -491,3 +491,119 @@ extern "C" int emu_ct_backward(const float* weights_flat, const float* states, a
                           f[8].data(), f[9].data(), f[10].data()};
   return grad_elem::ct_backward_sequence(ops, states, P.data(), B, N * N, iters, grad_out, g_sigma, g_mu, g_tau, g_state_in, w);
 }
+
+// pr backward (pr.cu: tfpnp_pr_iadmm_backward): shared sequence + element bodies; tfpnp_fft2 replaced by a direct DFT
+namespace {
+// un-centred ortho 2-D DFT of one N x N complex image (torch.fft.fft2 / ifft2 with norm="ortho")
+void dft2_plain_host(const cplx* in, cplx* out, int N, bool inverse) {
+  std::vector<double> cr((size_t)N * N), ci((size_t)N * N);
+  const double sgn = inverse ? 1.0 : -1.0, scale = 1.0 / std::sqrt((double)N);
+  for (int k = 0; k < N; ++k)
+    for (int n = 0; n < N; ++n) {
+      const double ang = sgn * 2.0 * M_PI * (double)((k * n) % N) / N;
+      cr[(size_t)k * N + n] = std::cos(ang) * scale; ci[(size_t)k * N + n] = std::sin(ang) * scale;
+    }
+  std::vector<double> tr((size_t)N * N), ti((size_t)N * N);
+  for (int r = 0; r < N; ++r)
+    for (int k = 0; k < N; ++k) {
+      double ar = 0, ai = 0;
+      for (int n = 0; n < N; ++n) {
+        const double xr = in[(size_t)r * N + n].x, xi = in[(size_t)r * N + n].y;
+        ar += xr * cr[(size_t)k * N + n] - xi * ci[(size_t)k * N + n];
+        ai += xr * ci[(size_t)k * N + n] + xi * cr[(size_t)k * N + n];
+      }
+      tr[(size_t)r * N + k] = ar; ti[(size_t)r * N + k] = ai;
+    }
+  for (int c = 0; c < N; ++c)
+    for (int k = 0; k < N; ++k) {
+      double ar = 0, ai = 0;
+      for (int n = 0; n < N; ++n) {
+        const double xr = tr[(size_t)n * N + c], xi = ti[(size_t)n * N + c];
+        ar += xr * cr[(size_t)k * N + n] - xi * ci[(size_t)k * N + n];
+        ai += xr * ci[(size_t)k * N + n] + xi * cr[(size_t)k * N + n];
+      }
+      out[(size_t)k * N + c].x = (float)ar; out[(size_t)k * N + c].y = (float)ai;
+    }
+}
+
+struct HostPrOps {
+  const float* flat; const cplx* mask; const float* y0; int B, M, N;
+  int HW() const { return N * N; }
+  size_t n() const { return (size_t)B * N * N; }
+  size_t nm() const { return n() * M; }
+  int slot_get(const cplx* state, cplx* buf, int k) {
+    for (size_t i = 0; i < n(); ++i) buf[i] = state[((i / HW()) * 3 + k) * HW() + i % HW()];
+    return 0;
+  }
+  int slot_put(cplx* state, cplx* buf, int k) {
+    for (size_t i = 0; i < n(); ++i) state[((i / HW()) * 3 + k) * HW() + i % HW()] = buf[i];
+    return 0;
+  }
+  int pre(const cplx* gz, const cplx* gu, const cplx* st_i, cplx* gzt, cplx* z) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::pr_pre_elem(i, gz, gu, st_i, gzt, z, HW());
+    return 0;
+  }
+  int mul(const cplx* img, cplx* out) {
+    for (size_t i = 0; i < nm(); ++i) grad_elem::pr_mul_elem(i, img, mask, out, M, HW());
+    return 0;
+  }
+  int fft(const cplx* in, cplx* out, bool inverse) {
+    for (int k = 0; k < B * M; ++k) dft2_plain_host(in + (size_t)k * HW(), out + (size_t)k * HW(), N, inverse);
+    return 0;
+  }
+  int h(cplx* W, cplx* Bc) {
+    for (size_t i = 0; i < nm(); ++i) grad_elem::pr_h_elem(i, W, Bc, y0);
+    return 0;
+  }
+  int acc(const cplx* E, cplx* out) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::pr_acc_elem(i, E, mask, out, M, HW());
+    return 0;
+  }
+  int mid(const cplx* st_i, const cplx* st_n, const cplx* gzt, const cplx* jc, const cplx* gzv, const float* mu_i,
+          const float* tau_i, const cplx* gx, cplx* gz, cplx* gu, float* gxt, float* v, float* t_tau, float* t_mu) {
+    for (size_t i = 0; i < n(); ++i)
+      grad_elem::pr_mid_elem(i, st_i, st_n, gzt, jc, gzv, mu_i, tau_i, gx, gz, gu, gxt, v, t_tau, t_mu, HW());
+    return 0;
+  }
+  int reduce(const float* term, float* out, int64_t stride) {
+    for (int b = 0; b < B; ++b) {
+      double s = 0;
+      for (int p = 0; p < HW(); ++p) s += term[(size_t)b * HW() + p];
+      out[b * stride] = (float)s;
+    }
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg_i, const float* gxt, float* gv, float* gsig, int64_t stride) {
+    return unet_vjp_host(flat, v, sg_i, 1, gxt, gv, gsig, stride, B, N, N);
+  }
+  int post(const float* gv, cplx* gx, cplx* gz, cplx* gu) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::pr_post_elem(i, gv, gx, gz, gu);
+    return 0;
+  }
+};
+}  // namespace
+
+extern "C" int emu_pr_backward(const float* weights_flat, const float* states, const float* y0, const float* mask, int M,
+                               const float* sigma_d, const float* mu, const float* tau, int B, int N, int iters,
+                               const float* grad_out, float* g_sigma, float* g_mu, float* g_tau, float* g_state_in) {
+  const size_t n = (size_t)B * N * N, nm = n * M;
+  std::vector<float> P((size_t)3 * B * iters);
+  for (int i = 0; i < iters; ++i)
+    for (int b = 0; b < B; ++b) {
+      P[(size_t)i * B + b] = sigma_d[b * iters + i];
+      P[(size_t)(iters + i) * B + b] = mu[b * iters + i];
+      P[(size_t)(2 * iters + i) * B + b] = tau[b * iters + i];
+    }
+  std::vector<cplx> c1[7], cm[4];
+  for (auto& v : c1) v.assign(n, cplx{0.f, 0.f});
+  for (auto& v : cm) v.assign(nm, cplx{0.f, 0.f});
+  std::vector<float> f1[5];
+  for (auto& v : f1) v.assign(n, 0.f);
+  HostPrOps ops{weights_flat, reinterpret_cast<const cplx*>(mask), y0, B, M, N};
+  grad_elem::PrGradBufs w{c1[0].data(), c1[1].data(), c1[2].data(), c1[3].data(), c1[4].data(), c1[5].data(), c1[6].data(),
+                          cm[0].data(), cm[1].data(), cm[2].data(), cm[3].data(), f1[0].data(), f1[1].data(), f1[2].data(),
+                          f1[3].data(), f1[4].data()};
+  return grad_elem::pr_backward_sequence(ops, reinterpret_cast<const cplx*>(states), P.data(), B, N * N, iters,
+                                         reinterpret_cast<const cplx*>(grad_out), g_sigma, g_mu, g_tau,
+                                         reinterpret_cast<cplx*>(g_state_in), w);
+}

@@ -1,8 +1,9 @@
-"""Reverse mode of the CS-MRI ADMM path (PnPEnv.forward under autograd, tfpnp/env/base.py:193-206,
-tfpnp/trainer/mddpg/trainer.py:173).
+"""Reverse mode of the four ADMM / iADMM solvers and of env.forward (PnPEnv.forward under autograd,
+tfpnp/env/base.py:193-206, tfpnp/trainer/mddpg/trainer.py:173).
 
-Fixture tests/golden/grad_csmri_small.npz holds the gradients PyTorch autograd gives through the UNMODIFIED reference
-classes (oracle/make_golden_grad.py).  CPU: autograd through the oracle and the two hand-derived restatements the CUDA
+Fixtures tests/golden/grad_{csmri,pr,spi}_small.npz and grad_env_csmri.npz hold the gradients PyTorch autograd gives through
+the UNMODIFIED reference classes (oracle/make_golden_grad.py); CT, whose reference is not runnable, is checked against
+autograd through the oracle.  CPU: autograd through the oracle and the two hand-derived restatements the CUDA
 code follows (the per-iteration adjoint recursion and the layer-by-layer denoiser VJP) against it.  GPU: the native
 backward (tfpnp_denoiser_vjp, tfpnp_csmri_admm_backward) against it.
 
@@ -195,6 +196,29 @@ def test_ct_gradients_cuda_sequence_on_cpu(emu):
         assert rel_err(mine, r)[0] <= 1e-3, (name, rel_err(mine, r))
 
 
+def test_pr_gradients_oracle_and_cuda_sequence_on_cpu(emu):
+    """PR (tasks/pr/solver.py:37-76): fixture = autograd through the unmodified reference; autograd through the oracle and
+    the CUDA sequence + element bodies (magnitude-projection Jacobian, CDP adjoint) run on the host against it."""
+    from tfpnp_b200.denoiser import flatten_state_dict
+    g = load_golden("grad_pr_small")
+    sd = weights("he")
+    keys = ("g_sigma_d", "g_mu", "g_tau", "g_state")
+    a = G.iadmm_pr_vjp_autograd(sd, g["state"], g["y0"], g["mask"], g["sigma_d"], g["mu"], g["tau"], g["gout"])
+    for mine, key in zip(a, keys):
+        assert rel_err(mine, g[key])[1] <= 1e-5, key
+    states = torch.stack(G.iadmm_pr_trajectory(sd, g["state"], g["y0"], g["mask"], g["sigma_d"], g["mu"], g["tau"])).contiguous()
+    flat = flatten_state_dict(sd)
+    B, it = g["sigma_d"].shape
+    M = g["mask"].shape[1]
+    outs = [torch.zeros(B, it) for _ in range(3)] + [torch.zeros_like(g["gout"])]
+    rc = emu.emu_pr_backward(_ptr(flat), _ptr(states), _ptr(g["y0"].contiguous()), _ptr(g["mask"].contiguous()), M,
+                             _ptr(g["sigma_d"].contiguous()), _ptr(g["mu"].contiguous()), _ptr(g["tau"].contiguous()), B, 32, it,
+                             _ptr(g["gout"].contiguous()), *[_ptr(o) for o in outs])
+    assert rc == 0
+    for mine, key in zip(outs, keys):
+        assert rel_err(mine, g[key])[0] <= 1e-3, (key, rel_err(mine, g[key]))
+
+
 def test_psnr_backward_element_body_on_cpu(emu):
     """psnr_bwd_elem (the reward's gradient, tfpnp/env/base.py:237-242 under autograd) against autograd."""
     from oracle import pnp_oracle as O
@@ -232,7 +256,8 @@ def test_reverse_mode_is_opt_in():
     import tfpnp_b200 as T
     assert T.ADMMSolver_CSMRI.differentiable is False and T.ADMMSolver_CSMRI._has_backward is True
     assert T.ADMMSolver_SPI.differentiable is False and T.ADMMSolver_SPI._has_backward is True
-    assert T.IADMMSolver_PR._has_backward is False and T.IADMMSolver_CT._has_backward is True
+    assert T.IADMMSolver_PR._has_backward is True and T.IADMMSolver_CT._has_backward is True
+    assert not hasattr(T.HQSSolver_CSMRI, '_has_backward')          # the other solver variants have no reverse mode
     assert T.UNetDenoiser2D.differentiable is False
 
 
@@ -387,3 +412,19 @@ def test_native_ct_backward_matches_oracle_gradients(dev):
     mine = torch.autograd.grad(out, (*ps, st), gout.to(dev))
     for a, r, name in zip(mine, ref, ("sigma_d", "mu", "tau", "state")):
         assert rel_err(a, r)[0] <= 2e-3, (name, rel_err(a, r))
+
+
+@pytest.mark.gpu
+@needs_grad_flag
+@pytest.mark.parametrize("prec,tol", [("fp32_simt", 2e-3), ("fp16", 3e-2)])
+def test_native_pr_backward_matches_reference_gradients(dev, prec, tol):
+    import tfpnp_b200 as T
+    g = load_golden("grad_pr_small")
+    s = T.IADMMSolver_PR(T.UNetDenoiser2D(state_dict=weights("he"), precision=prec))
+    s.differentiable = True
+    state = g["state"].to(dev).requires_grad_(True)
+    ps = [g[k].to(dev).requires_grad_(True) for k in ("sigma_d", "mu", "tau")]
+    out = s((state, (g["y0"].to(dev), g["mask"].to(dev))), tuple(ps))
+    mine = torch.autograd.grad(out, (*ps, state), g["gout"].to(dev))
+    for a, key in zip(mine, ("g_sigma_d", "g_mu", "g_tau", "g_state")):
+        assert rel_err(a, g[key])[0] <= tol, (prec, key, rel_err(a, g[key]))

@@ -556,5 +556,126 @@ int ct_backward_sequence(Ops& ops, const float* states, const float* P, int B, i
   return 0;
 }
 
+// ---- reverse mode of IADMMSolver_PR.forward (tasks/pr/solver.py:37-76; pr.cu: pr_backward) ------------------------------
+// One iteration: x' = (D(Re(z - u), sigma), 0);  z' = z - tau (g(z) + mu r),  r = z - x' - u;  u' = u + x' - z', with
+//   g(z) = mean_j conj(m_j) . IFFT(h(FFT(m_j . z))),   h(w) = (1 - y0/|w|) w          (cdp_forward / cdp_backward, ortho FFTs).
+// h is a map R^2 -> R^2 with the SYMMETRIC Jacobian J_h(w) b = b - y0 (b/|w| - w (w.b)/|w|^3), the FFT is unitary and the
+// adjoint of multiplying by conj(m) is multiplying by m, so  J_g^T c = mean_j conj(m_j) . IFFT(J_h(w_j) FFT(m_j . c)):
+// the forward operator with h replaced by its Jacobian.  With incoming (gx', gz', gu'):  gzt = gz' - gu';
+//   gz = gzt - tau (J_g^T gzt + mu gzt);  gxt = gx' + gu' + tau mu gzt;  gu = gu' + tau mu gzt;
+//   g_tau = -<gzt, g(z) + mu r>;  g_mu = -tau <gzt, r>;  (gv, g_sigma) = J_D^T Re(gxt);  gz += (gv,0);  gu -= (gv,0);  gx = 0.
+// States are [B,3,HW] complex; mask [B,M,HW] complex; y0 [B,M,HW] real (natural FFT order).
+
+TFPNP_HD cplx c_mul(cplx a, cplx b) { cplx r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+TFPNP_HD cplx c_mul_conj(cplx a, cplx m) { cplx r; r.x = a.x * m.x + a.y * m.y; r.y = a.y * m.x - a.x * m.y; return r; }   // a conj(m)
+
+// out[b,j,p] = mask[b,j,p] img[b,p];  i over B*M*HW
+TFPNP_HD void pr_mul_elem(size_t i, const cplx* img, const cplx* mask, cplx* out, int M, int HW) {
+  const size_t p = i % HW, b = i / ((size_t)M * HW);
+  out[i] = c_mul(img[b * HW + p], mask[i]);
+}
+// in place: W = FFT(m z) -> h(W);  Bc = FFT(m c) -> J_h(W) Bc;  i over B*M*HW
+TFPNP_HD void pr_h_elem(size_t i, cplx* W, cplx* Bc, const float* y0) {
+  const cplx w = W[i], b = Bc[i];
+  const float a = sqrtf(w.x * w.x + w.y * w.y);
+  const float y = y0[i];
+  const float ratio = (a - y) / a;                       // unguarded like the reference (solver.py:67)
+  W[i].x = ratio * w.x; W[i].y = ratio * w.y;
+  const float dot = w.x * b.x + w.y * b.y;
+  const float k = y * dot / (a * a * a);
+  Bc[i].x = b.x - y * b.x / a + k * w.x;
+  Bc[i].y = b.y - y * b.y / a + k * w.y;
+}
+// out[b,p] = (1/M) sum_j E[b,j,p] conj(mask[b,j,p]);  i over B*HW
+TFPNP_HD void pr_acc_elem(size_t i, const cplx* E, const cplx* mask, cplx* out, int M, int HW) {
+  const size_t p = i % HW, b = i / HW;
+  float sx = 0.f, sy = 0.f;
+  for (int j = 0; j < M; ++j) {
+    const size_t o = (b * M + j) * HW + p;
+    const cplx t = c_mul_conj(E[o], mask[o]);
+    sx += t.x; sy += t.y;
+  }
+  out[i].x = sx / (float)M; out[i].y = sy / (float)M;
+}
+TFPNP_HD void pr_pre_elem(size_t i, const cplx* GZ, const cplx* GU, const cplx* st_i, cplx* GZT, cplx* Z, int HW) {
+  const size_t b = i / HW, p = i % HW;
+  GZT[i].x = GZ[i].x - GU[i].x; GZT[i].y = GZ[i].y - GU[i].y;
+  Z[i] = st_i[(b * 3 + 1) * HW + p];
+}
+// Gz = g(z), JC = J_g^T gzt.  In place on (GZ, GU); gxt_re = Re(gx' + gu' + tau mu gzt); v = Re(z - u)
+TFPNP_HD void pr_mid_elem(size_t i, const cplx* st_i, const cplx* st_n, const cplx* GZT, const cplx* JC, const cplx* Gz,
+                          const float* mu, const float* tau, const cplx* GX, cplx* GZ, cplx* GU, float* gxt_re, float* v,
+                          float* term_tau, float* term_mu, int HW) {
+  const size_t b = i / HW, p = i % HW;
+  const float m = mu[b], t = tau[b];
+  const cplx z = st_i[(b * 3 + 1) * HW + p], u = st_i[(b * 3 + 2) * HW + p], xn = st_n[(b * 3 + 0) * HW + p];
+  const float rx = z.x - xn.x - u.x, ry = z.y - xn.y - u.y;
+  const cplx gzt = GZT[i], jc = JC[i], g = Gz[i];
+  cplx gu = GU[i];
+  GZ[i].x = gzt.x - t * (jc.x + m * gzt.x);
+  GZ[i].y = gzt.y - t * (jc.y + m * gzt.y);
+  gxt_re[i] = GX[i].x + gu.x + t * m * gzt.x;
+  gu.x += t * m * gzt.x; gu.y += t * m * gzt.y;
+  GU[i] = gu;
+  term_tau[i] = -(gzt.x * (g.x + m * rx) + gzt.y * (g.y + m * ry));
+  term_mu[i] = -t * (gzt.x * rx + gzt.y * ry);
+  v[i] = z.x - u.x;
+}
+
+struct PrGradBufs {
+  cplx *gx, *gz, *gu, *gzt, *z, *gzv, *jc;     // [B,HW]
+  cplx *w, *w2, *bc, *bc2;                      // [B,M,HW]
+  float *gxt, *v, *gv, *t_tau, *t_mu;           // [B,HW]
+};
+
+// Ops: slot_get / slot_put (complex), pre, mul, fft(in, out, inverse) on B*M images (un-centred, ortho), h, acc, mid, reduce,
+// den_vjp, post (= admm_post_elem).  P: [sigma | mu | tau][iters][B].
+template <class Ops>
+int pr_backward_sequence(Ops& ops, const cplx* states, const float* P, int B, int HW, int iters, const cplx* grad_out,
+                         float* g_sigma, float* g_mu, float* g_tau, cplx* g_state_in, const PrGradBufs& w) {
+#define TFPNP_SEQ(expr) do { int _s = (expr); if (_s != 0) return _s; } while (0)
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gx, 0));
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gz, 1));
+  TFPNP_SEQ(ops.slot_get(grad_out, w.gu, 2));
+  const size_t state_elems = (size_t)B * HW * 3;
+  const size_t np = (size_t)B * iters;
+  for (int i = iters - 1; i >= 0; --i) {
+    const cplx* st_i = states + (size_t)i * state_elems;
+    const cplx* st_n = st_i + state_elems;
+    const float* sg_i = P + (size_t)i * B;
+    const float* mu_i = P + np + (size_t)i * B;
+    const float* tau_i = P + 2 * np + (size_t)i * B;
+    TFPNP_SEQ(ops.pre(w.gz, w.gu, st_i, w.gzt, w.z));
+    TFPNP_SEQ(ops.mul(w.z, w.w2));                 // m_j z
+    TFPNP_SEQ(ops.fft(w.w2, w.w, false));          // W = FFT(m_j z)
+    TFPNP_SEQ(ops.mul(w.gzt, w.bc2));              // m_j gzt
+    TFPNP_SEQ(ops.fft(w.bc2, w.bc, false));        // Bc = FFT(m_j gzt)
+    TFPNP_SEQ(ops.h(w.w, w.bc));                   // W = h(W), Bc = J_h(W) Bc
+    TFPNP_SEQ(ops.fft(w.w, w.w2, true));
+    TFPNP_SEQ(ops.acc(w.w2, w.gzv));               // g(z)
+    TFPNP_SEQ(ops.fft(w.bc, w.bc2, true));
+    TFPNP_SEQ(ops.acc(w.bc2, w.jc));               // J_g^T gzt
+    TFPNP_SEQ(ops.mid(st_i, st_n, w.gzt, w.jc, w.gzv, mu_i, tau_i, w.gx, w.gz, w.gu, w.gxt, w.v, w.t_tau, w.t_mu));
+    TFPNP_SEQ(ops.reduce(w.t_tau, g_tau + i, iters));
+    TFPNP_SEQ(ops.reduce(w.t_mu, g_mu + i, iters));
+    TFPNP_SEQ(ops.den_vjp(w.v, sg_i, w.gxt, w.gv, g_sigma + i, iters));
+    TFPNP_SEQ(ops.post(w.gv, w.gx, w.gz, w.gu));    // gz.re += gv ... see pr_post_elem
+  }
+  if (g_state_in) {
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gx, 0));
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gz, 1));
+    TFPNP_SEQ(ops.slot_put(g_state_in, w.gu, 2));
+  }
+#undef TFPNP_SEQ
+  return 0;
+}
+// gz += (gv, 0);  gu -= (gv, 0);  gx = 0
+TFPNP_HD void pr_post_elem(size_t i, const float* gv, cplx* GX, cplx* GZ, cplx* GU) {
+  const float g = gv[i];
+  GX[i].x = 0.f; GX[i].y = 0.f;
+  GZ[i].x += g;
+  GU[i].x -= g;
+}
+
 }  // namespace grad_elem
 }  // namespace tfpnp

@@ -171,3 +171,174 @@ int pr_update(const float* x, float2* z, float2* u, float* d, float2* T, const f
 }
 
 }  // namespace tfpnp
+
+// ---- reverse mode: sequence and element bodies in grad_elem.cuh; FFTs through tfpnp_fft2 (fft_ops.cu) --------
+namespace tfpnp {
+namespace {
+
+__global__ void prg_slot_copy(const float2* __restrict__ state, float2* __restrict__ buf, int k, int HW, size_t n, int to_state) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2* s = const_cast<float2*>(state) + ((i / HW) * 3 + k) * HW + i % HW;
+  if (to_state) *s = buf[i]; else buf[i] = *s;
+}
+__global__ void prg_pre(const float2* __restrict__ GZ, const float2* __restrict__ GU, const float2* __restrict__ st_i,
+                        float2* __restrict__ GZT, float2* __restrict__ Z, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::pr_pre_elem(i, GZ, GU, st_i, GZT, Z, HW);
+}
+__global__ void prg_mul(const float2* __restrict__ img, const float2* __restrict__ mask, float2* __restrict__ out, int M, int HW,
+                        size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::pr_mul_elem(i, img, mask, out, M, HW);
+}
+__global__ void prg_h(float2* __restrict__ W, float2* __restrict__ Bc, const float* __restrict__ y0, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::pr_h_elem(i, W, Bc, y0);
+}
+__global__ void prg_acc(const float2* __restrict__ E, const float2* __restrict__ mask, float2* __restrict__ out, int M, int HW,
+                        size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::pr_acc_elem(i, E, mask, out, M, HW);
+}
+__global__ void prg_mid(const float2* __restrict__ st_i, const float2* __restrict__ st_n, const float2* __restrict__ GZT,
+                        const float2* __restrict__ JC, const float2* __restrict__ Gz, const float* __restrict__ mu,
+                        const float* __restrict__ tau, const float2* __restrict__ GX, float2* __restrict__ GZ,
+                        float2* __restrict__ GU, float* __restrict__ gxt, float* __restrict__ v, float* __restrict__ t_tau,
+                        float* __restrict__ t_mu, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::pr_mid_elem(i, st_i, st_n, GZT, JC, Gz, mu, tau, GX, GZ, GU, gxt, v, t_tau, t_mu, HW);
+}
+__global__ void prg_post(const float* __restrict__ gv, float2* __restrict__ GX, float2* __restrict__ GZ, float2* __restrict__ GU,
+                         size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::pr_post_elem(i, gv, GX, GZ, GU);
+}
+__global__ void __launch_bounds__(256)
+prg_image_sum(const float* __restrict__ term, float* __restrict__ out, int64_t stride, int HW) {
+  __shared__ float red[256];
+  const float* t = term + (size_t)blockIdx.x * HW;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) s += t[p];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x * stride] = red[0];
+}
+__global__ void prg_gather_params(const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2,
+                                  int64_t rs, int64_t cs, float* __restrict__ P, int B, int iters) {
+  const int n = B * iters;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int i = t / B, b = t % B;
+    const int64_t src = b * rs + i * cs;
+    P[t] = p0[src]; P[n + t] = p1[src]; P[2 * n + t] = p2[src];
+  }
+}
+
+struct PrGradOps {
+  Denoiser* den; const float2* mask; const float* y0; float2* fft_ws; int B, M, N; cudaStream_t st;
+  static constexpr int T = 256;
+  int HW() const { return N * N; }
+  size_t n() const { return (size_t)B * HW(); }
+  size_t nm() const { return n() * M; }
+  unsigned nb(size_t k) const { return (unsigned)((k + T - 1) / T); }
+  int slot_get(const float2* state, float2* buf, int k) {
+    prg_slot_copy<<<nb(n()), T, 0, st>>>(state, buf, k, HW(), n(), 0);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int slot_put(float2* state, float2* buf, int k) {
+    prg_slot_copy<<<nb(n()), T, 0, st>>>(state, buf, k, HW(), n(), 1);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int pre(const float2* gz, const float2* gu, const float2* st_i, float2* gzt, float2* z) {
+    prg_pre<<<nb(n()), T, 0, st>>>(gz, gu, st_i, gzt, z, HW(), n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int mul(const float2* img, float2* out) {
+    prg_mul<<<nb(nm()), T, 0, st>>>(img, mask, out, M, HW(), nm());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int fft(const float2* in, float2* out, bool inverse) {
+    TFPNP_COUNT_LAUNCH(); TFPNP_COUNT_LAUNCH();
+    return tfpnp_fft2(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), reinterpret_cast<float*>(fft_ws), B * M, N,
+                      inverse ? 1 : 0, 0, st);
+  }
+  int h(float2* W, float2* Bc) {
+    prg_h<<<nb(nm()), T, 0, st>>>(W, Bc, y0, nm());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int acc(const float2* E, float2* out) {
+    prg_acc<<<nb(n()), T, 0, st>>>(E, mask, out, M, HW(), n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int mid(const float2* st_i, const float2* st_n, const float2* gzt, const float2* jc, const float2* gzv, const float* mu_i,
+          const float* tau_i, const float2* gx, float2* gz, float2* gu, float* gxt, float* v, float* t_tau, float* t_mu) {
+    prg_mid<<<nb(n()), T, 0, st>>>(st_i, st_n, gzt, jc, gzv, mu_i, tau_i, gx, gz, gu, gxt, v, t_tau, t_mu, HW(), n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int reduce(const float* term, float* out, int64_t stride) {
+    prg_image_sum<<<B, 256, 0, st>>>(term, out, stride, HW());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg_i, const float* gxt, float* gv, float* gsig, int64_t stride) {
+    return den->vjp(v, sg_i, 1, gxt, gv, gsig, stride, B, N, N, st);
+  }
+  int post(const float* gv, float2* gx, float2* gz, float2* gu) {
+    prg_post<<<nb(n()), T, 0, st>>>(gv, gx, gz, gu, n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+};
+
+}  // namespace
+}  // namespace tfpnp
+
+extern "C" int tfpnp_pr_iadmm_backward(void* denoiser, const float* states, const float* y0, const float* mask, int n_masks,
+                                       const float* sigma_d, const float* mu, const float* tau, int64_t row_stride,
+                                       int64_t col_stride, int B, int N, int iters, const float* grad_out, float* grad_sigma_d,
+                                       float* grad_mu, float* grad_tau, float* grad_state_in, void* stream) {
+  using namespace tfpnp;
+  TFPNP_CHECK(denoiser && states && y0 && mask && sigma_d && mu && tau && grad_out && grad_sigma_d && grad_mu && grad_tau &&
+                  B > 0 && iters > 0 && n_masks > 0, "bad argument");
+  TFPNP_CHECK(N == 32 || N == 64 || N == 128 || N == 256, "FFT tasks support N in {32,64,128,256}, got %d", N);
+  g_launch_count = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)B * N * N, nm = n * n_masks;
+  DevBuf c1[7], cm[5], f1[5], P;
+  auto body = [&]() -> int {
+    for (DevBuf& b : c1) TFPNP_TRY(b.alloc(n * sizeof(float2)));
+    for (DevBuf& b : cm) TFPNP_TRY(b.alloc(nm * sizeof(float2)));
+    for (DevBuf& b : f1) TFPNP_TRY(b.alloc(n * sizeof(float)));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float)));
+    prg_gather_params<<<cdiv(B * iters, 256), 256, 0, st>>>(sigma_d, mu, tau, row_stride, col_stride, P.as<float>(), B, iters);
+    TFPNP_COUNT_LAUNCH();
+    PrGradOps ops{static_cast<Denoiser*>(denoiser), reinterpret_cast<const float2*>(mask), y0, cm[4].as<float2>(), B, n_masks, N, st};
+    grad_elem::PrGradBufs w{c1[0].as<float2>(), c1[1].as<float2>(), c1[2].as<float2>(), c1[3].as<float2>(), c1[4].as<float2>(),
+                            c1[5].as<float2>(), c1[6].as<float2>(), cm[0].as<float2>(), cm[1].as<float2>(), cm[2].as<float2>(),
+                            cm[3].as<float2>(), f1[0].as<float>(), f1[1].as<float>(), f1[2].as<float>(), f1[3].as<float>(),
+                            f1[4].as<float>()};
+    TFPNP_TRY(grad_elem::pr_backward_sequence(ops, reinterpret_cast<const float2*>(states), P.as<float>(), B, N * N, iters,
+                                              reinterpret_cast<const float2*>(grad_out), grad_sigma_d, grad_mu, grad_tau,
+                                              reinterpret_cast<float2*>(grad_state_in), w));
+    TFPNP_CUDA_OK(cudaGetLastError());
+    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers are freed on return
+    return 0;
+  };
+  const int rc = body();
+  for (DevBuf& b : c1) b.release();
+  for (DevBuf& b : cm) b.release();
+  for (DevBuf& b : f1) b.release();
+  P.release();
+  return rc;
+}

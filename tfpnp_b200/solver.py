@@ -9,10 +9,10 @@ unchanged.  ``forward`` marshals raw device pointers into ``tfpnp_solver_forward
 (include/tfpnp_b200.h); the iterated proximal loop itself is hand-written sm_100a CUDA.
 
 There is no PyTorch/CPU fallback.  The differentiable use (``PnPEnv.forward`` under
-autograd, tfpnp/env/base.py:193-206) is opt-in and exists for ``ADMMSolver_CSMRI``
-``ADMMSolver_SPI`` and ``IADMMSolver_CT`` (``solver.differentiable = True``: gradients w.r.t. the
-hyper-parameters and the input state through ``tfpnp_{csmri_admm,spi_admm,ct_iadmm}_backward``);
-everything else raises NotImplementedError under autograd.
+autograd, tfpnp/env/base.py:193-206) is opt-in and exists for the four ADMM / iADMM
+solvers (``solver.differentiable = True``: gradients w.r.t. the hyper-parameters and the input state
+through ``tfpnp_{csmri_admm,pr_iadmm,ct_iadmm,spi_admm}_backward``); the other solver variants raise
+NotImplementedError under autograd.
 """
 from __future__ import annotations
 
@@ -122,7 +122,7 @@ class _NativeADMM(PnPSolver):
         if self._wants_grad(variables, parameters) and not (self.differentiable and self._has_backward):
             raise NotImplementedError(
                 "the differentiable solver path (PnPEnv.forward under autograd, SURVEY 8f N4) is opt-in and built for "
-                "the CS-MRI / SPI / CT ADMM solvers only: set solver.differentiable = True")
+                "the four ADMM / iADMM solvers only: set solver.differentiable = True")
 
     def _run(self, handle, variables, aux0, aux1, aux1_stride, params, iter_num):
         B = variables.shape[0]
@@ -352,6 +352,7 @@ class IADMMSolver_PR(IADMMSolver):
     """tasks/pr/solver.py:15-76."""
     _task = _lib.TASK_PR
     _complex_state = True
+    _has_backward = True
 
     def filter_aux_inputs(self, state):     # solver.py:20-21
         return (state['y0'], state['mask'])
@@ -368,7 +369,53 @@ class IADMMSolver_PR(IADMMSolver):
         self._check_inputs(variables, (sigma_d, mu, tau))
         B, _, H, W, _ = variables.shape
         h = self._solver_handle(variables.device, H, W, n_masks=mask.shape[1])
+        if self._wants_grad(variables, (sigma_d, mu, tau)):
+            if iter_num is None:
+                iter_num = sigma_d.shape[-1]
+            return _PRIadmmFn.apply(self, h, variables, _f32c(y0), _f32c(mask), sigma_d, mu, tau, int(iter_num))
         return self._run(h, variables, _f32c(y0), _f32c(mask), 0, (sigma_d, mu, tau), iter_num)
+
+
+class _PRIadmmFn(torch.autograd.Function):
+    """autograd node for IADMMSolver_PR.forward: trajectory with the native forward, tfpnp_pr_iadmm_backward (pr.cu)."""
+
+    @staticmethod
+    def forward(ctx, solver, handle, variables, y0, mask, sigma_d, mu, tau, iter_num):
+        B = variables.shape[0]
+        ps = [p.detach().float().reshape(B, -1)[:, :iter_num].contiguous() for p in (sigma_d, mu, tau)]
+        if any(p.shape[1] < iter_num for p in ps):
+            raise IndexError(f"iter_num={iter_num} exceeds the hyper-parameter width")
+        states = [_f32c(variables.detach())]
+        with torch.no_grad():
+            for i in range(iter_num):
+                states.append(solver._run(handle, states[-1], y0, mask, 0, tuple(p[:, i:i + 1] for p in ps), 1))
+        ctx.solver = solver
+        ctx.meta = ([p.shape for p in (sigma_d, mu, tau)], [p.dtype for p in (sigma_d, mu, tau)], iter_num)
+        ctx.save_for_backward(torch.stack(states), y0, mask, *ps)
+        return states[-1].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        states, y0, mask, sg, m, t = ctx.saved_tensors
+        shapes, dtypes, it = ctx.meta
+        B, _, H, W, _ = gout.shape
+        gout = _f32c(gout)
+        grads = [torch.zeros(B, it, device=gout.device, dtype=torch.float32) for _ in range(3)]
+        g_state = torch.empty_like(gout)
+        with torch.cuda.device(gout.device):
+            _lib.check(_lib.lib().tfpnp_pr_iadmm_backward(
+                ctx.solver.denoiser._grad_handle(gout.device), states.data_ptr(), y0.data_ptr(), mask.data_ptr(), mask.shape[1],
+                sg.data_ptr(), m.data_ptr(), t.data_ptr(), it, 1, B, W, it, gout.data_ptr(), grads[0].data_ptr(),
+                grads[1].data_ptr(), grads[2].data_ptr(), g_state.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                "tfpnp_pr_iadmm_backward")
+
+        def widen(g, shape, dtype):
+            full = torch.zeros(B, max(1, math.prod(shape[1:])), device=g.device, dtype=torch.float32)
+            full[:, :it] = g
+            return full.reshape(shape).to(dtype)
+
+        gs, gm, gt = (widen(g, sh, dt) for g, sh, dt in zip(grads, shapes, dtypes))
+        return (None, None, g_state, None, None, gs, gm, gt, None)
 
 
 class RadonGenerator:
