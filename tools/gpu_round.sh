@@ -11,6 +11,8 @@ tail -6 gpurun_out/pytest_gpu.log
 echo "=== reverse mode (SURVEY 8f N4; written after round 1's GPU budget was spent, gated until it has passed here once)"
 TFPNP_TEST_GRAD=1 timeout 900 python -m pytest tests/test_grad.py -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_grad.log 2>&1
 tail -15 gpurun_out/pytest_grad.log
+echo "=== reverse-mode timing at the north-star shape (CUDA-core vs tensor-core VJP convolutions)"
+timeout 900 python tools/grad_bench.py > gpurun_out/grad_bench.log 2>&1; tail -5 gpurun_out/grad_bench.log
 echo "=== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
 echo "=== bench"
