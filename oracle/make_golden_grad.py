@@ -124,6 +124,24 @@ def main():
          G1=G1.numpy(), G2=G2.numpy(), eval_ob2=eval2.detach().numpy(), reward=reward.detach().numpy(), g_sigma_d=e_gs.numpy(),
          g_mu=e_gm.numpy(), wsum=weight_checksum(sd), init="he", seed=0, max_episode_step=3)
 
+    # 3b. the same for SPI (tasks/spi/env.py): real-valued state, policy observation (variables, x0, K, T)
+    d = synth.spi_batch(B, n, pack)
+    data = E.env_data("spi", d)
+    env = _load_ref_env("spi")(None, refshim.reference_solver("spi", sd), 3)
+    ob = env.reset(data={k: v.clone() for k, v in data.items()})
+    sg = (d["sigma_d"][:, :pack].clone()).requires_grad_(True)
+    mu = (d["mu"][:, :pack].clone()).requires_grad_(True)
+    ob2, reward = env.forward(ob, {"sigma_d": sg, "mu": mu, "idx_stop": torch.zeros(B, dtype=torch.long)})
+    eval2 = env.get_eval_ob(ob2)
+    G1 = torch.randn(eval2.shape, generator=g)
+    G2 = torch.randn(reward.shape, generator=g)
+    e_gs, e_gm = torch.autograd.grad((eval2 * G1).sum() + (reward * G2).sum(), (sg, mu), allow_unused=True)
+    e_gm = torch.zeros_like(mu) if e_gm is None else e_gm
+    print(f"  SPI env.forward: |d loss/d sigma_d| {e_gs.abs().max():.3e}, |d loss/d mu| {e_gm.abs().max():.3e}")
+    save("grad_env_spi", **{"data_" + k: v.numpy() for k, v in data.items()}, sigma_d=sg.detach().numpy(), mu=mu.detach().numpy(),
+         G1=G1.numpy(), G2=G2.numpy(), eval_ob2=eval2.detach().numpy(), reward=reward.detach().numpy(), g_sigma_d=e_gs.numpy(),
+         g_mu=e_gm.numpy(), wsum=weight_checksum(sd), init="he", seed=0, max_episode_step=3)
+
 
 if __name__ == "__main__":
     main()
