@@ -88,6 +88,11 @@ int tfpnp_denoiser_forward(void* handle, const float* x, const float* sigma,
  * checked on the CPU; not yet run on a GPU (tests gated behind TFPNP_TEST_GRAD=1). */
 int tfpnp_denoiser_vjp(void* handle, const float* x, const float* sigma, int64_t sigma_stride, const float* gout,
                        float* gx, float* gsigma, int B, int H, int W, void* stream);
+/* Debugging aid for the call above: copies the reverse-mode workspace of the handle's last tfpnp_denoiser_vjp (every layer's
+ * activation and the gradient buffers, layout = grad_elem::unet_vjp_workspace_layout in tfpnp_b200/csrc/grad_elem.cuh) to
+ * `out_host` (up to n_floats); *have_floats = its size.  tools/grad_layer_check.py compares it region by region with the CPU
+ * emulation to find the first layer that deviates. */
+int tfpnp_debug_grad_workspace(void* handle, float* out_host, size_t n_floats, size_t* have_floats);
 
 /* One denoiser layer on its own (kernel-level parity tests): ConvLayer = nn.Conv2d(3x3, pad 1,
  * bias) + LeakyReLU(0.2) (unet.py:8-22) over the channel concatenation of x0 [B,H,W,C0] and the

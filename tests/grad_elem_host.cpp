@@ -323,13 +323,15 @@ struct HostAdmmOps {
 };
 
 int unet_vjp_host(const float* weights_flat, const float* x, const float* sigma, int64_t sstride, const float* gout, float* gx,
-                  float* gsigma, int64_t gs_stride, int B, int H, int W, int tc = 0) {
+                  float* gsigma, int64_t gs_stride, int B, int H, int W, int tc = 0, float* ws_out = nullptr) {
   HostOps ops;
   ops.tc = tc;
   ops.flat = weights_flat; ops.B = B; ops.H = H; ops.W = W;
   ops.init();
   std::vector<float> ws(grad_elem::unet_vjp_workspace_floats(B, H, W), 0.f);
-  return grad_elem::unet_vjp_sequence(ops, x, sigma, sstride, gout, gx, gsigma, gs_stride, ws.data(), B, H, W);
+  const int rc = grad_elem::unet_vjp_sequence(ops, x, sigma, sstride, gout, gx, gsigma, gs_stride, ws.data(), B, H, W);
+  if (ws_out) memcpy(ws_out, ws.data(), ws.size() * sizeof(float));
+  return rc;
 }
 
 int HostAdmmOps::den_vjp(const float* v, const float* sg_i, const float* gxt, float* gv, float* gsig, int64_t stride) {
@@ -607,3 +609,10 @@ extern "C" int emu_pr_backward(const float* weights_flat, const float* states, c
                                          reinterpret_cast<const cplx*>(grad_out), g_sigma, g_mu, g_tau,
                                          reinterpret_cast<cplx*>(g_state_in), w);
 }
+
+// debugging aid (tools/grad_layer_check.py): the emulation's workspace and its region table
+extern "C" int emu_unet_vjp_ws(const float* weights_flat, const float* x, const float* sigma, const float* gout, float* gx,
+                               float* gsigma, int B, int H, int W, int mode, float* ws_out) {
+  return unet_vjp_host(weights_flat, x, sigma, 1, gout, gx, gsigma, 1, B, H, W, mode, ws_out);
+}
+extern "C" void emu_unet_vjp_layout(int B, int H, int W, size_t* out39) { grad_elem::unet_vjp_workspace_layout(B, H, W, out39); }

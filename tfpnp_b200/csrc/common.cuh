@@ -127,6 +127,8 @@ struct Denoiser {
     set_error("this denoiser engine has no reverse mode: create it with precision fp32_simt");
     return TFPNP_ERR_UNSUPPORTED;
   }
+  // debugging aid: the reverse-mode workspace of the last vjp() (device pointer, size in floats); nullptr if none
+  virtual const float* grad_workspace(size_t* n_floats) { *n_floats = 0; return nullptr; }
 };
 
 // pre-planned one-tile-per-CTA tensor-core 3x3 conv layer (unet_tc.cu): NHWC fp16 (hi [+ lo residual plane]) in/out,

@@ -150,6 +150,19 @@ inline size_t unet_vjp_workspace_floats(int B, int H, int W) {
   return units * B;
 }
 
+// Region table of that workspace for debugging (same carve order as unet_vjp_sequence): offsets (floats) of the 27
+// activations, then in2, pooled, upsampled, r, g_r, gA, gB, gcat[0..3]; 38 entries + the total as entry 38.
+inline void unet_vjp_workspace_layout(int B, int H, int W, size_t out[39]) {
+  const ConvSpec* sp = unet_conv_specs();
+  const size_t HW = (size_t)H * W;
+  size_t off = 0;
+  int k = 0;
+  for (int l = 0; l < kNumUnetConv3; ++l) { out[k++] = off; off += (((size_t)sp[l].cout * HW) >> (2 * sp[l].level)) * B; }
+  const size_t units[11] = {2, 8, 64, 1, 1, 32, 32, 96, 48, 24, 12};
+  for (int j = 0; j < 11; ++j) { out[k++] = off; off += units[j] * HW * B; }
+  out[k] = off;
+}
+
 // Ops: make_input, conv (forward layer: bias + LeakyReLU), maxpool, upsample, outc_pre, outc_bwd, dgrad (input gradient
 // of layer l), lrelu_bwd, pool_bwd, up_bwd, first_finish -- each returns 0 on success.  Tensors are NCHW fp32.
 template <class Ops>

@@ -442,6 +442,17 @@ int tfpnp_denoiser_vjp(void* h, const float* x, const float* sigma, int64_t sstr
   return static_cast<Denoiser*>(h)->vjp(x, sigma, sstride, gout, gx, gsigma, 1, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
+int tfpnp_debug_grad_workspace(void* h, float* out_host, size_t n_floats, size_t* have_floats) {
+  TFPNP_CHECK(h && have_floats, "bad argument");
+  size_t n = 0;
+  const float* ws = static_cast<Denoiser*>(h)->grad_workspace(&n);
+  *have_floats = n;
+  if (!out_host || !ws || n == 0) return 0;
+  TFPNP_CUDA_OK(cudaDeviceSynchronize());
+  TFPNP_CUDA_OK(cudaMemcpy(out_host, ws, (n < n_floats ? n : n_floats) * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int tfpnp_solver_create(const tfpnp_solver_config* cfg, void* denoiser, void** out) {
   return solver_create(cfg, static_cast<Denoiser*>(denoiser), out);
 }

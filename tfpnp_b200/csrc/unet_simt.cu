@@ -546,11 +546,15 @@ struct UNetSimt : Denoiser {
     }
   };
 
+  size_t gws_floats = 0;
+  const float* grad_workspace(size_t* n_floats) override { *n_floats = gws_floats; return gws.as<float>(); }
+
   int vjp(const float* x, const float* sigma, int64_t sstride, const float* gout, float* gx, float* gsigma,
           int64_t gs_stride, int B, int H, int W, cudaStream_t st) override {
     TFPNP_CHECK(H % 16 == 0 && W % 16 == 0 && H >= 16 && W >= 16, "UNet needs H,W multiples of 16, got %dx%d", H, W);
     TFPNP_TRY(ensure_grad_weights());
-    TFPNP_TRY(gws.alloc(grad_elem::unet_vjp_workspace_floats(B, H, W) * sizeof(float)));
+    gws_floats = grad_elem::unet_vjp_workspace_floats(B, H, W);
+    TFPNP_TRY(gws.alloc(gws_floats * sizeof(float)));
     {
       const char* e = getenv("TFPNP_GRAD_TC");          // tensor-core convolutions: opt-in until validated on a GPU
       grad_tc = e ? atoi(e) : 0;                        // 1: fp16 operands, 2: split-fp16 (FP16X3)

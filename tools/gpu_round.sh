@@ -11,6 +11,8 @@ tail -6 gpurun_out/pytest_gpu.log
 echo "=== reverse mode (SURVEY 8f N4; written after round 1's GPU budget was spent, gated until it has passed here once)"
 TFPNP_TEST_GRAD=1 timeout 900 python -m pytest tests/test_grad.py -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_grad.log 2>&1
 tail -15 gpurun_out/pytest_grad.log
+echo "=== reverse mode, layer by layer against the CPU emulation (first deviating region names the kernel)"
+for m in 0 2; do TFPNP_GRAD_TC=$m timeout 300 python tools/grad_layer_check.py > gpurun_out/grad_layers_$m.log 2>&1; grep -E "mode|deviates|gx|gsigma" gpurun_out/grad_layers_$m.log | head -12; done
 echo "=== reverse-mode timing at the north-star shape (CUDA-core vs tensor-core VJP convolutions)"
 timeout 900 python tools/grad_bench.py > gpurun_out/grad_bench.log 2>&1; tail -5 gpurun_out/grad_bench.log
 echo "=== smoke"
