@@ -15,6 +15,8 @@ echo "=== reverse mode, layer by layer against the CPU emulation (first deviatin
 for m in 0 2; do TFPNP_GRAD_TC=$m timeout 300 python tools/grad_layer_check.py > gpurun_out/grad_layers_$m.log 2>&1; grep -E "mode|deviates|gx|gsigma" gpurun_out/grad_layers_$m.log | head -12; done
 echo "=== reverse-mode timing at the north-star shape (CUDA-core vs tensor-core VJP convolutions)"
 timeout 900 python tools/grad_bench.py > gpurun_out/grad_bench.log 2>&1; tail -5 gpurun_out/grad_bench.log
+echo "=== reverse mode of all four tasks at their BASELINE per-GPU shapes (split-fp16 tensor-core VJP)"
+timeout 900 python tools/grad_tasks.py > gpurun_out/grad_tasks.log 2>&1; tail -6 gpurun_out/grad_tasks.log
 echo "=== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
 echo "=== bench"
