@@ -192,6 +192,14 @@ int tfpnp_pr_iadmm_backward(void* denoiser, const float* states, const float* y0
                             int64_t col_stride, int B, int N, int iters, const float* grad_out, float* grad_sigma_d,
                             float* grad_mu, float* grad_tau, float* grad_state_in, void* stream);
 
+/* Reverse mode of tfpnp_csmri_variant_forward (HQS / PG / APG / RED-ADMM, tasks/csmri/solver.py:60-201), same conventions:
+ * states [iters+1][B,V,N,N,2] recorded with iters = 1 calls; p0,p1,p2 as in the forward; grad_p0..2 [B,iters] contiguous
+ * (grad_p2 NULL for the two-parameter solvers); grad_state_in [B,V,N,N,2] or NULL.  ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+int tfpnp_csmri_variant_backward(int algo, void* denoiser, const float* states, const float* y0, const void* mask,
+                                 const float* p0, const float* p1, const float* p2, int64_t row_stride,
+                                 int64_t col_stride, int B, int N, int iters, const float* grad_out, float* grad_p0,
+                                 float* grad_p1, float* grad_p2, float* grad_state_in, void* stream);
+
 /* ---- CT operators (own discretisation of the reference geometry,
  *      tfpnp/utils/transforms.py:465-491) ------------------------------------- */
 /* img [B,1,N,N] <-> sino [B,1,views,ceil(sqrt(2)N)]; cos/sin: optional HOST tables as above */

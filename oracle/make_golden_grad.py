@@ -100,6 +100,33 @@ def main():
          g_sigma_d=p_ref[0].numpy(), g_mu=p_ref[1].numpy(), g_tau=p_ref[2].numpy(), g_state=p_ref[3].numpy(),
          wsum=weight_checksum(sd), init="he", seed=0)
 
+    # 2d. the other CS-MRI solvers of _solver_map (tasks/csmri/solver.py:60-201) under autograd
+    from . import pnp_oracle as O
+    d = synth.csmri_batch(2, 32, 3)
+    g7 = torch.Generator().manual_seed(77)
+    extra = {"tau": torch.rand(2, 3, generator=g7) * 1.5, "beta": torch.rand(2, 3, generator=g7) * 0.8,
+             "lamda": torch.rand(2, 3, generator=g7) * 0.5 + 0.05}
+    g = torch.Generator().manual_seed(37)
+    rec = {}
+    for name, fn, pk in (("hqs", O.hqs_csmri, ("sigma_d", "mu")), ("pg", O.pg_csmri, ("sigma_d", "tau")),
+                         ("apg", O.apg_csmri, ("sigma_d", "tau", "beta")), ("redadmm", O.redadmm_csmri, ("sigma_d", "mu", "lamda"))):
+        sol = refshim.reference_solver("csmri_" + name, sd)
+        state0 = sol.reset({"x0": d["x0"]})
+        cot = torch.randn(state0.shape, generator=g)
+        ps = [{**d, **extra}[k].clone().requires_grad_(True) for k in pk]
+        st = state0.clone().requires_grad_(True)
+        out = sol((st, (d["y0"], d["mask"])), tuple(ps))
+        ref = torch.autograd.grad(out, (*ps, st), cot)
+        ps2 = [{**d, **extra}[k].clone().requires_grad_(True) for k in pk]
+        st2 = state0.clone().requires_grad_(True)
+        mine = torch.autograd.grad(fn(sd, st2, d["y0"], d["mask"], *ps2), (*ps2, st2), cot)
+        print(f"  csmri {name} vjp (autograd through the oracle) vs reference: " + " ".join(f"{close(a, r, 1e-5):.1e}" for a, r in zip(mine, ref)))
+        rec[name + "_state0"] = state0.numpy(); rec[name + "_gout"] = cot.numpy()
+        for k, r in zip(pk + ("state",), ref):
+            rec[f"{name}_g_{k}"] = r.numpy()
+    save("grad_csmri_variants", **np_({k: d[k] for k in ("y0", "mask", "x0", "sigma_d", "mu")}), **np_(extra), **rec,
+         wsum=weight_checksum(sd), init="he", seed=0)
+
     # 3. the call the trainer differentiates: ob2, reward = env.forward(ob, action) (tfpnp/env/base.py:193-206), loss through the
     #    next observation the critic reads (get_eval_ob) and through the PSNR reward (trainer.py:173-189)
     from . import env_oracle as E

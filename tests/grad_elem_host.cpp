@@ -616,3 +616,73 @@ extern "C" int emu_unet_vjp_ws(const float* weights_flat, const float* x, const 
   return unet_vjp_host(weights_flat, x, sigma, 1, gout, gx, gsigma, 1, B, H, W, mode, ws_out);
 }
 extern "C" void emu_unet_vjp_layout(int B, int H, int W, size_t* out39) { grad_elem::unet_vjp_workspace_layout(B, H, W, out39); }
+
+// variant backward (csmri_variants.cu: tfpnp_csmri_variant_backward): shared sequence + element bodies
+namespace {
+struct HostVarOps {
+  HostAdmmOps base;                       // masked-FFT steps and the denoiser VJP of the ADMM emulation
+  int B, N;
+  int HW() const { return N * N; }
+  size_t n() const { return (size_t)B * N * N; }
+  int slot_get(const cplx* state, cplx* buf, int V, int k) {
+    for (size_t i = 0; i < n(); ++i) buf[i] = state[((i / HW()) * V + k) * HW() + i % HW()];
+    return 0;
+  }
+  int slot_put(cplx* state, cplx* buf, int V, int k) {
+    for (size_t i = 0; i < n(); ++i) state[((i / HW()) * V + k) * HW() + i % HW()] = buf[i];
+    return 0;
+  }
+  int pre(int algo, const cplx* st_i, const cplx* st_n, const cplx* g1, const cplx* g2, cplx* A, cplx* IN, int V) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::var_pre_elem(algo, i, st_i, st_n, g1, g2, A, IN, V, HW());
+    return 0;
+  }
+  int blend0(const cplx* A, const float* mu, cplx* Q) { return base.step(A, Q, mu, true, false); }
+  int resid(const cplx* in, bool with_y0, cplx* out) { return base.step(in, out, nullptr, false, with_y0); }
+  int mid(int algo, const cplx* st_i, const cplx* st_n, const cplx* A, const cplx* IN, const cplx* Q, const cplx* R, const float* p1,
+          const float* p2, cplx* g0, cplx* g1, cplx* g2, float* gxt, float* v, float* t1, float* t2, int V) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::var_mid_elem(algo, i, st_i, st_n, A, IN, Q, R, p1, p2, g0, g1, g2, gxt, v, t1, t2, V, HW());
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg, const float* gxt, float* gv, float* gsig, int64_t stride) {
+    return base.den_vjp(v, sg, gxt, gv, gsig, stride);
+  }
+  int post1(int algo, const float* gv, cplx* A, cplx* g0, cplx* g1) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::var_post1_elem(algo, i, gv, A, g0, g1);
+    return 0;
+  }
+  int post2(int algo, const cplx* A, const cplx* Q, const cplx* R, const float* p1, cplx* g0, cplx* g1, float* t1) {
+    for (size_t i = 0; i < n(); ++i) grad_elem::var_post2_elem(algo, i, A, Q, R, p1, g0, g1, t1, HW());
+    return 0;
+  }
+  int reduce(const float* term, float* out, int64_t stride) {
+    for (int b = 0; b < B; ++b) {
+      double s = 0;
+      for (int p = 0; p < HW(); ++p) s += term[(size_t)b * HW() + p];
+      out[b * stride] = (float)s;
+    }
+    return 0;
+  }
+};
+}  // namespace
+
+extern "C" int emu_variant_backward(int algo, const float* weights_flat, const float* states, const float* y0, const uint8_t* mask,
+                                    const float* p0, const float* p1, const float* p2, int B, int N, int iters,
+                                    const float* grad_out, float* g_p0, float* g_p1, float* g_p2, float* g_state_in) {
+  const size_t n = (size_t)B * N * N;
+  std::vector<float> P((size_t)3 * B * iters, 0.f);
+  const float* ps[3] = {p0, p1, p2};
+  for (int k = 0; k < 3; ++k)
+    if (ps[k])
+      for (int i = 0; i < iters; ++i)
+        for (int b = 0; b < B; ++b) P[((size_t)k * iters + i) * B + b] = ps[k][b * iters + i];
+  std::vector<cplx> c[7];
+  for (auto& v : c) v.assign(n, cplx{0.f, 0.f});
+  std::vector<float> f[5];
+  for (auto& v : f) v.assign(n, 0.f);
+  HostVarOps ops{HostAdmmOps{weights_flat, reinterpret_cast<const cplx*>(y0), mask, B, N}, B, N};
+  grad_elem::VarGradBufs w{c[0].data(), c[1].data(), c[2].data(), c[3].data(), c[4].data(), c[5].data(), c[6].data(),
+                           f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data()};
+  return grad_elem::variant_backward_sequence(ops, algo, reinterpret_cast<const cplx*>(states), P.data(), B, N * N, iters,
+                                              reinterpret_cast<const cplx*>(grad_out), g_p0, g_p1, g_p2,
+                                              reinterpret_cast<cplx*>(g_state_in), w);
+}

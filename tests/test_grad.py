@@ -219,6 +219,45 @@ def test_pr_gradients_oracle_and_cuda_sequence_on_cpu(emu):
         assert rel_err(mine, g[key])[0] <= 1e-3, (key, rel_err(mine, g[key]))
 
 
+VARIANTS = {"hqs": (1, ("sigma_d", "mu")), "pg": (2, ("sigma_d", "tau")), "apg": (3, ("sigma_d", "tau", "beta")),
+            "redadmm": (4, ("sigma_d", "mu", "lamda"))}
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_variant_gradients_oracle_and_cuda_sequence_on_cpu(emu, name):
+    """HQS / PG / APG / RED-ADMM (tasks/csmri/solver.py:60-201): fixture = autograd through the unmodified reference classes;
+    autograd through the oracle and the CUDA sequence + element bodies run on the host against it."""
+    from oracle import pnp_oracle as O
+    from tfpnp_b200.denoiser import flatten_state_dict
+    algo, keys = VARIANTS[name]
+    fn = {"hqs": O.hqs_csmri, "pg": O.pg_csmri, "apg": O.apg_csmri, "redadmm": O.redadmm_csmri}[name]
+    g = load_golden("grad_csmri_variants")
+    sd = weights("he")
+    state0, cot = g[name + "_state0"], g[name + "_gout"]
+    ref = [g[f"{name}_g_{k}"] for k in keys + ("state",)]
+    ps = [g[k].clone().requires_grad_(True) for k in keys]
+    st = state0.clone().requires_grad_(True)
+    mine = torch.autograd.grad(fn(sd, st, g["y0"], g["mask"], *ps), (*ps, st), cot)
+    for a, r in zip(mine, ref):
+        assert rel_err(a, r)[1] <= 1e-5
+    states = [state0]
+    with torch.no_grad():
+        for i in range(ps[0].shape[1]):
+            states.append(fn(sd, states[-1], g["y0"], g["mask"], *[q.detach()[:, i:i + 1] for q in ps]))
+    S = torch.stack(states).contiguous()
+    B, it = ps[0].shape
+    outs = [torch.zeros(B, it) for _ in range(3)]
+    gst = torch.zeros_like(state0)
+    pp = [q.detach().contiguous() for q in ps] + [None] * (3 - len(ps))
+    ptr = lambda x: _ptr(x) if x is not None else None
+    flat, y0c, m8, cotc = flatten_state_dict(sd), g["y0"].contiguous(), g["mask"].to(torch.uint8).contiguous(), cot.contiguous()
+    rc = emu.emu_variant_backward(algo, _ptr(flat), _ptr(S), _ptr(y0c), _ptr(m8), ptr(pp[0]), ptr(pp[1]), ptr(pp[2]), B, 32, it,
+                                  _ptr(cotc), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(gst))      # (tensors kept alive above)
+    assert rc == 0
+    for a, r, k in zip(outs[:len(ps)] + [gst], ref, keys + ("state",)):
+        assert rel_err(a, r)[0] <= 5e-3, (name, k, rel_err(a, r))
+
+
 def test_psnr_backward_element_body_on_cpu(emu):
     """psnr_bwd_elem (the reward's gradient, tfpnp/env/base.py:237-242 under autograd) against autograd."""
     from oracle import pnp_oracle as O
@@ -257,7 +296,7 @@ def test_reverse_mode_is_opt_in():
     assert T.ADMMSolver_CSMRI.differentiable is False and T.ADMMSolver_CSMRI._has_backward is True
     assert T.ADMMSolver_SPI.differentiable is False and T.ADMMSolver_SPI._has_backward is True
     assert T.IADMMSolver_PR._has_backward is True and T.IADMMSolver_CT._has_backward is True
-    assert not hasattr(T.HQSSolver_CSMRI, '_has_backward')          # the other solver variants have no reverse mode
+    assert T.HQSSolver_CSMRI.differentiable is False and T.REDADMMSolver_CSMRI.differentiable is False
     assert T.UNetDenoiser2D.differentiable is False
 
 
@@ -433,3 +472,21 @@ def test_native_pr_backward_matches_reference_gradients(dev, prec, tol):
     mine = torch.autograd.grad(out, (*ps, state), g["gout"].to(dev))
     for a, key in zip(mine, ("g_sigma_d", "g_mu", "g_tau", "g_state")):
         assert rel_err(a, g[key])[0] <= tol, (prec, key, rel_err(a, g[key]))
+
+
+@pytest.mark.gpu
+@needs_grad_flag
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_native_variant_backward_matches_reference_gradients(dev, name):
+    import tfpnp_b200 as T
+    algo, keys = VARIANTS[name]
+    g = load_golden("grad_csmri_variants")
+    cls = {"hqs": T.HQSSolver_CSMRI, "pg": T.PGSolver_CSMRI, "apg": T.APGSolver_CSMRI, "redadmm": T.REDADMMSolver_CSMRI}[name]
+    s = cls(T.UNetDenoiser2D(state_dict=weights("he"), precision="fp32_simt"))
+    s.differentiable = True
+    st = g[name + "_state0"].to(dev).requires_grad_(True)
+    ps = [g[k].to(dev).requires_grad_(True) for k in keys]
+    out = s((st, (g["y0"].to(dev), g["mask"].to(dev))), tuple(ps))
+    mine = torch.autograd.grad(out, (*ps, st), g[name + "_gout"].to(dev))
+    for a, k in zip(mine, keys + ("state",)):
+        assert rel_err(a, g[f"{name}_g_{k}"])[0] <= 5e-3, (name, k, rel_err(a, g[f"{name}_g_{k}"]))

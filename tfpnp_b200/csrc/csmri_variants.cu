@@ -427,6 +427,143 @@ int admm_backward(Denoiser* den, const float* states, const float* y0, const uin
   return rc;
 }
 
+
+// ---- reverse mode of HQS / PG / APG / RED-ADMM (grad_elem.cuh: variant_backward_sequence) ------------------------------------
+__global__ void var_slot_copy(const float2* __restrict__ state, float2* __restrict__ buf, int V, int k, int HW, size_t n, int to_state) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2* s = const_cast<float2*>(state) + ((i / HW) * V + k) * HW + i % HW;
+  if (to_state) *s = buf[i]; else buf[i] = *s;
+}
+__global__ void var_pre(int algo, const float2* __restrict__ st_i, const float2* __restrict__ st_n, const float2* __restrict__ G1,
+                        const float2* __restrict__ G2, float2* __restrict__ A, float2* __restrict__ IN, int V, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::var_pre_elem(algo, i, st_i, st_n, G1, G2, A, IN, V, HW);
+}
+__global__ void var_mid(int algo, const float2* __restrict__ st_i, const float2* __restrict__ st_n, const float2* __restrict__ A,
+                        const float2* __restrict__ IN, const float2* __restrict__ Q, const float2* __restrict__ R,
+                        const float* __restrict__ p1, const float* __restrict__ p2, float2* __restrict__ G0, float2* __restrict__ G1,
+                        float2* __restrict__ G2, float* __restrict__ gxt, float* __restrict__ v, float* __restrict__ t1,
+                        float* __restrict__ t2, int V, int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::var_mid_elem(algo, i, st_i, st_n, A, IN, Q, R, p1, p2, G0, G1, G2, gxt, v, t1, t2, V, HW);
+}
+__global__ void var_post1(int algo, const float* __restrict__ gv, float2* __restrict__ A, float2* __restrict__ G0,
+                          float2* __restrict__ G1, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::var_post1_elem(algo, i, gv, A, G0, G1);
+}
+__global__ void var_post2(int algo, const float2* __restrict__ A, const float2* __restrict__ Q, const float2* __restrict__ R,
+                          const float* __restrict__ p1, float2* __restrict__ G0, float2* __restrict__ G1, float* __restrict__ t1,
+                          int HW, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad_elem::var_post2_elem(algo, i, A, Q, R, p1, G0, G1, t1, HW);
+}
+__global__ void __launch_bounds__(256)
+var_image_sum(const float* __restrict__ term, float* __restrict__ out, int64_t stride, int HW) {
+  __shared__ float red[256];
+  const float* t = term + (size_t)blockIdx.x * HW;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) s += t[p];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x * stride] = red[0];
+}
+
+template <int R>
+struct VarGradOps {
+  static constexpr int N = 32 * R;
+  static constexpr int HW = N * N;
+  static constexpr int T256 = 256;
+  Denoiser* den; int B; cudaStream_t st;
+  float2 *T, *y0p, *zero; uint8_t* maskp;
+  size_t n() const { return (size_t)B * HW; }
+  unsigned nb() const { return (unsigned)((n() + T256 - 1) / T256); }
+  int slot_get(const float2* state, float2* buf, int V, int k) {
+    var_slot_copy<<<nb(), T256, 0, st>>>(state, buf, V, k, HW, n(), 0);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int slot_put(float2* state, float2* buf, int V, int k) {
+    var_slot_copy<<<nb(), T256, 0, st>>>(state, buf, V, k, HW, n(), 1);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int pre(int algo, const float2* st_i, const float2* st_n, const float2* g1, const float2* g2, float2* A, float2* IN, int V) {
+    var_pre<<<nb(), T256, 0, st>>>(algo, st_i, st_n, g1, g2, A, IN, V, HW, n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int blend0(const float2* A, const float* mu, float2* Q) { return masked_fft_step<R>(A, Q, T, zero, maskp, mu, MODE_BLEND, B, st); }
+  int resid(const float2* in, bool with_y0, float2* out) {
+    return masked_fft_step<R>(in, out, T, with_y0 ? y0p : zero, maskp, nullptr, MODE_RESIDUAL, B, st);
+  }
+  int mid(int algo, const float2* st_i, const float2* st_n, const float2* A, const float2* IN, const float2* Q, const float2* Rr,
+          const float* p1, const float* p2, float2* g0, float2* g1, float2* g2, float* gxt, float* v, float* t1, float* t2, int V) {
+    var_mid<<<nb(), T256, 0, st>>>(algo, st_i, st_n, A, IN, Q, Rr, p1, p2, g0, g1, g2, gxt, v, t1, t2, V, HW, n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int den_vjp(const float* v, const float* sg, const float* gxt, float* gv, float* gsig, int64_t stride) {
+    return den->vjp(v, sg, 1, gxt, gv, gsig, stride, B, N, N, st);
+  }
+  int post1(int algo, const float* gv, float2* A, float2* g0, float2* g1) {
+    var_post1<<<nb(), T256, 0, st>>>(algo, gv, A, g0, g1, n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int post2(int algo, const float2* A, const float2* Q, const float2* Rr, const float* p1, float2* g0, float2* g1, float* t1) {
+    var_post2<<<nb(), T256, 0, st>>>(algo, A, Q, Rr, p1, g0, g1, t1, HW, n());
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+  int reduce(const float* term, float* out, int64_t stride) {
+    var_image_sum<<<B, 256, 0, st>>>(term, out, stride, HW);
+    TFPNP_COUNT_LAUNCH();
+    return 0;
+  }
+};
+
+template <int R>
+int variant_backward(int algo, Denoiser* den, const float* states, const float* y0, const uint8_t* mask, const float* p0,
+                     const float* p1, const float* p2, int64_t rs, int64_t cs, int B, int iters, const float* grad_out, float* g_p0,
+                     float* g_p1, float* g_p2, float* g_state_in, cudaStream_t st) {
+  constexpr int N = 32 * R;
+  const int HW = N * N;
+  const size_t n = (size_t)B * HW;
+  DevBuf cb[10], fb[5], maskp, P;
+  auto body = [&]() -> int {
+    for (DevBuf& b : cb) TFPNP_TRY(b.alloc(n * sizeof(float2)));
+    for (DevBuf& b : fb) TFPNP_TRY(b.alloc(n * sizeof(float)));
+    TFPNP_TRY(maskp.alloc(n));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float)));
+    TFPNP_CUDA_OK(cudaMemsetAsync(cb[9].p, 0, n * sizeof(float2), st));                 // zero y0
+    TFPNP_CUDA_OK(cudaMemsetAsync(P.p, 0, (size_t)B * iters * 3 * sizeof(float), st));
+    gather_params3<<<cdiv(B * iters, 256), 256, 0, st>>>(p0, p1, p2, rs, cs, P.as<float>(), B, iters);
+    TFPNP_COUNT_LAUNCH();
+    TFPNP_TRY(csmri_prep(y0, mask, cb[8].as<float2>(), maskp.as<uint8_t>(), B, N, st));
+    VarGradOps<R> ops{den, B, st, cb[7].as<float2>(), cb[8].as<float2>(), cb[9].as<float2>(), maskp.as<uint8_t>()};
+    grad_elem::VarGradBufs w{cb[0].as<float2>(), cb[1].as<float2>(), cb[2].as<float2>(), cb[3].as<float2>(), cb[4].as<float2>(),
+                             cb[5].as<float2>(), cb[6].as<float2>(), fb[0].as<float>(), fb[1].as<float>(), fb[2].as<float>(),
+                             fb[3].as<float>(), fb[4].as<float>()};
+    TFPNP_TRY(grad_elem::variant_backward_sequence(ops, algo, reinterpret_cast<const float2*>(states), P.as<float>(), B, HW, iters,
+                                                   reinterpret_cast<const float2*>(grad_out), g_p0, g_p1, g_p2,
+                                                   reinterpret_cast<float2*>(g_state_in), w));
+    TFPNP_CUDA_OK(cudaGetLastError());
+    TFPNP_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+  };
+  const int rc = body();
+  for (DevBuf& b : cb) b.release();
+  for (DevBuf& b : fb) b.release();
+  maskp.release(); P.release();
+  return rc;
+}
+
 }  // namespace
 }  // namespace tfpnp
 
@@ -488,6 +625,27 @@ int tfpnp_csmri_admm_backward(void* denoiser, const float* states, const float* 
     case 64: return admm_backward<2>(den, states, y0, m8, sigma_d, mu, row_stride, col_stride, B, iters, grad_out, grad_sigma_d, grad_mu, grad_state_in, st);
     case 128: return admm_backward<4>(den, states, y0, m8, sigma_d, mu, row_stride, col_stride, B, iters, grad_out, grad_sigma_d, grad_mu, grad_state_in, st);
     default: return admm_backward<8>(den, states, y0, m8, sigma_d, mu, row_stride, col_stride, B, iters, grad_out, grad_sigma_d, grad_mu, grad_state_in, st);
+  }
+}
+
+int tfpnp_csmri_variant_backward(int algo, void* denoiser, const float* states, const float* y0, const void* mask, const float* p0,
+                                 const float* p1, const float* p2, int64_t row_stride, int64_t col_stride, int B, int N, int iters,
+                                 const float* grad_out, float* grad_p0, float* grad_p1, float* grad_p2, float* grad_state_in,
+                                 void* stream) {
+  TFPNP_CHECK(denoiser && states && y0 && mask && p0 && p1 && grad_out && grad_p0 && grad_p1 && B > 0 && iters > 0, "bad argument");
+  TFPNP_CHECK(algo >= TFPNP_ALGO_HQS && algo <= TFPNP_ALGO_REDADMM, "unknown CS-MRI solver variant %d", algo);
+  TFPNP_CHECK(algo < TFPNP_ALGO_APG || (p2 && grad_p2), "missing third hyper-parameter");
+  TFPNP_CHECK(N == 32 || N == 64 || N == 128 || N == 256, "FFT tasks support N in {32,64,128,256}, got %d", N);
+  g_launch_count = 0;
+  TFPNP_CUDA_OK(fft_tables_init());
+  Denoiser* den = static_cast<Denoiser*>(denoiser);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* m8 = static_cast<const uint8_t*>(mask);
+  switch (N) {
+    case 32: return variant_backward<1>(algo, den, states, y0, m8, p0, p1, p2, row_stride, col_stride, B, iters, grad_out, grad_p0, grad_p1, grad_p2, grad_state_in, st);
+    case 64: return variant_backward<2>(algo, den, states, y0, m8, p0, p1, p2, row_stride, col_stride, B, iters, grad_out, grad_p0, grad_p1, grad_p2, grad_state_in, st);
+    case 128: return variant_backward<4>(algo, den, states, y0, m8, p0, p1, p2, row_stride, col_stride, B, iters, grad_out, grad_p0, grad_p1, grad_p2, grad_state_in, st);
+    default: return variant_backward<8>(algo, den, states, y0, m8, p0, p1, p2, row_stride, col_stride, B, iters, grad_out, grad_p0, grad_p1, grad_p2, grad_state_in, st);
   }
 }
 

@@ -690,5 +690,127 @@ TFPNP_HD void pr_post_elem(size_t i, const float* gv, cplx* GX, cplx* GZ, cplx* 
   GU[i].x -= g;
 }
 
+// ---- reverse mode of the other CS-MRI solvers (tasks/csmri/solver.py:60-201; csmri_variants.cu: variant_backward) --------
+// Building blocks: the k-space blend with y0 = 0 and the masked projection F^-1 M F are self-adjoint (unitary F, real diagonal),
+// R(w) = ifft2c(M (fft2c(w) - y0)) is the masked residual.  algo: 1 HQS (x,z | sigma,mu), 2 PG (x | sigma,tau),
+// 3 APG (x_prev,s | sigma,tau,beta), 4 RED-ADMM (x,z,u | sigma,mu,lamda).  G0..G2: running cotangents of the state slots.
+//   HQS:  x' = D(Re z); z' = Blend_mu(x').            gxt = Re(gx' + Blend0(gz')); g_mu = <gz', R(x')>/(1+mu)^2; gz = (gv,0); gx = 0
+//   PG:   z = x - tau R(x); x' = D(Re z).             a = (gv,0); gx = a - tau P(a); g_tau = -<a, R(x)>          (P = F^-1 M F)
+//   APG:  z = s - tau R(s); x' = D(Re z); s' = x' + beta (x' - x).   gxt = Re(gx' + (1+beta) gs'); g_beta = <gs', x' - x>;
+//         gx = -beta gs'; a = (gv,0); gs = a - tau P(a); g_tau = -<a, R(s)>
+//   RED:  xh = D(Re x); x' = (lam xh + mu (z-u))/(mu+lam); z' = Blend_mu(x'+u); u' = u + x' - z'.   gzt = gz' - gu';
+//         q = Blend0(gzt); gx't = gx' + gu' + q; gu = gu' + q - mu/(mu+lam) gx't; gz = mu/(mu+lam) gx't; gxh = lam/(mu+lam) Re gx't;
+//         g_mu = <gzt, R(x'+u)>/(1+mu)^2 + <gx't, (z-u) - x'>/(mu+lam); g_lam = <gx't, xh - x'>/(mu+lam); gx = (gv,0)
+TFPNP_HD float c_dot(cplx a, cplx b) { return a.x * b.x + a.y * b.y; }
+
+TFPNP_HD void var_pre_elem(int algo, size_t i, const cplx* st_i, const cplx* st_n, const cplx* G1, const cplx* G2, cplx* A, cplx* IN,
+                           int V, int HW) {
+  const size_t b = i / HW, p = i % HW;
+  const cplx* si = st_i + (b * V) * HW + p;
+  const cplx* sn = st_n + (b * V) * HW + p;
+  if (algo == 1) { A[i] = G1[i]; IN[i] = sn[0]; }
+  else if (algo == 2) { IN[i] = si[0]; }
+  else if (algo == 3) { IN[i] = si[(size_t)HW]; }
+  else { A[i].x = G1[i].x - G2[i].x; A[i].y = G1[i].y - G2[i].y;
+         IN[i].x = sn[0].x + si[2 * (size_t)HW].x; IN[i].y = sn[0].y + si[2 * (size_t)HW].y; }
+}
+// after the FFT steps: Q = Blend0(A) (HQS, RED), R = R(IN).  Writes gxt, v (the denoiser VJP's cotangent / input), the
+// per-pixel terms of d/dp1, d/dp2, and updates the cotangents that do not depend on gv.
+TFPNP_HD void var_mid_elem(int algo, size_t i, const cplx* st_i, const cplx* st_n, const cplx* A, const cplx* IN, const cplx* Q,
+                           const cplx* R, const float* p1, const float* p2, cplx* G0, cplx* G1, cplx* G2, float* gxt, float* v,
+                           float* t1, float* t2, int V, int HW) {
+  const size_t b = i / HW, p = i % HW;
+  const cplx* si = st_i + (b * V) * HW + p;
+  const cplx* sn = st_n + (b * V) * HW + p;
+  t1[i] = 0.f; t2[i] = 0.f;
+  if (algo == 1) {
+    const float m = 1.f + p1[b];
+    t1[i] = c_dot(A[i], R[i]) / (m * m);
+    gxt[i] = G0[i].x + Q[i].x;
+    v[i] = si[(size_t)HW].x;
+  } else if (algo == 2) {
+    v[i] = IN[i].x - p1[b] * R[i].x;
+    gxt[i] = G0[i].x;
+  } else if (algo == 3) {
+    const float bt = p2[b];
+    const cplx gs = G1[i];
+    v[i] = IN[i].x - p1[b] * R[i].x;
+    gxt[i] = G0[i].x + (1.f + bt) * gs.x;
+    cplx d; d.x = sn[0].x - si[0].x; d.y = sn[0].y - si[0].y;
+    t2[i] = c_dot(gs, d);
+    G0[i].x = -bt * gs.x; G0[i].y = -bt * gs.y;
+  } else {
+    const float mu = p1[b], lam = p2[b], k = 1.f / (mu + lam), m = 1.f + mu;
+    const cplx q = Q[i], xn = sn[0], z = si[(size_t)HW], u = si[2 * (size_t)HW];
+    cplx g; g.x = G0[i].x + G2[i].x + q.x; g.y = G0[i].y + G2[i].y + q.y;          // cotangent of x'
+    cplx zu; zu.x = z.x - u.x; zu.y = z.y - u.y;
+    cplx xh; xh.x = ((mu + lam) * xn.x - mu * zu.x) / lam; xh.y = 0.f;               // x_half recovered from x'
+    cplx dl; dl.x = xh.x - xn.x; dl.y = xh.y - xn.y;
+    cplx dm; dm.x = zu.x - xn.x; dm.y = zu.y - xn.y;
+    t1[i] = c_dot(A[i], R[i]) / (m * m) + c_dot(g, dm) * k;
+    t2[i] = c_dot(g, dl) * k;
+    gxt[i] = lam * k * g.x;
+    G1[i].x = mu * k * g.x; G1[i].y = mu * k * g.y;
+    G2[i].x = G2[i].x + q.x - mu * k * g.x; G2[i].y = G2[i].y + q.y - mu * k * g.y;
+    v[i] = si[0].x;
+  }
+}
+// after the denoiser VJP: HQS / RED finish here; PG / APG set A = (gv, 0) for the projection step
+TFPNP_HD void var_post1_elem(int algo, size_t i, const float* gv, cplx* A, cplx* G0, cplx* G1) {
+  const float g = gv[i];
+  if (algo == 1) { G0[i].x = 0.f; G0[i].y = 0.f; G1[i].x = g; G1[i].y = 0.f; }
+  else if (algo == 4) { G0[i].x = g; G0[i].y = 0.f; }
+  else { A[i].x = g; A[i].y = 0.f; }
+}
+// PG / APG: Q = P(A);  g = A - tau Q;  t1 = -<A, R>
+TFPNP_HD void var_post2_elem(int algo, size_t i, const cplx* A, const cplx* Q, const cplx* R, const float* p1, cplx* G0, cplx* G1,
+                             float* t1, int HW) {
+  const size_t b = i / HW;
+  const float tau = p1[b];
+  cplx g; g.x = A[i].x - tau * Q[i].x; g.y = A[i].y - tau * Q[i].y;
+  t1[i] = -c_dot(A[i], R[i]);
+  if (algo == 2) G0[i] = g; else G1[i] = g;
+}
+
+struct VarGradBufs { cplx *g0, *g1, *g2, *A, *IN, *Q, *R; float *gxt, *v, *gv, *t1, *t2; };
+
+// Ops: slot_get / slot_put (V slots), pre, blend0(A, mu, Q), resid(in, with_y0, out), mid, den_vjp, post1, post2, reduce.
+// P: [p0 | p1 | p2][iters][B].  g_p2 may be null for the two-parameter solvers.
+template <class Ops>
+int variant_backward_sequence(Ops& ops, int algo, const cplx* states, const float* P, int B, int HW, int iters,
+                              const cplx* grad_out, float* g_p0, float* g_p1, float* g_p2, cplx* g_state_in,
+                              const VarGradBufs& w) {
+#define TFPNP_SEQ(expr) do { int _s = (expr); if (_s != 0) return _s; } while (0)
+  const int V = algo == 2 ? 1 : (algo == 4 ? 3 : 2);
+  cplx* G[3] = {w.g0, w.g1, w.g2};
+  for (int k = 0; k < V; ++k) TFPNP_SEQ(ops.slot_get(grad_out, G[k], V, k));
+  const size_t state_elems = (size_t)B * HW * V;
+  const size_t np = (size_t)B * iters;
+  for (int i = iters - 1; i >= 0; --i) {
+    const cplx* st_i = states + (size_t)i * state_elems;
+    const cplx* st_n = st_i + state_elems;
+    const float* p0 = P + (size_t)i * B;
+    const float* p1 = P + np + (size_t)i * B;
+    const float* p2 = P + 2 * np + (size_t)i * B;
+    TFPNP_SEQ(ops.pre(algo, st_i, st_n, w.g1, w.g2, w.A, w.IN, V));
+    if (algo == 1 || algo == 4) TFPNP_SEQ(ops.blend0(w.A, p1, w.Q));
+    TFPNP_SEQ(ops.resid(w.IN, true, w.R));
+    TFPNP_SEQ(ops.mid(algo, st_i, st_n, w.A, w.IN, w.Q, w.R, p1, p2, w.g0, w.g1, w.g2, w.gxt, w.v, w.t1, w.t2, V));
+    if (algo == 1 || algo == 4) TFPNP_SEQ(ops.reduce(w.t1, g_p1 + i, iters));
+    if (algo >= 3) TFPNP_SEQ(ops.reduce(w.t2, g_p2 + i, iters));
+    TFPNP_SEQ(ops.den_vjp(w.v, p0, w.gxt, w.gv, g_p0 + i, iters));
+    TFPNP_SEQ(ops.post1(algo, w.gv, w.A, w.g0, w.g1));
+    if (algo == 2 || algo == 3) {
+      TFPNP_SEQ(ops.resid(w.A, false, w.Q));
+      TFPNP_SEQ(ops.post2(algo, w.A, w.Q, w.R, p1, w.g0, w.g1, w.t1));
+      TFPNP_SEQ(ops.reduce(w.t1, g_p1 + i, iters));
+    }
+  }
+  if (g_state_in)
+    for (int k = 0; k < V; ++k) TFPNP_SEQ(ops.slot_put(g_state_in, G[k], V, k));
+#undef TFPNP_SEQ
+  return 0;
+}
+
 }  // namespace grad_elem
 }  // namespace tfpnp

@@ -11,8 +11,9 @@ unchanged.  ``forward`` marshals raw device pointers into ``tfpnp_solver_forward
 There is no PyTorch/CPU fallback.  The differentiable use (``PnPEnv.forward`` under
 autograd, tfpnp/env/base.py:193-206) is opt-in and exists for the four ADMM / iADMM
 solvers (``solver.differentiable = True``: gradients w.r.t. the hyper-parameters and the input state
-through ``tfpnp_{csmri_admm,pr_iadmm,ct_iadmm,spi_admm}_backward``); the other solver variants raise
-NotImplementedError under autograd.
+through ``tfpnp_{csmri_admm,pr_iadmm,ct_iadmm,spi_admm}_backward``) and for the HQS / PG / APG /
+RED-ADMM CS-MRI solvers (``tfpnp_csmri_variant_backward``); PGSolver_CT raises NotImplementedError
+under autograd.
 """
 from __future__ import annotations
 
@@ -245,6 +246,7 @@ class _CSMRIVariant(PnPSolver):
     _algo = None
     _nvar = None
     _param_keys = ()
+    differentiable = False      # reverse mode is opt-in
 
     def __init__(self, denoiser):
         if not isinstance(denoiser, UNetDenoiser2D):
@@ -273,11 +275,16 @@ class _CSMRIVariant(PnPSolver):
         params = tuple(parameters)
         if not variables.is_cuda:
             raise RuntimeError("tfpnp_b200 solvers run on CUDA (sm_100) tensors only; there is no CPU fallback")
-        if torch.is_grad_enabled() and (variables.requires_grad or any(p.requires_grad for p in params)):
-            raise NotImplementedError("the differentiable solver path is out of scope (SURVEY 8f N4)")
+        wants_grad = torch.is_grad_enabled() and (variables.requires_grad or any(p.requires_grad for p in params))
+        if wants_grad and not self.differentiable:
+            raise NotImplementedError("the differentiable solver path (SURVEY 8f N4) is opt-in: set solver.differentiable = True")
         B, _, H, W, _ = variables.shape
         if iter_num is None:
             iter_num = params[0].shape[-1]
+        if wants_grad:
+            m8 = mask.contiguous()
+            m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else (m8 != 0).view(torch.uint8)
+            return _CSMRIVariantFn.apply(self, variables, _f32c(y0), m8, int(iter_num), *params)
         dev = variables.device
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         h = self._solvers.get((idx, H))
@@ -311,6 +318,48 @@ class _CSMRIVariant(PnPSolver):
                 _lib.lib().tfpnp_csmri_variant_destroy(h)
         except Exception:
             pass
+
+
+class _CSMRIVariantFn(torch.autograd.Function):
+    """autograd node for the HQS / PG / APG / RED-ADMM solvers: trajectory with the native forward (one iteration per call),
+    tfpnp_csmri_variant_backward (csmri_variants.cu)."""
+
+    @staticmethod
+    def forward(ctx, solver, variables, y0, m8, iter_num, *params):
+        B = variables.shape[0]
+        ps = [p.detach().float().reshape(B, -1)[:, :iter_num].contiguous() for p in params]
+        if any(p.shape[1] < iter_num for p in ps):
+            raise IndexError(f"iter_num={iter_num} exceeds the hyper-parameter width")
+        states = [_f32c(variables.detach())]
+        with torch.no_grad():
+            for i in range(iter_num):
+                states.append(solver.forward((states[-1], (y0, m8)), tuple(p[:, i:i + 1] for p in ps), 1))
+        ctx.solver = solver
+        ctx.meta = ([p.shape for p in params], [p.dtype for p in params], iter_num)
+        ctx.save_for_backward(torch.stack(states), y0, m8, *ps)
+        return states[-1].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        states, y0, m8, *ps = ctx.saved_tensors
+        shapes, dtypes, it = ctx.meta
+        B, _, H, W, _ = gout.shape
+        gout = _f32c(gout)
+        grads = [torch.zeros(B, it, device=gout.device, dtype=torch.float32) for _ in ps]
+        g_state = torch.empty_like(gout)
+        ptr = lambda k, arr: arr[k].data_ptr() if k < len(arr) else None
+        with torch.cuda.device(gout.device):
+            _lib.check(_lib.lib().tfpnp_csmri_variant_backward(
+                ctx.solver._algo, ctx.solver.denoiser._grad_handle(gout.device), states.data_ptr(), y0.data_ptr(), m8.data_ptr(),
+                ptr(0, ps), ptr(1, ps), ptr(2, ps), it, 1, B, H, it, gout.data_ptr(), ptr(0, grads), ptr(1, grads), ptr(2, grads),
+                g_state.data_ptr(), torch.cuda.current_stream().cuda_stream), "tfpnp_csmri_variant_backward")
+
+        def widen(g, shape, dtype):
+            full = torch.zeros(B, max(1, math.prod(shape[1:])), device=g.device, dtype=torch.float32)
+            full[:, :it] = g
+            return full.reshape(shape).to(dtype)
+
+        return (None, g_state, None, None, None, *[widen(g, sh, dt) for g, sh, dt in zip(grads, shapes, dtypes)])
 
 
 class HQSSolver_CSMRI(_CSMRIVariant):
