@@ -79,9 +79,11 @@ void conv3x3_tc_host(const uint16_t* X, const uint16_t* Xlo, int K, const uint16
 }
 
 struct HostOps {
-  int tc = 0;                              // convolutions through the fp16 (1) / split-fp16 (2) NHWC path (TFPNP_GRAD_TC)
+  int tc = 0;                              // convolutions through the fp16 (1) / split-fp16 (2) NHWC path; 3: split-fp16 forward + fp16 gradients
+  bool bwd = false;                        // the op in flight is an input-gradient convolution
   std::vector<uint16_t> X, Y, Xlo, Ylo;
-  uint16_t* lo(std::vector<uint16_t>& v) { return tc == 2 ? v.data() : nullptr; }
+  bool lo_on() const { return tc == 2 || (tc == 3 && !bwd); }
+  uint16_t* lo(std::vector<uint16_t>& v) { return lo_on() ? v.data() : nullptr; }
   std::vector<float> scale;
   const float* flat;                       // state_dict floats
   size_t w_off[kNumUnetConv3], b_off[kNumUnetConv3], outc_w, outc_b;
@@ -113,7 +115,7 @@ struct HostOps {
   }
   void from_half(size_t yoff, float* dst, int C, int Ctot, int coff, int hw, const float* sc) {
     for (size_t i = 0; i < (size_t)B * C * hw; ++i)
-      grad_elem::from_half_nhwc_elem(i, Y.data() + yoff, tc == 2 ? Ylo.data() + yoff : nullptr, dst, C, Ctot, coff, hw, sc);
+      grad_elem::from_half_nhwc_elem(i, Y.data() + yoff, lo_on() ? Ylo.data() + yoff : nullptr, dst, C, Ctot, coff, hw, sc);
   }
   void reset_xy() {
     const size_t n = (size_t)96 * H * W * B;
@@ -123,6 +125,7 @@ struct HostOps {
     const ConvSpec& sp = unet_conv_specs()[l];
     if (C0 + C1 != sp.cin) return -1;
     if (tc && l >= 1) {                    // UNetSimt::GradOps::conv, tensor-core branch
+      bwd = false;
       reset_xy();
       to_half(s0, C0, C0 + C1, 0, h * w, nullptr);
       if (s1) to_half(s1, C1, C0 + C1, C0, h * w, nullptr);
@@ -178,6 +181,7 @@ struct HostOps {
   int dgrad(int l, const float* gin, float* gout, int h, int w) {
     const ConvSpec& sp = unet_conv_specs()[l];
     if (tc && l >= 1) {                    // UNetSimt::GradOps::dgrad, tensor-core branch
+      bwd = true;
       reset_xy();
       scale.assign(B, 1.f);
       const size_t per = (size_t)sp.cout * h * w;
@@ -194,7 +198,7 @@ struct HostOps {
         std::vector<uint16_t> wt16((size_t)9 * rows[p] * sp.cout), wl16(wt16.size());
         grad_elem::build_tc_weights(flat + w_off[l], sp.cout, sp.cin, true, r0, rows[p], wt16.data(), lo(wl16));
         conv3x3_tc_host(X.data(), lo(Xlo), sp.cout, wt16.data(), lo(wl16), nullptr, 1.0f, Y.data() + yoff,
-                        tc == 2 ? Ylo.data() + yoff : nullptr, rows[p], B, h, w);
+                        lo_on() ? Ylo.data() + yoff : nullptr, rows[p], B, h, w);
         from_half(yoff, gout, rows[p], sp.cin, coff, h * w, scale.data());
         yoff += (size_t)B * h * w * rows[p];
       }

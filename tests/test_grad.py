@@ -89,13 +89,14 @@ def test_cuda_vjp_sequence_on_cpu(emu):
     assert rel_err(gx, g["den_gx"])[1] <= 1e-5 and rel_err(gs, g["den_gsigma"])[1] <= 1e-5
 
 
-@pytest.mark.parametrize("mode,tol_x,tol_s", [(1, 5e-3, 1e-1), (2, 1e-5, 1e-4)])
+@pytest.mark.parametrize("mode,tol_x,tol_s", [(1, 5e-3, 1e-1), (2, 1e-5, 1e-4), (3, 2e-4, 5e-3)])
 def test_cuda_vjp_sequence_tensor_core_branch_on_cpu(emu, mode, tol_x, tol_s):
-    """TFPNP_GRAD_TC=1/2: the same sequence with every convolution on NHWC fp16 (mode 1) / split-fp16 (mode 2) copies --
+    """TFPNP_GRAD_TC=1/2/3: the same sequence with every convolution on NHWC fp16 (mode 1) / split-fp16 (mode 2) copies --
     per-image power-of-two gradient scale, channel-range scatter of the two parts of a decoder head's input gradient,
-    transposed + flipped fp16 weights -- with a loop convolution standing in for the tcgen05 kernel.  d/dsigma is a sum of
-    signed per-pixel terms that mostly cancel, so plain fp16 operands leave it at the 1e-1 level; the split-fp16 mode is
-    the accurate one."""
+    transposed + flipped fp16 weights -- with a loop convolution standing in for the tcgen05 kernel.  What costs accuracy is
+    the FORWARD recompute in plain fp16: it flips a few LeakyReLU / max-pool / clamp switches, and d/dsigma, a sum of signed
+    per-pixel terms that mostly cancel, moves at the 1e-1 level.  Plain fp16 GRADIENT convolutions are harmless: mode 3
+    (split-fp16 forward, fp16 gradients; 4 products per layer instead of 6) stays at 1e-3."""
     from tfpnp_b200.denoiser import flatten_state_dict
     g = load_golden("grad_csmri_small")
     flat = flatten_state_dict(weights("he"))
@@ -328,7 +329,7 @@ def test_native_denoiser_vjp_matches_reference_gradients(dev):
 
 @pytest.mark.gpu
 @needs_grad_flag
-@pytest.mark.parametrize("mode,tol_x,tol_s", [("1", 5e-3, 1e-1), ("2", 1e-3, 1e-3)])
+@pytest.mark.parametrize("mode,tol_x,tol_s", [("1", 5e-3, 1e-1), ("2", 1e-3, 1e-3), ("3", 1e-3, 5e-3)])
 def test_native_denoiser_vjp_tensor_core_branch(dev, monkeypatch, mode, tol_x, tol_s):
     """TFPNP_GRAD_TC: the convolutions of the reverse-mode sequences on the tcgen05 kernel (fp16 / split-fp16)."""
     import tfpnp_b200 as T

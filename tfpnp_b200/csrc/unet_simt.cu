@@ -338,7 +338,9 @@ struct UNetSimt : Denoiser {
 
 
   // tensor-core convolutions for the reverse-mode sequences (opt-in: TFPNP_GRAD_TC=1)
-  int grad_tc = 0;              // 0: fp32 CUDA cores; 1: tcgen05 fp16; 2: tcgen05 split-fp16 (FP16X3: hi + residual planes)
+  int grad_tc = 0;              // 0: fp32 CUDA cores; 1: tcgen05 fp16; 2: tcgen05 split-fp16 (FP16X3: hi + residual planes);
+                                // 3: split-fp16 forward recompute (it decides the LeakyReLU / max-pool / clamp switches, which is what
+                                //    the gradient is sensitive to) + plain fp16 gradient convolutions -- the recommended mix
   int tc_mode_built = 0;
   DevBuf tc_w, tc_wlo, tc_x, tc_xlo, tc_y, tc_ylo, tc_scale;
   size_t tcw_f[kNumUnetConv3], tcw_b[kNumUnetConv3][2];
@@ -357,7 +359,9 @@ struct UNetSimt : Denoiser {
 
   int ensure_tc(int B, int H, int W) {
     const ConvSpec* sp = unet_conv_specs();
-    const bool x3 = grad_tc == 2;
+    const bool x3 = grad_tc >= 2;            // residual planes exist (forward recompute: modes 2, 3)
+    const bool x3f = grad_tc >= 2;           // forward recompute in split-fp16
+    const bool x3b = grad_tc == 2;           // gradient convolutions in split-fp16
     if (tc_mode_built != grad_tc) { free_tc_plans(); tc_w.release(); tc_wlo.release(); tc_mode_built = grad_tc; }
     if (!tc_w.p) {
       size_t total = 0;
@@ -402,15 +406,16 @@ struct UNetSimt : Denoiser {
     const float* biases = weights.as<float>();
     for (int l = 1; l < kNumUnetConv3; ++l) {
       const int h = H >> sp[l].level, w = W >> sp[l].level;
-      TFPNP_TRY(conv_v1_plan(&tc_fwd[l], tc_x.as<__half>(), Xlo, sp[l].cin, W16 + tcw_f[l], x3 ? W16lo + tcw_f[l] : nullptr,
-                             biases + b_off[l], tc_y.as<__half>(), Ylo, B, h, w, sp[l].cout, 1, 0.2f));
+      TFPNP_TRY(conv_v1_plan(&tc_fwd[l], tc_x.as<__half>(), x3f ? Xlo : nullptr, sp[l].cin, W16 + tcw_f[l],
+                             x3f ? W16lo + tcw_f[l] : nullptr, biases + b_off[l], tc_y.as<__half>(), x3f ? Ylo : nullptr, B, h, w,
+                             sp[l].cout, 1, 0.2f));
       int rows[2];
       const int np = grad_elem::dgrad_parts(l, rows);
       size_t yoff = 0;
       for (int p = 0; p < np; ++p) {
-        TFPNP_TRY(conv_v1_plan(&tc_bwd[l][p], tc_x.as<__half>(), Xlo, sp[l].cout, W16 + tcw_b[l][p],
-                               x3 ? W16lo + tcw_b[l][p] : nullptr, zero_bias.as<float>(), tc_y.as<__half>() + yoff,
-                               x3 ? Ylo + yoff : nullptr, B, h, w, rows[p], 1, 1.0f));
+        TFPNP_TRY(conv_v1_plan(&tc_bwd[l][p], tc_x.as<__half>(), x3b ? Xlo : nullptr, sp[l].cout, W16 + tcw_b[l][p],
+                               x3b ? W16lo + tcw_b[l][p] : nullptr, zero_bias.as<float>(), tc_y.as<__half>() + yoff,
+                               x3b ? Ylo + yoff : nullptr, B, h, w, rows[p], 1, 1.0f));
         yoff += (size_t)B * h * w * rows[p];
       }
     }
@@ -459,17 +464,18 @@ struct UNetSimt : Denoiser {
       TFPNP_COUNT_LAUNCH();
       return 0;
     }
-    int to_half(const float* src, int C, int Ctot, int coff, int hw, const float* scale) {
+    bool lo_planes(bool backward) const { return u->grad_tc == 2 || (u->grad_tc == 3 && !backward); }
+    int to_half(const float* src, int C, int Ctot, int coff, int hw, const float* scale, bool backward) {
       const size_t n = (size_t)B * C * hw;
-      to_half_nhwc_simt<<<blocks(n), T, 0, st>>>(src, u->tc_x.as<uint16_t>(), u->grad_tc == 2 ? u->tc_xlo.as<uint16_t>() : nullptr,
+      to_half_nhwc_simt<<<blocks(n), T, 0, st>>>(src, u->tc_x.as<uint16_t>(), lo_planes(backward) ? u->tc_xlo.as<uint16_t>() : nullptr,
                                                  C, Ctot, coff, hw, scale, n);
       TFPNP_COUNT_LAUNCH();
       return 0;
     }
-    int from_half(size_t yoff, float* dst, int C, int Ctot, int coff, int hw, const float* scale) {
+    int from_half(size_t yoff, float* dst, int C, int Ctot, int coff, int hw, const float* scale, bool backward) {
       const size_t n = (size_t)B * C * hw;
       from_half_nhwc_simt<<<blocks(n), T, 0, st>>>(u->tc_y.as<uint16_t>() + yoff,
-                                                   u->grad_tc == 2 ? u->tc_ylo.as<uint16_t>() + yoff : nullptr, dst, C, Ctot, coff,
+                                                   lo_planes(backward) ? u->tc_ylo.as<uint16_t>() + yoff : nullptr, dst, C, Ctot, coff,
                                                    hw, scale, n);
       TFPNP_COUNT_LAUNCH();
       return 0;
@@ -477,11 +483,11 @@ struct UNetSimt : Denoiser {
     int conv(int l, const float* s0, int C0, const float* s1, int C1, float* out, int h, int w) {
       if (!u->grad_tc || l == 0) return u->conv(l, s0, C0, s1, C1, out, B, h, w, st);
       // tcgen05 path: cat[s0, s1] -> NHWC fp16 -> conv + bias + LeakyReLU -> fp32 NCHW
-      TFPNP_TRY(to_half(s0, C0, C0 + C1, 0, h * w, nullptr));
-      if (s1) TFPNP_TRY(to_half(s1, C1, C0 + C1, C0, h * w, nullptr));
+      TFPNP_TRY(to_half(s0, C0, C0 + C1, 0, h * w, nullptr, false));
+      if (s1) TFPNP_TRY(to_half(s1, C1, C0 + C1, C0, h * w, nullptr, false));
       TFPNP_TRY(conv_v1_launch(u->tc_fwd[l], st));
       const int cout = unet_conv_specs()[l].cout;
-      return from_half(0, out, cout, cout, 0, h * w, nullptr);
+      return from_half(0, out, cout, cout, 0, h * w, nullptr, false);
     }
     int maxpool(const float* in, float* out, int C, int h, int w) {
       maxpool2_simt<<<blocks((size_t)B * C * (h / 2) * (w / 2)), T, 0, st>>>(in, out, B * C, h, w);
@@ -513,13 +519,13 @@ struct UNetSimt : Denoiser {
       float* scale = u->tc_scale.as<float>();
       absmax_scale_simt<<<B, 256, 0, st>>>(gin, scale, (size_t)sp.cout * h * w);
       TFPNP_COUNT_LAUNCH();
-      TFPNP_TRY(to_half(gin, sp.cout, sp.cout, 0, h * w, scale));
+      TFPNP_TRY(to_half(gin, sp.cout, sp.cout, 0, h * w, scale, true));
       int rows[2];
       const int np = grad_elem::dgrad_parts(l, rows);
       size_t yoff = 0;
       for (int p = 0, coff = 0; p < np; coff += rows[p], ++p) {
         TFPNP_TRY(conv_v1_launch(u->tc_bwd[l][p], st));
-        TFPNP_TRY(from_half(yoff, gout, rows[p], sp.cin, coff, h * w, scale));
+        TFPNP_TRY(from_half(yoff, gout, rows[p], sp.cin, coff, h * w, scale, true));
         yoff += (size_t)B * h * w * rows[p];
       }
       return 0;
@@ -557,8 +563,8 @@ struct UNetSimt : Denoiser {
     TFPNP_TRY(gws.alloc(gws_floats * sizeof(float)));
     {
       const char* e = getenv("TFPNP_GRAD_TC");          // tensor-core convolutions: opt-in until validated on a GPU
-      grad_tc = e ? atoi(e) : 0;                        // 1: fp16 operands, 2: split-fp16 (FP16X3)
-      if (grad_tc < 0 || grad_tc > 2) grad_tc = 0;
+      grad_tc = e ? atoi(e) : 0;                        // 1: fp16 operands, 2: split-fp16 (FP16X3), 3: split-fp16 forward + fp16 gradients
+      if (grad_tc < 0 || grad_tc > 3) grad_tc = 0;
     }
     if (grad_tc) TFPNP_TRY(ensure_tc(B, H, W));
     GradOps ops{this, B, H, W, st};

@@ -1,7 +1,7 @@
 """Time the reverse mode at the north-star shape: one actor-update style call
     out = solver((state, aux), (sigma_d, mu)); out.backward(cotangent)
 for CS-MRI ADMM, env_batch 48, 128x128, action_pack 5, with the convolutions of the VJP on CUDA cores (TFPNP_GRAD_TC=0) and on
-the tensor cores (1: fp16, 2: split-fp16).  Prints one JSON line per mode; also the agreement of modes 1/2 with mode 0.
+the tensor cores (1: fp16, 2: split-fp16, 3: split-fp16 forward recompute + fp16 gradients).  Prints one JSON line per mode; also the agreement of modes 1/2 with mode 0.
 Run on the GPU box:  python tools/grad_bench.py [--batch 48] [--size 128] [--iters 5]
 """
 import argparse
@@ -34,7 +34,7 @@ def main():
     state = solver.reset(d)
     cot = torch.randn(state.shape, generator=g).to(dev)
     ref = None
-    for mode in ("0", "1", "2"):
+    for mode in ("0", "1", "2", "3"):
         os.environ["TFPNP_GRAD_TC"] = mode
         times = []
         for r in range(a.reps + 1):

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Reverse mode of every task once at its BASELINE per-GPU shape with action_pack = 5 (what one actor update differentiates):
 csmri 48x128^2, pr 36x256^2 (4 masks), ct 8x256^2 (60 views), spi 48x128^2.  Checks finiteness, prints the forward / backward
-wall time and the gradient norms as one JSON line per task.  TFPNP_GRAD_TC selects the VJP convolutions (default here: 2, the
-split-fp16 tensor-core branch; 0 = CUDA cores, slow at 256^2).   python tools/grad_tasks.py [csmri|pr|ct|spi|all]
+wall time and the gradient norms as one JSON line per task.  TFPNP_GRAD_TC selects the VJP convolutions (default here: 3, the
+split-fp16-forward / fp16-gradient tensor-core branch; 0 = CUDA cores, slow at 256^2).   python tools/grad_tasks.py [csmri|pr|ct|spi|all]
 """
 import json
 import os
@@ -11,7 +11,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("TFPNP_GRAD_TC", "2")
+os.environ.setdefault("TFPNP_GRAD_TC", "3")
 import torch  # noqa: E402
 import tfpnp_b200 as T  # noqa: E402
 
