@@ -13,6 +13,8 @@ Tolerances (relative to max|ref|, and relative L2), per precision mode of the de
 """
 import math
 
+import os
+
 import pytest
 import torch
 
@@ -92,6 +94,22 @@ def test_denoiser_tc_matches_simt_on_device(dev):
     ref = denoiser("fp32_simt", "he")(x, sigma)
     assert_close(denoiser("fp16x3", "he")(x, sigma), ref, 1e-4, "x3 vs simt")
     assert_close(denoiser("fp16", "he")(x, sigma), ref, 5e-3, "fp16 vs simt")
+
+
+@pytest.mark.skipif(os.environ.get("TFPNP_TEST_XFORM2", "0") != "1",
+                    reason="experimental transform-warp variant (written without a GPU): set TFPNP_TEST_XFORM2=1")
+def test_xform2_transform_warps_are_bit_identical(dev, monkeypatch):
+    """TFPNP_XFORM2=1 (row-independent transform warps of the fused up-sampling layers) performs the
+    same arithmetic in the same order: the denoiser output must be bit-identical at all three fused levels (32^2, 64^2, 128^2)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(3, 1, 128, 128, generator=g).to(dev)
+    sigma = (torch.rand(3, generator=g) * 0.2).to(dev)
+    den = denoiser("fp16", "he")
+    monkeypatch.setenv("TFPNP_XFORM2", "0")
+    ref = den(x, sigma).clone()
+    monkeypatch.setenv("TFPNP_XFORM2", "1")
+    out = den(x, sigma)
+    assert torch.equal(out, ref)
 
 
 # ------------------------------------------------------------------------------------------

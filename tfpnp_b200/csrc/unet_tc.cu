@@ -327,7 +327,10 @@ template <int KC, bool FUSE> constexpr int conv2_threads() { return 64 + 32 * co
 // {KC, 10 (x), 2 (image), 10 (y)} over the tensor viewed as {C, W, B, H}, i.e. smem row = y'*20 + img*10 + x', so the
 // sixteen 8-pixel row groups (y, img) of tap (ky,kx) start at row ky*20 + kx and are uniformly 10 rows apart (SBO) --
 // the same shifted-descriptor scheme as the 18x18 halo tile, one M-tile (one accumulator) per work item.
-template <int BN, int KC, bool RESIDENT, bool FUSE, bool SMALL = false>
+// XF2 (experiment, TFPNP_XFORM2=1; FUSE only): the transform warps compute every output row of their row group independently
+// from its four source vectors (same arithmetic, bit-identical results) instead of walking the rows with a dependent
+// load -> interpolate chain: more instructions, but they can all be in flight.
+template <int BN, int KC, bool RESIDENT, bool FUSE, bool SMALL = false, bool XF2 = false>
 __global__ void __launch_bounds__(conv2_threads<KC, FUSE>(), (FUSE || KC == 64) ? 1 : 2)
 conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   constexpr int NEPI = conv2_nepi<KC, FUSE>();
@@ -629,6 +632,44 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) hr[e] = ffma2(lx, __half22float2(bq.v[e]), fmul2(wx, __half22float2(a.v[e])));
           };
+          if constexpr (XF2) {
+            // every row on its own: 4 loads + 3 lerps per row, no state carried from row to row; batches of <= 5 rows keep
+            // the live registers under the kernel's 128-register cap
+            constexpr int RB = 5;
+#pragma unroll
+            for (int r0 = 0; r0 < RPG; r0 += RB) {
+              uint4 outs[RB];
+#pragma unroll
+              for (int q = 0; q < RB; ++q) {
+                const int rr = r0 + q;
+                outs[q] = make_uint4(0, 0, 0, 0);
+                if (rr < RPG && yrow[rr < RPG ? rr : 0] >= 0) {
+                  const int yr = yrow[rr < RPG ? rr : 0];
+                  const int y0 = yr >> 1, y1 = y0 + (yr & 1);
+                  float2 top[4], bot[4];
+                  hrow(y0, top);
+                  hrow(y1, bot);
+                  const float ly = lyv[rr < RPG ? rr : 0], wy = 1.f - ly;
+                  H8 o;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 v = ffma2(ly, bot[e], fmul2(wy, top[e]));
+                    o.v[e] = __floats2half2_rn(v.x, v.y);
+                  }
+                  outs[q] = *reinterpret_cast<uint4*>(&o);
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < RB; ++q) {
+                const int rr = r0 + q, r = r_begin + rr;
+                if (rr < RPG && r < kHaloH) {
+                  const int pr = r * kHaloW + k;
+                  const int swz = (ROW == 128) ? (pr & 7) : ((pr >> 1) & 3);
+                  *reinterpret_cast<uint4*>(dstA + pr * iROW + ((j ^ swz) << 4)) = outs[q];
+                }
+              }
+            }
+          } else {
 #pragma unroll
           for (int rr = 0; rr < RPG; ++rr) {
             const int r = r_begin + rr;
@@ -665,6 +706,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
               *reinterpret_cast<uint4*>(dstA + pr * iROW + ((j ^ swz) << 4)) = outv;
             }
           }
+          }   // !XF2
           fence_proxy_async();                               // generic-proxy smem writes -> visible to the MMA (async proxy)
           asm volatile("bar.sync 1, 288;" ::: "memory");     // the nine transform warps
           if (tid == 0) { mbar_arrive(&full_a[s]); mbar_arrive(&stg_empty[st]); TRACE(5, 2 * iu + 1); }
@@ -1191,17 +1233,17 @@ bool use_pdl() {
   return v != 0;
 }
 
-template <int BN, int KC, bool RES, bool FUSE, bool SMALL = false>
+template <int BN, int KC, bool RES, bool FUSE, bool SMALL = false, bool XF2 = false>
 int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
   static unsigned long long attr_set = 0;   // one bit per device (a function attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES, FUSE, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES, FUSE, SMALL, XF2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
     attr_set |= 1ull << (dev & 63);
   }
-  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE, SMALL>, dim3(c.grid), dim3(conv2_threads<KC, FUSE>()),
+  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE, SMALL, XF2>, dim3(c.grid), dim3(conv2_threads<KC, FUSE>()),
                           c.smem_bytes, st, use_pdl(), c.p.cluster, c.p));
   TFPNP_COUNT_LAUNCH();
   return 0;
@@ -1213,6 +1255,13 @@ int launch_conv2(const Conv2Plan& c, cudaStream_t st) {
     if (key == 128640 && !c.p.up_fused) return launch_conv2_t<128, 64, false, false, true>(c, st);
     set_error("conv2: no 8x8 variant for BN %d KC %d (resident %d)", c.BN, c.kc, (int)c.resident);
     return TFPNP_ERR_INVALID;
+  }
+  if (c.p.up_fused && env_int("TFPNP_XFORM2", 0) != 0) {   // experiment: row-independent transform warps (bit-identical results)
+    switch (key) {
+      case 32321: return launch_conv2_t<32, 32, true, true, false, true>(c, st);
+      case 64640: return launch_conv2_t<64, 64, false, true, false, true>(c, st);
+      case 128640: return launch_conv2_t<128, 64, false, true, false, true>(c, st);
+    }
   }
   if (c.p.up_fused) {
     switch (key) {      // the four decoder conv-0 layers of UNet(2,1): 96->32, 192->64, 384->128, 768->256

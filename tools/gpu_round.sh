@@ -17,6 +17,9 @@ echo "=== reverse-mode timing at the north-star shape (CUDA-core vs tensor-core 
 timeout 900 python tools/grad_bench.py > gpurun_out/grad_bench.log 2>&1; tail -5 gpurun_out/grad_bench.log
 echo "=== reverse mode of all four tasks at their BASELINE per-GPU shapes (split-fp16 tensor-core VJP)"
 timeout 900 python tools/grad_tasks.py > gpurun_out/grad_tasks.log 2>&1; tail -6 gpurun_out/grad_tasks.log
+echo "=== experiment: row-independent transform warps (TFPNP_XFORM2=1): bit-identity test, then the bench with it"
+TFPNP_TEST_XFORM2=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k xform2 -p no:cacheprovider 2>&1 | tail -2
+TFPNP_XFORM2=1 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_xform2.json 2>> gpurun_out/bench.err; cut -c1-220 gpurun_out/bench_xform2.json
 echo "=== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
 echo "=== bench"
