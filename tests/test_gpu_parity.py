@@ -110,6 +110,13 @@ def test_xform2_transform_warps_are_bit_identical(dev, monkeypatch):
     monkeypatch.setenv("TFPNP_XFORM2", "1")
     out = den(x, sigma)
     assert torch.equal(out, ref)
+    # variant 2: the three lerps in packed fp16 (three roundings instead of one) -- must stay inside the fp16 mode's budget
+    monkeypatch.setenv("TFPNP_XFORM2", "2")
+    out2 = den(x, sigma)
+    oracle = O.denoise(weights("he"), x.cpu(), sigma.cpu())
+    e0, e2 = rel_err(ref, oracle)[1], rel_err(out2, oracle)[1]
+    print(f"xform2=2: error vs oracle {e2:.2e} (default kernel {e0:.2e})")
+    assert e2 <= tol("fp16", "he")
 
 
 # ------------------------------------------------------------------------------------------

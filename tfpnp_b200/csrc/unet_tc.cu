@@ -327,10 +327,11 @@ template <int KC, bool FUSE> constexpr int conv2_threads() { return 64 + 32 * co
 // {KC, 10 (x), 2 (image), 10 (y)} over the tensor viewed as {C, W, B, H}, i.e. smem row = y'*20 + img*10 + x', so the
 // sixteen 8-pixel row groups (y, img) of tap (ky,kx) start at row ky*20 + kx and are uniformly 10 rows apart (SBO) --
 // the same shifted-descriptor scheme as the 18x18 halo tile, one M-tile (one accumulator) per work item.
-// XF2 (experiment, TFPNP_XFORM2=1; FUSE only): the transform warps compute every output row of their row group independently
-// from its four source vectors (same arithmetic, bit-identical results) instead of walking the rows with a dependent
-// load -> interpolate chain: more instructions, but they can all be in flight.
-template <int BN, int KC, bool RESIDENT, bool FUSE, bool SMALL = false, bool XF2 = false>
+// XF (experiments, TFPNP_XFORM2=1|2; FUSE only).  1: the transform warps compute every output row of their row group
+// independently from its four source vectors (same arithmetic, bit-identical results) instead of walking the rows with a
+// dependent load -> interpolate chain: more instructions, but they can all be in flight.
+// 2: the same with all three lerps in packed fp16 (HFMA2 / HMUL2, no conversions; three fp16 roundings instead of one).
+template <int BN, int KC, bool RESIDENT, bool FUSE, bool SMALL = false, int XF = 0>
 __global__ void __launch_bounds__(conv2_threads<KC, FUSE>(), (FUSE || KC == 64) ? 1 : 2)
 conv3x3_tc2(const __grid_constant__ Conv2Params p) {
   constexpr int NEPI = conv2_nepi<KC, FUSE>();
@@ -632,7 +633,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) hr[e] = ffma2(lx, __half22float2(bq.v[e]), fmul2(wx, __half22float2(a.v[e])));
           };
-          if constexpr (XF2) {
+          if constexpr (XF != 0) {
             // every row on its own: 4 loads + 3 lerps per row, no state carried from row to row; batches of <= 5 rows keep
             // the live registers under the kernel's 128-register cap
             constexpr int RB = 5;
@@ -646,15 +647,30 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
                 if (rr < RPG && yrow[rr < RPG ? rr : 0] >= 0) {
                   const int yr = yrow[rr < RPG ? rr : 0];
                   const int y0 = yr >> 1, y1 = y0 + (yr & 1);
-                  float2 top[4], bot[4];
-                  hrow(y0, top);
-                  hrow(y1, bot);
                   const float ly = lyv[rr < RPG ? rr : 0], wy = 1.f - ly;
                   H8 o;
+                  if constexpr (XF == 2) {
+                    const __half2 lx2 = __float2half2_rn(lx), wx2 = __float2half2_rn(wx);
+                    const __half2 ly2 = __float2half2_rn(ly), wy2 = __float2half2_rn(wy);
+                    const uint8_t* rp0 = stg + y0 * (kUpBox * iROW);
+                    const uint8_t* rp1 = stg + y1 * (kUpBox * iROW);
+                    const H8 a0 = *reinterpret_cast<const H8*>(rp0 + ox0), b0 = *reinterpret_cast<const H8*>(rp0 + ox1);
+                    const H8 a1 = *reinterpret_cast<const H8*>(rp1 + ox0), b1 = *reinterpret_cast<const H8*>(rp1 + ox1);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 v = ffma2(ly, bot[e], fmul2(wy, top[e]));
-                    o.v[e] = __floats2half2_rn(v.x, v.y);
+                    for (int e = 0; e < 4; ++e) {
+                      const __half2 top = __hfma2(lx2, b0.v[e], __hmul2(wx2, a0.v[e]));
+                      const __half2 bot = __hfma2(lx2, b1.v[e], __hmul2(wx2, a1.v[e]));
+                      o.v[e] = __hfma2(ly2, bot, __hmul2(wy2, top));
+                    }
+                  } else {
+                    float2 top[4], bot[4];
+                    hrow(y0, top);
+                    hrow(y1, bot);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 v = ffma2(ly, bot[e], fmul2(wy, top[e]));
+                      o.v[e] = __floats2half2_rn(v.x, v.y);
+                    }
                   }
                   outs[q] = *reinterpret_cast<uint4*>(&o);
                 }
@@ -706,7 +722,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
               *reinterpret_cast<uint4*>(dstA + pr * iROW + ((j ^ swz) << 4)) = outv;
             }
           }
-          }   // !XF2
+          }   // XF == 0
           fence_proxy_async();                               // generic-proxy smem writes -> visible to the MMA (async proxy)
           asm volatile("bar.sync 1, 288;" ::: "memory");     // the nine transform warps
           if (tid == 0) { mbar_arrive(&full_a[s]); mbar_arrive(&stg_empty[st]); TRACE(5, 2 * iu + 1); }
@@ -1233,17 +1249,17 @@ bool use_pdl() {
   return v != 0;
 }
 
-template <int BN, int KC, bool RES, bool FUSE, bool SMALL = false, bool XF2 = false>
+template <int BN, int KC, bool RES, bool FUSE, bool SMALL = false, int XF = 0>
 int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
   static unsigned long long attr_set = 0;   // one bit per device (a function attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES, FUSE, SMALL, XF2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc2<BN, KC, RES, FUSE, SMALL, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
     attr_set |= 1ull << (dev & 63);
   }
-  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE, SMALL, XF2>, dim3(c.grid), dim3(conv2_threads<KC, FUSE>()),
+  TFPNP_CUDA_OK(launch_ex(conv3x3_tc2<BN, KC, RES, FUSE, SMALL, XF>, dim3(c.grid), dim3(conv2_threads<KC, FUSE>()),
                           c.smem_bytes, st, use_pdl(), c.p.cluster, c.p));
   TFPNP_COUNT_LAUNCH();
   return 0;
@@ -1256,11 +1272,18 @@ int launch_conv2(const Conv2Plan& c, cudaStream_t st) {
     set_error("conv2: no 8x8 variant for BN %d KC %d (resident %d)", c.BN, c.kc, (int)c.resident);
     return TFPNP_ERR_INVALID;
   }
-  if (c.p.up_fused && env_int("TFPNP_XFORM2", 0) != 0) {   // experiment: row-independent transform warps (bit-identical results)
+  const int xf = c.p.up_fused ? env_int("TFPNP_XFORM2", 0) : 0;
+  if (xf == 1) {   // experiment: row-independent transform warps (bit-identical results)
     switch (key) {
-      case 32321: return launch_conv2_t<32, 32, true, true, false, true>(c, st);
-      case 64640: return launch_conv2_t<64, 64, false, true, false, true>(c, st);
-      case 128640: return launch_conv2_t<128, 64, false, true, false, true>(c, st);
+      case 32321: return launch_conv2_t<32, 32, true, true, false, 1>(c, st);
+      case 64640: return launch_conv2_t<64, 64, false, true, false, 1>(c, st);
+      case 128640: return launch_conv2_t<128, 64, false, true, false, 1>(c, st);
+    }
+  } else if (xf == 2) {   // experiment: the same with packed-fp16 lerps
+    switch (key) {
+      case 32321: return launch_conv2_t<32, 32, true, true, false, 2>(c, st);
+      case 64640: return launch_conv2_t<64, 64, false, true, false, 2>(c, st);
+      case 128640: return launch_conv2_t<128, 64, false, true, false, 2>(c, st);
     }
   }
   if (c.p.up_fused) {
