@@ -20,7 +20,7 @@ timeout 900 python tools/grad_tasks.py > gpurun_out/grad_tasks.log 2>&1; tail -6
 echo "=== experiment: row-independent transform warps (TFPNP_XFORM2=1): bit-identity test, then the bench with it"
 TFPNP_TEST_XFORM2=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k xform2 -p no:cacheprovider 2>&1 | tail -2
 TFPNP_TEST_XFORM2=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k xform2 -p no:cacheprovider 2>&1 | grep "xform2=2"
-for v in 1 2; do TFPNP_XFORM2=$v timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_xform2_$v.json 2>> gpurun_out/bench.err; cut -c1-220 gpurun_out/bench_xform2_$v.json; grep -o '"parity": {[^}]*}' gpurun_out/bench_xform2_$v.json; done
+for v in 1 2; do TFPNP_XFORM2=$v timeout 600 python bench.py > gpurun_out/bench_xform2_$v.json 2> gpurun_out/bench_xform2_$v.err; cut -c1-220 gpurun_out/bench_xform2_$v.json; grep -o '"parity": {[^}]*}' gpurun_out/bench_xform2_$v.json; done
 echo "=== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
 echo "=== bench"
