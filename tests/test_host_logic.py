@@ -27,6 +27,39 @@ def test_library_exports_every_declared_symbol():
     assert l.tfpnp_version() == 100
 
 
+def test_ctypes_signatures_match_the_header_types():
+    """Every parameter of every declaration in include/tfpnp_b200.h against the ctypes argtypes in tfpnp_b200/_lib.py: pointer
+    -> c_void_p / POINTER(...), int -> c_int, int64_t -> c_int64, size_t -> c_size_t, float -> c_float (a c_int bound to an
+    int64_t stride would pass garbage in the upper half on this ABI only by luck)."""
+    import ctypes as C
+    header = open(os.path.join(ROOT, "include", "tfpnp_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    decls = re.findall(r"\b([a-z_0-9 ]+?\**)\s*\b(tfpnp_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(decls) == len(_lib.SIGNATURES), (len(decls), len(_lib.SIGNATURES))
+
+    def kind(ctype_decl):
+        t = " ".join(ctype_decl.replace("const", " ").split())
+        if "*" in t:
+            return "ptr"
+        base = t.split()[0] if t.split() else "void"
+        return {"int": "int", "int64_t": "i64", "size_t": "size", "float": "float", "void": "void"}.get(base, base)
+
+    def ckind(a):
+        if a is C.c_void_p or a is C.c_char_p or (isinstance(a, type) and issubclass(a, C._Pointer)):
+            return "ptr"
+        return {C.c_int: "int", C.c_int64: "i64", C.c_size_t: "size", C.c_float: "float"}[a]
+
+    for ret, name, params in decls:
+        res, args = _lib.SIGNATURES[name]
+        plist = [q.strip() for q in params.split(",")] if params.strip() not in ("", "void") else []
+        kinds = []
+        for q in plist:
+            q = re.sub(r"\b[A-Za-z_][A-Za-z_0-9]*$", "", q).strip() if not q.endswith("*") else q      # drop the parameter name
+            kinds.append(kind(q))
+        assert kinds == [ckind(a) for a in args], (name, kinds, [ckind(a) for a in args])
+        assert kind(ret) == ("ptr" if res is C.c_char_p else ckind(res)), (name, ret)
+
+
 def test_library_is_sm100a_tcgen05():
     """The shipped cubin is sm_100a and contains the Blackwell tensor/TMA instructions."""
     out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
