@@ -239,10 +239,11 @@ int tfpnp_env_gather(const tfpnp_gather_item* items, int n_items, const int64_t*
 
 /* state['solver'][idx] = solver_state; state['output'][idx] = solver.get_output(solver_state)
  * (base.py:171-172 with base.py:101-104 / tasks/csmri/solver.py:9-18) fused.
- * solver_state [n_rows,3,HW(,2)]; state_solver [B,3,HW(,2)]; state_output [B,1,HW]. */
+ * solver_state [n_rows,V,HW(,2)]; state_solver [B,V,HW(,2)]; state_output [B,1,HW]; V = num_var is the
+ * solver's variable count (3 ADMM / iADMM / RED-ADMM, 2 HQS / APG, 1 PG: tfpnp/pnp/solver/base.py:87-214). */
 int tfpnp_env_scatter_state(const float* solver_state, const int64_t* idx, int n_rows,
                             float* state_solver, float* state_output, int64_t HW, int complex_state,
-                            void* stream);
+                            int num_var, void* stream);
 
 /* get_policy_ob (tasks/{csmri,pr,ct,spi}/env.py get_policy_ob): dst [n_rows, n_ch, HW] fp32 with
  * dst[r,c,i] = float(src_c[idx[r]*img_stride_c + offset_c + i*pix_stride_c]).  complex2real /

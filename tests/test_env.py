@@ -170,3 +170,62 @@ def test_env_kernels_bit_exact(dev):
     assert torch.equal(env.state["solver"], ref)
     assert torch.equal(env.state["output"][idx], s[:, :1, ..., 0])
     assert float(env.state["output"][1].abs().max()) == 0.0
+    # solvers with fewer variables (HQS / APG: 2, PG: 1; tfpnp/pnp/solver/base.py:118-214): the row stride follows num_var
+    for nv in (2, 1):
+        st = torch.randn(7, nv, 16, 16, 2, generator=g).to(dev)
+        env.state = {"solver": st.clone(), "output": torch.zeros(7, 1, 16, 16, device=dev)}
+        s = torch.randn(3, nv, 16, 16, 2, generator=g).to(dev)
+        env._scatter_state(s, idx)
+        ref = st.clone(); ref[idx] = s
+        assert torch.equal(env.state["solver"], ref)
+        assert torch.equal(env.state["output"][idx], s[:, :1, ..., 0])
+    from tfpnp_b200.env import CTEnv
+    renv = CTEnv(None, None, 3).to(dev)
+    st = torch.randn(5, 1, 16, 16, generator=g).to(dev)
+    renv.state = {"solver": st.clone(), "output": torch.zeros(5, 1, 16, 16, device=dev)}
+    s = torch.randn(2, 1, 16, 16, generator=g).to(dev)
+    renv._scatter_state(s, idx[:2] % 5)
+    ref = st.clone(); ref[idx[:2] % 5] = s
+    assert torch.equal(renv.state["solver"], ref) and torch.equal(renv.state["output"][idx[:2] % 5], s)
+    with pytest.raises(ValueError):                      # a solver whose rows do not match the environment's state
+        renv._scatter_state(torch.zeros(2, 3, 16, 16, device=dev), idx[:2] % 5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hqs", "pg"])
+def test_env_step_with_fewer_solver_variables(dev, name):
+    """PnPEnv is generic in solver.num_var (the reference's index_put is): an episode step with the 2-variable HQS and the
+    1-variable PG CS-MRI solvers equals calling the solver by hand and scattering with torch indexing."""
+    import tfpnp_b200 as T
+    from tfpnp_b200.env import CSMRIEnv
+    d = synth.csmri_batch(4, 32, 2)
+    den = T.UNetDenoiser2D(state_dict=weights("he"), precision="fp16x3")
+    solver = {"hqs": T.HQSSolver_CSMRI, "pg": T.PGSolver_CSMRI}[name](den)
+    env = CSMRIEnv(None, solver, 3).to(dev)
+    data = dict(gt=d["gt"], y0=d["y0"], mask=d["mask"], x0=d["x0"], ATy0=d["x0"], output=d["x0"][..., 0],
+                sigma_n=torch.full((4, 1, 32, 32, 2), 15 / 255))
+    ob = env.reset({k: v.clone() for k, v in data.items()})
+    nv = solver.num_var
+    assert tuple(env.state["solver"].shape) == (4, nv, 32, 32, 2)
+    keys = solver._param_keys
+    g = torch.Generator().manual_seed(1)
+    action = {k: (torch.rand(4, 2, generator=g) * 0.5 + 0.1).to(dev) for k in keys}
+    action["idx_stop"] = torch.tensor([0, 1, 0, 0], device=dev)
+    before = env.state["solver"].clone()
+    env.step(action)
+    with torch.no_grad():
+        want = solver((before, (env.state["y0"], env.state["mask"])), solver.filter_hyperparameter(action))
+    assert torch.equal(env.state["solver"], want)
+    assert torch.equal(env.state["output"], solver.get_output(want))
+    # second step on the 3 images left: rows idx_left = [0, 2, 3] only
+    action2 = {k: (torch.rand(3, 2, generator=g) * 0.5 + 0.1).to(dev) for k in keys}
+    action2["idx_stop"] = torch.tensor([0, 0, 0], device=dev)
+    before = env.state["solver"].clone()
+    env.step(action2)
+    left = torch.tensor([0, 2, 3], device=dev)
+    with torch.no_grad():
+        want = solver((before[left], (env.state["y0"][left], env.state["mask"][left])),
+                      solver.filter_hyperparameter(action2))
+    ref = before.clone(); ref[left] = want
+    assert torch.equal(env.state["solver"], ref)
+    assert torch.equal(env.state["solver"][1], before[1])

@@ -199,9 +199,52 @@ def test_csmri_call_semantics(dev):
         assert torch.equal(dd["state"].cpu(), d["state"])
         zero = s((dd["state"], (dd["y0"], dd["mask"])), (dd["sigma_d"], dd["mu"]), iter_num=0)
         assert torch.equal(zero[:, 1:], dd["state"][:, 1:])
+    s.differentiable = False                # gradient requests are refused loudly when the reverse mode is switched off
     with pytest.raises(NotImplementedError):
         with torch.enable_grad():
             s((dd["state"], (dd["y0"], dd["mask"])), (dd["sigma_d"].clone().requires_grad_(), dd["mu"]))
+
+
+def test_forward_validates_shapes_before_marshalling_pointers(dev):
+    """Mismatched or broadcast aux tensors raise in the reference (first broadcast); here they must raise on the host
+    instead of becoming out-of-bounds device reads (raw pointers cross the C ABI)."""
+    import tfpnp_b200 as T
+    den = denoiser("fp16", "he")
+    d = cu(synth.csmri_batch(3, 32, 2, seed=5), dev)
+    s = T.ADMMSolver_CSMRI(den)
+    ok = ((d["state"], (d["y0"], d["mask"])), (d["sigma_d"], d["mu"]))
+    with torch.no_grad():
+        s(*ok)
+        for bad in (((d["state"], (d["y0"][:2], d["mask"])), ok[1]),                      # fewer y0 rows than images
+                    ((d["state"], (d["y0"], d["mask"][:1])), ok[1]),                      # broadcast mask
+                    ((d["state"][:, :2], (d["y0"], d["mask"])), ok[1]),                   # two variables, not three
+                    ((d["state"], (d["y0"][:, :, :16], d["mask"])), ok[1]),               # wrong spatial size
+                    (ok[0], (d["sigma_d"][:2], d["mu"]))):                                # parameter rows != B
+            with pytest.raises(ValueError):
+                s(*bad)
+        h = T.HQSSolver_CSMRI(den)
+        st2 = h.reset(dict(x0=d["x0"]))
+        h((st2, (d["y0"], d["mask"])), (d["sigma_d"], d["mu"]))
+        with pytest.raises(ValueError):
+            h((d["state"], (d["y0"], d["mask"])), (d["sigma_d"], d["mu"]))                # 3-variable state into HQS
+        with pytest.raises(ValueError):
+            h((st2[:, :, :, :16], (d["y0"], d["mask"])), (d["sigma_d"], d["mu"]))         # non-square
+        p = cu(synth.pr_batch(2, 32, 2), dev)
+        pr = T.IADMMSolver_PR(den)
+        pr((p["state"], (p["y0"], p["mask"])), (p["sigma_d"], p["mu"], p["tau"]))
+        with pytest.raises(ValueError):
+            pr((p["state"], (p["y0"][:, :3], p["mask"])), (p["sigma_d"], p["mu"], p["tau"]))   # 3 magnitudes, 4 masks
+        sp = cu(synth.spi_batch(2, 32, 2), dev)
+        spi = T.ADMMSolver_SPI(den)
+        spi((sp["state"], (sp["x0"], sp["K"])), (sp["sigma_d"], sp["mu"]))
+        with pytest.raises(ValueError):
+            spi((sp["state"], (sp["x0"][:1], sp["K"])), (sp["sigma_d"], sp["mu"]))
+    # re-assigning the denoiser must not reuse a solver handle that captured the old native engine
+    s.denoiser = denoiser("fp16x3", "default")
+    with torch.no_grad():
+        a = s(*ok)
+        b = T.ADMMSolver_CSMRI(denoiser("fp16x3", "default"))(*ok)
+    assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("prec", ["fp16", "fp16x3"])

@@ -82,7 +82,7 @@ SIGNATURES = {
     "tfpnp_psnr_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "tfpnp_env_gather": (C.c_int, [C.POINTER(GatherItem), C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "tfpnp_env_scatter_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
-                                          C.c_int, C.c_void_p]),
+                                          C.c_int, C.c_int, C.c_void_p]),
     "tfpnp_env_policy_ob": (C.c_int, [C.POINTER(ObChannel), C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                       C.c_void_p]),
     "tfpnp_solver_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),

@@ -12,7 +12,7 @@ namespace tfpnp {
 namespace {
 
 constexpr int kMaxGather = 12;
-constexpr int kMaxObChan = 24;
+constexpr int kMaxObChan = 32;   // PR with 8 masks packs 5 + 3*8 = 29 channels (tasks/pr/env.py:10)
 
 struct GatherParams {
   const uint8_t* src[kMaxGather];
@@ -41,29 +41,31 @@ env_gather_kernel(const __grid_constant__ GatherParams p) {
   }
 }
 
-// solver_state [n,3,HW(,2)] -> state_solver[idx[r]] (whole row) and state_output[idx[r]] = x (real part)
+// solver_state [n,V,HW(,2)] -> state_solver[idx[r]] (whole row) and state_output[idx[r]] = x (real part);
+// V = solver.num_var: 3 for ADMM / iADMM / RED-ADMM, 2 for HQS / APG, 1 for PG (tfpnp/pnp/solver/base.py:87-214)
 template <bool COMPLEX>
 __global__ void __launch_bounds__(256)
 env_scatter_state_kernel(const float* __restrict__ st, const int64_t* __restrict__ idx, float* __restrict__ state_solver,
-                         float* __restrict__ state_output, int64_t HW) {
+                         float* __restrict__ state_output, int64_t HW, int num_var) {
   constexpr int E = COMPLEX ? 2 : 1;
   const int64_t r = blockIdx.y;
   const int64_t dr = idx ? idx[r] : r;
-  const float* s = st + r * 3 * HW * E;
-  float* ds = state_solver + dr * 3 * HW * E;
+  const float* s = st + r * num_var * HW * E;
+  float* ds = state_solver + dr * num_var * HW * E;
   float* dout = state_output + dr * HW;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += stride) {
     if (COMPLEX) {
       const float2 x = reinterpret_cast<const float2*>(s)[i];
       reinterpret_cast<float2*>(ds)[i] = x;
-      reinterpret_cast<float2*>(ds)[HW + i] = reinterpret_cast<const float2*>(s)[HW + i];
-      reinterpret_cast<float2*>(ds)[2 * HW + i] = reinterpret_cast<const float2*>(s)[2 * HW + i];
+      for (int v = 1; v < num_var; ++v)
+        reinterpret_cast<float2*>(ds)[v * HW + i] = reinterpret_cast<const float2*>(s)[v * HW + i];
       dout[i] = x.x;                       // get_output: x[..., 0] (tasks/csmri/solver.py:9-18)
     } else {
       const float x = s[i];
-      ds[i] = x; ds[HW + i] = s[HW + i]; ds[2 * HW + i] = s[2 * HW + i];
-      dout[i] = x;                         // get_output: first third of dim 1 (base.py:101-104)
+      ds[i] = x;
+      for (int v = 1; v < num_var; ++v) ds[v * HW + i] = s[v * HW + i];
+      dout[i] = x;                         // get_output: first 1/num_var of dim 1 (base.py:101-104)
     }
   }
 }
@@ -128,15 +130,16 @@ int tfpnp_env_gather(const tfpnp_gather_item* items, int n_items, const int64_t*
 }
 
 int tfpnp_env_scatter_state(const float* solver_state, const int64_t* idx, int n_rows, float* state_solver,
-                            float* state_output, int64_t HW, int complex_state, void* stream) {
+                            float* state_output, int64_t HW, int complex_state, int num_var, void* stream) {
   TFPNP_CHECK(solver_state && state_solver && state_output && HW > 0 && n_rows >= 0, "env_scatter_state: bad argument");
+  TFPNP_CHECK(num_var >= 1 && num_var <= 8, "env_scatter_state: num_var must be 1..8, got %d", num_var);
   if (n_rows == 0) return 0;
   int chunks = (int)((HW + 255) / 256);
   chunks = chunks > 64 ? 64 : chunks;
   dim3 grid(chunks, n_rows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (complex_state) env_scatter_state_kernel<true><<<grid, 256, 0, st>>>(solver_state, idx, state_solver, state_output, HW);
-  else env_scatter_state_kernel<false><<<grid, 256, 0, st>>>(solver_state, idx, state_solver, state_output, HW);
+  if (complex_state) env_scatter_state_kernel<true><<<grid, 256, 0, st>>>(solver_state, idx, state_solver, state_output, HW, num_var);
+  else env_scatter_state_kernel<false><<<grid, 256, 0, st>>>(solver_state, idx, state_solver, state_output, HW, num_var);
   TFPNP_COUNT_LAUNCH();
   TFPNP_CUDA_OK(cudaGetLastError());
   return 0;

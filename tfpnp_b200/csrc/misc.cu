@@ -2,6 +2,10 @@
 #include "tasks.cuh"
 #include <map>
 #include <memory>
+#include <mutex>
+#include <tuple>
+#include <vector>
+#include <algorithm>
 
 namespace tfpnp {
 namespace {
@@ -132,18 +136,45 @@ struct CtGradOps {
   }
 };
 
+// Geometry handles behind the stand-alone Radon entry points (tfpnp_radon_forward / _backward, tfpnp_ct_iadmm_backward).
+// One entry per (device, N, views, stream): the tables and the transpose scratch live on the device that asked, and two
+// streams never share a scratch buffer.  The tables are uploaded when the entry is created or when the caller's tables
+// differ from the cached host copy -- not on every call.  Guarded by a mutex (DataParallel-style use is thread-per-GPU).
 struct GeomCache {
-  std::map<std::pair<int, int>, std::unique_ptr<CtGeom>> m;
-  CtGeom* get(int N, int views, const float* c, const float* s) {
-    auto key = std::make_pair(N, views);
+  struct Entry {
+    CtGeom g;
+    std::vector<float> c, s;     // host copy of the uploaded tables (empty = the default linspace tables)
+  };
+  std::mutex mu;
+  std::map<std::tuple<int, int, int, cudaStream_t>, std::unique_ptr<Entry>> m;
+  CtGeom* get(int N, int views, const float* c, const float* s, cudaStream_t st, int reserve_B) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return nullptr; }
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_tuple(dev, N, views, st);
     auto it = m.find(key);
     if (it == m.end()) {
-      std::unique_ptr<CtGeom> g(new CtGeom());
-      if (g->init(N, views) != 0) return nullptr;
-      it = m.emplace(key, std::move(g)).first;
+      std::unique_ptr<Entry> e(new Entry());
+      if (e->g.init(N, views) != 0) return nullptr;
+      it = m.emplace(key, std::move(e)).first;
     }
-    if (c && s && it->second->set_tables(c, s) != 0) return nullptr;
-    return it->second.get();
+    Entry& e = *it->second;
+    if (c && s) {
+      const bool same = e.c.size() == (size_t)views && std::equal(c, c + views, e.c.begin()) &&
+                        std::equal(s, s + views, e.s.begin());
+      if (!same) {
+        // work queued on this stream may still read the old tables
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("stream sync before a table upload failed"); return nullptr; }
+        if (e.g.set_tables(c, s) != 0) return nullptr;
+        e.c.assign(c, c + views);
+        e.s.assign(s, s + views);
+      }
+    }
+    if (reserve_B > 0 && e.g.tbuf.bytes < (size_t)reserve_B * N * N * sizeof(float)) {
+      if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("stream sync before growing the scratch failed"); return nullptr; }
+      if (e.g.reserve(reserve_B) != 0) return nullptr;
+    }
+    return &e.g;
   }
 };
 GeomCache& geom_cache() { static GeomCache c; return c; }
@@ -183,16 +214,15 @@ int tfpnp_conv3x3_nhwc(const void* x0, int C0, const void* x1, int C1, const voi
 int tfpnp_radon_forward(const float* img, float* sino, int B, int N, int views, const float* cos_host,
                         const float* sin_host, void* stream) {
   TFPNP_CHECK(img && sino && B > 0 && N > 0 && views > 0, "bad argument");
-  CtGeom* g = geom_cache().get(N, views, cos_host, sin_host);
+  CtGeom* g = geom_cache().get(N, views, cos_host, sin_host, static_cast<cudaStream_t>(stream), B);
   if (!g) return TFPNP_ERR_CUDA;
-  TFPNP_TRY(g->reserve(B));
   return radon_forward(*g, img, nullptr, sino, B, static_cast<cudaStream_t>(stream));
 }
 
 int tfpnp_radon_backward(const float* sino, float* img, int B, int N, int views, const float* cos_host,
                          const float* sin_host, void* stream) {
   TFPNP_CHECK(img && sino && B > 0 && N > 0 && views > 0, "bad argument");
-  CtGeom* g = geom_cache().get(N, views, cos_host, sin_host);
+  CtGeom* g = geom_cache().get(N, views, cos_host, sin_host, static_cast<cudaStream_t>(stream), 0);
   if (!g) return TFPNP_ERR_CUDA;
   return radon_backward(*g, sino, img, B, static_cast<cudaStream_t>(stream));
 }
@@ -205,10 +235,9 @@ int tfpnp_ct_iadmm_backward(void* denoiser, const float* states, const float* y0
   TFPNP_CHECK(denoiser && states && y0 && sigma_d && mu && tau && grad_out && grad_sigma_d && grad_mu && grad_tau && B > 0 &&
                   iters > 0 && views > 0 && opnorm > 0.f, "bad argument");
   g_launch_count = 0;
-  CtGeom* g = geom_cache().get(N, views, cos_host, sin_host);
-  if (!g) return TFPNP_ERR_CUDA;
-  TFPNP_TRY(g->reserve(B));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CtGeom* g = geom_cache().get(N, views, cos_host, sin_host, st, B);
+  if (!g) return TFPNP_ERR_CUDA;
   const size_t n = (size_t)B * N * N;
   DevBuf bufs[11], sino, P;
   auto body = [&]() -> int {

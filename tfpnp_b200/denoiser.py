@@ -75,9 +75,10 @@ class UNetDenoiser2D(torch.nn.Module):
             self._handles[idx] = h = out
         return h
 
-    # Reverse mode is opt-in: set ``denoiser.differentiable = True``.  It runs on a second, fp32 engine
-    # built from the same weights (tfpnp_denoiser_vjp); round-1 status: compiled, not yet validated on a GPU.
-    differentiable = False
+    # Reverse mode: on by default, like autograd through the reference module; ``differentiable = False``
+    # turns a request for gradients into a NotImplementedError.  It runs on a second, fp32 engine built from the same
+    # weights (tfpnp_denoiser_vjp).
+    differentiable = True
 
     def _grad_handle(self, device: torch.device):
         """The fp32 engine that implements tfpnp_denoiser_vjp (this engine itself when precision == 'fp32_simt')."""
@@ -117,7 +118,7 @@ class UNetDenoiser2D(torch.nn.Module):
             raise RuntimeError("tfpnp_b200.UNetDenoiser2D runs on CUDA (sm_100) tensors only; no CPU fallback")
         if torch.is_grad_enabled() and (x.requires_grad or sigma.requires_grad):
             if not self.differentiable:
-                raise NotImplementedError("differentiable denoiser is opt-in (SURVEY 8f, N4): set .differentiable = True")
+                raise NotImplementedError("the differentiable denoiser was switched off (.differentiable = False)")
             return _DenoiseFn.apply(self, x, sigma)
         N, Cc, H, W = x.shape
         assert Cc == 1

@@ -240,10 +240,20 @@ class PnPEnv(DifferentiableEnv):
         st, out = self.state['solver'], self.state['output']
         HW = out[0].numel()
         n = s.shape[0]
+        # the reference's index_put works for any solver.num_var (3 ADMM, 2 HQS / APG, 1 PG); rows must agree
+        if tuple(s.shape[1:]) != tuple(st.shape[1:]) or s.dtype != torch.float32 or st.dtype != torch.float32:
+            raise ValueError(f"solver returned state rows {tuple(s.shape[1:])} {s.dtype}, the environment holds "
+                             f"{tuple(st.shape[1:])} {st.dtype}")
+        num_var = int(s.shape[1])
+        if s[0].numel() != num_var * HW * (2 if self._complex_state else 1):
+            raise ValueError(f"state row of {s[0].numel()} floats is not num_var={num_var} x HW={HW} x "
+                             f"{'2 (complex)' if self._complex_state else '1'}")
+        if idx is not None and int(idx.shape[0]) != n:
+            raise ValueError(f"{n} solver rows for {int(idx.shape[0])} active images")
         with torch.cuda.device(s.device):
             _lib.check(_lib.lib().tfpnp_env_scatter_state(
                 s.data_ptr(), idx.data_ptr() if idx is not None else None, n, st.data_ptr(), out.data_ptr(), HW,
-                1 if self._complex_state else 0, _stream(s.device)), "tfpnp_env_scatter_state")
+                1 if self._complex_state else 0, num_var, _stream(s.device)), "tfpnp_env_scatter_state")
 
     def _observation(self):
         """tasks/*/env.py `_observation`: every tensor of the state restricted to idx_left, one launch."""

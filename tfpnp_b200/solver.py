@@ -9,11 +9,11 @@ unchanged.  ``forward`` marshals raw device pointers into ``tfpnp_solver_forward
 (include/tfpnp_b200.h); the iterated proximal loop itself is hand-written sm_100a CUDA.
 
 There is no PyTorch/CPU fallback.  The differentiable use (``PnPEnv.forward`` under
-autograd, tfpnp/env/base.py:193-206) is opt-in and exists for the four ADMM / iADMM
-solvers (``solver.differentiable = True``: gradients w.r.t. the hyper-parameters and the input state
-through ``tfpnp_{csmri_admm,pr_iadmm,ct_iadmm,spi_admm}_backward``) and for the HQS / PG / APG /
-RED-ADMM CS-MRI solvers (``tfpnp_csmri_variant_backward``); PGSolver_CT raises NotImplementedError
-under autograd.
+autograd, tfpnp/env/base.py:193-206) exists for the four ADMM / iADMM solvers
+(gradients w.r.t. the hyper-parameters and the input state through
+``tfpnp_{csmri_admm,pr_iadmm,ct_iadmm,spi_admm}_backward``) and for the HQS / PG / APG / RED-ADMM
+CS-MRI solvers (``tfpnp_csmri_variant_backward``); it is on by default (``solver.differentiable``)
+and validated on a B200 (tests/test_grad.py); PGSolver_CT raises NotImplementedError under autograd.
 """
 from __future__ import annotations
 
@@ -61,6 +61,21 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
 
 
+def _expect(name, t, shape):
+    """Raise ValueError unless tensor ``t`` has exactly ``shape`` (the reference fails in its first broadcast; raw
+    pointers would read out of bounds instead)."""
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+def _expect_params(params, B):
+    for i, p in enumerate(params):
+        if p.dim() < 1 or p.shape[0] != B:
+            raise ValueError(f"hyper-parameter {i} must have a leading dimension of {B}, got {tuple(p.shape)}")
+        if not p.is_cuda:
+            raise RuntimeError("tfpnp_b200 solvers run on CUDA (sm_100) tensors only; there is no CPU fallback")
+
+
 class _NativeADMM(PnPSolver):
     """Shared host logic: handle cache + pointer marshalling for one task."""
     _task = None
@@ -72,7 +87,8 @@ class _NativeADMM(PnPSolver):
             raise TypeError("tfpnp_b200 solvers need a tfpnp_b200.UNetDenoiser2D / IRCNNDenoiser2D (the denoiser "
                             "runs inside the fused CUDA path)")
         super().__init__(denoiser)
-        self._solvers = {}      # (device idx, H, W, extra) -> handle
+        self._solvers = {}      # (device idx, H, W, extra, denoiser engine) -> handle
+        self._den_refs = []     # denoisers whose native engine a cached handle captured
         self.last_launch_count = 0
 
     @property
@@ -95,9 +111,13 @@ class _NativeADMM(PnPSolver):
     # -- native plumbing -------------------------------------------------------
     def _solver_handle(self, device, H, W, n_masks=0, views=0, opnorm=0.0, cos=None, sin=None):
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        key = (idx, H, W, n_masks, views, float(opnorm))
+        den_h = self.denoiser._handle(device)
+        # keyed on the native denoiser engine too: re-assigning solver.denoiser must not leave a cached solver
+        # handle pointing at the old (possibly destroyed) engine; _den_refs keeps every engine we captured alive
+        key = (idx, H, W, n_masks, views, float(opnorm), den_h.value)
         h = self._solvers.get(key)
         if h is None:
+            self._den_refs.append(self.denoiser)
             cfg = _lib.SolverConfig(self._task, H, W, n_masks, views, float(opnorm), None, None,
                                     1 if self.use_graph else 0)
             if cos is not None:
@@ -105,13 +125,13 @@ class _NativeADMM(PnPSolver):
                 cfg.ct_sin = C.cast(sin.data_ptr(), C.POINTER(C.c_float))
             out = C.c_void_p()
             with torch.cuda.device(idx):
-                _lib.check(_lib.lib().tfpnp_solver_create(C.byref(cfg), self.denoiser._handle(device), C.byref(out)),
-                           "tfpnp_solver_create")
+                _lib.check(_lib.lib().tfpnp_solver_create(C.byref(cfg), den_h, C.byref(out)), "tfpnp_solver_create")
             self._solvers[key] = h = out
         return h
 
-    # reverse mode: opt-in, ADMMSolver_CSMRI only
-    differentiable = False
+    # reverse mode: the four ADMM / iADMM solvers and the CS-MRI variants define a native backward;
+    # ``differentiable = False`` refuses gradient requests loudly
+    differentiable = True
     _has_backward = False
 
     def _wants_grad(self, variables, parameters):
@@ -122,8 +142,8 @@ class _NativeADMM(PnPSolver):
             raise RuntimeError("tfpnp_b200 solvers run on CUDA (sm_100) tensors only; there is no CPU fallback")
         if self._wants_grad(variables, parameters) and not (self.differentiable and self._has_backward):
             raise NotImplementedError(
-                "the differentiable solver path (PnPEnv.forward under autograd, SURVEY 8f N4) is opt-in and built for "
-                "the four ADMM / iADMM solvers only: set solver.differentiable = True")
+                "the differentiable solver path (PnPEnv.forward under autograd, SURVEY 8f N4) is built for the four "
+                "ADMM / iADMM solvers and the CS-MRI variants, and this solver has it switched off or lacks it")
 
     def _run(self, handle, variables, aux0, aux1, aux1_stride, params, iter_num):
         B = variables.shape[0]
@@ -151,9 +171,10 @@ class _NativeADMM(PnPSolver):
         return out
 
     def __del__(self):
-        try:
+        try:                                # solver handles first: they borrow the denoiser engines in _den_refs
             for h in self._solvers.values():
                 _lib.lib().tfpnp_solver_destroy(h)
+            self._solvers.clear()
         except Exception:
             pass
 
@@ -183,7 +204,15 @@ class ADMMSolver_CSMRI(ADMMSolver):
         y0, mask = tuple(aux)               # may be a one-shot generator (tfpnp/utils/misc.py:138-139)
         sigma_d, mu = parameters
         self._check_inputs(variables, (sigma_d, mu))
+        if variables.dim() != 5:
+            raise ValueError(f"variables must be [B,3,H,W,2], got {tuple(variables.shape)}")
         B, _, H, W, _ = variables.shape
+        _expect("variables", variables, (B, 3, H, W, 2))
+        _expect("y0", y0, (B, 1, H, W, 2))
+        _expect("mask", mask, (B, 1, H, W))
+        _expect_params((sigma_d, mu), B)
+        if H != W:
+            raise ValueError(f"square images only, got {H}x{W}")
         m8 = mask.contiguous()
         m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else (m8 != 0).view(torch.uint8)
         h = self._solver_handle(variables.device, H, W)
@@ -246,13 +275,14 @@ class _CSMRIVariant(PnPSolver):
     _algo = None
     _nvar = None
     _param_keys = ()
-    differentiable = False      # reverse mode is opt-in
+    differentiable = True       # reverse mode; False refuses gradient requests loudly
 
     def __init__(self, denoiser):
         if not isinstance(denoiser, UNetDenoiser2D):
             raise TypeError("tfpnp_b200 solvers need a tfpnp_b200.UNetDenoiser2D / IRCNNDenoiser2D")
         super().__init__(denoiser)
         self._solvers = {}
+        self._den_refs = []
         self.last_launch_count = 0
 
     @property
@@ -277,8 +307,18 @@ class _CSMRIVariant(PnPSolver):
             raise RuntimeError("tfpnp_b200 solvers run on CUDA (sm_100) tensors only; there is no CPU fallback")
         wants_grad = torch.is_grad_enabled() and (variables.requires_grad or any(p.requires_grad for p in params))
         if wants_grad and not self.differentiable:
-            raise NotImplementedError("the differentiable solver path (SURVEY 8f N4) is opt-in: set solver.differentiable = True")
+            raise NotImplementedError("the differentiable solver path was switched off (solver.differentiable = False)")
+        if variables.dim() != 5:
+            raise ValueError(f"variables must be [B,{self._nvar},H,W,2], got {tuple(variables.shape)}")
         B, _, H, W, _ = variables.shape
+        _expect("variables", variables, (B, self._nvar, H, W, 2))
+        _expect("y0", y0, (B, 1, H, W, 2))
+        _expect("mask", mask, (B, 1, H, W))
+        _expect_params(params, B)
+        if H != W:
+            raise ValueError(f"square images only, got {H}x{W}")
+        if len(params) != len(self._param_keys):
+            raise ValueError(f"{type(self).__name__} takes {len(self._param_keys)} hyper-parameters {self._param_keys}")
         if iter_num is None:
             iter_num = params[0].shape[-1]
         if wants_grad:
@@ -287,13 +327,15 @@ class _CSMRIVariant(PnPSolver):
             return _CSMRIVariantFn.apply(self, variables, _f32c(y0), m8, int(iter_num), *params)
         dev = variables.device
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        h = self._solvers.get((idx, H))
+        den_h = self.denoiser._handle(dev)
+        h = self._solvers.get((idx, H, den_h.value))
         if h is None:
             h = C.c_void_p()
+            self._den_refs.append(self.denoiser)
             with torch.cuda.device(idx):
-                _lib.check(_lib.lib().tfpnp_csmri_variant_create(self._algo, H, self.denoiser._handle(dev), C.byref(h)),
+                _lib.check(_lib.lib().tfpnp_csmri_variant_create(self._algo, H, den_h, C.byref(h)),
                            "tfpnp_csmri_variant_create")
-            self._solvers[(idx, H)] = h
+            self._solvers[(idx, H, den_h.value)] = h
         m8 = mask.contiguous()
         m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else (m8 != 0).view(torch.uint8)
         ps = [(p if p.dtype == torch.float32 else p.float()).reshape(B, -1) for p in params]
@@ -416,8 +458,17 @@ class IADMMSolver_PR(IADMMSolver):
         y0, mask = tuple(aux)
         sigma_d, mu, tau = parameters
         self._check_inputs(variables, (sigma_d, mu, tau))
+        if variables.dim() != 5 or mask.dim() != 5:
+            raise ValueError(f"variables must be [B,3,H,W,2] and mask [B,M,H,W,2], got {tuple(variables.shape)}, {tuple(mask.shape)}")
         B, _, H, W, _ = variables.shape
-        h = self._solver_handle(variables.device, H, W, n_masks=mask.shape[1])
+        M = mask.shape[1]
+        _expect("variables", variables, (B, 3, H, W, 2))
+        _expect("mask", mask, (B, M, H, W, 2))
+        _expect("y0", y0, (B, M, H, W))
+        _expect_params((sigma_d, mu, tau), B)
+        if H != W:
+            raise ValueError(f"square images only, got {H}x{W}")
+        h = self._solver_handle(variables.device, H, W, n_masks=M)
         if self._wants_grad(variables, (sigma_d, mu, tau)):
             if iter_num is None:
                 iter_num = sigma_d.shape[-1]
@@ -515,8 +566,15 @@ class IADMMSolver_CT(IADMMSolver):
         y0, view = tuple(aux)
         sigma_d, mu, tau = parameters
         self._check_inputs(variables, (sigma_d, mu, tau))
+        if variables.dim() != 4:
+            raise ValueError(f"variables must be [B,3,H,W], got {tuple(variables.shape)}")
         B, _, H, W = variables.shape
+        _expect("variables", variables, (B, 3, H, W))
+        _expect_params((sigma_d, mu, tau), B)
+        if H != W:
+            raise ValueError(f"square images only, got {H}x{W}")
         views = int(view[0, 0, 0, 0].item() * 120)          # solver.py:26 (one host sync per call)
+        _expect("y0", y0, (B, 1, views, math.ceil(math.sqrt(2.0) * W)))   # det_count, transforms.py:489
         opnorm = self.opnorm_override or self.radon_generator(W, views, variables.device)
         cos, sin = RadonGenerator.tables(views)
         h = self._solver_handle(variables.device, H, W, views=views, opnorm=opnorm, cos=cos, sin=sin)
@@ -633,7 +691,14 @@ class ADMMSolver_SPI(ADMMSolver):
         x0, K = tuple(aux)
         sigma_d, mu = parameters
         self._check_inputs(variables, (sigma_d, mu))
+        if variables.dim() != 4:
+            raise ValueError(f"variables must be [B,3,H,W], got {tuple(variables.shape)}")
         B, _, H, W = variables.shape
+        _expect("variables", variables, (B, 3, H, W))
+        _expect("x0", x0, (B, 1, H, W))
+        _expect_params((sigma_d, mu), B)
+        if K.dim() != 4 or K.shape[0] != B:
+            raise ValueError(f"K must be [B,1,H,W] (constant K/10 per image), got {tuple(K.shape)}")
         Kf = K if K.dtype == torch.float32 else K.float()
         Kv = Kf[:, 0, 0, 0]                                   # solver.py:32 (the *10 happens on device)
         h = self._solver_handle(variables.device, H, W)

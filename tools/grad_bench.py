@@ -34,19 +34,18 @@ def main():
     state = solver.reset(d)
     cot = torch.randn(state.shape, generator=g).to(dev)
     ref = None
+    sg0 = (torch.rand(B, it, generator=g) * 70 / 255).to(dev)      # the SAME parameters for every mode
+    mu0 = torch.rand(B, it, generator=g).to(dev)
     for mode in ("0", "1", "2", "3"):
         os.environ["TFPNP_GRAD_TC"] = mode
         times = []
         for r in range(a.reps + 1):
-            sg = (torch.rand(B, it, generator=g) * 70 / 255).to(dev).requires_grad_(True)
-            mu = torch.rand(B, it, generator=g).to(dev).requires_grad_(True)
-            if r == 0:
-                sg0, mu0 = sg.detach().clone(), mu.detach().clone()
             sg = sg0.clone().requires_grad_(True)
             mu = mu0.clone().requires_grad_(True)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             out = solver((state, (d["y0"], d["mask"])), (sg, mu))
+            torch.cuda.synchronize()
             t1 = time.perf_counter()
             gs, gm = torch.autograd.grad(out, (sg, mu), cot)
             torch.cuda.synchronize()
