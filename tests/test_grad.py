@@ -376,12 +376,15 @@ def test_native_solver_backward_matches_reference_gradients(dev, prec, tol):
 
 
 @pytest.mark.gpu
-def test_reverse_mode_off_by_default(dev):
+def test_reverse_mode_can_be_switched_off(dev):
     import tfpnp_b200 as T
     g = load_golden("grad_csmri_small")
     s = T.ADMMSolver_CSMRI(T.UNetDenoiser2D(state_dict=weights("he"), precision="fp16"))
-    with pytest.raises(NotImplementedError):
-        s((g["state"].to(dev), (g["y0"].to(dev), g["mask"].to(dev))), (g["sigma_d"].to(dev).requires_grad_(True), g["mu"].to(dev)))
+    args = ((g["state"].to(dev), (g["y0"].to(dev), g["mask"].to(dev))), (g["sigma_d"].to(dev).requires_grad_(True), g["mu"].to(dev)))
+    assert s(*args).requires_grad                       # on by default, as autograd through the reference module
+    s.differentiable = False
+    with pytest.raises(NotImplementedError):            # never a silent detach
+        s(*args)
 
 
 @pytest.mark.gpu
