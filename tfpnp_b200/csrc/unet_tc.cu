@@ -821,15 +821,17 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
 // to both CTAs (empty_* and tmem_full), and the peer's epilogue releases the accumulator on the leader's tmem_empty.
 // (Bring-up: tools/ubench/mma_pair.cu.)
 struct ConvPairParams {
-  CUtensorMap a_map[2];     // [source] half-halo boxes {64, 10, 18, 1}
-  CUtensorMap w_map;        // {64, 64 rows, 1 tap} over {Cin, Cout, 9}
+  CUtensorMap a_map[2][2];  // [source][plane] half-halo boxes {64, 10, 18, 1}
+  CUtensorMap w_map[2];     // [plane] {64, 64 rows, 1 tap} over {Cin, Cout, 9}
   int nchunk0, nchunk1;
   int tiles_w, tiles_h, num_m_tiles, num_n_tiles;
   int B, H, W, Cout;
   int num_a_stages, num_b_stages;
   const float* bias;
   __half* out_hi;
+  __half* out_lo;           // fp16 residual plane (split-fp16 mode) or nullptr
   __half* pool_hi;          // fused nn.MaxPool2d(2) output or nullptr
+  __half* pool_lo;
 };
 
 constexpr int kPairThreads = 64 + 32 * 8;
@@ -837,19 +839,29 @@ constexpr int kPairARows = 180, kPairABytes = 23552;            // 180 x 128 B, 
 constexpr int kPairSlab = 64 * 128;                             // one tap's half slab
 constexpr int kPairTPS = 9;                                     // taps per weight-ring stage (3: a kernel row, 9: a whole chunk)
 constexpr int kPairBStage = kPairTPS * kPairSlab;
+// split-fp16 (X3): separate rings -- A stages [hi half-halo | lo half-halo], weight stages of one kernel row
+// [3 taps x (W_hi half slab | W_lo half slab)]: 36 MMAs (3 taps x 4 k-steps x 3 products) = 1.2 us per weight stage, the same
+// tensor time per hand-shake as the fp16 kernel's whole-chunk stage
+constexpr int kPairX3AStage = 2 * kPairABytes;
+constexpr int kPairX3BStage = 3 * 2 * kPairSlab;
 
+template <bool X3>
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv3x3_pair(const __grid_constant__ ConvPairParams p) {
   constexpr int BN = 128, KC = 64, KSTEPS = 4;
   constexpr uint32_t ROW = 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int S = p.num_a_stages;                 // ring of chunk stages: [A half-halo | 9 half slabs]
+  const int S = p.num_a_stages;                 // fp16: ring of chunk stages [A half-halo | 9 half slabs]; X3: the A ring
+  const int SB = p.num_b_stages;                // X3: the weight ring
   const int nchunks = p.nchunk0 + p.nchunk1;
-  constexpr int kStage = kPairABytes + kPairBStage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * kStage);
+  constexpr int kStage = X3 ? kPairX3AStage : kPairABytes + kPairBStage;
+  uint8_t* sWr = smem + S * kStage;             // X3 weight ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * kStage + (X3 ? SB * kPairX3BStage : 0));
   uint64_t* full = bars;                        // [8]   (the leader's are the ones waited on)
   uint64_t* empty = bars + 8;                   // [8]
+  uint64_t* full_b = bars + 16;                 // [8]   X3 weight ring
+  uint64_t* empty_b = bars + 24;                // [8]
   uint64_t* tmem_full = bars + 48;              // [2]
   uint64_t* tmem_empty = bars + 50;             // [2]  (leader's collects both CTAs' epilogues)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 52);
@@ -859,12 +871,17 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
   const uint32_t rank = cluster_ctarank();
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&p.a_map[0]);
-    prefetch_tensormap(&p.w_map);
-    if (p.nchunk1) prefetch_tensormap(&p.a_map[1]);
+    prefetch_tensormap(&p.a_map[0][0]);
+    prefetch_tensormap(&p.w_map[0]);
+    if (p.nchunk1) prefetch_tensormap(&p.a_map[1][0]);
+    if (X3) {
+      prefetch_tensormap(&p.a_map[0][1]);
+      prefetch_tensormap(&p.w_map[1]);
+      if (p.nchunk1) prefetch_tensormap(&p.a_map[1][1]);
+    }
   }
   if (warp == 1) {
-    if (lane < 8) { mbar_init(&full[lane], 2); mbar_init(&empty[lane], 1); }
+    if (lane < 8) { mbar_init(&full[lane], 2); mbar_init(&empty[lane], 1); mbar_init(&full_b[lane], 2); mbar_init(&empty_b[lane], 1); }
     if (lane < 2) { mbar_init(&tmem_full[lane], 1); mbar_init(&tmem_empty[lane], 16); }
     fence_barrier_init();
   }
@@ -883,7 +900,7 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer (both CTAs): own half-halo + own half of the chunk's nine weight slabs ----------------
-      uint32_t ia = 0;
+      uint32_t ia = 0, ib = 0;
       for (int t = item0; t < total_items; t += item_step) {
         const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
         const int w0 = (m % p.tiles_w) * 16, h0 = ((m / p.tiles_w) % p.tiles_h) * 16;
@@ -894,25 +911,47 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
           const int s = ia % S;
           mbar_wait(&empty[s], ((ia / S) & 1) ^ 1);
           const uint32_t fb = mapa_u32(&full[s], 0);            // the LEADER's barrier
-          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (kPairARows * ROW + kPairBStage));
-          else mbar_arrive_cluster(fb);
           uint8_t* st = smem + s * kStage;
-          tma_load_4d_2sm(st, &p.a_map[src], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
+          if constexpr (!X3) {
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (kPairARows * ROW + kPairBStage));
+            else mbar_arrive_cluster(fb);
+            tma_load_4d_2sm(st, &p.a_map[src][0], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
 #pragma unroll
-          for (int tt = 0; tt < 9; ++tt)
-            tma_load_3d_2sm(st + kPairABytes + tt * kPairSlab, &p.w_map, fb, c * KC, nt * BN + 64 * (int)rank, tt);
+            for (int tt = 0; tt < 9; ++tt)
+              tma_load_3d_2sm(st + kPairABytes + tt * kPairSlab, &p.w_map[0], fb, c * KC, nt * BN + 64 * (int)rank, tt);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * 2u * (kPairARows * ROW));
+            else mbar_arrive_cluster(fb);
+            tma_load_4d_2sm(st, &p.a_map[src][0], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
+            tma_load_4d_2sm(st + kPairABytes, &p.a_map[src][1], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
+#pragma unroll 1
+            for (int tg = 0; tg < 3; ++tg, ++ib) {
+              const int sb = ib % SB;
+              mbar_wait(&empty_b[sb], ((ib / SB) & 1) ^ 1);
+              const uint32_t fbb = mapa_u32(&full_b[sb], 0);
+              if (rank == 0) mbar_arrive_expect_tx(&full_b[sb], 2u * kPairX3BStage);
+              else mbar_arrive_cluster(fbb);
+              uint8_t* wst = sWr + sb * kPairX3BStage;
+#pragma unroll
+              for (int tt = 0; tt < 3; ++tt) {
+                tma_load_3d_2sm(wst + (2 * tt) * kPairSlab, &p.w_map[0], fbb, c * KC, nt * BN + 64 * (int)rank, tg * 3 + tt);
+                tma_load_3d_2sm(wst + (2 * tt + 1) * kPairSlab, &p.w_map[1], fbb, c * KC, nt * BN + 64 * (int)rank, tg * 3 + tt);
+              }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      // ---------------- MMA issuer (leader only): one barrier wait and one release per chunk ----------------
+      // ---------------- MMA issuer (leader only) ----------------
       const uint32_t idesc = make_idesc_f16(256, BN);
       const uint32_t a_hi = (uint32_t)(make_smem_desc_ex(0, ROW, 10 * ROW, 0) >> 32);
       const uint32_t b_hi = (uint32_t)(make_smem_desc(0, ROW) >> 32);
       const uint32_t lo_flags = 1u << 16;
       const uint32_t s_lo = (smem_u32(smem) >> 4) | lo_flags;
-      uint32_t ia = 0, it = 0;
+      const uint32_t w_lo = (smem_u32(sWr) >> 4) | lo_flags;
+      uint32_t ia = 0, ib = 0, it = 0;
       for (int t = item0; t < total_items; t += item_step, ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -924,23 +963,57 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
           mbar_wait(&full[sa], (ia / S) & 1);
           tc_fence_after();
           const uint32_t a_lo = s_lo + sa * (kStage >> 4);
-          const uint32_t b_stage = a_lo + (kPairABytes >> 4);
-          if (elect_one()) {
+          if constexpr (!X3) {
+            // one barrier wait and one release per chunk
+            const uint32_t b_stage = a_lo + (kPairABytes >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_tap = a_lo + (((tap / 3) * 10 + tap % 3) * ROW >> 4);
-              const uint32_t b_lo = b_stage + tap * (kPairSlab >> 4);
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t a_tap = a_lo + (((tap / 3) * 10 + tap % 3) * ROW >> 4);
+                const uint32_t b_lo = b_stage + tap * (kPairSlab >> 4);
 #pragma unroll
-              for (int kk = 0; kk < KSTEPS; ++kk) {
-                umma2_f16(d0, pack_desc(a_tap + kk * 2, a_hi), pack_desc(b_lo + kk * 2, b_hi), idesc, accumulate);
-                accumulate = 1;
+                for (int kk = 0; kk < KSTEPS; ++kk) {
+                  umma2_f16(d0, pack_desc(a_tap + kk * 2, a_hi), pack_desc(b_lo + kk * 2, b_hi), idesc, accumulate);
+                  accumulate = 1;
+                }
               }
+              umma2_commit_mc(&empty[sa], 3);                     // frees the chunk stage in BOTH CTAs
+              if (c == nchunks - 1) umma2_commit_mc(&tmem_full[buf], 3);
             }
-            umma2_commit_mc(&empty[sa], 3);                     // frees the chunk stage in BOTH CTAs
-            if (c == nchunks - 1) umma2_commit_mc(&tmem_full[buf], 3);
+            accumulate = 1;
+            __syncwarp();
+          } else {
+#pragma unroll 1
+            for (int tg = 0; tg < 3; ++tg, ++ib) {
+              const int sb = ib % SB;
+              mbar_wait(&full_b[sb], (ib / SB) & 1);
+              tc_fence_after();
+              const uint32_t b_stage = w_lo + sb * (kPairX3BStage >> 4);
+              const uint32_t a_row = a_lo + ((tg * 10) * ROW >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int tt = 0; tt < 3; ++tt) {
+                  const uint32_t a_tap = a_row + (tt * ROW >> 4);
+                  const uint32_t bh = b_stage + (2 * tt) * (kPairSlab >> 4), bl = bh + (kPairSlab >> 4);
+#pragma unroll
+                  for (int kk = 0; kk < KSTEPS; ++kk) {
+                    const uint64_t ad = pack_desc(a_tap + kk * 2, a_hi);
+                    umma2_f16(d0, ad, pack_desc(bh + kk * 2, b_hi), idesc, accumulate);                               // a_hi w_hi
+                    umma2_f16(d0, ad, pack_desc(bl + kk * 2, b_hi), idesc, 1);                                        // a_hi w_lo
+                    umma2_f16(d0, pack_desc(a_tap + (kPairABytes >> 4) + kk * 2, a_hi), pack_desc(bh + kk * 2, b_hi), idesc, 1);   // a_lo w_hi
+                    accumulate = 1;
+                  }
+                }
+                umma2_commit_mc(&empty_b[sb], 3);
+                if (tg == 2) {
+                  umma2_commit_mc(&empty[sa], 3);
+                  if (c == nchunks - 1) umma2_commit_mc(&tmem_full[buf], 3);
+                }
+              }
+              accumulate = 1;
+              __syncwarp();
+            }
           }
-          accumulate = 1;
-          __syncwarp();
         }
       }
     }
@@ -970,7 +1043,7 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
         uint32_t (&r)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r64[32 * sl]);
         float v[32];
         epilogue_act32(r, sbias + n0 + c0, v);
-        epilogue_store_nhwc32(v, p.out_hi, nullptr, pix * p.Cout + n0 + c0);
+        epilogue_store_nhwc32(v, p.out_hi, X3 ? p.out_lo : nullptr, pix * p.Cout + n0 + c0);
         if (p.pool_hi) {                      // 2x2 max over (tw^1, th^1) = lanes ^1 and ^8
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -979,7 +1052,7 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
           }
           if (!(lane & 9)) {
             const size_t ppix = ((size_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-            epilogue_store_nhwc32(v, p.pool_hi, nullptr, ppix * p.Cout + n0 + c0);
+            epilogue_store_nhwc32(v, p.pool_hi, X3 ? p.pool_lo : nullptr, ppix * p.Cout + n0 + c0);
           }
         }
       }
@@ -993,6 +1066,8 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
   cluster_sync_all();                            // nobody leaves (or frees TMEM) while the peer may still signal it
   if (warp == 2) tmem_dealloc_2sm(tmem_base, 256);
 }
+
+#include "conv_x3.cuh"
 
 // ---- CUDA-core layers around the tensor-core convs ---------------------------------------
 
@@ -1235,6 +1310,7 @@ struct Conv2Plan {
   int kc = 0;
   bool resident = false;
   bool small = false;      // 8x8 images, two per M-tile (conv3x3_tc2<..., SMALL>)
+  bool x3n = false;        // split-fp16 with N-concatenated products (conv3x3_x3, conv_x3.cuh)
   int smem_bytes = 0;
   int grid = 0;
 };
@@ -1265,7 +1341,27 @@ int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
   return 0;
 }
 
+template <int BN, bool RES>
+int launch_conv_x3_t(const Conv2Plan& c, cudaStream_t st) {
+  static unsigned long long attr_set = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_set >> (dev & 63) & 1ull)) {
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_x3<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set |= 1ull << (dev & 63);
+  }
+  TFPNP_CUDA_OK(launch_ex(conv3x3_x3<BN, RES>, dim3(c.grid), dim3(64 + 32 * 8), c.smem_bytes, st, use_pdl(), c.p.cluster, c.p));
+  TFPNP_COUNT_LAUNCH();
+  return 0;
+}
+
 int launch_conv2(const Conv2Plan& c, cudaStream_t st) {
+  if (c.x3n) {
+    if (c.BN == 32) return c.resident ? launch_conv_x3_t<32, true>(c, st) : launch_conv_x3_t<32, false>(c, st);
+    if (c.BN == 64) return c.resident ? launch_conv_x3_t<64, true>(c, st) : launch_conv_x3_t<64, false>(c, st);
+    set_error("conv_x3: unsupported BN %d", c.BN);
+    return TFPNP_ERR_INVALID;
+  }
   const int key = c.BN * 1000 + c.kc * 10 + (c.resident ? 1 : 0);
   if (c.small) {
     if (key == 128640 && !c.p.up_fused) return launch_conv2_t<128, 64, false, false, true>(c, st);
@@ -1323,7 +1419,9 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   Conv2Params& p = c.p;
   c.small = (H == 8 && W == 8);
   const int Cin = C0 + C1;
-  const int kc = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  // split-fp16 on the 32/64-channel levels: the N-concatenated kernel (32-channel chunks, both planes in one stage)
+  c.x3n = x3 && !c.small && !fuse_up && (Cout == 32 || Cout == 64) && env_int("TFPNP_X3N", 1) != 0;
+  const int kc = (C0 % 64 == 0 && C1 % 64 == 0 && !c.x3n) ? 64 : 32;
   c.kc = kc;
   c.BN = Cout >= 128 ? 128 : Cout;
   if (kc == 32 && c.BN == 128) c.BN = 64;                   // (not a UNet(2,1) shape; keeps the variant table small)
@@ -1336,6 +1434,42 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   const int row_bytes = kc * 2;
   p.a_stage_bytes = ((c.small ? 200 : kHaloRows) * row_bytes + 1023) & ~1023;
   p.b_stage_bytes = c.BN * row_bytes;                       // multiple of 1024 for all (BN, kc) used
+  if (c.x3n) {
+    // stage = [hi plane | lo plane]; weights [W_hi | W_lo] per (tap, chunk); one CTA per SM
+    p.nprod = 1;                                            // the three products are issued per tap, not as K passes
+    p.a_stage_bytes *= 2;
+    const int slab2 = 2 * p.b_stage_bytes;
+    const int w_all = 9 * (Cin / kc) * slab2;
+    const int misc3 = 1024 + 1024 + 2048 + 256;
+    const int budget = 224 * 1024 - misc3;
+    c.resident = w_all + 2 * p.a_stage_bytes <= budget && env_int("TFPNP_CONV_RESIDENT", 1) != 0;
+    if (c.resident) {
+      p.num_b_stages = 0;
+      p.num_a_stages = (budget - w_all) / p.a_stage_bytes;
+      if (p.num_a_stages > 4) p.num_a_stages = 4;
+      c.smem_bytes = p.num_a_stages * p.a_stage_bytes + w_all + misc3;
+    } else {
+      p.num_a_stages = 3;
+      int sb = (budget - p.num_a_stages * p.a_stage_bytes) / (3 * slab2);
+      if (sb < 2) { p.num_a_stages = 2; sb = (budget - p.num_a_stages * p.a_stage_bytes) / (3 * slab2); }
+      p.num_b_stages = sb > kMaxStages ? kMaxStages : sb;
+      c.smem_bytes = p.num_a_stages * p.a_stage_bytes + p.num_b_stages * 3 * slab2 + misc3;
+    }
+    int dev3 = 0, sms3 = 148;
+    cudaGetDevice(&dev3);
+    cudaDeviceGetAttribute(&sms3, cudaDevAttrMultiProcessorCount, dev3);
+    int cs3 = 1;
+    if (!c.resident) {
+      cs3 = env_int("TFPNP_CONV_CLUSTER", 2);
+      while (cs3 > 1 && (p.num_m_tiles < cs3 || (c.BN / cs3) * row_bytes % 1024 != 0)) cs3 /= 2;
+    }
+    p.cluster = cs3;
+    p.up_fused = 0;
+    const int items3 = (p.num_m_tiles + cs3 - 1) / cs3;
+    const int maxc3 = sms3 / cs3;
+    c.grid = (items3 < maxc3 ? items3 : maxc3) * cs3;
+    return 0;
+  }
   const int w_bytes = 9 * (Cin / kc) * p.b_stage_bytes;
   p.up_fused = fuse_up ? 1 : 0;
   p.stg_bytes = (kUpBox * kUpBox * row_bytes + 1023) & ~1023;
@@ -1397,51 +1531,66 @@ int encode_halo_map(CUtensorMap* m, const __half* base, int C, int B, int H, int
 
 struct ConvPairPlan {
   ConvPairParams p;
+  bool x3 = false;
   int grid = 0, smem_bytes = 0;
 };
 
-// CTA-pair kernel: streamed weights, 64-channel chunks, Cout a multiple of 128, 16x16 tiling, fp16 mode (TFPNP_CONV_PAIR=0
-// falls back to the single-CTA kernel).  Measured: 14.6 / 16.6 / 39.7 us against 20.4 / 20.4 / 47.5 us (128->128 @32x32,
-// 256->256 @16x16, 768->256 @16x16, 48 images); 60.3k -> 63.8k image-iters/s end to end.
+// CTA-pair kernel: streamed weights, 64-channel chunks, Cout a multiple of 128, 16x16 tiling (TFPNP_CONV_PAIR=0
+// falls back to the single-CTA kernel).  Measured in fp16: 14.6 / 16.6 / 39.7 us against 20.4 / 20.4 / 47.5 us (128->128 @32x32,
+// 256->256 @16x16, 768->256 @16x16, 48 images); 60.3k -> 63.8k image-iters/s end to end.  Split-fp16 (x3): TFPNP_PAIR_X3=0
+// falls back to the single-CTA K-loop-over-products path.
 bool conv_pair_eligible(int C0, int C1, int Cout, int H, int W, bool x3, bool fuse_up) {
-  return env_int("TFPNP_CONV_PAIR", 1) != 0 && !x3 && !fuse_up && C0 % 64 == 0 && C1 % 64 == 0 && Cout % 128 == 0 &&
-         H % 16 == 0 && W % 16 == 0;
+  return env_int("TFPNP_CONV_PAIR", 1) != 0 && (!x3 || env_int("TFPNP_PAIR_X3", 1) != 0) && !fuse_up && C0 % 64 == 0 &&
+         C1 % 64 == 0 && Cout % 128 == 0 && H % 16 == 0 && W % 16 == 0;
 }
 
-int plan_conv_pair(ConvPairPlan& c, const __half* x0, int C0, const __half* x1, int C1, const __half* w_taps, const float* bias,
-                   __half* out, int B, int H, int W, int Cout) {
+// x*_lo / w_lo / out_lo: the fp16 residual planes (all non-null selects the split-fp16 instantiation)
+int plan_conv_pair(ConvPairPlan& c, const __half* x0, const __half* x0_lo, int C0, const __half* x1, const __half* x1_lo, int C1,
+                   const __half* w_taps, const __half* w_lo, const float* bias, __half* out, __half* out_lo, int B, int H, int W,
+                   int Cout) {
   ConvPairParams& p = c.p;
   memset(&p, 0, sizeof(p));
+  c.x3 = w_lo != nullptr;
   p.nchunk0 = C0 / 64; p.nchunk1 = C1 / 64;
   p.tiles_w = W / 16; p.tiles_h = H / 16;
   p.num_m_tiles = p.tiles_w * p.tiles_h * B;
   p.num_n_tiles = Cout / 128;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
-  p.bias = bias; p.out_hi = out;
+  p.bias = bias; p.out_hi = out; p.out_lo = c.x3 ? out_lo : nullptr;
   const int misc = 1024 /*align*/ + 512 /*barriers*/ + 2048 /*bias*/ + 256;
-  p.num_a_stages = 2;                              // chunk stages: [A half-halo 23 KB | nine half slabs 72 KB]
-  p.num_b_stages = 0;
-  c.smem_bytes = p.num_a_stages * (kPairABytes + kPairBStage) + misc;
+  if (!c.x3) {
+    p.num_a_stages = 2;                            // chunk stages: [A half-halo 23 KB | nine half slabs 72 KB]
+    p.num_b_stages = 0;
+    c.smem_bytes = p.num_a_stages * (kPairABytes + kPairBStage) + misc;
+  } else {
+    p.num_a_stages = 2;                            // [hi half-halo | lo half-halo] 46 KB
+    p.num_b_stages = 2;                            // one kernel row of [W_hi | W_lo] half slabs, 48 KB
+    c.smem_bytes = p.num_a_stages * kPairX3AStage + p.num_b_stages * kPairX3BStage + misc;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int items = p.num_m_tiles * p.num_n_tiles;
   const int pairs = items < sms / 2 ? items : sms / 2;
   c.grid = 2 * pairs;
-  const __half* srcs[2] = {x0, x1};
+  const __half* srcs[2][2] = {{x0, x0_lo}, {x1, x1_lo}};
   const int cs[2] = {C0, C1};
   for (int s = 0; s < 2; ++s) {
-    if (!srcs[s]) { p.a_map[s] = p.a_map[0]; continue; }
+    if (!srcs[s][0]) { p.a_map[s][0] = p.a_map[0][0]; p.a_map[s][1] = p.a_map[0][1]; continue; }
     cuuint64_t dims[4] = {(cuuint64_t)cs[s], (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)cs[s] * 2, (cuuint64_t)W * cs[s] * 2, (cuuint64_t)H * W * cs[s] * 2};
     cuuint32_t box[4] = {64, 10, 18, 1};
-    TFPNP_TRY(encode_map(&p.a_map[s], const_cast<__half*>(srcs[s]), 4, dims, strides, box, 128));
+    TFPNP_TRY(encode_map(&p.a_map[s][0], const_cast<__half*>(srcs[s][0]), 4, dims, strides, box, 128));
+    if (c.x3) TFPNP_TRY(encode_map(&p.a_map[s][1], const_cast<__half*>(srcs[s][1]), 4, dims, strides, box, 128));
+    else p.a_map[s][1] = p.a_map[s][0];
   }
   const int Cin = C0 + C1;
   cuuint64_t wd[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
   cuuint64_t ws[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
   cuuint32_t wb[3] = {64, 64, 1};
-  TFPNP_TRY(encode_map(&p.w_map, const_cast<__half*>(w_taps), 3, wd, ws, wb, 128));
+  TFPNP_TRY(encode_map(&p.w_map[0], const_cast<__half*>(w_taps), 3, wd, ws, wb, 128));
+  if (c.x3) TFPNP_TRY(encode_map(&p.w_map[1], const_cast<__half*>(w_lo), 3, wd, ws, wb, 128));
+  else p.w_map[1] = p.w_map[0];
   return 0;
 }
 
@@ -1450,10 +1599,12 @@ int launch_conv_pair(const ConvPairPlan& c, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set |= 1ull << (dev & 63);
   }
-  TFPNP_CUDA_OK(launch_ex(conv3x3_pair, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
+  if (c.x3) TFPNP_CUDA_OK(launch_ex(conv3x3_pair<true>, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
+  else TFPNP_CUDA_OK(launch_ex(conv3x3_pair<false>, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
   TFPNP_COUNT_LAUNCH();
   return 0;
 }
@@ -1615,12 +1766,14 @@ struct UNetTc : Denoiser {
     convsp[l].grid = 0;
     if (conv_pair_eligible(s0.C, s1 ? s1->C : 0, unet_conv_specs()[l].cout, dst.H, dst.W, x3, low != nullptr)) {
       ConvPairPlan& c = convsp[l];
-      TFPNP_TRY(plan_conv_pair(c, s0.hi, s0.C, s1 ? s1->hi : nullptr, s1 ? s1->C : 0, w_hi.as<__half>() + w_off[l],
-                               biases.as<float>() + b_off[l], dst.hi, B, dst.H, dst.W, unet_conv_specs()[l].cout));
+      TFPNP_TRY(plan_conv_pair(c, s0.hi, x3 ? s0.lo : nullptr, s0.C, s1 ? s1->hi : nullptr, (s1 && x3) ? s1->lo : nullptr,
+                               s1 ? s1->C : 0, w_hi.as<__half>() + w_off[l], x3 ? w_lo.as<__half>() + w_off[l] : nullptr,
+                               biases.as<float>() + b_off[l], dst.hi, x3 ? dst.lo : nullptr, B, dst.H, dst.W,
+                               unet_conv_specs()[l].cout));
       convs2[l].grid = 0;
       fused_up[l] = false;
       fused_pool[l] = env_int("TFPNP_CONV_FUSE", 1) != 0 && (l == 2 || l == 5 || l == 8 || l == 11);
-      if (fused_pool[l]) c.p.pool_hi = S2.hi;
+      if (fused_pool[l]) { c.p.pool_hi = S2.hi; c.p.pool_lo = x3 ? S2.lo : nullptr; }
       return 0;
     }
     if (conv2_eligible(dst.H, dst.W) ||
@@ -1811,7 +1964,7 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
   TFPNP_TRY(set_conv_attrs());
   if (conv_pair_eligible(C0, C1, Cout, H, W, false, false)) {
     ConvPairPlan cp;
-    TFPNP_TRY(plan_conv_pair(cp, x0, C0, x1, C1, w_taps, bias, out, B, H, W, Cout));
+    TFPNP_TRY(plan_conv_pair(cp, x0, nullptr, C0, x1, nullptr, C1, w_taps, nullptr, bias, out, nullptr, B, H, W, Cout));
     TFPNP_TRY(launch_conv_pair(cp, st));
     TFPNP_CUDA_OK(cudaGetLastError());
     return 0;

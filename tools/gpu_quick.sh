@@ -1,7 +1,6 @@
 #!/bin/bash
-# scratch: quick check after a change (edit freely); the end-of-block run is tools/gpu_round.sh
+# scratch: quick check after a change (edit freely)
 mkdir -p gpurun_out
-rm -f gpurun_out/*.ncu-rep
-echo "=== pytest -m gpu"; timeout 600 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider 2>&1 | tail -4
-echo "=== smoke"; timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-echo "=== bench"; timeout 300 python bench.py > gpurun_out/bench.json 2>gpurun_out/bench.err; cut -c1-1800 gpurun_out/bench.json
+echo "=== pytest denoiser"; timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_conv.py -m gpu -q --timeout 300 -p no:cacheprovider -x -k "denoiser or conv" 2>&1 | tail -8
+echo "=== bench x3"; timeout 300 python bench.py --precision fp16x3 --no-cpu-baseline > gpurun_out/bench_x3.json 2>gpurun_out/bench.err; cut -c1-400 gpurun_out/bench_x3.json; tail -3 gpurun_out/bench.err
+echo "=== bench fp16"; timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_fp16.json 2>gpurun_out/bench.err; cut -c1-300 gpurun_out/bench_fp16.json; tail -3 gpurun_out/bench.err
