@@ -84,8 +84,8 @@ int tfpnp_denoiser_forward(void* handle, const float* x, const float* sigma,
  * PnPEnv.forward, tfpnp/env/base.py:193-206): for a cotangent gout [B,1,H,W] of `out`,
  *   gx [B,1,H,W] = d<out,gout>/dx,   gsigma [B] = d<out,gout>/dsigma   (weights are frozen: denoiser/base.py:19-21).
  * Recomputes the forward pass keeping every activation (fp32).  Only the TFPNP_PREC_FP32_SIMT engine implements it
- * (first correct path; others return TFPNP_ERR_UNSUPPORTED).  ROUND-1 STATUS: compiled, host logic and derivation
- * checked on the CPU; not yet run on a GPU (tests gated behind TFPNP_TEST_GRAD=1). */
+ * (first correct path; others return TFPNP_ERR_UNSUPPORTED).  STATUS: validated on a B200 against autograd through the unmodified
+ * reference (tests/test_grad.py, part of the default -m gpu suite since round 2). */
 int tfpnp_denoiser_vjp(void* handle, const float* x, const float* sigma, int64_t sigma_stride, const float* gout,
                        float* gx, float* gsigma, int B, int H, int W, void* stream);
 /* Debugging aid for the call above: copies the reverse-mode workspace of the handle's last tfpnp_denoiser_vjp (every layer's
@@ -93,6 +93,14 @@ int tfpnp_denoiser_vjp(void* handle, const float* x, const float* sigma, int64_t
  * `out_host` (up to n_floats); *have_floats = its size.  tools/grad_layer_check.py compares it region by region with the CPU
  * emulation to find the first layer that deviates. */
 int tfpnp_debug_grad_workspace(void* handle, float* out_host, size_t n_floats, size_t* have_floats);
+
+/* Measurement aid (tools/layer_profile.py -> profiles/): runs `reps` denoiser calls eagerly on `stream` with a CUDA event
+ * after every kernel launch and returns the mean device time of each launch of one call, in launch order, in ms_out[0..n)
+ * (n = *n_out <= cap; `names` receives n NUL-terminated labels of 48 bytes each, e.g. "l05 128->128 @32 pair").  Warm caches,
+ * back-to-back launches, no profiler attached; programmatic dependent launch is off inside it, so the figures include each
+ * kernel's own prologue.  Tensor-core engines only.  Synchronises the stream. */
+int tfpnp_denoiser_layer_profile(void* handle, const float* x, const float* sigma, float* out, int B, int H, int W, int reps,
+                                 float* ms_out, int cap, int* n_out, char* names, void* stream);
 
 /* One denoiser layer on its own (kernel-level parity tests): ConvLayer = nn.Conv2d(3x3, pad 1,
  * bias) + LeakyReLU(0.2) (unet.py:8-22) over the channel concatenation of x0 [B,H,W,C0] and the
@@ -157,8 +165,7 @@ int tfpnp_csmri_variant_forward(void* handle, const float* state_in, const float
  *   sigma_d, mu   [B,iters] strided like tfpnp_solver_forward;  y0 [B,1,N,N,2] f32;  mask [B,1,N,N] u8
  *   grad_out      [B,3,N,N,2] cotangent of the final state
  *   grad_sigma_d, grad_mu   [B,iters] contiguous (written);  grad_state_in [B,3,N,N,2] or NULL
- * `denoiser` must implement tfpnp_denoiser_vjp.  Synchronises the stream before returning (scratch is per call).
- * ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+ * `denoiser` must implement tfpnp_denoiser_vjp.  Synchronises the stream before returning (scratch is per call). */
 int tfpnp_csmri_admm_backward(void* denoiser, const float* states, const float* y0, const void* mask,
                               const float* sigma_d, const float* mu, int64_t row_stride, int64_t col_stride, int B,
                               int N, int iters, const float* grad_out, float* grad_sigma_d, float* grad_mu,
@@ -167,7 +174,7 @@ int tfpnp_csmri_admm_backward(void* denoiser, const float* states, const float* 
 /* Reverse mode of ADMMSolver_SPI.forward (tasks/spi/solver.py:17-51), same conventions: states [iters+1][B,3,H,W] real,
  * x0 [B,1,H,W], K [B] with element stride K_stride (the reference's K tensor, i.e. K/10).  Only the closed-form branch of
  * spi_inverse (K1 == 0, transforms.py:415) carries a gradient: the reference's bisection iterates are constants under
- * autograd.  ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+ * autograd. */
 int tfpnp_spi_admm_backward(void* denoiser, const float* states, const float* x0, const float* K, int64_t K_stride,
                             const float* sigma_d, const float* mu, int64_t row_stride, int64_t col_stride, int B, int H,
                             int W, int iters, const float* grad_out, float* grad_sigma_d, float* grad_mu,
@@ -176,7 +183,7 @@ int tfpnp_spi_admm_backward(void* denoiser, const float* states, const float* x0
 /* Reverse mode of IADMMSolver_CT.forward (tasks/ct/solver.py:17-53), same conventions: states [iters+1][B,3,N,N] real,
  * y0 [B,1,views,ceil(sqrt(2)N)], the geometry arguments of tfpnp_radon_forward, opnorm as given to the solver;
  * additionally grad_tau [B,iters].  Uses A^T A = (A^T A)^T (the backprojector is the exact transpose of the projector).
- * ROUND-1 STATUS: as tfpnp_denoiser_vjp; like the CT forward path, pinned to this build's own Radon pair only. */
+ * Like the CT forward path, pinned to this build's own Radon pair only. */
 int tfpnp_ct_iadmm_backward(void* denoiser, const float* states, const float* y0, int views, float opnorm,
                             const float* cos_host, const float* sin_host, const float* sigma_d, const float* mu,
                             const float* tau, int64_t row_stride, int64_t col_stride, int B, int N, int iters,
@@ -186,7 +193,7 @@ int tfpnp_ct_iadmm_backward(void* denoiser, const float* states, const float* y0
 /* Reverse mode of IADMMSolver_PR.forward (tasks/pr/solver.py:37-76), same conventions: states [iters+1][B,3,N,N,2],
  * y0 [B,M,N,N] f32, mask [B,M,N,N,2] f32 (unit-modulus CDP masks), M = n_masks.  The magnitude projection
  * h(w) = (1 - y0/|w|) w has a symmetric real Jacobian, so the adjoint of the gradient operator is the operator itself with h
- * replaced by that Jacobian (pr.cu).  FFTs through tfpnp_fft2.  ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+ * replaced by that Jacobian (pr.cu).  FFTs through tfpnp_fft2. */
 int tfpnp_pr_iadmm_backward(void* denoiser, const float* states, const float* y0, const float* mask, int n_masks,
                             const float* sigma_d, const float* mu, const float* tau, int64_t row_stride,
                             int64_t col_stride, int B, int N, int iters, const float* grad_out, float* grad_sigma_d,
@@ -194,7 +201,7 @@ int tfpnp_pr_iadmm_backward(void* denoiser, const float* states, const float* y0
 
 /* Reverse mode of tfpnp_csmri_variant_forward (HQS / PG / APG / RED-ADMM, tasks/csmri/solver.py:60-201), same conventions:
  * states [iters+1][B,V,N,N,2] recorded with iters = 1 calls; p0,p1,p2 as in the forward; grad_p0..2 [B,iters] contiguous
- * (grad_p2 NULL for the two-parameter solvers); grad_state_in [B,V,N,N,2] or NULL.  ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+ * (grad_p2 NULL for the two-parameter solvers); grad_state_in [B,V,N,N,2] or NULL. */
 int tfpnp_csmri_variant_backward(int algo, void* denoiser, const float* states, const float* y0, const void* mask,
                                  const float* p0, const float* p1, const float* p2, int64_t row_stride,
                                  int64_t col_stride, int B, int N, int iters, const float* grad_out, float* grad_p0,
@@ -222,7 +229,7 @@ int tfpnp_fft2(const float* in, float* out, float* workspace, int n_imgs, int N,
  * psnr[b] = 10 log10(1 / mean((clamp(out[b],0,1) - gt[b])^2)); out, gt: [B,HW] */
 int tfpnp_psnr(const float* out, const float* gt, float* psnr, int B, int64_t HW, void* stream);
 /* Reverse mode of tfpnp_psnr (the reward is part of the actor loss, tfpnp/trainer/mddpg/trainer.py:189):
- * grad_out[b,p] = grad_psnr[b] * d psnr[b] / d out[b,p]; `psnr` is the forward result.  ROUND-1 STATUS: as tfpnp_denoiser_vjp. */
+ * grad_out[b,p] = grad_psnr[b] * d psnr[b] / d out[b,p]; `psnr` is the forward result. */
 int tfpnp_psnr_backward(const float* out, const float* gt, const float* psnr, const float* grad_psnr, float* grad_out, int B,
                         int64_t HW, void* stream);
 
@@ -254,8 +261,10 @@ int tfpnp_env_policy_ob(const tfpnp_ob_channel* ch, int n_ch, const int64_t* idx
                         int64_t HW, float* dst, void* stream);
 
 /* ---- introspection used by tests / bench ---------------------------------- */
-/* measured device time (ms) of the denoiser part and the data-fidelity part of the last
- * forward when profiling is enabled with tfpnp_solver_set_profiling(handle, 1) */
+/* measured device time (ms) of the denoiser part and the data-fidelity part of the last forward.
+ * tfpnp_solver_set_profiling(handle, mode): 0 off; 1 = eager launches with CUDA events between the segments (no graph:
+ * slower than the shipped path); 2 = the events are recorded by event nodes INSIDE the captured graph, i.e. the timed
+ * launch is the same single graph launch as the product path plus 2 event nodes per iteration (what bench.py reports). */
 int tfpnp_solver_set_profiling(void* handle, int enable);
 int tfpnp_solver_get_profile(void* handle, float* denoiser_ms, float* update_ms);
 

@@ -49,8 +49,9 @@ void conv3x3_tc_host(const uint16_t* X, const uint16_t* Xlo, int K, const uint16
   for (size_t i = 0; i < wf.size(); ++i) wf[i] = grad_elem::h2f_bits(Wt[i]);
   if (Xlo) {
     xl.resize(xf.size()); wl.resize(wf.size());
-    for (size_t i = 0; i < xf.size(); ++i) xl[i] = grad_elem::h2f_bits(Xlo[i]);
-    for (size_t i = 0; i < wf.size(); ++i) wl[i] = grad_elem::h2f_bits(Wlo[i]);
+    // residual planes are stored scaled by kLoScale (grad_elem.cuh); the kernels scale the correction sums back
+    for (size_t i = 0; i < xf.size(); ++i) xl[i] = grad_elem::h2f_bits(Xlo[i]) * grad_elem::kLoInv;
+    for (size_t i = 0; i < wf.size(); ++i) wl[i] = grad_elem::h2f_bits(Wlo[i]) * grad_elem::kLoInv;
   }
   for (int b = 0; b < B; ++b)
     for (int y = 0; y < H; ++y)
@@ -74,7 +75,7 @@ void conv3x3_tc_host(const uint16_t* X, const uint16_t* Xlo, int K, const uint16
           const float v = acc > slope * acc ? acc : slope * acc;
           const size_t o = (((size_t)b * H + y) * W + x) * rows + r;
           Y[o] = grad_elem::f2h_bits(v);
-          if (Ylo) Ylo[o] = grad_elem::f2h_bits(v - grad_elem::h2f_bits(Y[o]));
+          if (Ylo) Ylo[o] = grad_elem::f2h_bits((v - grad_elem::h2f_bits(Y[o])) * grad_elem::kLoScale);
         }
 }
 

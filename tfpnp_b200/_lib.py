@@ -46,6 +46,9 @@ SIGNATURES = {
     "tfpnp_denoiser_vjp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tfpnp_debug_grad_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "tfpnp_denoiser_layer_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.c_char_p,
+                                               C.c_void_p]),
     "tfpnp_conv3x3_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tfpnp_solver_create": (C.c_int, [C.POINTER(SolverConfig), C.c_void_p, C.POINTER(C.c_void_p)]),

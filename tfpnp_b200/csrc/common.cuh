@@ -127,6 +127,13 @@ struct Denoiser {
     set_error("this denoiser engine has no reverse mode: create it with precision fp32_simt");
     return TFPNP_ERR_UNSUPPORTED;
   }
+  // measurement aid: per-launch device times of one forward (tfpnp_denoiser_layer_profile); names: 48 bytes per launch
+  virtual int layer_profile(const float* x, const float* sigma, float* out, int B, int H, int W, int reps, float* ms_out,
+                            int cap, int* n_out, char* names, cudaStream_t st) {
+    (void)x; (void)sigma; (void)out; (void)B; (void)H; (void)W; (void)reps; (void)ms_out; (void)cap; (void)n_out; (void)names; (void)st;
+    set_error("this denoiser engine has no per-launch profile");
+    return TFPNP_ERR_UNSUPPORTED;
+  }
   // debugging aid: the reverse-mode workspace of the last vjp() (device pointer, size in floats); nullptr if none
   virtual const float* grad_workspace(size_t* n_floats) { *n_floats = 0; return nullptr; }
 };

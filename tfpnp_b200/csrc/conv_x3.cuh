@@ -7,12 +7,14 @@
 //   * ONE halo tile per plane per chunk -- a_hi and a_lo are each fetched once (the K-loop-over-products form fetched
 //     a_hi twice and every weight slab up to twice);
 //   * N-concatenation: [W_hi | W_lo] of a (tap, chunk) sit back to back in shared memory, so a_hi w_hi and a_hi w_lo are ONE
-//     tcgen05.mma with N = 2 BN writing D[:, 0:BN] and D[:, BN:2BN]; a second MMA with N = BN adds a_lo w_hi into D[:, 0:BN].
+//     tcgen05.mma with N = 2 BN writing D[:, 0:BN] and D[:, BN:2BN]; a second MMA with N = BN adds a_lo w_hi into D[:, BN:2BN].
+//     (The residual planes a_lo, w_lo are stored x 2^11 so that they stay in fp16's normal range -- grad_elem.cuh kLoScale -- so
+//     both correction products belong in the second column block, which the epilogue scales back.)
 //     Below N = 128 an SS-mode MMA is bound by the shared-memory operand read, 32 + N/4 cycles per 128 x N x 16 (measured,
 //     profiles/r01_ubench_mma_chip.txt), so the three products cost 88 cycles at BN = 32 (fp16: 40) and 115 at BN = 64
 //     (fp16: 48) instead of three times the fp16 figure;
-//   * the epilogue adds the two column blocks (the small terms are accumulated apart from the big one, which also helps the
-//     rounding), applies bias + LeakyReLU and writes the fp16 hi plane and the fp16 residual plane.
+//   * the epilogue computes main + corrections / 2^11 (the small terms are accumulated apart from the big one, which also helps
+//     the rounding), applies bias + LeakyReLU and writes the fp16 hi plane and the scaled fp16 residual plane.
 // 32-channel chunks (64-byte rows) so that two planes x 3-4 stages of halo tiles plus the resident / streamed weights fit;
 // one CTA per SM, eight epilogue warps (two per TMEM lane quadrant, one per M-tile half), accumulators double-buffered.
 
@@ -168,10 +170,11 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
 #pragma unroll
               for (int kk = 0; kk < KSTEPS; ++kk) {
                 const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
+                const uint64_t bdl = bd;       // N = BN reads the first BN rows of the slab pair = W_hi
                 umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc2, accumulate);
                 umma_f16(d0 + 2 * BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc2, accumulate);
-                umma_f16(d0, pack_desc(a_tap + plane16 + kk * 2, a_hi), bd, idesc1, 1);
-                umma_f16(d0 + 2 * BN, pack_desc(a_tap + plane16 + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc1, 1);
+                umma_f16(d0 + BN, pack_desc(a_tap + plane16 + kk * 2, a_hi), bdl, idesc1, 1);
+                umma_f16(d0 + 3 * BN, pack_desc(a_tap + plane16 + (8 * ROW >> 4) + kk * 2, a_hi), bdl, idesc1, 1);
                 accumulate = 1;
               }
             }
@@ -195,10 +198,11 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
 #pragma unroll
                 for (int kk = 0; kk < KSTEPS; ++kk) {
                   const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
+                  const uint64_t bdl = bd;     // N = BN reads the first BN rows of the slab pair = W_hi
                   umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc2, accumulate);
                   umma_f16(d0 + 2 * BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc2, accumulate);
-                  umma_f16(d0, pack_desc(a_tap + plane16 + kk * 2, a_hi), bd, idesc1, 1);
-                  umma_f16(d0 + 2 * BN, pack_desc(a_tap + plane16 + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc1, 1);
+                  umma_f16(d0 + BN, pack_desc(a_tap + plane16 + kk * 2, a_hi), bdl, idesc1, 1);
+                  umma_f16(d0 + 3 * BN, pack_desc(a_tap + plane16 + (8 * ROW >> 4) + kk * 2, a_hi), bdl, idesc1, 1);
                   accumulate = 1;
                 }
               }
@@ -244,7 +248,7 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
         tmem_ld_32x32(tbase + BN + c0, rc);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])));
         float v[32];
         epilogue_act32(r, sbias + c0, v);
         if (p.outc_w) {                       // last layer: 1x1 conv + residual + clamp, fp32 out (BN == 32)

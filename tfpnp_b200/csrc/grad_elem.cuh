@@ -285,6 +285,13 @@ TFPNP_HD float pow2_scale(float maxabs) {
 
 // src [B,C,HW] fp32 -> channels [coff, coff+C) of dst [B,HW,Ctot] fp16 bits, times scale[b] (nullable); i over B*C*HW.
 // dst_lo (nullable): the fp16 residual plane of the split-fp16 (FP16X3) mode, v = hi + lo to ~22 bits.
+// Split-fp16 operands: v = hi + lo / kLoScale with hi = fp16(v), lo = fp16((v - hi) * kLoScale).  The residual is stored
+// scaled by 2^11 so that it lives in fp16's NORMAL range next to hi (an unscaled residual of a weight of magnitude 0.03 is
+// 7e-6, a subnormal with 6e-8 steps: only ~7 of its 11 bits survive, which cost a factor 10 in accuracy -- measured in round 2).
+// The kernels accumulate the two correction products in their own TMEM columns and scale them back in the epilogue.
+constexpr float kLoScale = 2048.f;
+constexpr float kLoInv = 1.f / 2048.f;
+
 TFPNP_HD void to_half_nhwc_elem(size_t i, const float* src, uint16_t* dst, uint16_t* dst_lo, int C, int Ctot, int coff, int HW,
                                 const float* scale) {
   const size_t p = i % HW, bc = i / HW;
@@ -294,7 +301,7 @@ TFPNP_HD void to_half_nhwc_elem(size_t i, const float* src, uint16_t* dst, uint1
   const size_t o = (b * HW + p) * Ctot + coff + c;
   const uint16_t hi = f2h_bits(v);
   dst[o] = hi;
-  if (dst_lo) dst_lo[o] = f2h_bits(v - h2f_bits(hi));
+  if (dst_lo) dst_lo[o] = f2h_bits((v - h2f_bits(hi)) * kLoScale);
 }
 // src [B,HW,C] fp16 bits (+ residual plane) -> channels [coff, coff+C) of dst [B,Ctot,HW] fp32, divided by scale[b] (nullable)
 TFPNP_HD void from_half_nhwc_elem(size_t i, const uint16_t* src, const uint16_t* src_lo, float* dst, int C, int Ctot, int coff,
@@ -304,7 +311,7 @@ TFPNP_HD void from_half_nhwc_elem(size_t i, const uint16_t* src, const uint16_t*
   const size_t b = bc / C;
   const float inv = scale ? 1.f / scale[b] : 1.f;      // a power of two: exact
   const size_t o = (b * HW + p) * C + c;
-  const float v = h2f_bits(src[o]) + (src_lo ? h2f_bits(src_lo[o]) : 0.f);
+  const float v = h2f_bits(src[o]) + (src_lo ? h2f_bits(src_lo[o]) * kLoInv : 0.f);
   dst[(b * Ctot + coff + c) * HW + p] = v * inv;
 }
 
@@ -321,7 +328,7 @@ inline void build_tc_weights(const float* w, int cout, int cin, bool transpose_f
         const float v = transpose_flip ? w[((size_t)k * cin + (row0 + r)) * 9 + (8 - t)] : w[((size_t)(row0 + r) * cin + k) * 9 + t];
         const size_t o = ((size_t)t * rows + r) * K + k;
         out[o] = f2h_bits(v);
-        if (out_lo) out_lo[o] = f2h_bits(v - h2f_bits(out[o]));
+        if (out_lo) out_lo[o] = f2h_bits((v - h2f_bits(out[o])) * kLoScale);
       }
     }
 }

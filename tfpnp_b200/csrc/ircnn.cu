@@ -55,7 +55,7 @@ ircnn_first_kernel(const float* __restrict__ d, const float* __restrict__ sigma,
       __half2 hh = __floats2half2_rn(a0, a1);
       hi[j / 2] = *reinterpret_cast<uint32_t*>(&hh);
       float2 back = __half22float2(hh);
-      __half2 ll = __floats2half2_rn(a0 - back.x, a1 - back.y);
+      __half2 ll = __floats2half2_rn((a0 - back.x) * grad_elem::kLoScale, (a1 - back.y) * grad_elem::kLoScale);
       lo[j / 2] = *reinterpret_cast<uint32_t*>(&ll);
     }
     *reinterpret_cast<uint4*>(out_hi + o + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -89,7 +89,10 @@ ircnn_last_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ i
         const uint4 vl = *reinterpret_cast<const uint4*>(in_lo + o + c8 * 8);
         const __half2* l = reinterpret_cast<const __half2*>(&vl);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(l[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = __half22float2(l[i]);
+          f[2 * i] = fmaf(t.x, grad_elem::kLoInv, f[2 * i]); f[2 * i + 1] = fmaf(t.y, grad_elem::kLoInv, f[2 * i + 1]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc = fmaf(wb.w[k * 64 + c8 * 8 + i], f[i], acc);
@@ -130,7 +133,7 @@ struct IrcnnTc : Denoiser {
             const __half h = __float2half_rn(v);
             const size_t idx = l * per + ((size_t)t * 64 + o) * 64 + c;
             hhi[idx] = h;
-            hlo[idx] = __float2half_rn(v - __half2float(h));
+            hlo[idx] = __float2half_rn((v - __half2float(h)) * grad_elem::kLoScale);
           }
       for (int i = 0; i < 64; ++i) hb[l * 64 + i] = host[off + i];
       off += 64;

@@ -99,9 +99,10 @@ struct Solver {
   DevBuf x, z, u, d, T, aux0p, aux1p, params, k10, resid;
   CtGeom geom;
   std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+  std::map<std::pair<int, int>, cudaGraphExec_t> graphs_prof;   // the same loop captured WITH event-record nodes (profiling == 2)
   cudaStream_t cap_stream = nullptr;
   int64_t last_launches = 0;
-  bool profiling = false;
+  int profiling = 0;       // 0 off; 1 eager launches with events; 2 events recorded by nodes of the captured graph
   std::vector<cudaEvent_t> events;
   int prof_iters = 0;
   int den_generation = -1;
@@ -111,8 +112,7 @@ struct Solver {
     const size_t el = complex_state ? sizeof(float2) : sizeof(float);
     if (B > cap_B) {
       // growing the workspaces invalidates captured graphs (they bake the addresses)
-      for (auto& g : graphs) cudaGraphExecDestroy(g.second);
-      graphs.clear();
+      drop_graphs();
       TFPNP_TRY(x.alloc(B * HW * sizeof(float)));
       TFPNP_TRY(d.alloc(B * HW * sizeof(float)));
       TFPNP_TRY(z.alloc(B * HW * el));
@@ -142,12 +142,18 @@ struct Solver {
     }
     const int need_it = iters > cap_it ? iters : cap_it;
     if ((size_t)cap_B * need_it * 3 * sizeof(float) > params.bytes) {
-      for (auto& g : graphs) cudaGraphExecDestroy(g.second);
-      graphs.clear();
+      drop_graphs();
       TFPNP_TRY(params.alloc((size_t)cap_B * need_it * 3 * sizeof(float)));
     }
     cap_it = need_it;
     return 0;
+  }
+
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    for (auto& g : graphs_prof) cudaGraphExecDestroy(g.second);
+    graphs.clear();
+    graphs_prof.clear();
   }
 
   bool split_batch(int B) const { return den2 != nullptr && B >= split_min_batch; }
@@ -166,6 +172,13 @@ struct Solver {
   }
 
   // enqueue the iteration loop on `st` (no allocation, no sync: graph-capturable)
+  // prof_external: the loop is being captured -- record the events as event-record NODES of the graph
+  // (cudaEventRecordExternal); a plain cudaEventRecord on a capturing stream only creates a capture-internal dependency
+  bool prof_external = false;
+  void rec(cudaEvent_t e, cudaStream_t st) {
+    if (prof_external) cudaEventRecordWithFlags(e, st, cudaEventRecordExternal);
+    else cudaEventRecord(e, st);
+  }
   int enqueue_loop(int B, int iters, cudaStream_t st, bool prof) {
     const int N = cfg.W;
     const size_t HW = (size_t)cfg.H * cfg.W;
@@ -176,17 +189,17 @@ struct Solver {
       const float* sig = P + (size_t)i * B;
       const float* mu = P + n + (size_t)i * B;
       const float* tau = P + 2 * n + (size_t)i * B;
-      if (prof) cudaEventRecord(events[ev++], st);
+      if (prof) rec(events[ev++], st);
       if (cfg.task == TFPNP_TASK_SPI) {
         TFPNP_TRY(spi_update(x.as<float>(), z.as<float>(), u.as<float>(), d.as<float>(),
                              aux0p.as<float>(), k10.as<float>(), mu, B, (int)HW, st));
-        if (prof) cudaEventRecord(events[ev++], st);
+        if (prof) rec(events[ev++], st);
         TFPNP_TRY(denoise(sig, B, st));
-        if (prof) cudaEventRecord(events[ev++], st);
+        if (prof) rec(events[ev++], st);
         continue;
       }
       TFPNP_TRY(denoise(sig, B, st));
-      if (prof) cudaEventRecord(events[ev++], st);
+      if (prof) rec(events[ev++], st);
       switch (cfg.task) {
         case TFPNP_TASK_CSMRI:
           TFPNP_TRY(csmri_update(x.as<float>(), z.as<float2>(), u.as<float2>(), d.as<float>(), T.as<float2>(),
@@ -201,7 +214,7 @@ struct Solver {
                               aux0p.as<float>(), 1.0f / (cfg.opnorm * cfg.opnorm), mu, tau, B, st));
           break;
       }
-      if (prof) cudaEventRecord(events[ev++], st);
+      if (prof) rec(events[ev++], st);
     }
     return 0;
   }
@@ -225,8 +238,7 @@ struct Solver {
     }
     const int gen = den->generation + (den2 ? den2->generation : 0);
     if (gen != den_generation) {      // a denoiser workspace moved
-      for (auto& g : graphs) cudaGraphExecDestroy(g.second);
-      graphs.clear();
+      drop_graphs();
       den_generation = gen;
     }
     const int T256 = 256;
@@ -261,8 +273,15 @@ struct Solver {
         TFPNP_CUDA_OK(cudaMemcpyAsync(aux0p.p, aux0, (size_t)B * HW * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     // 2. the iteration loop
-    const bool graphable = cfg.use_graph && !profiling && iters > 0;
+    const bool graphable = cfg.use_graph && profiling != 1 && iters > 0;
     if (graphable) {
+      const bool gp = profiling == 2;
+      auto& graphs = gp ? this->graphs_prof : this->graphs;
+      if (gp) {
+        size_t need = (size_t)iters * 3 + 2;
+        while (events.size() < need) { cudaEvent_t e; TFPNP_CUDA_OK(cudaEventCreate(&e)); events.push_back(e); }
+        prof_iters = iters;
+      }
       auto key = std::make_pair(B, iters);
       auto it = graphs.find(key);
       if (it == graphs.end()) {
@@ -270,7 +289,9 @@ struct Solver {
         cudaGraph_t graph = nullptr;
         int64_t before = g_launch_count;
         TFPNP_CUDA_OK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_loop(B, iters, cap_stream, false);
+        prof_external = gp;
+        int rc = enqueue_loop(B, iters, cap_stream, gp);
+        prof_external = false;
         cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
         if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
         TFPNP_CUDA_OK(ce);
@@ -285,12 +306,12 @@ struct Solver {
       TFPNP_CUDA_OK(cudaGraphLaunch(it->second, st));
       g_launch_count += graph_nodes[key];
     } else {
-      if (profiling) {
+      if (profiling == 1) {
         size_t need = (size_t)iters * 3 + 2;
         while (events.size() < need) { cudaEvent_t e; TFPNP_CUDA_OK(cudaEventCreate(&e)); events.push_back(e); }
         prof_iters = iters;
       }
-      TFPNP_TRY(enqueue_loop(B, iters, st, profiling));
+      TFPNP_TRY(enqueue_loop(B, iters, st, profiling == 1));
     }
     // 3. hand the state back in the reference layout
     if (complex_state)
@@ -325,7 +346,7 @@ struct Solver {
     if (side) cudaStreamDestroy(side);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
-    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    drop_graphs();
     for (auto e : events) cudaEventDestroy(e);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     x.release(); z.release(); u.release(); d.release(); T.release(); aux0p.release(); aux1p.release();
@@ -442,6 +463,14 @@ int tfpnp_denoiser_vjp(void* h, const float* x, const float* sigma, int64_t sstr
   return static_cast<Denoiser*>(h)->vjp(x, sigma, sstride, gout, gx, gsigma, 1, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
+int tfpnp_denoiser_layer_profile(void* h, const float* x, const float* sigma, float* out, int B, int H, int W, int reps,
+                                 float* ms_out, int cap, int* n_out, char* names, void* stream) {
+  TFPNP_CHECK(h && x && sigma && out && ms_out && n_out && names && B > 0 && reps > 0 && cap > 0, "bad argument");
+  Denoiser* d = static_cast<Denoiser*>(h);
+  TFPNP_TRY(d->prepare(B, H, W));
+  return d->layer_profile(x, sigma, out, B, H, W, reps, ms_out, cap, n_out, names, static_cast<cudaStream_t>(stream));
+}
+
 int tfpnp_debug_grad_workspace(void* h, float* out_host, size_t n_floats, size_t* have_floats) {
   TFPNP_CHECK(h && have_floats, "bad argument");
   size_t n = 0;
@@ -471,7 +500,7 @@ int tfpnp_solver_forward(void* h, const float* state_in, const void* aux0, const
 int64_t tfpnp_solver_last_launch_count(void* h) { return h ? static_cast<Solver*>(h)->last_launches : -1; }
 int tfpnp_solver_set_profiling(void* h, int enable) {
   TFPNP_CHECK(h, "null handle");
-  static_cast<Solver*>(h)->profiling = enable != 0;
+  static_cast<Solver*>(h)->profiling = enable;
   return 0;
 }
 int tfpnp_solver_get_profile(void* h, float* den_ms, float* upd_ms) {

@@ -19,12 +19,15 @@
 #include <map>
 #include <cstring>
 #include <cstdlib>
+#include <string>
 
 namespace tfpnp {
 namespace {
 
 using namespace sm100;
 
+using grad_elem::kLoScale;           // residual planes of the split-fp16 mode are stored x 2^11 (grad_elem.cuh)
+using grad_elem::kLoInv;
 constexpr int kTileM = 128;          // pixels per CTA tile (UMMA M)
 constexpr int kConvThreads = 192;    // 6 warps
 
@@ -113,7 +116,7 @@ __device__ __forceinline__ void epilogue_store_nhwc32(const float (&v)[32], __ha
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float2 back = __half22float2(*reinterpret_cast<__half2*>(&hi[j]));
-      __half2 ll = __floats2half2_rn(v[2 * j] - back.x, v[2 * j + 1] - back.y);
+      __half2 ll = __floats2half2_rn((v[2 * j] - back.x) * kLoScale, (v[2 * j + 1] - back.y) * kLoScale);
       lo[j] = *reinterpret_cast<uint32_t*>(&ll);
     }
 #pragma unroll
@@ -134,7 +137,7 @@ struct ConvCfg {
   static constexpr int kABytes = kTileM * 128;   // room for kc = 64
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // [main | corrections of the split-fp16 mode]
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
 
@@ -214,10 +217,14 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
         tc_fence_after();
         const uint32_t a_lo = ((smem_u32(smem) + s * Cfg::kStageBytes) >> 4) | (1u << 16);
         const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
+        // split-fp16: product 0 (a_hi w_hi) -> columns [0, BN); products 1, 2 (a_lo w_hi, a_hi w_lo; residual planes are
+        // stored x 2^11) -> columns [BN, 2 BN), scaled back in the epilogue
+        const int prod = it % p.nprod, t = it / p.nprod;
+        const uint32_t dcol = tmem_base + (prod ? BN : 0);
         if (elect_one()) {
           for (int kk = 0; kk < ksteps; ++kk) {
-            umma_f16(tmem_base, pack_desc(a_lo + kk * 2, desc_hi), pack_desc(b_lo + kk * 2, desc_hi), idesc,
-                     (it | kk) != 0);
+            umma_f16(dcol, pack_desc(a_lo + kk * 2, desc_hi), pack_desc(b_lo + kk * 2, desc_hi), idesc,
+                     ((t | kk) != 0 || prod == 2) ? 1u : 0u);
           }
           umma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
         }
@@ -240,7 +247,15 @@ conv3x3_tc(const __grid_constant__ ConvParams p) {
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
-      tmem_ld_wait();
+      if (p.nprod == 3) {
+        uint32_t rc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + BN + c0, rc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])));
+      } else {
+        tmem_ld_wait();
+      }
       epilogue_store32(r, sbias + c0, p.out_hi, p.out_lo, pix * p.Cout + n0 + c0, valid, p.slope);
     }
   }
@@ -499,6 +514,7 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
         if (lane == 0) TRACE(2, it);
         const uint32_t d0 = tmem_base + buf * (2 * BN);   // left half; right half at +BN
         uint32_t accumulate = 0;
+        uint32_t acc_corr = 0;     // SMALL split-fp16: products 1, 2 accumulate in columns [BN, 2 BN) (residual planes are x 2^11)
         for (int c = 0; c < nchunks; ++c) {
           for (int prod = 0; prod < p.nprod; ++prod) {
             mbar_wait(&full_a[sa], pha);
@@ -535,8 +551,11 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
                 const uint32_t b_stage = sW_lo + sb * (TPS * SLAB >> 4);
                 // first tap of the stage: kernel row (tg*TPS)/3, column (tg*TPS)%3
                 const uint32_t a_row = a_lo + ((((tg * TPS) / 3) * TAP_ROWS + (tg * TPS) % 3) * ROW >> 4);
+                const bool corr = SMALL && prod > 0;
                 if (elect_one()) {
                   if (!(p.dbg & 2)) {
+                    uint32_t acc = corr ? acc_corr : accumulate;
+                    const uint32_t dd = corr ? d0 + BN : d0;
 #pragma unroll
                     for (int tt = 0; tt < TPS; ++tt) {
                       const uint32_t a_tap = a_row + (tt * ROW >> 4);
@@ -544,16 +563,16 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
 #pragma unroll
                       for (int kk = 0; kk < KSTEPS; ++kk) {
                         const uint64_t bd = pack_desc(b_lo + kk * 2, b_hi);
-                        umma_f16(d0, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, accumulate);
-                        if (!SMALL) umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, accumulate);
-                        accumulate = 1;
+                        umma_f16(dd, pack_desc(a_tap + kk * 2, a_hi), bd, idesc, acc);
+                        if (!SMALL) umma_f16(d0 + BN, pack_desc(a_tap + (8 * ROW >> 4) + kk * 2, a_hi), bd, idesc, acc);
+                        acc = 1;
                       }
                     }
                   }
                   if (cs == 1) umma_commit(&empty_b[sb]);
                   else umma_commit_mc(&empty_b[sb], cmask);
                 }
-                accumulate = 1;
+                if (corr) acc_corr = 1; else accumulate = 1;
                 __syncwarp();
                 if (++sb == (uint32_t)SB) { sb = 0; phb ^= 1; }
               }
@@ -757,6 +776,22 @@ conv3x3_tc2(const __grid_constant__ Conv2Params p) {
       if (warp == 2 && lane == 0) TRACE(6, it);
       // the two M-tile halves sit side by side in TMEM: walk their 2*BN columns in blocks of 64
       // (one tcgen05.ld round trip per two 32-column slices)
+      if (SMALL && p.nprod == 3) {
+        // split-fp16 at the 8x8 level: main product in columns [0, BN), the two correction products (x 2^11) in [BN, 2 BN)
+#pragma unroll 1
+        for (int c0 = cb_begin; c0 < cb_end; c0 += 32) {
+          uint32_t r[32], rc[32];
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + c0;
+          tmem_ld_32x32(ta, r);
+          tmem_ld_32x32(ta + BN, rc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])));
+          float v[32];
+          epilogue_act32(r, sbias + n0 + c0, v);
+          if (real_tile && b < p.B) epilogue_store_nhwc32(v, p.out_hi, p.out_lo, pix * p.Cout + n0 + c0);
+        }
+      } else
 #pragma unroll 1
       for (int cb = cb_begin; cb < cb_end; cb += 64) {
         if (p.dbg & 32) break;                  // knock-out: no TMEM reads, no epilogue math
@@ -832,6 +867,7 @@ struct ConvPairParams {
   __half* out_lo;           // fp16 residual plane (split-fp16 mode) or nullptr
   __half* pool_hi;          // fused nn.MaxPool2d(2) output or nullptr
   __half* pool_lo;
+  int single_buf;           // experiment (TFPNP_PAIR_SINGLE=1): one accumulator buffer, 256 TMEM columns in the X3 instantiation
 };
 
 constexpr int kPairThreads = 64 + 32 * 8;
@@ -885,7 +921,10 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
     if (lane < 2) { mbar_init(&tmem_full[lane], 1); mbar_init(&tmem_empty[lane], 16); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc_2sm(tmem_slot, 256);
+  const uint32_t kTmem = (X3 && !p.single_buf) ? 512 : 256;     // X3: two buffers of [main | corrections (x 2^11)]
+  constexpr uint32_t kBufCols = X3 ? 2 * BN : BN;
+  const bool single = X3 && p.single_buf;
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, kTmem);
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
@@ -953,10 +992,10 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
       const uint32_t w_lo = (smem_u32(sWr) >> 4) | lo_flags;
       uint32_t ia = 0, ib = 0, it = 0;
       for (int t = item0; t < total_items; t += item_step, ++it) {
-        const uint32_t buf = it & 1;
-        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        const uint32_t buf = single ? 0 : (it & 1);
+        mbar_wait(&tmem_empty[buf], ((single ? it : (it >> 1)) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + buf * BN;
+        const uint32_t d0 = tmem_base + buf * kBufCols;
         uint32_t accumulate = 0;
         for (int c = 0; c < nchunks; ++c, ++ia) {
           const int sa = ia % S;
@@ -999,8 +1038,8 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
                   for (int kk = 0; kk < KSTEPS; ++kk) {
                     const uint64_t ad = pack_desc(a_tap + kk * 2, a_hi);
                     umma2_f16(d0, ad, pack_desc(bh + kk * 2, b_hi), idesc, accumulate);                               // a_hi w_hi
-                    umma2_f16(d0, ad, pack_desc(bl + kk * 2, b_hi), idesc, 1);                                        // a_hi w_lo
-                    umma2_f16(d0, pack_desc(a_tap + (kPairABytes >> 4) + kk * 2, a_hi), pack_desc(bh + kk * 2, b_hi), idesc, 1);   // a_lo w_hi
+                    umma2_f16(d0 + BN, ad, pack_desc(bl + kk * 2, b_hi), idesc, accumulate);                          // a_hi w_lo
+                    umma2_f16(d0 + BN, pack_desc(a_tap + (kPairABytes >> 4) + kk * 2, a_hi), pack_desc(bh + kk * 2, b_hi), idesc, 1);   // a_lo w_hi
                     accumulate = 1;
                   }
                 }
@@ -1031,16 +1070,27 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
       const int b = m / (p.tiles_w * p.tiles_h);
       const int n0 = nt * BN;
       const size_t pix = ((size_t)b * p.H + h) * p.W + w;
-      const uint32_t buf = it & 1;
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      const uint32_t buf = single ? 0 : (it & 1);
+      mbar_wait(&tmem_full[buf], (single ? it : (it >> 1)) & 1);
       tc_fence_after();
       uint32_t r64[64];
-      tmem_ld_32x64(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + e * 64, r64);
-      tmem_ld_wait();
+      if constexpr (!X3) {
+        tmem_ld_32x64(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + e * 64, r64);
+        tmem_ld_wait();
+      }
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl) {
         const int c0 = e * 64 + 32 * sl;
         uint32_t (&r)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r64[32 * sl]);
+        if constexpr (X3) {                    // main + corrections / 2^11
+          uint32_t (&rc)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r64[32 * (sl ^ 1)]);
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBufCols + c0;
+          tmem_ld_32x32(ta, r);
+          tmem_ld_32x32(ta + BN, rc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])));
+        }
         float v[32];
         epilogue_act32(r, sbias + n0 + c0, v);
         epilogue_store_nhwc32(v, p.out_hi, X3 ? p.out_lo : nullptr, pix * p.Cout + n0 + c0);
@@ -1064,7 +1114,7 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                            // nobody leaves (or frees TMEM) while the peer may still signal it
-  if (warp == 2) tmem_dealloc_2sm(tmem_base, 256);
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, kTmem);
 }
 
 #include "conv_x3.cuh"
@@ -1111,7 +1161,7 @@ conv_first_kernel(const float* __restrict__ d, const float* __restrict__ sigma, 
       __half2 hh = __floats2half2_rn(a0, a1);
       hi[j / 2] = *reinterpret_cast<uint32_t*>(&hh);
       float2 back = __half22float2(hh);
-      __half2 ll = __floats2half2_rn(a0 - back.x, a1 - back.y);
+      __half2 ll = __floats2half2_rn((a0 - back.x) * kLoScale, (a1 - back.y) * kLoScale);
       lo[j / 2] = *reinterpret_cast<uint32_t*>(&ll);
     }
     *reinterpret_cast<uint4*>(out_hi + o + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -1127,7 +1177,10 @@ __device__ __forceinline__ void load8(const __half* hi, const __half* lo, size_t
   if (lo) {
     H8 l = *reinterpret_cast<const H8*>(lo + off);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(l.v[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __half22float2(l.v[i]);
+      f[2 * i] = fmaf(t.x, kLoInv, f[2 * i]); f[2 * i + 1] = fmaf(t.y, kLoInv, f[2 * i + 1]);
+    }
   }
 }
 __device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const float (&f)[8]) {
@@ -1136,7 +1189,7 @@ __device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const
   for (int i = 0; i < 4; ++i) {
     a.v[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
     float2 back = __half22float2(a.v[i]);
-    l.v[i] = __floats2half2_rn(f[2 * i] - back.x, f[2 * i + 1] - back.y);
+    l.v[i] = __floats2half2_rn((f[2 * i] - back.x) * kLoScale, (f[2 * i + 1] - back.y) * kLoScale);
   }
   *reinterpret_cast<H8*>(hi + off) = a;
   if (lo) *reinterpret_cast<H8*>(lo + off) = l;
@@ -1211,8 +1264,8 @@ upsample2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
     for (int i = 0; i < 4; ++i) {
       const float2 fa = __half22float2(a.v[i]), fb = __half22float2(b.v[i]);
       const float2 fc = __half22float2(c.v[i]), fd = __half22float2(d.v[i]);
-      r[2 * i] += w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
-      r[2 * i + 1] += w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
+      r[2 * i] += (w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x) * kLoInv;
+      r[2 * i + 1] += (w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y) * kLoInv;
     }
   }
   const int oo = (y * Wo + x) * C + c8 * 8;
@@ -1225,7 +1278,7 @@ upsample2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_l
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 back = __half22float2(hi.v[i]);
-      lo.v[i] = __floats2half2_rn(r[2 * i] - back.x, r[2 * i + 1] - back.y);
+      lo.v[i] = __floats2half2_rn((r[2 * i] - back.x) * kLoScale, (r[2 * i + 1] - back.y) * kLoScale);
     }
     *reinterpret_cast<H8*>(out_lo + img_out + oo) = lo;
   }
@@ -1320,9 +1373,10 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 // programmatic dependent launch between the kernels of one denoiser call (TFPNP_PDL=0 disables)
+thread_local bool g_no_pdl = false;   // set while tfpnp_denoiser_layer_profile times launches one by one
 bool use_pdl() {
   static int v = env_int("TFPNP_PDL", 1);
-  return v != 0;
+  return v != 0 && !g_no_pdl;
 }
 
 template <int BN, int KC, bool RES, bool FUSE, bool SMALL = false, int XF = 0>
@@ -1420,7 +1474,13 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   c.small = (H == 8 && W == 8);
   const int Cin = C0 + C1;
   // split-fp16 on the 32/64-channel levels: the N-concatenated kernel (32-channel chunks, both planes in one stage)
-  c.x3n = x3 && !c.small && !fuse_up && (Cout == 32 || Cout == 64) && env_int("TFPNP_X3N", 1) != 0;
+  c.x3n = x3 && !c.small && !fuse_up && (Cout == 32 || Cout == 64);
+  if (x3 && !c.x3n && !c.small) {
+    // (the K-loop-over-products form of conv3x3_tc2 has no room for the separate correction accumulator the scaled residual
+    // planes need, except at the 8x8 level; everything else of a split-fp16 UNet runs on conv3x3_x3 / conv3x3_pair<true>)
+    set_error("split-fp16: no halo-tile kernel for %d+%d -> %d at %dx%d", C0, C1, Cout, H, W);
+    return TFPNP_ERR_UNSUPPORTED;
+  }
   const int kc = (C0 % 64 == 0 && C1 % 64 == 0 && !c.x3n) ? 64 : 32;
   c.kc = kc;
   c.BN = Cout >= 128 ? 128 : Cout;
@@ -1537,11 +1597,10 @@ struct ConvPairPlan {
 
 // CTA-pair kernel: streamed weights, 64-channel chunks, Cout a multiple of 128, 16x16 tiling (TFPNP_CONV_PAIR=0
 // falls back to the single-CTA kernel).  Measured in fp16: 14.6 / 16.6 / 39.7 us against 20.4 / 20.4 / 47.5 us (128->128 @32x32,
-// 256->256 @16x16, 768->256 @16x16, 48 images); 60.3k -> 63.8k image-iters/s end to end.  Split-fp16 (x3): TFPNP_PAIR_X3=0
-// falls back to the single-CTA K-loop-over-products path.
+// 256->256 @16x16, 768->256 @16x16, 48 images); 60.3k -> 63.8k image-iters/s end to end.  The split-fp16 mode always uses it.
 bool conv_pair_eligible(int C0, int C1, int Cout, int H, int W, bool x3, bool fuse_up) {
-  return env_int("TFPNP_CONV_PAIR", 1) != 0 && (!x3 || env_int("TFPNP_PAIR_X3", 1) != 0) && !fuse_up && C0 % 64 == 0 &&
-         C1 % 64 == 0 && Cout % 128 == 0 && H % 16 == 0 && W % 16 == 0;
+  return (x3 || env_int("TFPNP_CONV_PAIR", 1) != 0) && !fuse_up && C0 % 64 == 0 && C1 % 64 == 0 && Cout % 128 == 0 &&
+         H % 16 == 0 && W % 16 == 0;
 }
 
 // x*_lo / w_lo / out_lo: the fp16 residual planes (all non-null selects the split-fp16 instantiation)
@@ -1551,6 +1610,7 @@ int plan_conv_pair(ConvPairPlan& c, const __half* x0, const __half* x0_lo, int C
   ConvPairParams& p = c.p;
   memset(&p, 0, sizeof(p));
   c.x3 = w_lo != nullptr;
+  p.single_buf = env_int("TFPNP_PAIR_SINGLE", 0);
   p.nchunk0 = C0 / 64; p.nchunk1 = C1 / 64;
   p.tiles_w = W / 16; p.tiles_h = H / 16;
   p.num_m_tiles = p.tiles_w * p.tiles_h * B;
@@ -1681,7 +1741,7 @@ struct UNetTc : Denoiser {
             __half h = __float2half_rn(v);
             size_t idx = woff + ((size_t)t * co + o) * ci + c;
             hhi[idx] = h;
-            hlo[idx] = __float2half_rn(v - __half2float(h));
+            hlo[idx] = __float2half_rn((v - __half2float(h)) * kLoScale);
           }
       woff += (size_t)9 * co * ci;
     }
@@ -1709,6 +1769,63 @@ struct UNetTc : Denoiser {
     TFPNP_TRY(encode_map(&maps[0], a.hi, 4, dims, strides, box, kc * 2));
     if (x3) TFPNP_TRY(encode_map(&maps[1], a.lo, 4, dims, strides, box, kc * 2));
     else maps[1] = maps[0];
+    return 0;
+  }
+
+  // per-launch timing (tfpnp_denoiser_layer_profile): an event after every launch of forward()
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<std::string> prof_names;
+  size_t prof_n = 0;
+  void mark(cudaStream_t st, const char* name) {
+    if (!prof_on) return;
+    if (prof_n == prof_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); prof_ev.push_back(e); prof_names.push_back(name); }
+    cudaEventRecord(prof_ev[prof_n++], st);
+  }
+  std::string conv_label(int l) const {
+    const ConvSpec& sp = unet_conv_specs()[l];
+    const char* kind = "v1";
+    int h = 0;
+    if (convsp[l].grid > 0) { kind = convsp[l].x3 ? "pair-x3" : "pair"; h = convsp[l].p.H; }
+    else if (convs2[l].grid > 0) {
+      const Conv2Plan& c = convs2[l];
+      h = c.p.H;
+      kind = c.x3n ? (c.resident ? "x3n-res" : "x3n") : c.small ? "small" : c.p.up_fused ? "fuse-up" : c.resident ? "tc2-res" : "tc2";
+    } else h = convs[l].H;
+    char buf[48];
+    snprintf(buf, sizeof(buf), "l%02d %d->%d @%d %s", l, sp.cin, sp.cout, h, kind);
+    return buf;
+  }
+
+  int layer_profile(const float* x, const float* sigma, float* out, int B, int H, int W, int reps, float* ms_out, int cap,
+                    int* n_out, char* names, cudaStream_t st) override {
+    g_no_pdl = true;
+    prof_on = true;
+    std::vector<double> acc;
+    int rc = 0;
+    for (int r = 0; r < reps + 1 && rc == 0; ++r) {        // first repetition is a warm-up
+      prof_n = 0;
+      mark(st, "start");
+      rc = forward(x, sigma, 1, out, B, H, W, st);
+      if (rc != 0) break;
+      if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("layer_profile: sync failed"); rc = TFPNP_ERR_CUDA; break; }
+      if (acc.empty()) acc.assign(prof_n - 1, 0.0);
+      if (r == 0) continue;
+      for (size_t i = 1; i < prof_n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, prof_ev[i - 1], prof_ev[i]);
+        acc[i - 1] += ms;
+      }
+    }
+    prof_on = false;
+    g_no_pdl = false;
+    if (rc != 0) return rc;
+    const int n = (int)acc.size() < cap ? (int)acc.size() : cap;
+    for (int i = 0; i < n; ++i) {
+      ms_out[i] = (float)(acc[i] / reps);
+      snprintf(names + 48 * i, 48, "%s", prof_names[i + 1].c_str());
+    }
+    *n_out = n;
     return 0;
   }
 
@@ -1870,6 +1987,11 @@ struct UNetTc : Denoiser {
   }
 
   int launch_conv(int l, cudaStream_t st) {
+    const int rc = launch_conv_impl(l, st);
+    if (prof_on && rc == 0) mark(st, conv_label(l).c_str());
+    return rc;
+  }
+  int launch_conv_impl(int l, cudaStream_t st) {
     if (convsp[l].grid > 0) return launch_conv_pair(convsp[l], st);
     if (convs2[l].grid > 0) {
       // debugging aid: TFPNP_TRACE_LAYER=l + TFPNP_TRACE_FILE dump CTA 0's role timeline of layer l (eager calls only)
@@ -1905,6 +2027,7 @@ struct UNetTc : Denoiser {
     TFPNP_CUDA_OK(launch_ex(conv_first_kernel, dim3(cdiv(W, 128), H, B), dim3(128), 0, st, use_pdl(), 1, x, sigma, sstride,
                             first_w, S0.hi, x3 ? S0.lo : nullptr, H, W));
     TFPNP_COUNT_LAUNCH();
+    mark(st, "l00 2->32 first (CUDA cores)");
     TFPNP_TRY(launch_conv(1, st));
     TFPNP_TRY(launch_conv(2, st));
     for (int lv = 1; lv <= 4; ++lv) {
@@ -1913,6 +2036,7 @@ struct UNetTc : Denoiser {
         TFPNP_CUDA_OK(launch_ex(maxpool2_nhwc, dim3(cdiv(w * (ch[lv - 1] / 8), T), h, B), dim3(T), 0, st, use_pdl(), 1,
                                 skip[lv - 1].hi, skip[lv - 1].lo, S0.hi, S0.lo, 2 * h, 2 * w, ch[lv - 1]));
         TFPNP_COUNT_LAUNCH();
+        mark(st, "maxpool");
       }
       for (int k = 0; k < 3; ++k) TFPNP_TRY(launch_conv(3 * lv + k, st));
     }
@@ -1922,7 +2046,7 @@ struct UNetTc : Denoiser {
       if (!fused_up[15 + 3 * k])
       TFPNP_CUDA_OK(launch_ex(x3 ? upsample2_nhwc<true> : upsample2_nhwc<false>, dim3(cdiv(w * (ch[lv + 1] / 8), T), h, B),
                               dim3(T), 0, st, use_pdl(), 1, src.hi, src.lo, S0.hi, S0.lo, h / 2, w / 2, ch[lv + 1]));
-      if (!fused_up[15 + 3 * k]) TFPNP_COUNT_LAUNCH();
+      if (!fused_up[15 + 3 * k]) { TFPNP_COUNT_LAUNCH(); char nb[48]; snprintf(nb, sizeof(nb), "upsample %d ch -> @%d", ch[lv + 1], h); mark(st, nb); }
       for (int j = 0; j < 3; ++j) {
         const int l = 15 + 3 * k + j;
         if (l == 26 && fused_outc) { convs2[l].p.d_in = x; convs2[l].p.x_out = out; }
@@ -1934,6 +2058,7 @@ struct UNetTc : Denoiser {
       TFPNP_CUDA_OK(launch_ex(outc_nhwc, dim3((unsigned)((npix + T - 1) / T)), dim3(T), 0, st, use_pdl(), 1, S2.hi, S2.lo,
                               w_out.as<float>(), w_out.as<float>() + 32, x, out, npix));
       TFPNP_COUNT_LAUNCH();
+      mark(st, "outconv");
     }
     TFPNP_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1952,6 +2077,7 @@ struct UNetTc : Denoiser {
   ~UNetTc() override {
     if (shares_weights) { w_hi.p = w_lo.p = biases.p = w_out.p = nullptr; }
     w_hi.release(); w_lo.release(); biases.release(); w_out.release(); act.release();
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
   }
 };
 

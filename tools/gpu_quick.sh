@@ -1,6 +1,11 @@
 #!/bin/bash
-# scratch: quick check after a change (edit freely)
 mkdir -p gpurun_out
-echo "=== pytest denoiser"; timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_conv.py -m gpu -q --timeout 300 -p no:cacheprovider -x -k "denoiser or conv" 2>&1 | tail -8
-echo "=== bench x3"; timeout 300 python bench.py --precision fp16x3 --no-cpu-baseline > gpurun_out/bench_x3.json 2>gpurun_out/bench.err; cut -c1-400 gpurun_out/bench_x3.json; tail -3 gpurun_out/bench.err
-echo "=== bench fp16"; timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_fp16.json 2>gpurun_out/bench.err; cut -c1-300 gpurun_out/bench_fp16.json; tail -3 gpurun_out/bench.err
+for v in 0 1; do
+echo "=== PAIR_SINGLE=$v"; TFPNP_PAIR_SINGLE=$v timeout 600 python bench.py --steps 4 --tasks csmri --no-cpu-baseline > gpurun_out/bench_s$v.json 2>gpurun_out/bench.err; tail -3 gpurun_out/bench.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_s$v.json"))
+print("csmri x3 value", round(d["value"]), "ms", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"]), "| fp16", round(d["fp16"]["value"]), round(d["fp16"]["e2e"]))
+PY
+done
+TFPNP_PAIR_SINGLE=1 timeout 200 python tools/layer_profile.py --precision fp16x3 | grep -E "pair|per call"
