@@ -18,15 +18,32 @@
 // 32-channel chunks (64-byte rows) so that two planes x 3-4 stages of halo tiles plus the resident / streamed weights fit;
 // one CTA per SM, eight epilogue warps (two per TMEM lane quadrant, one per M-tile half), accumulators double-buffered.
 
-template <int BN, bool RESIDENT>
-__global__ void __launch_bounds__(64 + 32 * 8, 1)
+//
+// FUSE: the decoder heads (96 -> 32 @ full resolution, 192 -> 64 @ half resolution): source 1 is the bilinear x2 up-sampling
+// (align_corners=True, unet.py:99) of a low-resolution tensor that is never materialised (in split-fp16 the up-sampled tensor
+// is 200 MB per plane pair at 48 x 128^2 x 64 channels, written and read back once per call: ~250 us of a 1.8 ms call).
+// The producer stages the 11 x 11 low-resolution window of both planes (unswizzled TMA box); nine transform warps interpolate
+// in fp32 from hi + lo / 2^11, split the result again and write both planes of the 18 x 18 halo tile into the swizzled A
+// stage.  Work item of a transform thread = (coarse row interval i, fine column k, 8-channel group j): it loads the two
+// source rows of the interval at the column's two source pixels ONCE (8 x LDS.128 for both planes), interpolates
+// horizontally, then emits the 1-3 fine rows that fall into the interval -- no state carried from row to row, all loads of
+// an item in flight together.  Four epilogue warps (each takes both M-tile halves) keep the CTA at 480 threads.
+constexpr int kX3StgPlane = 61 * 128;                  // 121 rows x 64 B = 7744, padded to the TMA's 128-byte alignment
+constexpr int kX3StgSlot = 2 * kX3StgPlane;            // [hi | lo]
+constexpr int kX3XformThreads = 288;
+
+template <bool FUSE> constexpr int conv_x3_nepi() { return FUSE ? 4 : 8; }
+template <bool FUSE> constexpr int conv_x3_threads() { return 64 + 32 * conv_x3_nepi<FUSE>() + (FUSE ? kX3XformThreads : 0); }
+
+template <int BN, bool RESIDENT, bool FUSE>
+__global__ void __launch_bounds__(conv_x3_threads<FUSE>(), 1)
 conv3x3_x3(const __grid_constant__ Conv2Params p) {
   static_assert(BN == 32 || BN == 64, "N-concatenated split-fp16 products: BN = 32 or 64");
   constexpr int KC = 32, KSTEPS = 2, TPS = 3;
   constexpr uint32_t ROW = KC * 2;                  // 64-byte pixel rows (SWIZZLE_64B)
   constexpr uint32_t SLAB = BN * ROW;               // one plane of one (tap, chunk) weight slab
   constexpr uint32_t SLAB2 = 2 * SLAB;              // [W_hi | W_lo]
-  constexpr int NEPI = 8;
+  constexpr int NEPI = conv_x3_nepi<FUSE>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nchunks = p.nchunk0 + p.nchunk1;
@@ -35,7 +52,8 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
   uint8_t* sA = smem;
   uint8_t* sW = smem + SA * p.a_stage_bytes;
   const int w_region = RESIDENT ? 9 * nchunks * (int)SLAB2 : SB * TPS * (int)SLAB2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + w_region);
+  uint8_t* sStg = sW + w_region;                                  // [2][kX3StgSlot] low-resolution windows (FUSE only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + (FUSE ? 2 * kX3StgSlot : 0));
   uint64_t* full_a = bars;
   uint64_t* empty_a = bars + kMaxStages;
   uint64_t* full_b = bars + 2 * kMaxStages;
@@ -43,8 +61,16 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
   uint64_t* w_full = bars + 4 * kMaxStages;
   uint64_t* tmem_full = w_full + 1;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* sbias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 12);   // [Cout]
+  uint64_t* stg_full = tmem_empty + 2;   // [2]
+  uint64_t* stg_empty = stg_full + 2;    // [2]
+  // FUSE: a stage of the A ring is claimed by the TMA producer (source-0 chunks) or by the transform warps (fused chunks).
+  // A claimant that skipped the other party's uses of a slot could not tell mbarrier phases apart by parity (it may be two
+  // phases ahead: measured as a data race with resident weights, where nothing else throttles the producer), so every slot
+  // has TWO release barriers: the MMA warp signals empty_a[s] when the NEXT use of slot s is a TMA chunk and empty_x[s] when
+  // it is a fused chunk; each party then sees exactly one phase per claim of its own.
+  uint64_t* empty_x = stg_empty + 2;     // [kMaxStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_x + kMaxStages);
+  float* sbias = reinterpret_cast<float*>(bars + 5 * kMaxStages + 12);   // [Cout]
   float* soutc = sbias + 512;                                            // [33] fused outconv weights + bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,9 +93,11 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
     if (lane < kMaxStages) {
       mbar_init(&full_a[lane], 1); mbar_init(&empty_a[lane], 1);
       mbar_init(&full_b[lane], 1); mbar_init(&empty_b[lane], cs);
+      mbar_init(&empty_x[lane], 1);
     } else if (lane < kMaxStages + 2) {
       const int i = lane - kMaxStages;
       mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NEPI);
+      mbar_init(&stg_full[i], 1); mbar_init(&stg_empty[i], 1);
     } else if (lane == kMaxStages + 2) {
       mbar_init(w_full, 1);
     }
@@ -97,7 +125,10 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      uint32_t ia = 0, ib = 0;
+      uint32_t ia = 0, ib = 0, iu = 0;
+      uint32_t tcnt[kMaxStages];               // FUSE: releases of each slot this thread has consumed (phase counter)
+#pragma unroll
+      for (int i = 0; i < kMaxStages; ++i) tcnt[i] = 0;
       const int rows_mc = BN / cs;
       for (int t = item0; t < total_items; t += item_step) {
         int m = t * cs + crank;
@@ -108,10 +139,27 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
           const int src = c < p.nchunk0 ? 0 : 1;
           const int cc = (src == 0 ? c : c - p.nchunk0) * KC;
           const int s = ia % SA;
-          mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_a[s], 2u * (uint32_t)kHaloRows * ROW);
-          tma_load_4d(sA + s * p.a_stage_bytes, &p.a_map[src][0], &full_a[s], cc, w0 - 1, h0 - 1, b);
-          tma_load_4d(sA + s * p.a_stage_bytes + plane, &p.a_map[src][1], &full_a[s], cc, w0 - 1, h0 - 1, b);
+          if (FUSE && src == 1) {
+            // hand the low-resolution window (both planes) to the transform warps as soon as a staging slot is free; they
+            // claim A stage s themselves and fill it
+            const int st = iu & 1;
+            mbar_wait(&stg_empty[st], ((iu >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&stg_full[st], 2u * (uint32_t)(kUpBox * kUpBox) * ROW);
+            const int ys = (int)(p.up_sy * (float)(h0 > 0 ? h0 - 1 : 0));
+            const int xs = (int)(p.up_sx * (float)(w0 > 0 ? w0 - 1 : 0));
+            tma_load_4d(sStg + st * kX3StgSlot, &p.a_map[1][0], &stg_full[st], cc, xs, ys, b);
+            tma_load_4d(sStg + st * kX3StgSlot + kX3StgPlane, &p.a_map[1][1], &stg_full[st], cc, xs, ys, b);
+            ++iu;
+          } else {
+            if (FUSE) {
+              if (ia >= (uint32_t)SA) { mbar_wait(&empty_a[s], tcnt[s] & 1); ++tcnt[s]; }   // first use of a slot: free
+            } else {
+              mbar_wait(&empty_a[s], ((ia / SA) & 1) ^ 1);
+            }
+            mbar_arrive_expect_tx(&full_a[s], 2u * (uint32_t)kHaloRows * ROW);
+            tma_load_4d(sA + s * p.a_stage_bytes, &p.a_map[src][0], &full_a[s], cc, w0 - 1, h0 - 1, b);
+            tma_load_4d(sA + s * p.a_stage_bytes + plane, &p.a_map[src][1], &full_a[s], cc, w0 - 1, h0 - 1, b);
+          }
           if (!RESIDENT) {
 #pragma unroll 1
             for (int tg = 0; tg < 9 / TPS; ++tg, ++ib) {
@@ -161,6 +209,8 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
         tc_fence_after();
         const uint32_t ah = sA_lo + sa * a_stage16;     // hi plane; lo plane at + plane16
         const bool last = c == nchunks - 1;
+        // who claims this slot next: chunk (c + SA) of the tile cycle
+        uint64_t* rel_a = (FUSE && ((c + SA) % nchunks) >= p.nchunk0) ? &empty_x[sa] : &empty_a[sa];
         if (RESIDENT) {
           if (elect_one()) {
 #pragma unroll
@@ -178,7 +228,7 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
                 accumulate = 1;
               }
             }
-            umma_commit(&empty_a[sa]);
+            umma_commit(rel_a);
             if (last) umma_commit(&tmem_full[buf]);
           }
           accumulate = 1;
@@ -214,7 +264,7 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
             if (++sb == (uint32_t)SB) { sb = 0; phb ^= 1; }
           }
           if (elect_one()) {
-            umma_commit(&empty_a[sa]);
+            umma_commit(rel_a);
             if (last) umma_commit(&tmem_full[buf]);
           }
           __syncwarp();
@@ -222,24 +272,124 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
         if (++sa == (uint32_t)SA) { sa = 0; pha ^= 1; }
       }
     }
-  } else {
-    // ---------------- epilogue: warp pair member e takes M-tile half e ----------------
+  } else if (FUSE && warp >= 2 + NEPI) {
+    // ---------------- transform warps: bilinear x2 (align_corners=True) of the staged low-resolution window -> A stage ----
+    const int tid = threadIdx.x - (64 + 32 * NEPI);          // 0..287
+    const int i0 = tid / 72, slot = tid % 72;                // intervals i0, i0 + 4, i0 + 8 of fine column k, channel group j
+    const int k = slot >> 2, j = slot & 3;
+    const int Hin = p.H >> 1, Win = p.W >> 1;
+    constexpr int iROW = (int)ROW;
+    uint32_t ia = 0, iu = 0;
+    uint32_t xc0 = 0, xc1 = 0, xc2 = 0, xc3 = 0;             // releases of slots 0..3 consumed by the transform warps (SA <= 4)
+    auto store_px = [&](uint8_t* dstA, int r, uint4 vhi, uint4 vlo) {
+      const int pr = r * kHaloW + k;
+      const int off = pr * iROW + ((j ^ ((pr >> 1) & 3)) << 4);      // TMA-compatible SWIZZLE_64B of the A stage
+      *reinterpret_cast<uint4*>(dstA + off) = vhi;
+      *reinterpret_cast<uint4*>(dstA + plane + off) = vlo;
+    };
+    for (int t = item0; t < total_items; t += item_step) {
+      int m = t * cs + crank;
+      if (m >= p.num_m_tiles) m = p.num_m_tiles - 1;
+      const int w0 = (m % p.tiles_w) * 16, h0 = ((m / p.tiles_w) % p.tiles_h) * 16;
+      const int ys = (int)(p.up_sy * (float)(h0 > 0 ? h0 - 1 : 0));
+      const int xs = (int)(p.up_sx * (float)(w0 > 0 ? w0 - 1 : 0));
+      // column set-up (fixed for the tile)
+      const int xo = w0 - 1 + k;
+      const bool x_ok = xo >= 0 && xo < p.W;
+      const float fx = p.up_sx * (float)xo;
+      const int x0 = (int)fx;
+      const int x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+      const float lx = fx - (float)x0, wx = 1.f - lx;
+      const int ox0 = (x0 - xs) * iROW + j * 16, ox1 = (x1 - xs) * iROW + j * 16;
+      for (int c = 0; c < nchunks; ++c, ++ia) {
+        if (c < p.nchunk0) continue;                         // source 0 comes by TMA
+        const int s = ia % SA, st = iu & 1;
+        mbar_wait(&stg_full[st], (iu >> 1) & 1);
+        if (ia >= (uint32_t)SA) {                            // the staging load ran ahead of the A ring: claim the stage here
+          uint32_t& xc = s == 0 ? xc0 : s == 1 ? xc1 : s == 2 ? xc2 : xc3;
+          mbar_wait(&empty_x[s], xc & 1);
+          ++xc;
+        }
+        const uint8_t* stg = sStg + st * kX3StgSlot;
+        uint8_t* dstA = sA + s * p.a_stage_bytes;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        if (!x_ok) {                                         // conv zero padding left / right of the image
+          for (int r = i0; r < kHaloH; r += 4) store_px(dstA, r, zero, zero);
+        } else {
+          if (i0 == 0 && h0 == 0) store_px(dstA, 0, zero, zero);                       // ... above
+          if (i0 == 3 && h0 + 16 == p.H) store_px(dstA, kHaloH - 1, zero, zero);       // ... below
+#pragma unroll 1
+          for (int i = i0; i < kUpBox - 1; i += 4) {
+            const int Y = ys + i;
+            if (Y >= Hin) break;
+            int r = 2 * i - 1;
+            if (h0 - 1 + r < 0) r = 1 - h0;                  // first fine row inside the image
+            while (r < kHaloH && (int)(p.up_sy * (float)(h0 - 1 + r)) < Y) ++r;
+            if (r >= kHaloH || h0 - 1 + r >= p.H || (int)(p.up_sy * (float)(h0 - 1 + r)) != Y) continue;
+            // the interval's two source rows at the column's two source pixels, both planes: value = hi + lo / 2^11
+            const uint8_t* rp0 = stg + i * (kUpBox * iROW);
+            const uint8_t* rp1 = rp0 + (Y < Hin - 1 ? kUpBox * iROW : 0);
+            const H8 a0h = *reinterpret_cast<const H8*>(rp0 + ox0), b0h = *reinterpret_cast<const H8*>(rp0 + ox1);
+            const H8 a1h = *reinterpret_cast<const H8*>(rp1 + ox0), b1h = *reinterpret_cast<const H8*>(rp1 + ox1);
+            const H8 a0l = *reinterpret_cast<const H8*>(rp0 + kX3StgPlane + ox0), b0l = *reinterpret_cast<const H8*>(rp0 + kX3StgPlane + ox1);
+            const H8 a1l = *reinterpret_cast<const H8*>(rp1 + kX3StgPlane + ox0), b1l = *reinterpret_cast<const H8*>(rp1 + kX3StgPlane + ox1);
+            float2 top[4], bot[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 va0 = ffma2(kLoInv, __half22float2(a0l.v[e]), __half22float2(a0h.v[e]));
+              const float2 vb0 = ffma2(kLoInv, __half22float2(b0l.v[e]), __half22float2(b0h.v[e]));
+              const float2 va1 = ffma2(kLoInv, __half22float2(a1l.v[e]), __half22float2(a1h.v[e]));
+              const float2 vb1 = ffma2(kLoInv, __half22float2(b1l.v[e]), __half22float2(b1h.v[e]));
+              top[e] = ffma2(lx, vb0, fmul2(wx, va0));
+              bot[e] = ffma2(lx, vb1, fmul2(wx, va1));
+            }
+#pragma unroll 1
+            for (; r < kHaloH; ++r) {
+              const int yo = h0 - 1 + r;
+              if (yo >= p.H) break;
+              const float fy = p.up_sy * (float)yo;
+              if ((int)fy != Y) break;
+              const float ly = fy - (float)Y, wy = 1.f - ly;
+              H8 ohi, olo;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 v = ffma2(ly, bot[e], fmul2(wy, top[e]));
+                ohi.v[e] = __floats2half2_rn(v.x, v.y);
+                const float2 back = __half22float2(ohi.v[e]);
+                olo.v[e] = __floats2half2_rn((v.x - back.x) * kLoScale, (v.y - back.y) * kLoScale);
+              }
+              if (p.dbg & 256) olo = H8{};                 // debugging aid: drop the residual plane of the interpolated tile
+              store_px(dstA, r, *reinterpret_cast<uint4*>(&ohi), *reinterpret_cast<uint4*>(&olo));
+            }
+          }
+        }
+        fence_proxy_async();                                 // generic-proxy smem writes -> visible to the MMA (async proxy)
+        asm volatile("bar.sync 1, 288;" ::: "memory");       // the nine transform warps
+        if (tid == 0) { mbar_arrive(&full_a[s]); mbar_arrive(&stg_empty[st]); }
+        ++iu;
+      }
+    }
+  } else if (warp >= 2 && warp < 2 + NEPI) {
+    // ---------------- epilogue: 8 warps -> warp pair member e takes M-tile half e; 4 warps (FUSE) -> both halves each ----
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
     const int ml = q * 32 + lane;
     const int tw = ml & 7, th = ml >> 3;
+    constexpr int NHALF = NEPI == 8 ? 1 : 2;
     uint32_t it = 0;
     for (int t = item0; t < total_items; t += item_step, ++it) {
       int m = t * cs + crank;
       const bool real_tile = m < p.num_m_tiles;
       if (!real_tile) m = p.num_m_tiles - 1;
-      const int w = (m % p.tiles_w) * 16 + tw + half * 8;
-      const int h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
       const int b = m / (p.tiles_w * p.tiles_h);
-      const size_t pix = ((size_t)b * p.H + h) * p.W + w;
+      const int h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
       const uint32_t buf = it & 1;
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
+#pragma unroll 1
+      for (int hh = 0; hh < NHALF; ++hh) {
+      const int half = NEPI == 8 ? (warp - 2) >> 2 : hh;
+      const int w = (m % p.tiles_w) * 16 + tw + half * 8;
+      const size_t pix = ((size_t)b * p.H + h) * p.W + w;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (4 * BN) + half * (2 * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -270,6 +420,7 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
             epilogue_store_nhwc32(v, p.pool_hi, p.pool_lo, ppix * p.Cout + c0);
           }
         }
+      }
       }
       tc_fence_before();
       __syncwarp();

@@ -1395,24 +1395,32 @@ int launch_conv2_t(const Conv2Plan& c, cudaStream_t st) {
   return 0;
 }
 
-template <int BN, bool RES>
+template <int BN, bool RES, bool FUSE>
 int launch_conv_x3_t(const Conv2Plan& c, cudaStream_t st) {
   static unsigned long long attr_set = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_x3<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_x3<BN, RES, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set |= 1ull << (dev & 63);
   }
-  TFPNP_CUDA_OK(launch_ex(conv3x3_x3<BN, RES>, dim3(c.grid), dim3(64 + 32 * 8), c.smem_bytes, st, use_pdl(), c.p.cluster, c.p));
+  TFPNP_CUDA_OK(launch_ex(conv3x3_x3<BN, RES, FUSE>, dim3(c.grid), dim3(conv_x3_threads<FUSE>()), c.smem_bytes, st, use_pdl(),
+                          c.p.cluster, c.p));
   TFPNP_COUNT_LAUNCH();
   return 0;
 }
 
 int launch_conv2(const Conv2Plan& c, cudaStream_t st) {
+  if (c.x3n && c.p.up_fused) {      // the decoder heads 96 -> 32 (resident weights) and 192 -> 64 (streamed)
+    if (c.BN == 32 && c.resident) return launch_conv_x3_t<32, true, true>(c, st);
+    if (c.BN == 32 && !c.resident) return launch_conv_x3_t<32, false, true>(c, st);
+    if (c.BN == 64 && !c.resident) return launch_conv_x3_t<64, false, true>(c, st);
+    set_error("conv_x3: no fused-upsample variant for BN %d (resident %d)", c.BN, (int)c.resident);
+    return TFPNP_ERR_INVALID;
+  }
   if (c.x3n) {
-    if (c.BN == 32) return c.resident ? launch_conv_x3_t<32, true>(c, st) : launch_conv_x3_t<32, false>(c, st);
-    if (c.BN == 64) return c.resident ? launch_conv_x3_t<64, true>(c, st) : launch_conv_x3_t<64, false>(c, st);
+    if (c.BN == 32) return c.resident ? launch_conv_x3_t<32, true, false>(c, st) : launch_conv_x3_t<32, false, false>(c, st);
+    if (c.BN == 64) return c.resident ? launch_conv_x3_t<64, true, false>(c, st) : launch_conv_x3_t<64, false, false>(c, st);
     set_error("conv_x3: unsupported BN %d", c.BN);
     return TFPNP_ERR_INVALID;
   }
@@ -1474,7 +1482,7 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
   c.small = (H == 8 && W == 8);
   const int Cin = C0 + C1;
   // split-fp16 on the 32/64-channel levels: the N-concatenated kernel (32-channel chunks, both planes in one stage)
-  c.x3n = x3 && !c.small && !fuse_up && (Cout == 32 || Cout == 64);
+  c.x3n = x3 && !c.small && (Cout == 32 || Cout == 64);
   if (x3 && !c.x3n && !c.small) {
     // (the K-loop-over-products form of conv3x3_tc2 has no room for the separate correction accumulator the scaled residual
     // planes need, except at the 8x8 level; everything else of a split-fp16 UNet runs on conv3x3_x3 / conv3x3_pair<true>)
@@ -1500,13 +1508,14 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
     p.a_stage_bytes *= 2;
     const int slab2 = 2 * p.b_stage_bytes;
     const int w_all = 9 * (Cin / kc) * slab2;
-    const int misc3 = 1024 + 1024 + 2048 + 256;
-    const int budget = 224 * 1024 - misc3;
-    c.resident = w_all + 2 * p.a_stage_bytes <= budget && env_int("TFPNP_CONV_RESIDENT", 1) != 0;
+    const int misc3 = 1024 + 1024 + 2048 + 256 + (fuse_up ? 2 * kX3StgSlot : 0);   // align + barriers + bias + outc (+ staging)
+    const int budget = 227 * 1024 - misc3;
+    c.resident = w_all + 2 * p.a_stage_bytes <= budget && env_int("TFPNP_CONV_RESIDENT", 1) != 0 &&
+                 Cin / kc <= env_int("TFPNP_X3N_RES_MAXCHUNKS", 3);
     if (c.resident) {
       p.num_b_stages = 0;
       p.num_a_stages = (budget - w_all) / p.a_stage_bytes;
-      if (p.num_a_stages > 4) p.num_a_stages = 4;
+      if (p.num_a_stages > 4) p.num_a_stages = 4;      // (the fused variant tracks at most 4 slots)
       c.smem_bytes = p.num_a_stages * p.a_stage_bytes + w_all + misc3;
     } else {
       p.num_a_stages = 3;
@@ -1524,7 +1533,9 @@ int plan_conv2_geometry(Conv2Plan& c, int C0, int C1, int Cout, int B, int H, in
       while (cs3 > 1 && (p.num_m_tiles < cs3 || (c.BN / cs3) * row_bytes % 1024 != 0)) cs3 /= 2;
     }
     p.cluster = cs3;
-    p.up_fused = 0;
+    p.up_fused = fuse_up ? 1 : 0;
+    p.up_sy = (float)(H / 2 - 1) / (float)(H - 1);
+    p.up_sx = (float)(W / 2 - 1) / (float)(W - 1);
     const int items3 = (p.num_m_tiles + cs3 - 1) / cs3;
     const int maxc3 = sms3 / cs3;
     c.grid = (items3 < maxc3 ? items3 : maxc3) * cs3;
@@ -1862,7 +1873,8 @@ struct UNetTc : Denoiser {
                                  (cuuint64_t)low->H * low->W * low->C * 2};
         cuuint32_t box[4] = {(cuuint32_t)c.kc, (cuuint32_t)kUpBox, (cuuint32_t)kUpBox, 1};
         TFPNP_TRY(encode_map(&p.a_map[1][0], low->hi, 4, dims, strides, box, -1));
-        p.a_map[1][1] = p.a_map[1][0];
+        if (x3) TFPNP_TRY(encode_map(&p.a_map[1][1], low->lo, 4, dims, strides, box, -1));
+        else p.a_map[1][1] = p.a_map[1][0];
         continue;
       }
       TFPNP_TRY(encode_halo_map(&p.a_map[s][0], srcs[s]->hi, srcs[s]->C, B, dst.H, dst.W, c.kc));
@@ -1976,8 +1988,10 @@ struct UNetTc : Denoiser {
       // the block input: x5 for the first block, else the previous block's output in S2
       Act low = view(k == 0 ? skip[4] : S2, ch[lv + 1], h / 2, w / 2);
       // fused up-sampling pays where the up-sampled tensor is large; TFPNP_FUSE_UP_MIN = smallest output height fused
-      const bool fuse_up = !x3 && conv2_eligible(h, w) && env_int("TFPNP_CONV_FUSE_UP", 1) != 0 &&
-                           h >= env_int("TFPNP_FUSE_UP_MIN", 32);   // measured: 16x16 outputs are faster un-fused
+      // (split-fp16: the two heads that run on conv3x3_x3, 96 -> 32 and 192 -> 64)
+      const bool fuse_up = conv2_eligible(h, w) && env_int("TFPNP_CONV_FUSE_UP", 1) != 0 &&
+                           (x3 ? (ch[lv] <= env_int("TFPNP_X3_FUSE_MAXCH", 64) && ch[lv] >= env_int("TFPNP_X3_FUSE_MINCH", 32) && env_int("TFPNP_X3_FUSE_UP", 1) != 0)
+                               : h >= env_int("TFPNP_FUSE_UP_MIN", 32));   // measured (fp16): 16x16 outputs are faster un-fused
       TFPNP_TRY(plan_conv(l0, skip[lv], &up, view(S1, ch[lv], h, w), B, fuse_up ? &low : nullptr));
       TFPNP_TRY(plan_conv(l0 + 1, view(S1, ch[lv], h, w), nullptr, view(S0, ch[lv], h, w), B));
       TFPNP_TRY(plan_conv(l0 + 2, view(S0, ch[lv], h, w), nullptr, view(S2, ch[lv], h, w), B));
