@@ -432,3 +432,182 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
   if (cs > 1) cluster_sync_all();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
+
+// ==========================================================================================
+// Split-fp16 on CTA pairs (tcgen05.mma.cta_group::2) for the 128/256/512-channel levels, whole-chunk stages
+// ==========================================================================================
+// Same work decomposition as conv3x3_pair (16x16 super-tile x 128 couts per pair, CTA r owns the 16x8 half r and rows
+// [64 r, 64 r + 64) of every weight slab), but with 32-channel chunks so that ONE ring stage holds everything a chunk needs in
+// both planes: [A_hi half-halo | A_lo half-halo | 9 taps x (W_hi half slab | W_lo half slab)] = 96 KB, two stages, ONE
+// full / empty barrier pair per chunk and 54 MMAs (9 taps x 2 k-steps x 3 products = 1.8 us of tensor work) per hand-shake.
+// (The first x3 instantiation of conv3x3_pair used 64-channel chunks with a separate A ring and kernel-row weight stages --
+// the layout that was 1.8x slower than whole-chunk stages in the fp16 bring-up, DESIGN.md 9.1 -- 43 us for 128->128 @32^2.)
+// Accumulators: [main | corrections (residual planes are x 2^11)] x 2 buffers = 512 TMEM columns.
+constexpr int kPX3APlane = 12288;                       // 180 rows x 64 B = 11520, padded to a multiple of 1024
+constexpr int kPX3Slab = 64 * 64;                       // one tap's half slab (64 of the 128 couts), one plane
+constexpr int kPX3Stage = 2 * kPX3APlane + 9 * 2 * kPX3Slab;   // 98304
+
+__global__ void __launch_bounds__(kPairThreads, 1)
+conv3x3_pair_x3(const __grid_constant__ ConvPairParams p) {
+  constexpr int BN = 128, KC = 32, KSTEPS = 2;
+  constexpr uint32_t ROW = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.num_a_stages;
+  const int nchunks = p.nchunk0 + p.nchunk1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * kPX3Stage);
+  uint64_t* full = bars;                        // [8]   (the leader's are the ones waited on)
+  uint64_t* empty = bars + 8;                   // [8]
+  uint64_t* tmem_full = bars + 48;              // [2]
+  uint64_t* tmem_empty = bars + 50;             // [2]  (leader's collects both CTAs' epilogues)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 52);
+  float* sbias = reinterpret_cast<float*>(bars + 54);           // [Cout] <= 512
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.a_map[0][0]); prefetch_tensormap(&p.a_map[0][1]);
+    prefetch_tensormap(&p.w_map[0]); prefetch_tensormap(&p.w_map[1]);
+    if (p.nchunk1) { prefetch_tensormap(&p.a_map[1][0]); prefetch_tensormap(&p.a_map[1][1]); }
+  }
+  if (warp == 1) {
+    if (lane < 8) { mbar_init(&full[lane], 2); mbar_init(&empty[lane], 1); }
+    if (lane < 2) { mbar_init(&tmem_full[lane], 1); mbar_init(&tmem_empty[lane], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // peer's barriers initialised, TMEM allocated in both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int total_items = p.num_m_tiles * p.num_n_tiles;
+  const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs): own half-halo planes + own half of the chunk's nine slab pairs ----------------
+      uint32_t ia = 0;
+      for (int t = item0; t < total_items; t += item_step) {
+        const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
+        const int w0 = (m % p.tiles_w) * 16, h0 = ((m / p.tiles_w) % p.tiles_h) * 16;
+        const int b = m / (p.tiles_w * p.tiles_h);
+        for (int c = 0; c < nchunks; ++c, ++ia) {
+          const int src = c < p.nchunk0 ? 0 : 1;
+          const int cc = (src == 0 ? c : c - p.nchunk0) * KC;
+          const int s = ia % S;
+          mbar_wait(&empty[s], ((ia / S) & 1) ^ 1);
+          const uint32_t fb = mapa_u32(&full[s], 0);            // the LEADER's barrier
+          uint8_t* st = smem + s * kPX3Stage;
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (2u * kPairARows * ROW + 9u * 2u * kPX3Slab));
+          else mbar_arrive_cluster(fb);
+          tma_load_4d_2sm(st, &p.a_map[src][0], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
+          tma_load_4d_2sm(st + kPX3APlane, &p.a_map[src][1], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
+          uint8_t* wst = st + 2 * kPX3APlane;
+#pragma unroll
+          for (int tt = 0; tt < 9; ++tt) {
+            tma_load_3d_2sm(wst + (2 * tt) * kPX3Slab, &p.w_map[0], fb, c * KC, nt * BN + 64 * (int)rank, tt);
+            tma_load_3d_2sm(wst + (2 * tt + 1) * kPX3Slab, &p.w_map[1], fb, c * KC, nt * BN + 64 * (int)rank, tt);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ---------------- MMA issuer (leader only): one barrier wait and one release per chunk ----------------
+      const uint32_t idesc = make_idesc_f16(256, BN);
+      const uint32_t a_hi = (uint32_t)(make_smem_desc_ex(0, ROW, 10 * ROW, 0) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_smem_desc(0, ROW) >> 32);
+      const uint32_t s_lo = (smem_u32(smem) >> 4) | (1u << 16);
+      uint32_t ia = 0, it = 0;
+      for (int t = item0; t < total_items; t += item_step, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * (2 * BN);         // [main | corrections]
+        uint32_t accumulate = 0;
+        for (int c = 0; c < nchunks; ++c, ++ia) {
+          const int sa = ia % S;
+          mbar_wait(&full[sa], (ia / S) & 1);
+          tc_fence_after();
+          const uint32_t a_lo = s_lo + sa * (kPX3Stage >> 4);
+          const uint32_t b_stage = a_lo + (2 * kPX3APlane >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_tap = a_lo + (((tap / 3) * 10 + tap % 3) * ROW >> 4);
+              const uint32_t bh = b_stage + (2 * tap) * (kPX3Slab >> 4), bl = bh + (kPX3Slab >> 4);
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                const uint64_t ad = pack_desc(a_tap + kk * 2, a_hi);
+                const uint64_t bhd = pack_desc(bh + kk * 2, b_hi);
+                umma2_f16(d0, ad, bhd, idesc, accumulate);                                                        // a_hi w_hi
+                umma2_f16(d0 + BN, ad, pack_desc(bl + kk * 2, b_hi), idesc, accumulate);                          // a_hi w_lo
+                umma2_f16(d0 + BN, pack_desc(a_tap + (kPX3APlane >> 4) + kk * 2, a_hi), bhd, idesc, 1);           // a_lo w_hi
+                accumulate = 1;
+              }
+            }
+            umma2_commit_mc(&empty[sa], 3);                     // frees the chunk stage in BOTH CTAs
+            if (c == nchunks - 1) umma2_commit_mc(&tmem_full[buf], 3);
+          }
+          accumulate = 1;
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): own 128 rows; the two warps of a quadrant split the 128 columns ----------------
+    const int q = warp & 3;
+    const int e = (warp - 2) >> 2;
+    const int ml = q * 32 + lane;
+    const int tw = ml & 7, th = ml >> 3;
+    const uint32_t te = mapa_u32(&tmem_empty[0], 0);            // the leader's tmem_empty[0]; [1] is 8 bytes further
+    uint32_t it = 0;
+    for (int t = item0; t < total_items; t += item_step, ++it) {
+      const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
+      const int w = (m % p.tiles_w) * 16 + 8 * (int)rank + tw, h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
+      const int b = m / (p.tiles_w * p.tiles_h);
+      const int n0 = nt * BN;
+      const size_t pix = ((size_t)b * p.H + h) * p.W + w;
+      const uint32_t buf = it & 1;
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sl = 0; sl < 2; ++sl) {
+        const int c0 = e * 64 + 32 * sl;
+        uint32_t r[32], rc[32];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * BN) + c0;
+        tmem_ld_32x32(ta, r);
+        tmem_ld_32x32(ta + BN, rc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])));
+        float v[32];
+        epilogue_act32(r, sbias + n0 + c0, v);
+        epilogue_store_nhwc32(v, p.out_hi, p.out_lo, pix * p.Cout + n0 + c0);
+        if (p.pool_hi) {                      // 2x2 max over (tw^1, th^1) = lanes ^1 and ^8
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
+          }
+          if (!(lane & 9)) {
+            const size_t ppix = ((size_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+            epilogue_store_nhwc32(v, p.pool_hi, p.pool_lo, ppix * p.Cout + n0 + c0);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(te + buf * 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // nobody leaves (or frees TMEM) while the peer may still signal it
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}

@@ -1603,6 +1603,7 @@ int encode_halo_map(CUtensorMap* m, const __half* base, int C, int B, int H, int
 struct ConvPairPlan {
   ConvPairParams p;
   bool x3 = false;
+  bool x3_kc32 = false;     // conv3x3_pair_x3: 32-channel whole-chunk stages (default for split-fp16; TFPNP_PAIR_X3_KC64=1: first layout)
   int grid = 0, smem_bytes = 0;
 };
 
@@ -1621,8 +1622,10 @@ int plan_conv_pair(ConvPairPlan& c, const __half* x0, const __half* x0_lo, int C
   ConvPairParams& p = c.p;
   memset(&p, 0, sizeof(p));
   c.x3 = w_lo != nullptr;
+  c.x3_kc32 = c.x3 && env_int("TFPNP_PAIR_X3_KC64", 0) == 0;
+  const int kc = c.x3_kc32 ? 32 : 64;
   p.single_buf = env_int("TFPNP_PAIR_SINGLE", 0);
-  p.nchunk0 = C0 / 64; p.nchunk1 = C1 / 64;
+  p.nchunk0 = C0 / kc; p.nchunk1 = C1 / kc;
   p.tiles_w = W / 16; p.tiles_h = H / 16;
   p.num_m_tiles = p.tiles_w * p.tiles_h * B;
   p.num_n_tiles = Cout / 128;
@@ -1633,6 +1636,10 @@ int plan_conv_pair(ConvPairPlan& c, const __half* x0, const __half* x0_lo, int C
     p.num_a_stages = 2;                            // chunk stages: [A half-halo 23 KB | nine half slabs 72 KB]
     p.num_b_stages = 0;
     c.smem_bytes = p.num_a_stages * (kPairABytes + kPairBStage) + misc;
+  } else if (c.x3_kc32) {
+    p.num_a_stages = 2;                            // chunk stages: [A_hi | A_lo half-halos 24 KB | nine slab pairs 72 KB]
+    p.num_b_stages = 0;
+    c.smem_bytes = p.num_a_stages * kPX3Stage + misc;
   } else {
     p.num_a_stages = 2;                            // [hi half-halo | lo half-halo] 46 KB
     p.num_b_stages = 2;                            // one kernel row of [W_hi | W_lo] half slabs, 48 KB
@@ -1650,17 +1657,17 @@ int plan_conv_pair(ConvPairPlan& c, const __half* x0, const __half* x0_lo, int C
     if (!srcs[s][0]) { p.a_map[s][0] = p.a_map[0][0]; p.a_map[s][1] = p.a_map[0][1]; continue; }
     cuuint64_t dims[4] = {(cuuint64_t)cs[s], (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)cs[s] * 2, (cuuint64_t)W * cs[s] * 2, (cuuint64_t)H * W * cs[s] * 2};
-    cuuint32_t box[4] = {64, 10, 18, 1};
-    TFPNP_TRY(encode_map(&p.a_map[s][0], const_cast<__half*>(srcs[s][0]), 4, dims, strides, box, 128));
-    if (c.x3) TFPNP_TRY(encode_map(&p.a_map[s][1], const_cast<__half*>(srcs[s][1]), 4, dims, strides, box, 128));
+    cuuint32_t box[4] = {(cuuint32_t)kc, 10, 18, 1};
+    TFPNP_TRY(encode_map(&p.a_map[s][0], const_cast<__half*>(srcs[s][0]), 4, dims, strides, box, 2 * kc));
+    if (c.x3) TFPNP_TRY(encode_map(&p.a_map[s][1], const_cast<__half*>(srcs[s][1]), 4, dims, strides, box, 2 * kc));
     else p.a_map[s][1] = p.a_map[s][0];
   }
   const int Cin = C0 + C1;
   cuuint64_t wd[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
   cuuint64_t ws[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
-  cuuint32_t wb[3] = {64, 64, 1};
-  TFPNP_TRY(encode_map(&p.w_map[0], const_cast<__half*>(w_taps), 3, wd, ws, wb, 128));
-  if (c.x3) TFPNP_TRY(encode_map(&p.w_map[1], const_cast<__half*>(w_lo), 3, wd, ws, wb, 128));
+  cuuint32_t wb[3] = {(cuuint32_t)kc, 64, 1};
+  TFPNP_TRY(encode_map(&p.w_map[0], const_cast<__half*>(w_taps), 3, wd, ws, wb, 2 * kc));
+  if (c.x3) TFPNP_TRY(encode_map(&p.w_map[1], const_cast<__half*>(w_lo), 3, wd, ws, wb, 2 * kc));
   else p.w_map[1] = p.w_map[0];
   return 0;
 }
@@ -1672,9 +1679,11 @@ int launch_conv_pair(const ConvPairPlan& c, cudaStream_t st) {
   if (!(attr_set >> (dev & 63) & 1ull)) {
     TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set |= 1ull << (dev & 63);
   }
-  if (c.x3) TFPNP_CUDA_OK(launch_ex(conv3x3_pair<true>, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
+  if (c.x3_kc32) TFPNP_CUDA_OK(launch_ex(conv3x3_pair_x3, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
+  else if (c.x3) TFPNP_CUDA_OK(launch_ex(conv3x3_pair<true>, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
   else TFPNP_CUDA_OK(launch_ex(conv3x3_pair<false>, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
   TFPNP_COUNT_LAUNCH();
   return 0;
@@ -1797,7 +1806,7 @@ struct UNetTc : Denoiser {
     const ConvSpec& sp = unet_conv_specs()[l];
     const char* kind = "v1";
     int h = 0;
-    if (convsp[l].grid > 0) { kind = convsp[l].x3 ? "pair-x3" : "pair"; h = convsp[l].p.H; }
+    if (convsp[l].grid > 0) { kind = convsp[l].x3_kc32 ? "pair-x3/32" : convsp[l].x3 ? "pair-x3/64" : "pair"; h = convsp[l].p.H; }
     else if (convs2[l].grid > 0) {
       const Conv2Plan& c = convs2[l];
       h = c.p.H;
