@@ -1118,12 +1118,17 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
 }
 
 #include "conv_x3.cuh"
+#include "conv_ws.cuh"
 
 // ---- CUDA-core layers around the tensor-core convs ---------------------------------------
 
 // inc.conv-0: 3x3 conv over cat[d, sigma*ones] (2 ch, denoiser/base.py:29-30) -> 32 ch, fp32 FFMA
 // (K = 18: 0.2 % of the FLOPs), bias + LeakyReLU, NHWC fp16 out.  The 576 weights + 32 biases travel
 // as kernel parameters, so every FFMA takes its weight straight from the constant bank.
+// Tried in round 2 and rejected by measurement (34 us today at 48 x 128^2): folding the constant sigma channel into a
+// per-channel term (10 instead of 18 FMAs per output, two threads per pixel: 37 us -- the kernel is not FMA-bound), and
+// register-resident weights with a thread walking a 32-row strip (91 us: too few threads in flight); deferring the
+// programmatic launch trigger to the end of the CTA (no change).
 struct FirstLayerW { float w[32 * 18]; float b[32]; };
 
 __global__ void __launch_bounds__(128)
@@ -1689,6 +1694,82 @@ int launch_conv_pair(const ConvPairPlan& c, cudaStream_t st) {
   return 0;
 }
 
+struct ConvWsPlan {
+  ConvWsParams p;
+  bool x3 = false;
+  int grid = 0, smem_bytes = 0;
+};
+
+// Weight-stationary pair kernel (conv_ws.cuh): single-source layers on 16x16 tiles whose 64-cout weight slice fits next to a
+// 3-deep A ring.  In the UNet: 64->128, 128->128 @ H/4 and 128->256, 256->256 @ H/8 in fp16; 64->128, 128->128 in split-fp16.
+bool conv_ws_eligible(int C0, int C1, int Cout, int H, int W, bool x3) {
+  // measured (round 2, graph-timed, 48 images): 16.7 / 16.8 us against 14.6 / 16.7 us of the streamed-weight pair kernel for
+  // 128->128 @32^2 / 256->256 @16^2 -- with NO weight streaming at all the layer time does not move, i.e. the deep levels are
+  // bound by the per-kernel fixed costs (prologue, first-tile latency, last-tile epilogue, drain: ~7 us of a ~15 us layer), not
+  // by L2 -> SM weight traffic.  Kept as an experiment (TFPNP_CONV_WS=1), off by default.
+  if (env_int("TFPNP_CONV_WS", 0) == 0 || C1 != 0 || Cout % 128 != 0 || H % 16 != 0 || W % 16 != 0) return false;
+  const int kc = x3 ? 32 : 64;
+  if (C0 % kc != 0) return false;
+  const int wpair = (x3 ? 2 : 1) * 32 * kc * 2;
+  const int astage = x3 ? 2 * kPX3APlane : kPairABytes;
+  return 9 * (C0 / kc) * wpair + 3 * astage + 2048 <= 227 * 1024;
+}
+
+int plan_conv_ws(ConvWsPlan& c, const __half* x, const __half* x_lo, int C0, const __half* w_taps, const __half* w_lo,
+                 const float* bias, __half* out, __half* out_lo, int B, int H, int W, int Cout) {
+  ConvWsParams& p = c.p;
+  memset(&p, 0, sizeof(p));
+  c.x3 = w_lo != nullptr;
+  const int kc = c.x3 ? 32 : 64;
+  p.nchunks = C0 / kc;
+  p.tiles_w = W / 16; p.tiles_h = H / 16;
+  p.num_m_tiles = p.tiles_w * p.tiles_h * B;
+  p.n_slices = Cout / 64;
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.bias = bias; p.out_hi = out; p.out_lo = c.x3 ? out_lo : nullptr;
+  const int wpair = (c.x3 ? 2 : 1) * 32 * kc * 2;
+  const int astage = c.x3 ? 2 * kPX3APlane : kPairABytes;
+  const int w_all = 9 * p.nchunks * wpair;
+  int S = (227 * 1024 - 2048 - w_all) / astage;
+  p.num_a_stages = S > 6 ? 6 : S;
+  c.smem_bytes = p.num_a_stages * astage + w_all + 2048;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_slice = (sms / 2) / p.n_slices;                      // pairs per cout slice
+  if (per_slice > p.num_m_tiles) per_slice = p.num_m_tiles;
+  if (per_slice < 1) { set_error("conv_ws: %d cout slices do not fit %d SM pairs", p.n_slices, sms / 2); return TFPNP_ERR_INVALID; }
+  c.grid = 2 * per_slice * p.n_slices;
+  cuuint64_t dims[4] = {(cuuint64_t)C0, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C0 * 2, (cuuint64_t)W * C0 * 2, (cuuint64_t)H * W * C0 * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, 10, 18, 1};
+  TFPNP_TRY(encode_map(&p.a_map[0], const_cast<__half*>(x), 4, dims, strides, box, 2 * kc));
+  if (c.x3) TFPNP_TRY(encode_map(&p.a_map[1], const_cast<__half*>(x_lo), 4, dims, strides, box, 2 * kc));
+  else p.a_map[1] = p.a_map[0];
+  cuuint64_t wd[3] = {(cuuint64_t)C0, (cuuint64_t)Cout, 9};
+  cuuint64_t ws[2] = {(cuuint64_t)C0 * 2, (cuuint64_t)C0 * Cout * 2};
+  cuuint32_t wb[3] = {(cuuint32_t)kc, 32, 1};
+  TFPNP_TRY(encode_map(&p.w_map[0], const_cast<__half*>(w_taps), 3, wd, ws, wb, 2 * kc));
+  if (c.x3) TFPNP_TRY(encode_map(&p.w_map[1], const_cast<__half*>(w_lo), 3, wd, ws, wb, 2 * kc));
+  else p.w_map[1] = p.w_map[0];
+  return 0;
+}
+
+int launch_conv_ws(const ConvWsPlan& c, cudaStream_t st) {
+  static unsigned long long attr_set = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_set >> (dev & 63) & 1ull)) {
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set |= 1ull << (dev & 63);
+  }
+  if (c.x3) TFPNP_CUDA_OK(launch_ex(conv3x3_pair_ws<true>, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
+  else TFPNP_CUDA_OK(launch_ex(conv3x3_pair_ws<false>, dim3(c.grid), dim3(kPairThreads), c.smem_bytes, st, use_pdl(), 2, c.p));
+  TFPNP_COUNT_LAUNCH();
+  return 0;
+}
+
 int launch_conv_params(const ConvParams& p, int BN, cudaStream_t st) {
   dim3 grid(p.tiles_w * p.tiles_h * cdiv(p.B, p.TB), p.Cout / BN);
   switch (BN) {
@@ -1729,6 +1810,7 @@ struct UNetTc : Denoiser {
   std::vector<int> conv_bn;
   std::vector<Conv2Plan> convs2; // v2 (halo-tile) plans; grid == 0 -> layer uses v1
   std::vector<ConvPairPlan> convsp; // CTA-pair plans (default where eligible); grid == 0 -> layer uses v2 / v1
+  std::vector<ConvWsPlan> convsw;   // weight-stationary pair plans (first choice where eligible)
 
   int init(const float* host) {
     const ConvSpec* sp = unet_conv_specs();
@@ -1749,6 +1831,7 @@ struct UNetTc : Denoiser {
       if (l == 0) {
         for (int i = 0; i < 576; ++i) first_w.w[i] = w[i];   // [32][2][9]
         for (int i = 0; i < 32; ++i) first_w.b[i] = b[i];
+
         w_off[l] = 0;
         continue;
       }
@@ -1806,7 +1889,8 @@ struct UNetTc : Denoiser {
     const ConvSpec& sp = unet_conv_specs()[l];
     const char* kind = "v1";
     int h = 0;
-    if (convsp[l].grid > 0) { kind = convsp[l].x3_kc32 ? "pair-x3/32" : convsp[l].x3 ? "pair-x3/64" : "pair"; h = convsp[l].p.H; }
+    if (convsw[l].grid > 0) { kind = convsw[l].x3 ? "pair-ws-x3" : "pair-ws"; h = convsw[l].p.H; }
+    else if (convsp[l].grid > 0) { kind = convsp[l].x3_kc32 ? "pair-x3/32" : convsp[l].x3 ? "pair-x3/64" : "pair"; h = convsp[l].p.H; }
     else if (convs2[l].grid > 0) {
       const Conv2Plan& c = convs2[l];
       h = c.p.H;
@@ -1824,6 +1908,11 @@ struct UNetTc : Denoiser {
     std::vector<double> acc;
     int rc = 0;
     for (int r = 0; r < reps + 1 && rc == 0; ++r) {        // first repetition is a warm-up
+      // an un-timed call first, so that the timed launches are enqueued behind a busy GPU (no host launch gaps in the intervals)
+      prof_on = false;
+      rc = forward(x, sigma, 1, out, B, H, W, st);
+      prof_on = true;
+      if (rc != 0) break;
       prof_n = 0;
       mark(st, "start");
       rc = forward(x, sigma, 1, out, B, H, W, st);
@@ -1902,6 +1991,18 @@ struct UNetTc : Denoiser {
   // build ConvParams for layer l reading (src0 [, src1]) and writing dst
   int plan_conv(int l, const Act& s0, const Act* s1, const Act& dst, int B, const Act* low = nullptr) {
     convsp[l].grid = 0;
+    convsw[l].grid = 0;
+    if (!low && conv_ws_eligible(s0.C, s1 ? s1->C : 0, unet_conv_specs()[l].cout, dst.H, dst.W, x3)) {
+      ConvWsPlan& c = convsw[l];
+      TFPNP_TRY(plan_conv_ws(c, s0.hi, x3 ? s0.lo : nullptr, s0.C, w_hi.as<__half>() + w_off[l],
+                             x3 ? w_lo.as<__half>() + w_off[l] : nullptr, biases.as<float>() + b_off[l], dst.hi,
+                             x3 ? dst.lo : nullptr, B, dst.H, dst.W, unet_conv_specs()[l].cout));
+      convs2[l].grid = 0;
+      fused_up[l] = false;
+      fused_pool[l] = env_int("TFPNP_CONV_FUSE", 1) != 0 && (l == 2 || l == 5 || l == 8 || l == 11);
+      if (fused_pool[l]) { c.p.pool_hi = S2.hi; c.p.pool_lo = x3 ? S2.lo : nullptr; }
+      return 0;
+    }
     if (conv_pair_eligible(s0.C, s1 ? s1->C : 0, unet_conv_specs()[l].cout, dst.H, dst.W, x3, low != nullptr)) {
       ConvPairPlan& c = convsp[l];
       TFPNP_TRY(plan_conv_pair(c, s0.hi, x3 ? s0.lo : nullptr, s0.C, s1 ? s1->hi : nullptr, (s1 && x3) ? s1->lo : nullptr,
@@ -1979,6 +2080,7 @@ struct UNetTc : Denoiser {
     conv_bn.assign(kNumUnetConv3, 0);
     convs2.assign(kNumUnetConv3, Conv2Plan{});
     convsp.assign(kNumUnetConv3, ConvPairPlan{});
+    convsw.assign(kNumUnetConv3, ConvWsPlan{});
     auto view = [](const Act& buf, int C, int h, int w) { Act a = buf; a.C = C; a.H = h; a.W = w; return a; };
     // encoder level 0: first -> S0 ; conv1: S0 -> S1 ; conv2: S1 -> x1
     TFPNP_TRY(plan_conv(1, view(S0, 32, H, W), nullptr, view(S1, 32, H, W), B));
@@ -2015,6 +2117,7 @@ struct UNetTc : Denoiser {
     return rc;
   }
   int launch_conv_impl(int l, cudaStream_t st) {
+    if (convsw[l].grid > 0) return launch_conv_ws(convsw[l], st);
     if (convsp[l].grid > 0) return launch_conv_pair(convsp[l], st);
     if (convs2[l].grid > 0) {
       // debugging aid: TFPNP_TRACE_LAYER=l + TFPNP_TRACE_FILE dump CTA 0's role timeline of layer l (eager calls only)
@@ -2111,6 +2214,13 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
   TFPNP_CHECK(C0 > 0 && C0 % 32 == 0 && C1 % 32 == 0, "channel counts must be multiples of 32");
   TFPNP_CHECK(Cout == 32 || Cout == 64 || Cout % 128 == 0, "Cout must be 32, 64 or a multiple of 128");
   TFPNP_TRY(set_conv_attrs());
+  if (conv_ws_eligible(C0, C1, Cout, H, W, false)) {
+    ConvWsPlan cw;
+    TFPNP_TRY(plan_conv_ws(cw, x0, nullptr, C0, w_taps, nullptr, bias, out, nullptr, B, H, W, Cout));
+    TFPNP_TRY(launch_conv_ws(cw, st));
+    TFPNP_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (conv_pair_eligible(C0, C1, Cout, H, W, false, false)) {
     ConvPairPlan cp;
     TFPNP_TRY(plan_conv_pair(cp, x0, nullptr, C0, x1, nullptr, C1, w_taps, nullptr, bias, out, nullptr, B, H, W, Cout));
