@@ -59,8 +59,10 @@ csmri_rows_fwd(const float* __restrict__ x, const float2* __restrict__ u, float2
   for (int j = 0; j < R; ++j) tr[32 * j + f.lane] = v[j];
 }
 
+// (launch bounds: 6 CTAs per SM, so that the 768 CTAs of the 48 x 128^2 case are ONE wave -- at the 4 per SM the register
+// count allowed before, the 1.3 waves made this latency-bound kernel take two round trips)
 template <int R>
-__global__ void __launch_bounds__(COLS_PER_CTA * 32)
+__global__ void __launch_bounds__(COLS_PER_CTA * 32, R <= 4 ? 6 : 3)
 csmri_cols(float2* __restrict__ T, const float2* __restrict__ y0p, const uint8_t* __restrict__ maskp,
            const float* __restrict__ mu) {
   constexpr int N = 32 * R;
@@ -131,9 +133,11 @@ csmri_rows_inv(const float2* __restrict__ T, const float* __restrict__ x, float2
   }
 }
 
-// ---- one launch per iteration: the whole update of an image inside a 2-CTA cluster -------------------------------
-// CTA `rank` of the cluster owns image rows [rank*N/2, (rank+1)*N/2) for the two row passes and columns (frequency
-// positions) [rank*N/2, ...) for the column pass.  The two transposes between the passes go through shared memory:
+// ---- one launch per iteration: the whole update of an image inside a cluster of CL CTAs ---------------------------
+// CTA `rank` of the cluster owns image rows [rank*N/CL, (rank+1)*N/CL) for the two row passes and columns (frequency
+// positions) [rank*N/CL, ...) for the column pass.  CL = 4 at 128x128: 192 CTAs with 66 KB of shared memory each fit the
+// chip in ONE wave (the first version, CL = 2, was 96 x 2 CTAs of 132 KB = 1.3 waves of one CTA per SM, which is why it
+// lost end to end although it saved two launches).  The two transposes between the passes go through shared memory:
 // every warp scatters its FFT output into the [col][row] (then [row][col]) tile of the CTA that owns the column (row)
 // -- its own tile or, through distributed shared memory (st.shared::cluster), its peer's -- so the intermediate T
 // never touches L2/HBM.  Same arithmetic, in the same order, as the three-kernel path above (equal up to the
@@ -146,12 +150,12 @@ __device__ __forceinline__ void st_cluster_f2(const float2* local_ptr, uint32_t 
 
 constexpr int FUSED_WARPS = 16;
 
-template <int R>
+template <int R, int CL>
 __global__ void __launch_bounds__(FUSED_WARPS * 32, 1)
 csmri_fused(const float* __restrict__ x, float2* __restrict__ z, float2* __restrict__ u, float* __restrict__ d,
             const float2* __restrict__ y0p, const uint8_t* __restrict__ maskp, const float* __restrict__ mu) {
-  constexpr int N = 32 * R, HALF = N / 2, PITCH = N + 1, RPW = HALF / FUSED_WARPS;
-  static_assert(RPW >= 1, "csmri_fused needs N >= 64");
+  constexpr int N = 32 * R, HALF = N / CL, PITCH = N + 1, RPW = HALF / FUSED_WARPS;   // HALF = rows (columns) per CTA
+  static_assert(RPW >= 1, "csmri_fused needs N / CL >= 16");
   extern __shared__ float2 fsm[];
   float2* tA = fsm;                     // [HALF cols][PITCH]: column-major input of the column pass
   float2* tB = fsm + HALF * PITCH;      // [HALF rows][PITCH]: row-major input of the inverse row pass
@@ -161,7 +165,7 @@ csmri_fused(const float* __restrict__ x, float2* __restrict__ z, float2* __restr
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const int b = blockIdx.x >> 1;
+  const int b = blockIdx.x / CL;
   const int warp = threadIdx.x >> 5;
   WarpFFT<R> f;
   f.init();                             // twiddles: overlaps the tail of the denoiser's last kernel
@@ -267,19 +271,19 @@ csmri_fused(const float* __restrict__ x, float2* __restrict__ z, float2* __restr
   }
 }
 
-template <int R>
+template <int R, int CL>
 int launch_fused(const float* x, float2* z, float2* u, float* d, const float2* y0p, const uint8_t* maskp,
                  const float* mu, int B, cudaStream_t st) {
   constexpr int N = 32 * R;
-  constexpr int smem = 2 * (N / 2) * (N + 1) * (int)sizeof(float2);
+  constexpr int smem = 2 * (N / CL) * (N + 1) * (int)sizeof(float2);
   static unsigned long long attr_set = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(attr_set >> (dev & 63) & 1ull)) {
-    TFPNP_CUDA_OK(cudaFuncSetAttribute(csmri_fused<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TFPNP_CUDA_OK(cudaFuncSetAttribute(csmri_fused<R, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set |= 1ull << (dev & 63);
   }
-  TFPNP_CUDA_OK(launch_ex(csmri_fused<R>, dim3(2 * B), dim3(FUSED_WARPS * 32), smem, st, true, 2, x, z, u, d, y0p, maskp, mu));
+  TFPNP_CUDA_OK(launch_ex(csmri_fused<R, CL>, dim3(CL * B), dim3(FUSED_WARPS * 32), smem, st, true, CL, x, z, u, d, y0p, maskp, mu));
   TFPNP_COUNT_LAUNCH();
   return 0;
 }
@@ -293,8 +297,9 @@ int launch_update(const float* x, float2* z, float2* u, float* d, float2* T, con
     // iteration, but the whole step gets 1.9 % SLOWER (24.39 vs 23.93 ms): 96 clusters with 132 KB of shared memory each
     // and scattered 8-byte DSMEM stores hold up the start of the next denoiser call more than the two saved launches
     // give back.  Kept (tested against the three-kernel path) as the base for a bulk-DSMEM transpose.
-    static const bool fused = getenv("TFPNP_CSMRI_FUSED") != nullptr && atoi(getenv("TFPNP_CSMRI_FUSED")) != 0;
-    if (fused) return launch_fused<R>(x, z, u, d, y0p, maskp, mu, B, st);
+    static const int fused = getenv("TFPNP_CSMRI_FUSED") ? atoi(getenv("TFPNP_CSMRI_FUSED")) : 0;
+    if (fused == 2) return launch_fused<R, 2>(x, z, u, d, y0p, maskp, mu, B, st);
+    if (fused == 4) return launch_fused<R, R == 4 ? 4 : 2>(x, z, u, d, y0p, maskp, mu, B, st);
   }
   const int row_blocks = B * N / ROWS_PER_CTA;
   csmri_rows_fwd<R><<<row_blocks, ROWS_PER_CTA * 32, 0, st>>>(x, u, T);

@@ -11,6 +11,8 @@
 // loop and is not reproducible against a fixture: not built.)
 #include "tasks.cuh"
 #include "fft.cuh"
+#include <map>
+#include <cstdlib>
 
 namespace tfpnp {
 namespace {
@@ -202,10 +204,23 @@ struct VariantSolver {
   size_t cap_params = 0;
   DevBuf c0, c1, c2, c3, G, T, xr, d, y0p, maskp, params;   // complex images c0..c3, G, T; real x, d
   int64_t last_launches = 0;
+  // the iteration loop of a call is ONE CUDA-graph launch, keyed by (B, iters), like the ADMM solvers (solver.cu): the graph
+  // only touches the resident buffers; the caller's tensors are read / written by the copy kernels around it
+  bool use_graph = true;
+  std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+  std::map<std::pair<int, int>, int64_t> graph_nodes;
+  cudaStream_t cap_stream = nullptr;
+  int den_generation = -1;
+
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    graphs.clear();
+  }
 
   int ensure(int B, int iters) {
     const size_t HW = (size_t)N * N;
     if (B > cap_B) {
+      drop_graphs();                       // the graphs bake the workspace addresses
       for (DevBuf* b : {&c0, &c1, &c2, &c3, &G, &T, &y0p}) TFPNP_TRY(b->alloc(B * HW * sizeof(float2)));
       TFPNP_TRY(xr.alloc(B * HW * sizeof(float)));
       TFPNP_TRY(d.alloc(B * HW * sizeof(float)));
@@ -213,7 +228,57 @@ struct VariantSolver {
       cap_B = B;
     }
     const size_t need = (size_t)B * (iters > 0 ? iters : 1) * 3 * sizeof(float);
-    if (need > cap_params) { TFPNP_TRY(params.alloc(need)); cap_params = params.bytes; }
+    if (need > cap_params) { drop_graphs(); TFPNP_TRY(params.alloc(need)); cap_params = params.bytes; }
+    return 0;
+  }
+
+  // the iteration loop on stream `st`: resident buffers only (graph-capturable: no allocation, no synchronisation)
+  template <int R>
+  int enqueue_loop(int B, int iters, cudaStream_t st) {
+    const int HW = N * N;
+    const size_t n = (size_t)B * HW;
+    const int T256 = 256;
+    const unsigned nb = (unsigned)((n + T256 - 1) / T256);
+    const float* P = params.as<float>();
+    const size_t np = (size_t)B * iters;
+    float2 *X = c0.as<float2>(), *Z = c1.as<float2>(), *U = c2.as<float2>(), *IN = c3.as<float2>(), *g = G.as<float2>();
+    float *x = xr.as<float>(), *dd = d.as<float>();
+    auto step = [&](const float2* in, int mode, const float* mu) {
+      return masked_fft_step<R>(in, g, T.as<float2>(), y0p.as<float2>(), maskp.as<uint8_t>(), mu, mode, B, st);
+    };
+    auto denoise = [&](const float* sig) { return den->forward(dd, sig, 1, x, B, N, N, st); };
+#define VLAUNCH(kernel, ...) do { kernel<<<nb, T256, 0, st>>>(__VA_ARGS__); TFPNP_COUNT_LAUNCH(); } while (0)
+    for (int i = 0; i < iters; ++i) {
+      switch (algo) {
+        case TFPNP_ALGO_HQS:              // state (x, z); params (sigma_d, mu)
+          TFPNP_TRY(denoise(P + (size_t)i * B));
+          VLAUNCH(real_to_complex, x, X, n);
+          TFPNP_TRY(step(X, MODE_BLEND, P + np + (size_t)i * B));
+          VLAUNCH(hqs_finish, g, Z, dd, n);
+          break;
+        case TFPNP_ALGO_PG:               // state x; params (sigma_d, tau)
+          TFPNP_TRY(step(X, MODE_RESIDUAL, nullptr));
+          VLAUNCH(grad_step, X, g, P + np + (size_t)i * B, dd, HW, n);
+          TFPNP_TRY(denoise(P + (size_t)i * B));
+          VLAUNCH(real_to_complex, x, X, n);
+          break;
+        case TFPNP_ALGO_APG:              // state (x, s); params (sigma_d, tau, beta); X holds x_prev, U holds s
+          TFPNP_TRY(step(U, MODE_RESIDUAL, nullptr));
+          VLAUNCH(grad_step, U, g, P + np + (size_t)i * B, dd, HW, n);
+          TFPNP_TRY(denoise(P + (size_t)i * B));
+          VLAUNCH(apg_extrapolate, x, X, U, P + 2 * np + (size_t)i * B, HW, n);
+          break;
+        default: {                        // RED-ADMM: state (x, z, u); params (sigma_d, mu, lamda)
+          const float* mu = P + np + (size_t)i * B;
+          TFPNP_TRY(denoise(P + (size_t)i * B));
+          VLAUNCH(red_xstep, x, X, Z, U, IN, mu, P + 2 * np + (size_t)i * B, HW, n);
+          TFPNP_TRY(step(IN, MODE_BLEND, mu));
+          VLAUNCH(red_finish, g, X, Z, U, dd, n);
+          break;
+        }
+      }
+    }
+#undef VLAUNCH
     return 0;
   }
 
@@ -224,6 +289,7 @@ struct VariantSolver {
     const size_t n = (size_t)B * HW;
     const int T256 = 256;
     const unsigned nb = (unsigned)((n + T256 - 1) / T256);
+    TFPNP_CHECK(algo >= TFPNP_ALGO_HQS && algo <= TFPNP_ALGO_REDADMM, "unknown CS-MRI solver variant %d", algo);
     const int V = algo == TFPNP_ALGO_PG ? 1 : (algo == TFPNP_ALGO_REDADMM ? 3 : 2);
     const float2* sin = reinterpret_cast<const float2*>(state_in);
     float2* sout = reinterpret_cast<float2*>(state_out);
@@ -233,71 +299,66 @@ struct VariantSolver {
     TFPNP_COUNT_LAUNCH();
     TFPNP_TRY(csmri_prep(y0, mask, y0p.as<float2>(), maskp.as<uint8_t>(), B, N, st));
     TFPNP_TRY(den->prepare(B, N, N));
-    const float* P = params.as<float>();
-    const size_t np = (size_t)B * iters;
-    float2 *X = c0.as<float2>(), *Z = c1.as<float2>(), *U = c2.as<float2>(), *IN = c3.as<float2>(), *g = G.as<float2>();
-    float *x = xr.as<float>(), *dd = d.as<float>();
-    auto step = [&](const float2* in, int mode, const float* mu) {
-      return masked_fft_step<R>(in, g, T.as<float2>(), y0p.as<float2>(), maskp.as<uint8_t>(), mu, mode, B, st);
-    };
-    auto denoise = [&](const float* sig) { return den->forward(dd, sig, 1, x, B, N, N, st); };
+    if (den->generation != den_generation) { drop_graphs(); den_generation = den->generation; }   // a denoiser workspace moved
+    float2 *X = c0.as<float2>(), *Z = c1.as<float2>(), *U = c2.as<float2>();
+    float* dd = d.as<float>();
 #define VLAUNCH(kernel, ...) do { kernel<<<nb, T256, 0, st>>>(__VA_ARGS__); TFPNP_COUNT_LAUNCH(); } while (0)
+    // 1. the caller's state -> resident buffers
     switch (algo) {
-      case TFPNP_ALGO_HQS: {            // state (x, z); params (sigma_d, mu)
-        VLAUNCH(slot_copy, sin, Z, dd, V, 1, HW, n, 0);                   // d = Re z
-        for (int i = 0; i < iters; ++i) {
-          TFPNP_TRY(denoise(P + (size_t)i * B));
-          VLAUNCH(real_to_complex, x, X, n);
-          TFPNP_TRY(step(X, MODE_BLEND, P + np + (size_t)i * B));
-          VLAUNCH(hqs_finish, g, Z, dd, n);
-        }
+      case TFPNP_ALGO_HQS: VLAUNCH(slot_copy, sin, Z, dd, V, 1, HW, n, 0); break;                   // d = Re z
+      case TFPNP_ALGO_PG: VLAUNCH(slot_copy, sin, X, nullptr, V, 0, HW, n, 0); break;
+      case TFPNP_ALGO_APG:
+        VLAUNCH(slot_copy, sin, X, nullptr, V, 0, HW, n, 0);
+        VLAUNCH(slot_copy, sin, U, nullptr, V, 1, HW, n, 0);
+        break;
+      default:
+        VLAUNCH(slot_copy, sin, X, dd, V, 0, HW, n, 0);                                              // d = Re x
+        VLAUNCH(slot_copy, sin, Z, nullptr, V, 1, HW, n, 0);
+        VLAUNCH(slot_copy, sin, U, nullptr, V, 2, HW, n, 0);
+        break;
+    }
+    // 2. the iteration loop: one graph launch
+    if (use_graph) {
+      auto key = std::make_pair(B, iters);
+      auto it = graphs.find(key);
+      if (it == graphs.end()) {
+        if (!cap_stream) TFPNP_CUDA_OK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        const int64_t before = g_launch_count;
+        TFPNP_CUDA_OK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_loop<R>(B, iters, cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+        TFPNP_CUDA_OK(ce);
+        cudaGraphExec_t exec = nullptr;
+        TFPNP_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        graphs[key] = exec;
+        graph_nodes[key] = g_launch_count - before;
+        g_launch_count = before;
+        it = graphs.find(key);
+      }
+      TFPNP_CUDA_OK(cudaGraphLaunch(it->second, st));
+      g_launch_count += graph_nodes[key];
+    } else {
+      TFPNP_TRY(enqueue_loop<R>(B, iters, st));
+    }
+    // 3. resident buffers -> the caller's output state
+    switch (algo) {
+      case TFPNP_ALGO_HQS:
         VLAUNCH(slot_copy, sout, X, nullptr, V, 0, HW, n, 1);
         VLAUNCH(slot_copy, sout, Z, nullptr, V, 1, HW, n, 1);
         break;
-      }
-      case TFPNP_ALGO_PG: {             // state x; params (sigma_d, tau)
-        VLAUNCH(slot_copy, sin, X, nullptr, V, 0, HW, n, 0);
-        for (int i = 0; i < iters; ++i) {
-          TFPNP_TRY(step(X, MODE_RESIDUAL, nullptr));
-          VLAUNCH(grad_step, X, g, P + np + (size_t)i * B, dd, HW, n);
-          TFPNP_TRY(denoise(P + (size_t)i * B));
-          VLAUNCH(real_to_complex, x, X, n);
-        }
-        VLAUNCH(slot_copy, sout, X, nullptr, V, 0, HW, n, 1);
-        break;
-      }
-      case TFPNP_ALGO_APG: {            // state (x, s); params (sigma_d, tau, beta)
-        VLAUNCH(slot_copy, sin, X, nullptr, V, 0, HW, n, 0);             // X holds x_prev
-        VLAUNCH(slot_copy, sin, U, nullptr, V, 1, HW, n, 0);             // U holds s
-        for (int i = 0; i < iters; ++i) {
-          TFPNP_TRY(step(U, MODE_RESIDUAL, nullptr));
-          VLAUNCH(grad_step, U, g, P + np + (size_t)i * B, dd, HW, n);
-          TFPNP_TRY(denoise(P + (size_t)i * B));
-          VLAUNCH(apg_extrapolate, x, X, U, P + 2 * np + (size_t)i * B, HW, n);
-        }
+      case TFPNP_ALGO_PG: VLAUNCH(slot_copy, sout, X, nullptr, V, 0, HW, n, 1); break;
+      case TFPNP_ALGO_APG:
         VLAUNCH(slot_copy, sout, X, nullptr, V, 0, HW, n, 1);
         VLAUNCH(slot_copy, sout, U, nullptr, V, 1, HW, n, 1);
         break;
-      }
-      case TFPNP_ALGO_REDADMM: {        // state (x, z, u); params (sigma_d, mu, lamda)
-        VLAUNCH(slot_copy, sin, X, dd, V, 0, HW, n, 0);                  // d = Re x
-        VLAUNCH(slot_copy, sin, Z, nullptr, V, 1, HW, n, 0);
-        VLAUNCH(slot_copy, sin, U, nullptr, V, 2, HW, n, 0);
-        for (int i = 0; i < iters; ++i) {
-          const float* mu = P + np + (size_t)i * B;
-          TFPNP_TRY(denoise(P + (size_t)i * B));
-          VLAUNCH(red_xstep, x, X, Z, U, IN, mu, P + 2 * np + (size_t)i * B, HW, n);
-          TFPNP_TRY(step(IN, MODE_BLEND, mu));
-          VLAUNCH(red_finish, g, X, Z, U, dd, n);
-        }
+      default:
         VLAUNCH(slot_copy, sout, X, nullptr, V, 0, HW, n, 1);
         VLAUNCH(slot_copy, sout, Z, nullptr, V, 1, HW, n, 1);
         VLAUNCH(slot_copy, sout, U, nullptr, V, 2, HW, n, 1);
         break;
-      }
-      default:
-        set_error("unknown CS-MRI solver variant %d", algo);
-        return TFPNP_ERR_INVALID;
     }
 #undef VLAUNCH
     TFPNP_CUDA_OK(cudaGetLastError());
@@ -305,6 +366,8 @@ struct VariantSolver {
   }
 
   ~VariantSolver() {
+    drop_graphs();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     for (DevBuf* b : {&c0, &c1, &c2, &c3, &G, &T, &xr, &d, &y0p, &maskp, &params}) b->release();
   }
 };
@@ -577,6 +640,8 @@ int tfpnp_csmri_variant_create(int algo, int N, void* denoiser, void** out) {
   TFPNP_CHECK(N == 32 || N == 64 || N == 128 || N == 256, "FFT tasks support N in {32,64,128,256}, got %d", N);
   VariantSolver* s = new VariantSolver();
   s->algo = algo; s->N = N; s->den = static_cast<Denoiser*>(denoiser);
+  const char* e = getenv("TFPNP_VARIANT_GRAPH");       // 0: eager launches (debugging)
+  s->use_graph = !e || atoi(e) != 0;
   *out = s;
   return 0;
 }

@@ -49,14 +49,6 @@ def all_gather_batch(local: torch.Tensor, n_total: int) -> torch.Tensor:
 
 
 def all_gather_psnr(local: torch.Tensor, n_total: int) -> torch.Tensor:
-    """Gather the [B_local,1] PSNR vectors of all ranks into [n_total,1] (rank order = batch order)."""
-    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
-        return local
-    world = dist.get_world_size()
-    sizes = [shard_bounds(n_total, r, world) for r in range(world)]
-    pad = max(hi - lo for lo, hi in sizes)
-    buf = torch.zeros(pad, 1, dtype=local.dtype, device=local.device)
-    buf[: local.shape[0]] = local
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf)
-    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
+    """Gather the [B_local,1] PSNR vectors of all ranks into [n_total,1] (rank order = batch order): the one exchange of the
+    data path."""
+    return all_gather_batch(local, n_total)
