@@ -38,6 +38,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 runs the CPU legs (reference arm, cpu_baseline, parity oracle) and
+# needs the host's cores for them -- must be set before torch (and its OpenMP runtime) is imported
+if int(os.environ.get("RANK", "0")) == 0 and os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import torch  # noqa: E402
 
 ITERS = 30
@@ -283,7 +288,9 @@ def main():
     tasks = [t for t in args.tasks.split(",") if t in TASKS]
     if "csmri" not in tasks:
         tasks.insert(0, "csmri")
-    cpu_legs = rank == 0 and not args.no_cpu_baseline
+    # the CPU legs (cpu_baseline + parity against the oracle) run at N = 1 only: at N > 1 the other ranks would sit in the
+    # final barrier for minutes while rank 0 computes on the host
+    cpu_legs = rank == 0 and world == 1 and not args.no_cpu_baseline
     sd_default = T.random_unet_state_dict(0)
     other = "fp16" if args.precision != "fp16" else "fp16x3"
 
