@@ -300,17 +300,61 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
       const int x0 = (int)fx;
       const int x1 = x0 + (x0 < Win - 1 ? 1 : 0);
       const float lx = fx - (float)x0, wx = 1.f - lx;
-      const int ox0 = (x0 - xs) * iROW + j * 16, ox1 = (x1 - xs) * iROW + j * 16;
+      const int ox0 = (x0 - xs) * 128 + j * 32, ox1 = (x1 - xs) * 128 + j * 32;      // fp32 staging rows of 128 bytes
+      // row set-up (fixed for the tile): first fine row and number of fine rows of this thread's three coarse intervals
+      int rf[3], cn[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int i = i0 + 4 * q, Y = ys + i;
+        rf[q] = 0; cn[q] = 0;
+        if (x_ok && i < kUpBox - 1 && Y < Hin) {
+          int r = 2 * i - 1;
+          if (h0 - 1 + r < 0) r = 1 - h0;                    // first fine row inside the image
+          while (r < kHaloH && (int)(p.up_sy * (float)(h0 - 1 + r)) < Y) ++r;
+          int n = 0;
+          while (r + n < kHaloH && h0 - 1 + r + n < p.H && (int)(p.up_sy * (float)(h0 - 1 + r + n)) == Y) ++n;
+          rf[q] = r; cn[q] = n;
+        }
+      }
       for (int c = 0; c < nchunks; ++c, ++ia) {
         if (c < p.nchunk0) continue;                         // source 0 comes by TMA
         const int s = ia % SA, st = iu & 1;
         mbar_wait(&stg_full[st], (iu >> 1) & 1);
+        uint8_t* stg = sStg + st * kX3StgSlot;
+        // pre-pass: [hi plane | lo plane] fp16 -> fp32 pixel rows IN PLACE (121 x 32 channels x 4 bytes = exactly the slot), so
+        // that every staged value is combined and converted once instead of once per fine pixel that reads it
+        {
+          uint4 ph[2], pl[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int gi = tid + kX3XformThreads * q;
+            if (gi < 4 * kUpBox * kUpBox) {
+              ph[q] = *reinterpret_cast<const uint4*>(stg + gi * 16);
+              pl[q] = *reinterpret_cast<const uint4*>(stg + kX3StgPlane + gi * 16);
+            }
+          }
+          asm volatile("bar.sync 1, 288;" ::: "memory");     // every fp16 value is in registers
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int gi = tid + kX3XformThreads * q;
+            if (gi < 4 * kUpBox * kUpBox) {
+              const __half2* hh = reinterpret_cast<const __half2*>(&ph[q]);
+              const __half2* ll = reinterpret_cast<const __half2*>(&pl[q]);
+              float2 f[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) f[e] = ffma2(kLoInv, __half22float2(ll[e]), __half22float2(hh[e]));
+              float4* dst = reinterpret_cast<float4*>(stg + gi * 32);
+              dst[0] = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
+              dst[1] = make_float4(f[2].x, f[2].y, f[3].x, f[3].y);
+            }
+          }
+          asm volatile("bar.sync 1, 288;" ::: "memory");
+        }
         if (ia >= (uint32_t)SA) {                            // the staging load ran ahead of the A ring: claim the stage here
           uint32_t& xc = s == 0 ? xc0 : s == 1 ? xc1 : s == 2 ? xc2 : xc3;
           mbar_wait(&empty_x[s], xc & 1);
           ++xc;
         }
-        const uint8_t* stg = sStg + st * kX3StgSlot;
         uint8_t* dstA = sA + s * p.a_stage_bytes;
         const uint4 zero = make_uint4(0, 0, 0, 0);
         if (!x_ok) {                                         // conv zero padding left / right of the image
@@ -318,37 +362,30 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
         } else {
           if (i0 == 0 && h0 == 0) store_px(dstA, 0, zero, zero);                       // ... above
           if (i0 == 3 && h0 + 16 == p.H) store_px(dstA, kHaloH - 1, zero, zero);       // ... below
-#pragma unroll 1
-          for (int i = i0; i < kUpBox - 1; i += 4) {
-            const int Y = ys + i;
-            if (Y >= Hin) break;
-            int r = 2 * i - 1;
-            if (h0 - 1 + r < 0) r = 1 - h0;                  // first fine row inside the image
-            while (r < kHaloH && (int)(p.up_sy * (float)(h0 - 1 + r)) < Y) ++r;
-            if (r >= kHaloH || h0 - 1 + r >= p.H || (int)(p.up_sy * (float)(h0 - 1 + r)) != Y) continue;
-            // the interval's two source rows at the column's two source pixels, both planes: value = hi + lo / 2^11
-            const uint8_t* rp0 = stg + i * (kUpBox * iROW);
-            const uint8_t* rp1 = rp0 + (Y < Hin - 1 ? kUpBox * iROW : 0);
-            const H8 a0h = *reinterpret_cast<const H8*>(rp0 + ox0), b0h = *reinterpret_cast<const H8*>(rp0 + ox1);
-            const H8 a1h = *reinterpret_cast<const H8*>(rp1 + ox0), b1h = *reinterpret_cast<const H8*>(rp1 + ox1);
-            const H8 a0l = *reinterpret_cast<const H8*>(rp0 + kX3StgPlane + ox0), b0l = *reinterpret_cast<const H8*>(rp0 + kX3StgPlane + ox1);
-            const H8 a1l = *reinterpret_cast<const H8*>(rp1 + kX3StgPlane + ox0), b1l = *reinterpret_cast<const H8*>(rp1 + kX3StgPlane + ox1);
-            float2 top[4], bot[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 va0 = ffma2(kLoInv, __half22float2(a0l.v[e]), __half22float2(a0h.v[e]));
-              const float2 vb0 = ffma2(kLoInv, __half22float2(b0l.v[e]), __half22float2(b0h.v[e]));
-              const float2 va1 = ffma2(kLoInv, __half22float2(a1l.v[e]), __half22float2(a1h.v[e]));
-              const float2 vb1 = ffma2(kLoInv, __half22float2(b1l.v[e]), __half22float2(b1h.v[e]));
-              top[e] = ffma2(lx, vb0, fmul2(wx, va0));
-              bot[e] = ffma2(lx, vb1, fmul2(wx, va1));
-            }
+          for (int q = 0; q < 3; ++q) {
+            if (cn[q] == 0) continue;
+            const int i = i0 + 4 * q, Y = ys + i;
+            // the interval's two source rows at the column's two source pixels
+            const uint8_t* rp0 = stg + i * (kUpBox * 128);
+            const uint8_t* rp1 = rp0 + (Y < Hin - 1 ? kUpBox * 128 : 0);
+            const float4 a0a = *reinterpret_cast<const float4*>(rp0 + ox0), a0b = *reinterpret_cast<const float4*>(rp0 + ox0 + 16);
+            const float4 b0a = *reinterpret_cast<const float4*>(rp0 + ox1), b0b = *reinterpret_cast<const float4*>(rp0 + ox1 + 16);
+            const float4 a1a = *reinterpret_cast<const float4*>(rp1 + ox0), a1b = *reinterpret_cast<const float4*>(rp1 + ox0 + 16);
+            const float4 b1a = *reinterpret_cast<const float4*>(rp1 + ox1), b1b = *reinterpret_cast<const float4*>(rp1 + ox1 + 16);
+            float2 top[4], bot[4];
+            top[0] = ffma2(lx, make_float2(b0a.x, b0a.y), fmul2(wx, make_float2(a0a.x, a0a.y)));
+            top[1] = ffma2(lx, make_float2(b0a.z, b0a.w), fmul2(wx, make_float2(a0a.z, a0a.w)));
+            top[2] = ffma2(lx, make_float2(b0b.x, b0b.y), fmul2(wx, make_float2(a0b.x, a0b.y)));
+            top[3] = ffma2(lx, make_float2(b0b.z, b0b.w), fmul2(wx, make_float2(a0b.z, a0b.w)));
+            bot[0] = ffma2(lx, make_float2(b1a.x, b1a.y), fmul2(wx, make_float2(a1a.x, a1a.y)));
+            bot[1] = ffma2(lx, make_float2(b1a.z, b1a.w), fmul2(wx, make_float2(a1a.z, a1a.w)));
+            bot[2] = ffma2(lx, make_float2(b1b.x, b1b.y), fmul2(wx, make_float2(a1b.x, a1b.y)));
+            bot[3] = ffma2(lx, make_float2(b1b.z, b1b.w), fmul2(wx, make_float2(a1b.z, a1b.w)));
 #pragma unroll 1
-            for (; r < kHaloH; ++r) {
-              const int yo = h0 - 1 + r;
-              if (yo >= p.H) break;
-              const float fy = p.up_sy * (float)yo;
-              if ((int)fy != Y) break;
+            for (int n = 0; n < cn[q]; ++n) {
+              const int r = rf[q] + n;
+              const float fy = p.up_sy * (float)(h0 - 1 + r);
               const float ly = fy - (float)Y, wy = 1.f - ly;
               H8 ohi, olo;
 #pragma unroll
@@ -358,7 +395,6 @@ conv3x3_x3(const __grid_constant__ Conv2Params p) {
                 const float2 back = __half22float2(ohi.v[e]);
                 olo.v[e] = __floats2half2_rn((v.x - back.x) * kLoScale, (v.y - back.y) * kLoScale);
               }
-              if (p.dbg & 256) olo = H8{};                 // debugging aid: drop the residual plane of the interpolated tile
               store_px(dstA, r, *reinterpret_cast<uint4*>(&ohi), *reinterpret_cast<uint4*>(&olo));
             }
           }

@@ -1435,7 +1435,7 @@ int launch_conv2(const Conv2Plan& c, cudaStream_t st) {
     set_error("conv2: no 8x8 variant for BN %d KC %d (resident %d)", c.BN, c.kc, (int)c.resident);
     return TFPNP_ERR_INVALID;
   }
-  const int xf = c.p.up_fused ? env_int("TFPNP_XFORM2", 0) : 0;
+  const int xf = c.p.up_fused ? env_int("TFPNP_XFORM2", 2) : 0;   // 2 (default since round 2: +1.2 %, packed-fp16 lerps); 1: row-independent fp32; 0: row walk
   if (xf == 1) {   // experiment: row-independent transform warps (bit-identical results)
     switch (key) {
       case 32321: return launch_conv2_t<32, 32, true, true, false, 1>(c, st);

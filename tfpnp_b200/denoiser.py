@@ -49,7 +49,7 @@ def flatten_state_dict(sd) -> torch.Tensor:
 
 
 class UNetDenoiser2D(torch.nn.Module):
-    def __init__(self, ckpt_path=None, state_dict=None, precision="fp16"):
+    def __init__(self, ckpt_path=None, state_dict=None, precision="fp16x3"):
         super().__init__()
         if state_dict is None:
             if ckpt_path is None:
@@ -195,7 +195,7 @@ class IRCNNDenoiser2D(UNetDenoiser2D):
     (tfpnp/pnp/denoiser/base.py:23-32): ``clamp(x - net(cat[x, sigma map]), 0, 1)``.  Same call signature,
     usable with every solver of this package."""
 
-    def __init__(self, ckpt_path=None, state_dict=None, precision="fp16"):
+    def __init__(self, ckpt_path=None, state_dict=None, precision="fp16x3"):
         torch.nn.Module.__init__(self)
         if state_dict is None:
             if ckpt_path is None:
@@ -231,7 +231,7 @@ class IRCNNDenoiser2D(UNetDenoiser2D):
         return h
 
 
-def create_denoiser(opt, ckpt_path=None, state_dict=None, precision="fp16"):
+def create_denoiser(opt, ckpt_path=None, state_dict=None, precision="fp16x3"):
     """Mirror of tfpnp.pnp.create_denoiser (tfpnp/pnp/__init__.py:5-13), plus 'ircnn'."""
     print(f'[i] use denoiser: {opt.denoiser}')
     if opt.denoiser == 'unet':
