@@ -491,7 +491,9 @@ conv3x3_pair_x3(const __grid_constant__ ConvPairParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.num_a_stages;
   const int nchunks = p.nchunk0 + p.nchunk1;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * kPX3Stage);
+  const uint32_t aplane = (uint32_t)p.a_plane;                  // kPX3APlane, or 13 KB for the 8x8 level (200 rows)
+  const uint32_t stage = 2 * aplane + 9 * 2 * kPX3Slab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage);
   uint64_t* full = bars;                        // [8]   (the leader's are the ones waited on)
   uint64_t* empty = bars + 8;                   // [8]
   uint64_t* tmem_full = bars + 48;              // [2]
@@ -538,12 +540,17 @@ conv3x3_pair_x3(const __grid_constant__ ConvPairParams p) {
           const int s = ia % S;
           mbar_wait(&empty[s], ((ia / S) & 1) ^ 1);
           const uint32_t fb = mapa_u32(&full[s], 0);            // the LEADER's barrier
-          uint8_t* st = smem + s * kPX3Stage;
-          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (2u * kPairARows * ROW + 9u * 2u * kPX3Slab));
+          uint8_t* st = smem + s * stage;
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (2u * (uint32_t)p.a_rows * ROW + 9u * 2u * kPX3Slab));
           else mbar_arrive_cluster(fb);
-          tma_load_4d_2sm(st, &p.a_map[src][0], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
-          tma_load_4d_2sm(st + kPX3APlane, &p.a_map[src][1], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
-          uint8_t* wst = st + 2 * kPX3APlane;
+          if (p.small) {                                       // four 8x8 images per pair, two per CTA ({C, W, B, H} view)
+            tma_load_4d_2sm(st, &p.a_map[src][0], fb, cc, -1, 4 * m + 2 * (int)rank, -1);
+            tma_load_4d_2sm(st + aplane, &p.a_map[src][1], fb, cc, -1, 4 * m + 2 * (int)rank, -1);
+          } else {
+            tma_load_4d_2sm(st, &p.a_map[src][0], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
+            tma_load_4d_2sm(st + aplane, &p.a_map[src][1], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
+          }
+          uint8_t* wst = st + 2 * aplane;
 #pragma unroll
           for (int tt = 0; tt < 9; ++tt) {
             tma_load_3d_2sm(wst + (2 * tt) * kPX3Slab, &p.w_map[0], fb, c * KC, nt * BN + 64 * (int)rank, tt);
@@ -570,12 +577,13 @@ conv3x3_pair_x3(const __grid_constant__ ConvPairParams p) {
           const int sa = ia % S;
           mbar_wait(&full[sa], (ia / S) & 1);
           tc_fence_after();
-          const uint32_t a_lo = s_lo + sa * (kPX3Stage >> 4);
-          const uint32_t b_stage = a_lo + (2 * kPX3APlane >> 4);
+          const uint32_t a_lo = s_lo + sa * (stage >> 4);
+          const uint32_t b_stage = a_lo + (2 * aplane >> 4);
+          const uint32_t tapr = (uint32_t)p.tap_rows;
           if (elect_one()) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_tap = a_lo + (((tap / 3) * 10 + tap % 3) * ROW >> 4);
+              const uint32_t a_tap = a_lo + (((tap / 3) * tapr + tap % 3) * ROW >> 4);
               const uint32_t bh = b_stage + (2 * tap) * (kPX3Slab >> 4), bl = bh + (kPX3Slab >> 4);
 #pragma unroll
               for (int kk = 0; kk < KSTEPS; ++kk) {
@@ -583,7 +591,7 @@ conv3x3_pair_x3(const __grid_constant__ ConvPairParams p) {
                 const uint64_t bhd = pack_desc(bh + kk * 2, b_hi);
                 umma2_f16(d0, ad, bhd, idesc, accumulate);                                                        // a_hi w_hi
                 umma2_f16(d0 + BN, ad, pack_desc(bl + kk * 2, b_hi), idesc, accumulate);                          // a_hi w_lo
-                umma2_f16(d0 + BN, pack_desc(a_tap + (kPX3APlane >> 4) + kk * 2, a_hi), bhd, idesc, 1);           // a_lo w_hi
+                umma2_f16(d0 + BN, pack_desc(a_tap + (aplane >> 4) + kk * 2, a_hi), bhd, idesc, 1);               // a_lo w_hi
                 accumulate = 1;
               }
             }
@@ -605,8 +613,11 @@ conv3x3_pair_x3(const __grid_constant__ ConvPairParams p) {
     uint32_t it = 0;
     for (int t = item0; t < total_items; t += item_step, ++it) {
       const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
-      const int w = (m % p.tiles_w) * 16 + 8 * (int)rank + tw, h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
-      const int b = m / (p.tiles_w * p.tiles_h);
+      // small: M row = (y*2 + img)*8 + x of this CTA's images 4m + 2 rank, + 1
+      const int w = p.small ? tw : (m % p.tiles_w) * 16 + 8 * (int)rank + tw;
+      const int h = p.small ? (th >> 1) : ((m / p.tiles_w) % p.tiles_h) * 16 + th;
+      const int b = p.small ? 4 * m + 2 * (int)rank + (th & 1) : m / (p.tiles_w * p.tiles_h);
+      const bool b_ok = b < p.B;
       const int n0 = nt * BN;
       const size_t pix = ((size_t)b * p.H + h) * p.W + w;
       const uint32_t buf = it & 1;
@@ -624,7 +635,7 @@ conv3x3_pair_x3(const __grid_constant__ ConvPairParams p) {
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])));
         float v[32];
         epilogue_act32(r, sbias + n0 + c0, v);
-        epilogue_store_nhwc32(v, p.out_hi, p.out_lo, pix * p.Cout + n0 + c0);
+        if (b_ok) epilogue_store_nhwc32(v, p.out_hi, p.out_lo, pix * p.Cout + n0 + c0);
         if (p.pool_hi) {                      // 2x2 max over (tw^1, th^1) = lanes ^1 and ^8
 #pragma unroll
           for (int j = 0; j < 32; ++j) {

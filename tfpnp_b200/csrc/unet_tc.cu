@@ -868,6 +868,13 @@ struct ConvPairParams {
   __half* pool_hi;          // fused nn.MaxPool2d(2) output or nullptr
   __half* pool_lo;
   int single_buf;           // experiment (TFPNP_PAIR_SINGLE=1): one accumulator buffer, 256 TMEM columns in the X3 instantiation
+  // 8x8 images (the 512-channel level of a 128x128 input): one M = 256 tile = FOUR images, two per CTA.  The A box is
+  // {KC, 10 (x), 2 (image), 10 (y)} over the tensor viewed as {C, W, B, H} (as in conv3x3_tc2<..., SMALL>): smem row = y'*20 + img*10 + x',
+  // tap (ky,kx) starts at row ky*20 + kx, the sixteen 8-pixel row groups (y, img) are 10 rows apart.
+  int small;
+  int a_rows;               // rows one A box carries: 180 (half-halo) or 200 (small)
+  int a_plane;              // bytes reserved per A plane (a_rows x row bytes, padded to 1 KB)
+  int tap_rows;             // smem rows between kernel rows ky: 10 or 20
 };
 
 constexpr int kPairThreads = 64 + 32 * 8;
@@ -891,7 +898,7 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
   const int S = p.num_a_stages;                 // fp16: ring of chunk stages [A half-halo | 9 half slabs]; X3: the A ring
   const int SB = p.num_b_stages;                // X3: the weight ring
   const int nchunks = p.nchunk0 + p.nchunk1;
-  constexpr int kStage = X3 ? kPairX3AStage : kPairABytes + kPairBStage;
+  const int kStage = X3 ? kPairX3AStage : p.a_plane + kPairBStage;
   uint8_t* sWr = smem + S * kStage;             // X3 weight ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * kStage + (X3 ? SB * kPairX3BStage : 0));
   uint64_t* full = bars;                        // [8]   (the leader's are the ones waited on)
@@ -952,12 +959,13 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
           const uint32_t fb = mapa_u32(&full[s], 0);            // the LEADER's barrier
           uint8_t* st = smem + s * kStage;
           if constexpr (!X3) {
-            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (kPairARows * ROW + kPairBStage));
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * ((uint32_t)p.a_rows * ROW + kPairBStage));
             else mbar_arrive_cluster(fb);
-            tma_load_4d_2sm(st, &p.a_map[src][0], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
+            if (p.small) tma_load_4d_2sm(st, &p.a_map[src][0], fb, cc, -1, 4 * m + 2 * (int)rank, -1);
+            else tma_load_4d_2sm(st, &p.a_map[src][0], fb, cc, w0 - 1 + 8 * (int)rank, h0 - 1, b);
 #pragma unroll
             for (int tt = 0; tt < 9; ++tt)
-              tma_load_3d_2sm(st + kPairABytes + tt * kPairSlab, &p.w_map[0], fb, c * KC, nt * BN + 64 * (int)rank, tt);
+              tma_load_3d_2sm(st + p.a_plane + tt * kPairSlab, &p.w_map[0], fb, c * KC, nt * BN + 64 * (int)rank, tt);
           } else {
             if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * 2u * (kPairARows * ROW));
             else mbar_arrive_cluster(fb);
@@ -1004,11 +1012,12 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
           const uint32_t a_lo = s_lo + sa * (kStage >> 4);
           if constexpr (!X3) {
             // one barrier wait and one release per chunk
-            const uint32_t b_stage = a_lo + (kPairABytes >> 4);
+            const uint32_t b_stage = a_lo + ((uint32_t)p.a_plane >> 4);
+            const uint32_t tapr = (uint32_t)p.tap_rows;
             if (elect_one()) {
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
-                const uint32_t a_tap = a_lo + (((tap / 3) * 10 + tap % 3) * ROW >> 4);
+                const uint32_t a_tap = a_lo + (((tap / 3) * tapr + tap % 3) * ROW >> 4);
                 const uint32_t b_lo = b_stage + tap * (kPairSlab >> 4);
 #pragma unroll
                 for (int kk = 0; kk < KSTEPS; ++kk) {
@@ -1066,8 +1075,11 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
     uint32_t it = 0;
     for (int t = item0; t < total_items; t += item_step, ++it) {
       const int nt = t % p.num_n_tiles, m = t / p.num_n_tiles;
-      const int w = (m % p.tiles_w) * 16 + 8 * (int)rank + tw, h = ((m / p.tiles_w) % p.tiles_h) * 16 + th;
-      const int b = m / (p.tiles_w * p.tiles_h);
+      // small: M row = (y*2 + img)*8 + x of this CTA's images 4m + 2 rank, + 1
+      const int w = p.small ? tw : (m % p.tiles_w) * 16 + 8 * (int)rank + tw;
+      const int h = p.small ? (th >> 1) : ((m / p.tiles_w) % p.tiles_h) * 16 + th;
+      const int b = p.small ? 4 * m + 2 * (int)rank + (th & 1) : m / (p.tiles_w * p.tiles_h);
+      const bool b_ok = b < p.B;
       const int n0 = nt * BN;
       const size_t pix = ((size_t)b * p.H + h) * p.W + w;
       const uint32_t buf = single ? 0 : (it & 1);
@@ -1093,7 +1105,7 @@ conv3x3_pair(const __grid_constant__ ConvPairParams p) {
         }
         float v[32];
         epilogue_act32(r, sbias + n0 + c0, v);
-        epilogue_store_nhwc32(v, p.out_hi, X3 ? p.out_lo : nullptr, pix * p.Cout + n0 + c0);
+        if (b_ok) epilogue_store_nhwc32(v, p.out_hi, X3 ? p.out_lo : nullptr, pix * p.Cout + n0 + c0);
         if (p.pool_hi) {                      // 2x2 max over (tw^1, th^1) = lanes ^1 and ^8
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -1615,9 +1627,10 @@ struct ConvPairPlan {
 // CTA-pair kernel: streamed weights, 64-channel chunks, Cout a multiple of 128, 16x16 tiling (TFPNP_CONV_PAIR=0
 // falls back to the single-CTA kernel).  Measured in fp16: 14.6 / 16.6 / 39.7 us against 20.4 / 20.4 / 47.5 us (128->128 @32x32,
 // 256->256 @16x16, 768->256 @16x16, 48 images); 60.3k -> 63.8k image-iters/s end to end.  The split-fp16 mode always uses it.
-bool conv_pair_eligible(int C0, int C1, int Cout, int H, int W, bool x3, bool fuse_up) {
-  return (x3 || env_int("TFPNP_CONV_PAIR", 1) != 0) && !fuse_up && C0 % 64 == 0 && C1 % 64 == 0 && Cout % 128 == 0 &&
-         H % 16 == 0 && W % 16 == 0;
+bool conv_pair_eligible(int C0, int C1, int Cout, int H, int W, bool x3, bool fuse_up, int B = 4) {
+  if (!(x3 || env_int("TFPNP_CONV_PAIR", 1) != 0) || fuse_up || C0 % 64 != 0 || C1 % 64 != 0 || Cout % 128 != 0) return false;
+  if (H == 8 && W == 8) return B >= 2 && env_int("TFPNP_PAIR_SMALL", 1) != 0 && (!x3 || env_int("TFPNP_PAIR_X3_KC64", 0) == 0);
+  return H % 16 == 0 && W % 16 == 0;
 }
 
 // x*_lo / w_lo / out_lo: the fp16 residual planes (all non-null selects the split-fp16 instantiation)
@@ -1631,8 +1644,12 @@ int plan_conv_pair(ConvPairPlan& c, const __half* x0, const __half* x0_lo, int C
   const int kc = c.x3_kc32 ? 32 : 64;
   p.single_buf = env_int("TFPNP_PAIR_SINGLE", 0);
   p.nchunk0 = C0 / kc; p.nchunk1 = C1 / kc;
-  p.tiles_w = W / 16; p.tiles_h = H / 16;
-  p.num_m_tiles = p.tiles_w * p.tiles_h * B;
+  p.small = (H == 8 && W == 8) ? 1 : 0;
+  p.a_rows = p.small ? 200 : kPairARows;
+  p.a_plane = (p.a_rows * kc * 2 + 1023) & ~1023;
+  p.tap_rows = p.small ? 20 : 10;
+  p.tiles_w = p.small ? 1 : W / 16; p.tiles_h = p.small ? 1 : H / 16;
+  p.num_m_tiles = p.small ? (B + 3) / 4 : p.tiles_w * p.tiles_h * B;
   p.num_n_tiles = Cout / 128;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
   p.bias = bias; p.out_hi = out; p.out_lo = c.x3 ? out_lo : nullptr;
@@ -1640,11 +1657,11 @@ int plan_conv_pair(ConvPairPlan& c, const __half* x0, const __half* x0_lo, int C
   if (!c.x3) {
     p.num_a_stages = 2;                            // chunk stages: [A half-halo 23 KB | nine half slabs 72 KB]
     p.num_b_stages = 0;
-    c.smem_bytes = p.num_a_stages * (kPairABytes + kPairBStage) + misc;
+    c.smem_bytes = p.num_a_stages * (p.a_plane + kPairBStage) + misc;
   } else if (c.x3_kc32) {
     p.num_a_stages = 2;                            // chunk stages: [A_hi | A_lo half-halos 24 KB | nine slab pairs 72 KB]
     p.num_b_stages = 0;
-    c.smem_bytes = p.num_a_stages * kPX3Stage + misc;
+    c.smem_bytes = p.num_a_stages * (2 * p.a_plane + 9 * 2 * kPX3Slab) + misc;
   } else {
     p.num_a_stages = 2;                            // [hi half-halo | lo half-halo] 46 KB
     p.num_b_stages = 2;                            // one kernel row of [W_hi | W_lo] half slabs, 48 KB
@@ -1663,6 +1680,12 @@ int plan_conv_pair(ConvPairPlan& c, const __half* x0, const __half* x0_lo, int C
     cuuint64_t dims[4] = {(cuuint64_t)cs[s], (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)cs[s] * 2, (cuuint64_t)W * cs[s] * 2, (cuuint64_t)H * W * cs[s] * 2};
     cuuint32_t box[4] = {(cuuint32_t)kc, 10, 18, 1};
+    if (p.small) {          // {C, W, B, H} view, box {kc, 10, 2, 10}
+      TFPNP_TRY(encode_small_map(&p.a_map[s][0], srcs[s][0], cs[s], B, H, W, kc));
+      if (c.x3) TFPNP_TRY(encode_small_map(&p.a_map[s][1], srcs[s][1], cs[s], B, H, W, kc));
+      else p.a_map[s][1] = p.a_map[s][0];
+      continue;
+    }
     TFPNP_TRY(encode_map(&p.a_map[s][0], const_cast<__half*>(srcs[s][0]), 4, dims, strides, box, 2 * kc));
     if (c.x3) TFPNP_TRY(encode_map(&p.a_map[s][1], const_cast<__half*>(srcs[s][1]), 4, dims, strides, box, 2 * kc));
     else p.a_map[s][1] = p.a_map[s][0];
@@ -2003,7 +2026,7 @@ struct UNetTc : Denoiser {
       if (fused_pool[l]) { c.p.pool_hi = S2.hi; c.p.pool_lo = x3 ? S2.lo : nullptr; }
       return 0;
     }
-    if (conv_pair_eligible(s0.C, s1 ? s1->C : 0, unet_conv_specs()[l].cout, dst.H, dst.W, x3, low != nullptr)) {
+    if (conv_pair_eligible(s0.C, s1 ? s1->C : 0, unet_conv_specs()[l].cout, dst.H, dst.W, x3, low != nullptr, B)) {
       ConvPairPlan& c = convsp[l];
       TFPNP_TRY(plan_conv_pair(c, s0.hi, x3 ? s0.lo : nullptr, s0.C, s1 ? s1->hi : nullptr, (s1 && x3) ? s1->lo : nullptr,
                                s1 ? s1->C : 0, w_hi.as<__half>() + w_off[l], x3 ? w_lo.as<__half>() + w_off[l] : nullptr,
@@ -2011,7 +2034,8 @@ struct UNetTc : Denoiser {
                                unet_conv_specs()[l].cout));
       convs2[l].grid = 0;
       fused_up[l] = false;
-      fused_pool[l] = env_int("TFPNP_CONV_FUSE", 1) != 0 && (l == 2 || l == 5 || l == 8 || l == 11);
+      // (8x8 tiles interleave two images per row group: the epilogue's lane-shuffle pooling does not apply there)
+      fused_pool[l] = env_int("TFPNP_CONV_FUSE", 1) != 0 && !c.p.small && (l == 2 || l == 5 || l == 8 || l == 11);
       if (fused_pool[l]) { c.p.pool_hi = S2.hi; c.p.pool_lo = x3 ? S2.lo : nullptr; }
       return 0;
     }
@@ -2221,7 +2245,7 @@ int conv3x3_nhwc_standalone(const __half* x0, int C0, const __half* x1, int C1, 
     TFPNP_CUDA_OK(cudaGetLastError());
     return 0;
   }
-  if (conv_pair_eligible(C0, C1, Cout, H, W, false, false)) {
+  if (conv_pair_eligible(C0, C1, Cout, H, W, false, false, B)) {
     ConvPairPlan cp;
     TFPNP_TRY(plan_conv_pair(cp, x0, nullptr, C0, x1, nullptr, C1, w_taps, nullptr, bias, out, nullptr, B, H, W, Cout));
     TFPNP_TRY(launch_conv_pair(cp, st));

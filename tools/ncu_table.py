@@ -28,21 +28,27 @@ if a.period:
     data = data[:a.period]
 
 
+def cols(name):
+    exact = [i for i, h in enumerate(hdr) if h == name]
+    return exact + [i for i, h in enumerate(hdr) if h.endswith("." + name)]
+
+
 def col(name):
-    for i, h in enumerate(hdr):
-        if h == name or h.endswith("." + name):
-            return i
-    return None
+    c = cols(name)
+    return c[0] if c else None
 
 
 def val(r, name, scale_units=None):
-    i = col(name)
-    if i is None or i >= len(r) or r[i] == "":
-        return float("nan")
-    v = float(r[i].replace(",", ""))
-    if scale_units:
-        v *= scale_units.get(units[i], 1)
-    return v
+    for i in cols(name):          # (the "TriageCompute" copies of a metric are empty unless that section was collected)
+        if i < len(r) and r[i] not in ("", "no data", "n/a"):
+            try:
+                v = float(r[i].replace(",", ""))
+            except ValueError:
+                continue
+            if scale_units:
+                v *= scale_units.get(units[i], 1)
+            return v
+    return float("nan")
 
 
 BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -64,6 +70,8 @@ for r in data:
     lts = val(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed")
     regs = val(r, "launch__registers_per_thread")
     smem = val(r, "launch__shared_mem_per_block_dynamic", BYTES) / 1e3
+    if smem < 1:                       # some ncu versions report the column in Kbyte without a unit row entry
+        smem = val(r, "launch__shared_mem_per_block_dynamic")
     grid = r[col("Grid Size")].replace(" ", "")
     tot += t
     if upd_re.search(name):
