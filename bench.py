@@ -283,6 +283,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     pk = peaks()
+    # the PSNR all-gather: torch.distributed by default; TFPNP_NATIVE_COMM=1 -> the NCCL communicator behind the C ABI
+    native_comm = T.NativeComm.from_torch_distributed(dev) if (world > 1 and os.environ.get("TFPNP_NATIVE_COMM") == "1") else None
+    gather_psnr = (lambda p_, n_: native_comm.all_gather_psnr(p_)) if native_comm is not None else T.all_gather_psnr
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     copy_stream = torch.cuda.Stream(dev)
     tasks = [t for t in args.tasks.split(",") if t in TASKS]
@@ -331,7 +334,7 @@ def main():
 
         def solve(t):
             out = solver((t["state"], tuple(t[k] for k in aux)), tuple(t[k] for k in par))
-            return out, T.all_gather_psnr(T.torch_psnr(solver.get_output(out), t["gt"]), B_total)
+            return out, gather_psnr(T.torch_psnr(solver.get_output(out), t["gt"]), B_total)
 
         def step_resident():
             with torch.no_grad():
@@ -501,6 +504,7 @@ def main():
                    "global_batch": cfg["B"] * world, "iters_per_step": ITERS,
                    "l2": "256 MiB flush write between timed steps", "weights": "seeded default-init UNet(2,1)",
                    "inputs": "synthesised on the GPU by tfpnp_b200.*_measure (SURVEY 8d shapes and ranges)",
+                   "psnr_all_gather": "tfpnp_comm_allgather_psnr (NCCL behind the C ABI)" if native_comm is not None else "torch.distributed",
                    "lib_sha16": lib_sha16()},
         "e2e": hd["e2e"], "gpu_launches": hd["gpu_launches"], "clocks": clocks,
         "roofline": hd["roofline"], "roofline_update": hd["roofline_update"],

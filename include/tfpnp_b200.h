@@ -260,6 +260,19 @@ typedef struct { const void* src; int64_t img_stride; int64_t offset; int32_t pi
 int tfpnp_env_policy_ob(const tfpnp_ob_channel* ch, int n_ch, const int64_t* idx, int n_rows,
                         int64_t HW, float* dst, void* stream);
 
+/* ---- multi-GPU: the one exchange of the data path ------------------------------
+ * env_batch shards over ranks with no data-path collective; after the last iteration the per-image PSNR vectors
+ * (tfpnp/env/base.py:237-242) are all-gathered.  Replaces DataParallelWithCallback's gather
+ * (tfpnp/policy/sync_batchnorm/replicate.py:50-75).  NCCL is resolved at run time (dlopen "libnccl.so.2"); the Python host
+ * can use torch.distributed instead (tfpnp_b200/dist.py does by default).
+ *   tfpnp_comm_unique_id      rank 0 creates the 128-byte ncclUniqueId; the host broadcasts it by any means
+ *   tfpnp_comm_init           every rank, with its device current: communicator of `world` ranks
+ *   tfpnp_comm_allgather_psnr out[world * n_local] = concat over ranks of local[n_local] (equal shards), on `stream` */
+int tfpnp_comm_unique_id(void* id_out, size_t id_bytes);
+int tfpnp_comm_init(const void* id, size_t id_bytes, int rank, int world, void** comm_out);
+int tfpnp_comm_destroy(void* comm);
+int tfpnp_comm_allgather_psnr(void* comm, const float* local, int n_local, float* out, void* stream);
+
 /* ---- introspection used by tests / bench ---------------------------------- */
 /* measured device time (ms) of the denoiser part and the data-fidelity part of the last forward.
  * tfpnp_solver_set_profiling(handle, mode): 0 off; 1 = eager launches with CUDA events between the segments (no graph:

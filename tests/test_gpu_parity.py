@@ -373,6 +373,16 @@ def test_psnr_vs_oracle(dev):
     assert torch.allclose(p.cpu(), O.psnr(out, gt), rtol=1e-5, atol=1e-4)
 
 
+def test_native_comm_single_rank(dev):
+    """tfpnp_comm_* (NCCL behind the C ABI): a one-rank communicator gathers the PSNR vector onto itself."""
+    import tfpnp_b200 as T
+    comm = T.NativeComm(T.NativeComm.create_unique_id(), 0, 1, dev)
+    p = torch.arange(5, dtype=torch.float32, device=dev).reshape(5, 1) + 0.25
+    out = comm.all_gather_psnr(p)
+    torch.cuda.synchronize()
+    assert torch.equal(out, p)
+
+
 def test_native_library_is_loaded(dev):
     import tfpnp_b200 as T
     maps = open("/proc/self/maps").read()

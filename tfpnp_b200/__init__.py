@@ -14,5 +14,5 @@ from .solver import (PnPSolver, ADMMSolver, IADMMSolver, ADMMSolver_CSMRI, IADMM
 from .ops import (radon_forward, radon_backward, torch_psnr, conv3x3_lrelu_nhwc, fft2, ifft2, complex_mul,  # noqa: F401
                   cdp_forward, cdp_backward)
 from .measure import csmri_measure, pr_measure, spi_measure, ct_measure, radial_mask  # noqa: F401
-from .dist import shard_batch, shard_bounds, all_gather_psnr, all_gather_batch  # noqa: F401
+from .dist import shard_batch, shard_bounds, all_gather_psnr, all_gather_batch, NativeComm  # noqa: F401
 from .env import Batch, Env, DifferentiableEnv, PnPEnv, CSMRIEnv, PREnv, CTEnv, SPIEnv  # noqa: F401

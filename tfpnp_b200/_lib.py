@@ -88,6 +88,10 @@ SIGNATURES = {
                                           C.c_int, C.c_int, C.c_void_p]),
     "tfpnp_env_policy_ob": (C.c_int, [C.POINTER(ObChannel), C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                       C.c_void_p]),
+    "tfpnp_comm_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "tfpnp_comm_init": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "tfpnp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "tfpnp_comm_allgather_psnr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "tfpnp_solver_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "tfpnp_solver_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }

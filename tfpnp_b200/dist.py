@@ -52,3 +52,59 @@ def all_gather_psnr(local: torch.Tensor, n_total: int) -> torch.Tensor:
     """Gather the [B_local,1] PSNR vectors of all ranks into [n_total,1] (rank order = batch order): the one exchange of the
     data path."""
     return all_gather_batch(local, n_total)
+
+
+class NativeComm:
+    """The NCCL communicator behind the C ABI (``tfpnp_comm_*``, include/tfpnp_b200.h): the PSNR all-gather for
+    hosts that do not want a torch.distributed process group on the data path.  The 128-byte ncclUniqueId is created on rank 0
+    and handed to the other ranks by the caller (``from_torch_distributed`` uses one broadcast of the existing group for that
+    bootstrap; any other channel -- a file, MPI, an environment variable -- works as well)."""
+
+    ID_BYTES = 128
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: torch.device):
+        import ctypes as C
+        from . import _lib
+        if len(unique_id) != self.ID_BYTES:
+            raise ValueError(f"ncclUniqueId is {self.ID_BYTES} bytes, got {len(unique_id)}")
+        self.rank, self.world, self.device = rank, world, device
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, self.ID_BYTES)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().tfpnp_comm_init(buf, self.ID_BYTES, rank, world, C.byref(self._h)), "tfpnp_comm_init")
+
+    @staticmethod
+    def create_unique_id() -> bytes:
+        import ctypes as C
+        from . import _lib
+        buf = C.create_string_buffer(NativeComm.ID_BYTES)
+        _lib.check(_lib.lib().tfpnp_comm_unique_id(buf, NativeComm.ID_BYTES), "tfpnp_comm_unique_id")
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device: torch.device):
+        rank, world = dist.get_rank(), dist.get_world_size()
+        on_dev = dist.get_backend() == "nccl"
+        t = torch.zeros(cls.ID_BYTES, dtype=torch.uint8, device=device if on_dev else "cpu")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.create_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return cls(bytes(t.cpu().numpy().tobytes()), rank, world, device)
+
+    def all_gather_psnr(self, local: torch.Tensor) -> torch.Tensor:
+        """[B_local,1] fp32 on this rank's device -> [world * B_local, 1] (rank order = batch order; equal shards)."""
+        from . import _lib
+        local = local.contiguous().float()
+        out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=torch.float32, device=local.device)
+        with torch.cuda.device(local.device):
+            _lib.check(_lib.lib().tfpnp_comm_allgather_psnr(self._h, local.data_ptr(), local.numel(), out.data_ptr(),
+                                                            torch.cuda.current_stream().cuda_stream), "tfpnp_comm_allgather_psnr")
+        return out
+
+    def __del__(self):
+        try:
+            from . import _lib
+            if self._h:
+                _lib.lib().tfpnp_comm_destroy(self._h)
+        except Exception:
+            pass
