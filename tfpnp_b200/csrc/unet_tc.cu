@@ -1238,66 +1238,84 @@ maxpool2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo
   store8(out_hi, out_lo, ((b * Ho + y) * Wo + x) * C + c8 * 8, m);
 }
 
-// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet.py:99), NHWC;
-// grid (x*C8 blocks, Ho, B).  Instruction-lean: the kernel was issue-bound at ~300 instructions per
-// 8 channels; here the row set-up is block-uniform, offsets are 32-bit within the image, the four
-// taps are combined with precomputed weights (4 FMA per channel) and the fp16-residual plane is
-// only touched in the X3 instantiation.
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet.py:99), NHWC, for the decoder heads whose
+// up-sampling is not fused into the convolution.  One CTA per (output row, image): the two source rows of that output row
+// (both planes in split-fp16) are staged in shared memory with coalesced 16-byte loads, then every thread interpolates
+// (pixel, 8-channel group) items out of shared memory.  (The first version read its four corners straight from global
+// memory: 4x the output size in L2 traffic -- 34.6 us for the 256-channel 16^2 -> 32^2 tensor of the split-fp16 mode,
+// where this one moves 2x the INPUT.)
 template <bool X3>
 __global__ void __launch_bounds__(256)
 upsample2_nhwc(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, __half* __restrict__ out_hi,
                __half* __restrict__ out_lo, int H, int W, int C) {
+  extern __shared__ uint4 up_smem[];              // [plane][row 0/1][W * C / 8] 16-byte groups
   pdl_launch_dependents();
   pdl_wait();
   const int Ho = 2 * H, Wo = 2 * W, C8 = C >> 3;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Wo * C8) return;
-  const int c8 = idx % C8, x = idx / C8, y = blockIdx.y;
+  const int y = blockIdx.x, bimg = blockIdx.y;
   const float sy = (float)(H - 1) / (float)(Ho - 1), sx = (float)(W - 1) / (float)(Wo - 1);
-  const float fy = sy * y, fx = sx * x;
-  const int y0 = (int)fy, x0 = (int)fx;
-  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
-  const float ly = fy - y0, lx = fx - x0;
-  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const size_t img_in = (size_t)blockIdx.z * H * W * C, img_out = (size_t)blockIdx.z * Ho * Wo * C;
-  const int o00 = (y0 * W + x0) * C + c8 * 8, o01 = (y0 * W + x1) * C + c8 * 8;
-  const int o10 = (y1 * W + x0) * C + c8 * 8, o11 = (y1 * W + x1) * C + c8 * 8;
-  float r[8];
+  const float fy = sy * y;
+  const int y0 = (int)fy;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
+  const float ly = fy - y0;
+  const int row16 = W * C8;                       // 16-byte groups per source row
+  const size_t img_in = (size_t)bimg * H * W * C;
   {
-    const H8 a = *reinterpret_cast<const H8*>(in_hi + img_in + o00), b = *reinterpret_cast<const H8*>(in_hi + img_in + o01);
-    const H8 c = *reinterpret_cast<const H8*>(in_hi + img_in + o10), d = *reinterpret_cast<const H8*>(in_hi + img_in + o11);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 fa = __half22float2(a.v[i]), fb = __half22float2(b.v[i]);
-      const float2 fc = __half22float2(c.v[i]), fd = __half22float2(d.v[i]);
-      r[2 * i] = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
-      r[2 * i + 1] = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
+    const uint4* s0 = reinterpret_cast<const uint4*>(in_hi + img_in + (size_t)y0 * W * C);
+    const uint4* s1 = reinterpret_cast<const uint4*>(in_hi + img_in + (size_t)y1 * W * C);
+    for (int i = threadIdx.x; i < row16; i += blockDim.x) { up_smem[i] = s0[i]; up_smem[row16 + i] = s1[i]; }
+    if (X3) {
+      const uint4* l0 = reinterpret_cast<const uint4*>(in_lo + img_in + (size_t)y0 * W * C);
+      const uint4* l1 = reinterpret_cast<const uint4*>(in_lo + img_in + (size_t)y1 * W * C);
+      for (int i = threadIdx.x; i < row16; i += blockDim.x) { up_smem[2 * row16 + i] = l0[i]; up_smem[3 * row16 + i] = l1[i]; }
     }
   }
-  if (X3) {
-    const H8 a = *reinterpret_cast<const H8*>(in_lo + img_in + o00), b = *reinterpret_cast<const H8*>(in_lo + img_in + o01);
-    const H8 c = *reinterpret_cast<const H8*>(in_lo + img_in + o10), d = *reinterpret_cast<const H8*>(in_lo + img_in + o11);
+  __syncthreads();
+  const size_t out_row = ((size_t)bimg * Ho + y) * Wo * C;
+  for (int idx = threadIdx.x; idx < Wo * C8; idx += blockDim.x) {
+    const int c8 = idx % C8, x = idx / C8;
+    const float fx = sx * x;
+    const int x0 = (int)fx;
+    const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float lx = fx - x0;
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    float r[8];
+    {
+      const H8 a = *reinterpret_cast<const H8*>(&up_smem[x0 * C8 + c8]), b = *reinterpret_cast<const H8*>(&up_smem[x1 * C8 + c8]);
+      const H8 c = *reinterpret_cast<const H8*>(&up_smem[row16 + x0 * C8 + c8]), d = *reinterpret_cast<const H8*>(&up_smem[row16 + x1 * C8 + c8]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 fa = __half22float2(a.v[i]), fb = __half22float2(b.v[i]);
-      const float2 fc = __half22float2(c.v[i]), fd = __half22float2(d.v[i]);
-      r[2 * i] += (w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x) * kLoInv;
-      r[2 * i + 1] += (w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y) * kLoInv;
+      for (int i = 0; i < 4; ++i) {
+        const float2 fa = __half22float2(a.v[i]), fb = __half22float2(b.v[i]);
+        const float2 fc = __half22float2(c.v[i]), fd = __half22float2(d.v[i]);
+        r[2 * i] = w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
+        r[2 * i + 1] = w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
+      }
     }
-  }
-  const int oo = (y * Wo + x) * C + c8 * 8;
-  H8 hi;
+    if (X3) {
+      const uint4* lo = up_smem + 2 * row16;
+      const H8 a = *reinterpret_cast<const H8*>(&lo[x0 * C8 + c8]), b = *reinterpret_cast<const H8*>(&lo[x1 * C8 + c8]);
+      const H8 c = *reinterpret_cast<const H8*>(&lo[row16 + x0 * C8 + c8]), d = *reinterpret_cast<const H8*>(&lo[row16 + x1 * C8 + c8]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) hi.v[i] = __floats2half2_rn(r[2 * i], r[2 * i + 1]);
-  *reinterpret_cast<H8*>(out_hi + img_out + oo) = hi;
-  if (X3) {
-    H8 lo;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 back = __half22float2(hi.v[i]);
-      lo.v[i] = __floats2half2_rn((r[2 * i] - back.x) * kLoScale, (r[2 * i + 1] - back.y) * kLoScale);
+      for (int i = 0; i < 4; ++i) {
+        const float2 fa = __half22float2(a.v[i]), fb = __half22float2(b.v[i]);
+        const float2 fc = __half22float2(c.v[i]), fd = __half22float2(d.v[i]);
+        r[2 * i] += (w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x) * kLoInv;
+        r[2 * i + 1] += (w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y) * kLoInv;
+      }
     }
-    *reinterpret_cast<H8*>(out_lo + img_out + oo) = lo;
+    H8 hi;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hi.v[i] = __floats2half2_rn(r[2 * i], r[2 * i + 1]);
+    *reinterpret_cast<H8*>(out_hi + out_row + (size_t)idx * 8) = hi;
+    if (X3) {
+      H8 lo;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 back = __half22float2(hi.v[i]);
+        lo.v[i] = __floats2half2_rn((r[2 * i] - back.x) * kLoScale, (r[2 * i + 1] - back.y) * kLoScale);
+      }
+      *reinterpret_cast<H8*>(out_lo + out_row + (size_t)idx * 8) = lo;
+    }
   }
 }
 
@@ -1370,6 +1388,8 @@ int set_conv_attrs() {
   TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<32>::kSmemBytes));
   TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
   TFPNP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
+  TFPNP_CUDA_OK(cudaFuncSetAttribute(upsample2_nhwc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  TFPNP_CUDA_OK(cudaFuncSetAttribute(upsample2_nhwc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   done_mask |= 1ull << (dev & 63);
   return 0;
 }
@@ -2126,7 +2146,9 @@ struct UNetTc : Denoiser {
       // (split-fp16: the two heads that run on conv3x3_x3, 96 -> 32 and 192 -> 64)
       const bool fuse_up = conv2_eligible(h, w) && env_int("TFPNP_CONV_FUSE_UP", 1) != 0 &&
                            (x3 ? (ch[lv] <= env_int("TFPNP_X3_FUSE_MAXCH", 64) && ch[lv] >= env_int("TFPNP_X3_FUSE_MINCH", 32) && env_int("TFPNP_X3_FUSE_UP", 1) != 0)
-                               : h >= env_int("TFPNP_FUSE_UP_MIN", 32));   // measured (fp16): 16x16 outputs are faster un-fused
+                               : h >= env_int("TFPNP_FUSE_UP_MIN", 64));   // measured (fp16, round 2, row-staged up-sampling kernel):
+                                                                              // 384->128 @32^2 un-fused on the pair kernel 14.7 + 40.8 us
+                                                                              // against 68.8 us fused; 16x16 outputs: un-fused since round 1
       TFPNP_TRY(plan_conv(l0, skip[lv], &up, view(S1, ch[lv], h, w), B, fuse_up ? &low : nullptr));
       TFPNP_TRY(plan_conv(l0 + 1, view(S1, ch[lv], h, w), nullptr, view(S0, ch[lv], h, w), B));
       TFPNP_TRY(plan_conv(l0 + 2, view(S0, ch[lv], h, w), nullptr, view(S2, ch[lv], h, w), B));
@@ -2193,9 +2215,12 @@ struct UNetTc : Denoiser {
     for (int k = 0; k < 4; ++k) {
       int lv = 3 - k, h = H >> lv, w = W >> lv;
       const Act& src = k == 0 ? skip[4] : S2;
-      if (!fused_up[15 + 3 * k])
-      TFPNP_CUDA_OK(launch_ex(x3 ? upsample2_nhwc<true> : upsample2_nhwc<false>, dim3(cdiv(w * (ch[lv + 1] / 8), T), h, B),
-                              dim3(T), 0, st, use_pdl(), 1, src.hi, src.lo, S0.hi, S0.lo, h / 2, w / 2, ch[lv + 1]));
+      if (!fused_up[15 + 3 * k]) {
+        const int up_smem = (x3 ? 4 : 2) * (w / 2) * ch[lv + 1] * 2;     // [plane][2 rows][W_in * C] fp16
+        TFPNP_CHECK(up_smem <= 200 * 1024, "upsample: a source row pair of %d bytes does not fit shared memory", up_smem);
+        TFPNP_CUDA_OK(launch_ex(x3 ? upsample2_nhwc<true> : upsample2_nhwc<false>, dim3(h, B), dim3(T), up_smem, st, use_pdl(), 1,
+                                src.hi, src.lo, S0.hi, S0.lo, h / 2, w / 2, ch[lv + 1]));
+      }
       if (!fused_up[15 + 3 * k]) { TFPNP_COUNT_LAUNCH(); char nb[48]; snprintf(nb, sizeof(nb), "upsample %d ch -> @%d", ch[lv + 1], h); mark(st, nb); }
       for (int j = 0; j < 3; ++j) {
         const int l = 15 + 3 * k + j;
