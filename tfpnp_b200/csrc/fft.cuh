@@ -25,22 +25,22 @@ __host__ __device__ inline int bitrev5(int l) {
 // frequency index stored at position c (register c/32, lane c%32) after a forward pass
 __host__ __device__ inline int fft_pos_to_freq(int c, int R) { return (c >> 5) + R * bitrev5(c & 31); }
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+__host__ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
   return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 // multiply by -i (forward) or +i (inverse)
 template <bool INV>
-__device__ __forceinline__ float2 mul_mi(float2 a) {
+__host__ __device__ __forceinline__ float2 mul_mi(float2 a) {
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
 
 template <bool INV>
-__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+__host__ __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
   float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi<INV>(csub(a1, a3));
   a0 = cadd(t0, t2);
   a2 = csub(t0, t2);
@@ -83,6 +83,7 @@ __device__ __forceinline__ void dft_regs(float2 (&v)[R]) {
 // tfpnp_fft2, tfpnp_csmri_variant_forward do).
 constexpr int kFftTwRows = 13;
 static __device__ float2 g_fft_tw[4][kFftTwRows][32];
+static __device__ float2 g_fft_tw256[256];   // W_256^e = exp(-2 pi i e / 256): lane twiddles of the 16x16 transform (fft256.cuh)
 
 static inline cudaError_t fft_tables_init() {
   static unsigned long long done_mask = 0;   // one bit per device (the table is per translation unit and device)
@@ -108,7 +109,13 @@ static inline cudaError_t fft_tables_init() {
       }
     }
   }
+  static float2 h256[256];
+  for (int k = 0; k < 256; ++k) {
+    h256[k].x = (float)cos(pi * (double)k / 128.0);
+    h256[k].y = (float)(-sin(pi * (double)k / 128.0));
+  }
   e = cudaMemcpyToSymbol(g_fft_tw, h, sizeof(h));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_fft_tw256, h256, sizeof(h256));
   if (e == cudaSuccess) done_mask |= 1ull << (dev & 63);
   return e;
 }

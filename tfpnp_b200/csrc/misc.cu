@@ -170,7 +170,7 @@ struct GeomCache {
         e.s.assign(s, s + views);
       }
     }
-    if (reserve_B > 0 && e.g.tbuf.bytes < (size_t)reserve_B * N * N * sizeof(float)) {
+    if (reserve_B > 0 && e.g.tbuf.bytes < e.g.scratch_bytes(reserve_B)) {
       if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("stream sync before growing the scratch failed"); return nullptr; }
       if (e.g.reserve(reserve_B) != 0) return nullptr;
     }

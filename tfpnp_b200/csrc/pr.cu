@@ -11,8 +11,10 @@
 //   cols     : 16 columns per CTA            col FFT -> magnitude projection -> inverse col FFT
 //   rows_inv : warp per (image, row)         M inverse row FFTs -> * conj(mask_j) -> mean
 //                                            -> z, u, d update
+#include <cstdlib>
 #include "tasks.cuh"
 #include "fft.cuh"
+#include "fft256.cuh"
 
 namespace tfpnp {
 namespace {
@@ -133,6 +135,207 @@ pr_rows_inv(const float2* __restrict__ T, const float2* __restrict__ mask, const
   }
 }
 
+
+// ---- N = 256: half-warp transforms, 16 points per lane (fft256.cuh) -----------------------------------------------------------
+// Same three passes; frequencies stay in natural order, so y0p is just |y0| transposed to [B][M][col][row].
+constexpr int kHw = 16;   // half-warps (= transforms) per 256-thread CTA
+
+__global__ void pr256_prep_kernel(const float* __restrict__ y0, float* __restrict__ y0p) {
+  __shared__ float t[32][33];
+  const size_t bm = blockIdx.z;
+  const float* src = y0 + bm * 65536;
+  float* dst = y0p + bm * 65536;
+  const int x0 = blockIdx.x * 32, y0_ = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) t[i][threadIdx.x] = src[(size_t)(y0_ + i) * 256 + x0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) dst[(size_t)(x0 + i) * 256 + y0_ + threadIdx.x] = t[threadIdx.x][i];
+}
+
+__global__ void __launch_bounds__(kHw * 16)
+pr256_rows_fwd(const float2* __restrict__ z, const float2* __restrict__ mask, float2* __restrict__ T, int M) {
+  __shared__ float2 s_tw[256];
+  __shared__ float2 s_x[kHw][kF256Slots];
+  s_tw[threadIdx.x] = g_fft_tw256[threadIdx.x];
+  __syncthreads();
+  const int hw = threadIdx.x >> 4, t = threadIdx.x & 15;
+  const size_t row = (size_t)blockIdx.x * kHw + hw;   // over (b, j, r)
+  const int r = row & 255;
+  const size_t b = row / ((size_t)256 * M);
+  const float2* zr = z + (b * 256 + r) * 256;
+  const float2* mr = mask + row * 256;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = cmul(zr[t + 16 * j], __ldcs(mr + t + 16 * j));   // masks: streamed (evict-first), T stays in L2
+  fft256_run<false, 1>(v, t, s_x[hw], s_tw);
+  float2* tr = T + row * 256;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) tr[t + 16 * j] = v[j];
+}
+
+// C columns of one (image, mask) spectrum per CTA, one half-warp per column.  The tile keeps element n of a column at row
+// n + (n >> 4): exactly the exchange slots of fft256_run with stride = pitch, so the transforms run in place.
+template <int C, int OCC>
+__global__ void __launch_bounds__(C * 16, OCC * 256 / (C * 16))
+pr256_cols(float2* __restrict__ T, const float* __restrict__ y0p) {
+  constexpr int PITCH = C + 1;
+  __shared__ float2 s_tw[256];
+  __shared__ float2 tile[kF256Slots * PITCH];
+  for (int i = threadIdx.x; i < 256; i += C * 16) s_tw[i] = g_fft_tw256[i];
+  const size_t bm = blockIdx.y;
+  const int c0 = blockIdx.x * C;
+  float2* Tb = T + bm * 65536;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {                    // 256 * C elements / (16 C threads): 16 independent loads per thread
+    const int i = threadIdx.x + q * C * 16;
+    const int r = i / C, cc = i % C;
+    tile[(r + (r >> 4)) * PITCH + cc] = Tb[(size_t)r * 256 + c0 + cc];
+  }
+  const int w = threadIdx.x >> 4, t = threadIdx.x & 15;
+  const float* yc = y0p + (bm * 256 + c0 + w) * 256;
+  float yv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) yv[j] = __ldcs(yc + t + 16 * j);   // in flight during the forward transform
+  __syncthreads();
+  float2* base = tile + w;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = base[(17 * j + t) * PITCH];
+  fft256_run<false, PITCH>(v, t, base, s_tw);
+  const float inv_n = 1.0f / 256.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float2 a = make_float2(v[j].x * inv_n, v[j].y * inv_n);     // Az
+    float yh = sqrtf(a.x * a.x + a.y * a.y);                    // complex_abs, transforms.py:118
+    float ratio = (yh - yv[j]) / yh;                            // meas_err / y_hat, solver.py:66-67
+    v[j] = make_float2(ratio * a.x, ratio * a.y);
+  }
+  fft256_run<true, PITCH>(v, t, base, s_tw);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) base[(17 * j + t) * PITCH] = v[j];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int i = threadIdx.x + q * C * 16;
+    const int r = i / C, cc = i % C;
+    Tb[(size_t)r * 256 + c0 + cc] = tile[(r + (r >> 4)) * PITCH + cc];
+  }
+}
+
+template <int OCC>
+__global__ void __launch_bounds__(kHw * 16, OCC)
+pr256_rows_inv(const float2* __restrict__ T, const float2* __restrict__ mask, const float* __restrict__ x,
+               float2* __restrict__ z, float2* __restrict__ u, float* __restrict__ d,
+               const float* __restrict__ mu, const float* __restrict__ tau, int M) {
+  __shared__ float2 s_tw[256];
+  __shared__ float2 s_x[kHw][kF256Slots];
+  s_tw[threadIdx.x] = g_fft_tw256[threadIdx.x];
+  __syncthreads();
+  // four rows per CTA, four half-warps per row: half-warp (ri, ml) inverts the spectra of masks ml, ml + 4, ... of its row,
+  // the four partial sums meet in shared memory.  (One half-warp looping over the masks left the SM waiting on each load.)
+  const int hw = threadIdx.x >> 4, t = threadIdx.x & 15;
+  const int ri = hw >> 2, ml = hw & 3;
+  const size_t row = (size_t)blockIdx.x * 4 + ri;     // over (b, r)
+  const int r = row & 255;
+  const size_t b = row >> 8;
+  const float inv_n = 1.0f / 256.0f;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
+  for (int m = ml; m < M; m += 4) {
+    const size_t mrow = ((b * M + m) * 256 + r) * 256;
+    float2 acc[16], mk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = v[j];       // (M <= 4: zero, folded away by the first trip)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = T[mrow + t + 16 * j];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) mk[j] = __ldcs(mask + mrow + t + 16 * j);
+    fft256_run<true, 1>(v, t, s_x[hw], s_tw);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float2 q = make_float2(v[j].x * inv_n, v[j].y * inv_n);
+      v[j] = cadd(acc[j], cmulc(q, mk[j]));   // * conj(mask), transforms.py:319
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s_x[hw][t + 16 * j] = v[j];
+  __syncthreads();
+  const int fr = threadIdx.x >> 6;                      // finalise: 64 threads per row, coalesced
+  const size_t frow = (size_t)blockIdx.x * 4 + fr;
+  const size_t fb = frow >> 8;
+  const float mu_b = mu[fb], tau_b = tau[fb], inv_m = 1.0f / (float)M;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int px = (threadIdx.x & 63) + 64 * q;
+    float2 g = s_x[fr * 4][px];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) g = cadd(g, s_x[fr * 4 + k][px]);
+    g = make_float2(g.x * inv_m, g.y * inv_m);                         // .mean(1), transforms.py:320
+    const size_t i = frow * 256 + px;
+    float2 zz = z[i], uu = __ldcs(u + i);
+    float xx = __ldcs(x + i);
+    zz.x = zz.x - tau_b * (g.x + mu_b * (zz.x - (xx + uu.x)));        // solver.py:69
+    zz.y = zz.y - tau_b * (g.y + mu_b * (zz.y - uu.y));
+    uu.x = uu.x + xx - zz.x;                                           // solver.py:72
+    uu.y = uu.y - zz.y;
+    z[i] = zz;
+    __stcs(u + i, uu);
+    d[i] = zz.x - uu.x;
+  }
+}
+
+// TFPNP_PR_FFT16=0 keeps the warp-wide transform at N = 256 (A/B switch; read once)
+bool pr_use_fft16() {
+  static const int v = getenv("TFPNP_PR_FFT16") ? atoi(getenv("TFPNP_PR_FFT16")) : 1;
+  return v != 0;
+}
+int pr256_cols_width() {
+  static const int v = getenv("TFPNP_PR_COLS") ? atoi(getenv("TFPNP_PR_COLS")) : 16;
+  return v;
+}
+
+int pr256_occ() {   // tens: CTAs of 256 threads per SM the column kernel is compiled for, units: same for rows_inv
+  static const int v = getenv("TFPNP_PR_OCC") ? atoi(getenv("TFPNP_PR_OCC")) : 22;
+  return v;
+}
+int pr256_chunk() {
+  static const int v = getenv("TFPNP_PR_CHUNK") ? atoi(getenv("TFPNP_PR_CHUNK")) : 0;
+  return v;
+}
+
+// TFPNP_PR_CHUNK=n runs the three passes over chunks of n images so that one chunk's spectra stay in L2 (experiment, off:
+// 36 images in chunks of 9 / 6 / 3 measured 254 / 272 / 495 us per iteration against 208 un-chunked -- the passes are bound by
+// per-launch latency, not by HBM bytes).
+int launch_update256(const float* x, float2* z, float2* u, float* d, float2* T, const float* y0p,
+                     const float2* mask, const float* mu, const float* tau, int B, int M, cudaStream_t st) {
+  const int chunk = pr256_chunk() > 0 ? pr256_chunk() : B;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    const size_t oi = (size_t)b0 * 65536, om = oi * M;
+    pr256_rows_fwd<<<nb * M * 256 / kHw, kHw * 16, 0, st>>>(z + oi, mask + om, T + om, M);
+    TFPNP_COUNT_LAUNCH();
+    const int occ = pr256_occ();
+    const dim3 g8(256 / 8, nb * M), g16(256 / 16, nb * M);
+    if (pr256_cols_width() == 8) {
+      if (occ / 10 == 3) pr256_cols<8, 3><<<g8, 8 * 16, 0, st>>>(T + om, y0p + om);
+      else pr256_cols<8, 2><<<g8, 8 * 16, 0, st>>>(T + om, y0p + om);
+    } else {
+      if (occ / 10 == 3) pr256_cols<16, 3><<<g16, 16 * 16, 0, st>>>(T + om, y0p + om);
+      else pr256_cols<16, 2><<<g16, 16 * 16, 0, st>>>(T + om, y0p + om);
+    }
+    TFPNP_COUNT_LAUNCH();
+    if (occ % 10 == 3)
+      pr256_rows_inv<3><<<nb * 256 / 4, kHw * 16, 0, st>>>(T + om, mask + om, x + oi, z + oi, u + oi, d + oi, mu + b0, tau + b0, M);
+    else
+      pr256_rows_inv<2><<<nb * 256 / 4, kHw * 16, 0, st>>>(T + om, mask + om, x + oi, z + oi, u + oi, d + oi, mu + b0, tau + b0, M);
+    TFPNP_COUNT_LAUNCH();
+  }
+  TFPNP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <int R>
 int launch_update(const float* x, float2* z, float2* u, float* d, float2* T, const float* y0p,
                   const float2* mask, const float* mu, const float* tau, int B, int M, cudaStream_t st) {
@@ -152,7 +355,8 @@ int launch_update(const float* x, float2* z, float2* u, float* d, float2* T, con
 int pr_prep(const float* y0, float* y0p, int B, int M, int N, cudaStream_t st) {
   TFPNP_CUDA_OK(fft_tables_init());   // twiddles: once per device, outside any graph capture
   size_t n = (size_t)B * M * N * N;
-  pr_prep_kernel<<<(unsigned)(n / 256), 256, 0, st>>>(y0, y0p, N, N / 32);
+  if (N == 256 && pr_use_fft16()) pr256_prep_kernel<<<dim3(8, 8, B * M), dim3(32, 8), 0, st>>>(y0, y0p);
+  else pr_prep_kernel<<<(unsigned)(n / 256), 256, 0, st>>>(y0, y0p, N, N / 32);
   TFPNP_COUNT_LAUNCH();
   TFPNP_CUDA_OK(cudaGetLastError());
   return 0;
@@ -164,7 +368,9 @@ int pr_update(const float* x, float2* z, float2* u, float* d, float2* T, const f
     case 32: return launch_update<1>(x, z, u, d, T, y0p, mask, mu, tau, B, M, st);
     case 64: return launch_update<2>(x, z, u, d, T, y0p, mask, mu, tau, B, M, st);
     case 128: return launch_update<4>(x, z, u, d, T, y0p, mask, mu, tau, B, M, st);
-    case 256: return launch_update<8>(x, z, u, d, T, y0p, mask, mu, tau, B, M, st);
+    case 256:
+      if (pr_use_fft16()) return launch_update256(x, z, u, d, T, y0p, mask, mu, tau, B, M, st);
+      return launch_update<8>(x, z, u, d, T, y0p, mask, mu, tau, B, M, st);
   }
   set_error("pr: unsupported size %d", N);
   return TFPNP_ERR_INVALID;

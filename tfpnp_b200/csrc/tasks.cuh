@@ -33,7 +33,9 @@ int pr_update(const float* x, float2* z, float2* u, float* d, float2* T, const f
 struct CtGeom {
   int N = 0, views = 0, det = 0;
   DevBuf cs, sn;  // fp32 cos/sin tables [views]
-  mutable DevBuf tbuf;                                       // transposed image scratch [B,N,N] for the column-driven views
+  bool bins_always_inside = false;                           // set_tables: unit-norm rows and det >= sqrt(2) N (ct.cu)
+  mutable DevBuf tbuf;                                       // zero-padded image + transposed image scratch, 2 x [B,N,N+4]
+  size_t scratch_bytes(int B) const;
   int reserve(int B) const;                                  // size tbuf (never during graph capture)
   int init(int N, int views);                                // tables as torch.linspace would give
   int set_tables(const float* cos_host, const float* sin_host);  // caller-supplied tables [views]
