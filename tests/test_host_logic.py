@@ -207,3 +207,15 @@ def test_gloo_world2_psnr_gather(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_pdl_kernels_read_dependent_data_after_the_wait():
+    """tools/check_pdl_sass.py: no kernel that executes griddepcontrol.wait loads through a const __restrict__ pointer
+    (ld.global.nc, which nvcc may hoist) before it -- the bug csmri_rows_inv had in round 2."""
+    import shutil, subprocess, sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_pdl_sass.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "kernels execute griddepcontrol.wait" in r.stdout

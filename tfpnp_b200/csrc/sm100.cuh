@@ -103,6 +103,17 @@ __device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap
 // wait: block until the preceding grid has fully completed and its memory is visible.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// pdl_wait() for kernels that read the predecessor's output through `const __restrict__` pointers: nvcc treats such
+// memory as immutable for the whole kernel (ld.global.nc) and DID hoist those loads above the wait's "memory" clobber
+// (csmri_rows_inv, round 2: wrong results as soon as the kernel really overlapped its predecessor).  Passing the pointers
+// through an empty asm after the wait makes their values data-dependent on it.  tools/check_pdl_sass.py audits the SASS.
+template <class T>
+__device__ __forceinline__ void pdl_launder(T*& p) { asm volatile("" : "+l"(p) : : "memory"); }
+template <class... P>
+__device__ __forceinline__ void pdl_wait_then(P*&... ptrs) {
+  pdl_wait();
+  (pdl_launder(ptrs), ...);
+}
 
 // ---- clusters -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
