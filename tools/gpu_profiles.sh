@@ -16,20 +16,23 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"
   --log-file gpurun_out/launches_$p.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --tasks csmri --precision $p > gpurun_out/ncu_b_$p.log 2>&1
 python tools/launch_summary.py gpurun_out/launches_$p.csv > gpurun_out/launches_${p}_summary.txt; tail -1 gpurun_out/launches_${p}_summary.txt
 echo "=== ncu --set full: every kernel of one inner iteration, $p"
-# one inner iteration = 29 denoiser + 3 update launches (fp16x3: two un-fused up-samplings) / 28 + 3 (fp16)
-if [ $p = fp16x3 ]; then PERIOD=32; else PERIOD=31; fi
-timeout 900 ncu --set full --clock-control none -k regex:"conv|upsample|csmri_rows|csmri_cols" -s 70 -c $PERIOD \
+# one inner iteration = the launches from one first-layer kernel to the next (denoiser layers + up-samplings + 3 update kernels)
+timeout 900 ncu --set full --clock-control none -k regex:"conv|upsample|csmri_rows|csmri_cols" -s 70 -c 72 \
   -o /tmp/iter_full_$p -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --tasks csmri --precision $p > gpurun_out/ncu_full_$p.log 2>&1
 tail -1 gpurun_out/ncu_full_$p.log
 # (the .ncu-rep files are ~55 MB each: summarised here, only the tables travel back)
-python tools/ncu_table.py /tmp/iter_full_$p.ncu-rep --period $PERIOD --json gpurun_out/traffic_$p.json > gpurun_out/ncu_iter_full_$p.txt
+python tools/ncu_table.py /tmp/iter_full_$p.ncu-rep --period-from conv_first --json gpurun_out/traffic_$p.json > gpurun_out/ncu_iter_full_$p.txt
 tail -1 gpurun_out/ncu_iter_full_$p.txt
 done
 echo "=== ncu --set full: update kernels of the other tasks"
 for t in pr ct spi; do
-timeout 300 ncu --set full --clock-control none -k regex:"pr_|radon|ct_|transpose|spi_" -s 3 -c 6 -o /tmp/upd_$t -f python tools/run_tasks.py $t > gpurun_out/ncu_upd_$t.log 2>&1
+timeout 300 ncu --set full --clock-control none -k regex:"pr_|pr256|radon|ct_|transpose|spi_" -s 3 -c 6 -o /tmp/upd_$t -f python tools/run_tasks.py $t > gpurun_out/ncu_upd_$t.log 2>&1
 tail -1 gpurun_out/ncu_upd_$t.log
 python tools/ncu_table.py /tmp/upd_$t.ncu-rep > gpurun_out/ncu_upd_$t.txt
+python tools/ncu_stalls.py /tmp/upd_$t.ncu-rep >> gpurun_out/ncu_upd_$t.txt
 done
+timeout 300 ncu --set full --clock-control none -k regex:"csmri_rows|csmri_cols" -s 3 -c 3 -o /tmp/upd_csmri -f python tools/run_tasks.py csmri > gpurun_out/ncu_upd_csmri.log 2>&1
+python tools/ncu_table.py /tmp/upd_csmri.ncu-rep > gpurun_out/ncu_upd_csmri.txt
+python tools/ncu_stalls.py /tmp/upd_csmri.ncu-rep >> gpurun_out/ncu_upd_csmri.txt
 sha256sum tfpnp_b200/libtfpnp_b200.so | cut -c1-16 > gpurun_out/lib_sha16.txt
 du -sh gpurun_out

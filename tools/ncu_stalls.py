@@ -2,7 +2,7 @@
 """Issue / stall summary per kernel from an `ncu --set full` report (reads `ncu -i <rep> --page raw --csv`).
 
     python tools/ncu_stalls.py /tmp/upd_pr.ncu-rep > gpurun_out/ncu_stalls_pr.txt
-Columns: duration, issue-active %, achieved warps/SM, executed warp instructions, DRAM %, and the top stall reasons
+Columns: duration, issue-active %, achieved warps/SM, executed warp instructions, L2 %, and the top stall reasons
 (warps stalled per issue slot).  Complements tools/ncu_table.py (bytes and pipes)."""
 import csv, io, subprocess, sys
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -23,4 +23,4 @@ for r in data:
     top = ", ".join(f"{n} {v:.2f}" for v, n in st[:5] if v == v)
     print(f"{name[:40]:40s} {f(r,'gpu__time_duration.sum'):8.1f} us  issue {f(r,'sm__issue_active.avg.pct_of_peak_sustained_elapsed'):5.1f}%  "
           f"warps/SM {f(r,'sm__warps_active.avg.pct_of_peak_sustained_active')*0.64:5.1f}  inst {f(r,'smsp__inst_executed.sum')/1e6:6.1f}M  "
-          f"dram {f(r,'dram__throughput.avg.pct_of_peak_sustained_elapsed'):5.1f}%  lts {f(r,'lts__throughput.avg.pct_of_peak_sustained_elapsed'):5.1f}%  | {top}")
+          f"lts {f(r,'lts__throughput.avg.pct_of_peak_sustained_elapsed'):5.1f}%  | {top}")

@@ -6,6 +6,8 @@
 Reads the report with `ncu -i <rep> --page raw --csv` (works without a GPU).  `--period N` keeps the first N launches
 (= one inner iteration).  The JSON side file carries the DRAM bytes per iteration split into denoiser / update kernels
 (what bench.py prints as `roofline.traffic` -- only when regenerated from the shipped binary in the same round).
+The dram% column is dram__throughput.avg.pct_of_peak_sustained_elapsed when the report has it, else (read + write bytes) /
+duration over the measured copy bandwidth in MEASURED_PEAKS.json.
 Numbers under ncu are cold-cache, serialised replays: compare shares and percentages, not absolutes."""
 import argparse
 import csv
@@ -16,15 +18,22 @@ import subprocess
 ap = argparse.ArgumentParser()
 ap.add_argument("report")
 ap.add_argument("--period", type=int, default=0)
+ap.add_argument("--period-from", default=None, help="regex: keep the launches from the first matching kernel up to (not including) its next occurrence")
 ap.add_argument("--json", default=None)
-ap.add_argument("--update-regex", default="csmri|pr_|ct_|radon|spi_")
+ap.add_argument("--update-regex", default="csmri|pr_|pr256|ct_|radon|pad_transpose|spi_")
 a = ap.parse_args()
 
 raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 hdr, units, data = rows[hi], rows[hi + 1], rows[hi + 2:]
-if a.period:
+if a.period_from:
+    import re as _re
+    kn = hdr.index("Kernel Name")
+    hits = [i for i, r in enumerate(data) if _re.search(a.period_from, r[kn])]
+    if len(hits) >= 2:
+        data = data[hits[0]:hits[1]]
+elif a.period:
     data = data[:a.period]
 
 
@@ -51,6 +60,11 @@ def val(r, name, scale_units=None):
     return float("nan")
 
 
+try:
+    import os as _os
+    HBM_GBS = json.load(open(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    HBM_GBS = 6549.8
 BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 US = {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}
 import re
@@ -66,6 +80,8 @@ for r in data:
         tens = val(r, "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed")
     dram = val(r, "dram__throughput.avg.pct_of_peak_sustained_elapsed")
     dr, dw = val(r, "dram__bytes_read.sum", BYTES), val(r, "dram__bytes_write.sum", BYTES)
+    if dram != dram and t > 0:          # (this ncu's --set full has no dram__throughput pct: bytes / time over the measured copy bandwidth)
+        dram = 100.0 * (dr + dw) / (t * 1e-6) / (HBM_GBS * 1e9)
     l2 = val(r, "lts__t_sectors.sum") * 32
     lts = val(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed")
     regs = val(r, "launch__registers_per_thread")

@@ -18,7 +18,6 @@ d["note"] = "one inner iteration (a window of exactly one period of the launch s
 json.dump(d, open("profiles/${R}_traffic_csmri_$p.json", "w"))
 PY
 done
-for t in pr ct spi; do cat gpurun_out/ncu_upd_$t.txt; done > profiles/${R}_update_kernels.txt
-grep -E "kernel|csmri" gpurun_out/ncu_iter_full_fp16x3.txt >> profiles/${R}_update_kernels.txt
+for t in csmri pr ct spi; do echo "== $t"; cat gpurun_out/ncu_upd_$t.txt; done > profiles/${R}_update_kernels.txt
 cp gpurun_out/gpu.txt profiles/${R}_gpu.txt
 ls -la profiles/${R}_*
