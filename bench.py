@@ -80,17 +80,20 @@ def peaks():
 
 
 def lib_sha16():
-    p = os.path.join(ROOT, "tfpnp_b200", "libtfpnp_b200.so")
+    """Hash of the CUDA sources the library is built from (tools/src_hash.py; nvcc output is not bit-reproducible, so the
+    captures under profiles/ are tied to the source state, not to the .so bytes)."""
     try:
-        return hashlib.sha256(open(p, "rb").read()).hexdigest()[:16]
-    except OSError:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from src_hash import src_sha16
+        return src_sha16(ROOT)
+    except Exception:
         return None
 
 
 def ncu_traffic(task, precision):
     """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one inner iteration's kernels from an `ncu --set full`
-    capture of this command (tools/ncu_table.py --json).  Only trusted when the capture was taken from the binary that is
-    running now (the file records the library's hash); otherwise `traffic` is null."""
+    capture of this command (tools/ncu_table.py --json).  Only trusted when the capture was taken from the source state that is
+    running now (the file records tools/src_hash.py's hash of csrc/); otherwise `traffic` is null."""
     p = os.path.join(ROOT, "profiles", f"r02_traffic_{task}_{precision}.json")
     if not os.path.exists(p):
         return None
@@ -98,7 +101,7 @@ def ncu_traffic(task, precision):
         d = json.load(open(p))
     except Exception:
         return None
-    if d.get("lib_sha16") and d.get("lib_sha16") != lib_sha16():
+    if d.get("src_sha16") != lib_sha16():
         return None
     return d
 
@@ -505,7 +508,7 @@ def main():
                    "l2": "256 MiB flush write between timed steps", "weights": "seeded default-init UNet(2,1)",
                    "inputs": "synthesised on the GPU by tfpnp_b200.*_measure (SURVEY 8d shapes and ranges)",
                    "psnr_all_gather": "tfpnp_comm_allgather_psnr (NCCL behind the C ABI)" if native_comm is not None else "torch.distributed",
-                   "lib_sha16": lib_sha16()},
+                   "src_sha16": lib_sha16()},
         "e2e": hd["e2e"], "gpu_launches": hd["gpu_launches"], "clocks": clocks,
         "roofline": hd["roofline"], "roofline_update": hd["roofline_update"],
         other: hd[other],

@@ -34,5 +34,5 @@ done
 timeout 300 ncu --set full --clock-control none -k regex:"csmri_rows|csmri_cols" -s 3 -c 3 -o /tmp/upd_csmri -f python tools/run_tasks.py csmri > gpurun_out/ncu_upd_csmri.log 2>&1
 python tools/ncu_table.py /tmp/upd_csmri.ncu-rep > gpurun_out/ncu_upd_csmri.txt
 python tools/ncu_stalls.py /tmp/upd_csmri.ncu-rep >> gpurun_out/ncu_upd_csmri.txt
-sha256sum tfpnp_b200/libtfpnp_b200.so | cut -c1-16 > gpurun_out/lib_sha16.txt
+python tools/src_hash.py > gpurun_out/src_sha16.txt
 du -sh gpurun_out

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Turns the captures tools/gpu_profiles.sh left in gpurun_out/ into the tracked summaries under profiles/ (runs here, no GPU).
 R=${1:-r02}
-SHA=$(cat gpurun_out/lib_sha16.txt)
+SHA=$(cat gpurun_out/src_sha16.txt)
 cp gpurun_out/bench.json profiles/${R}_bench.json
 cp gpurun_out/bench_reference.json profiles/${R}_bench_reference.json
 for p in fp16x3 fp16; do
@@ -13,7 +13,7 @@ for p in fp16x3 fp16; do
   python - <<PY
 import json
 d = json.load(open("/tmp/traffic_$p.json"))
-d["lib_sha16"] = "$SHA"
+d["src_sha16"] = "$SHA"
 d["note"] = "one inner iteration (a window of exactly one period of the launch sequence): one denoiser call + one update; cold-cache replays"
 json.dump(d, open("profiles/${R}_traffic_csmri_$p.json", "w"))
 PY
