@@ -55,6 +55,10 @@ typedef enum {
 
 int tfpnp_version(void);
 const char* tfpnp_last_error(void);
+/* The reverse-mode entry points (tfpnp_*_backward) take their scratch from a pool of cached device blocks kept per
+ * (device, stream); this frees the pool (the reference has no counterpart: torch's caching allocator,
+ * torch.cuda.empty_cache()). */
+int tfpnp_release_cached_scratch(void);
 
 /* ---- denoiser: UNetDenoiser2D (tfpnp/pnp/denoiser/base.py:7-32) ------------ */
 

@@ -5,7 +5,7 @@ Host-side mirror of the reference interface for ONE hot path:
 single-photon imaging, with the UNet prox_sigma denoiser, implemented as hand-written
 sm_100a CUDA in ``libtfpnp_b200.so`` (C ABI: include/tfpnp_b200.h).  No fallback paths.
 """
-from ._lib import build, lib, LIB_PATH  # noqa: F401
+from ._lib import build, lib, LIB_PATH, release_cached_scratch  # noqa: F401
 from .denoiser import UNetDenoiser2D, IRCNNDenoiser2D, create_denoiser, random_unet_state_dict  # noqa: F401
 from .solver import (PnPSolver, ADMMSolver, IADMMSolver, ADMMSolver_CSMRI, IADMMSolver_PR,  # noqa: F401
                      HQSSolver_CSMRI, PGSolver_CSMRI, APGSolver_CSMRI, REDADMMSolver_CSMRI, PGSolver_CT,

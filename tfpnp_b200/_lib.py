@@ -38,6 +38,7 @@ class ObChannel(C.Structure):
 SIGNATURES = {
     "tfpnp_version": (C.c_int, []),
     "tfpnp_last_error": (C.c_char_p, []),
+    "tfpnp_release_cached_scratch": (C.c_int, []),
     "tfpnp_denoiser_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "tfpnp_ircnn_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "tfpnp_denoiser_destroy": (C.c_int, [C.c_void_p]),
@@ -131,3 +132,9 @@ def check(status: int, what: str):
     if status != 0:
         msg = lib().tfpnp_last_error()
         raise RuntimeError(f"{what} failed (status {status}): {msg.decode() if msg else '?'}")
+
+
+def release_cached_scratch():
+    """Free the per-(device, stream) pool of device blocks the reverse-mode entry points draw their scratch from
+    (the counterpart of torch.cuda.empty_cache() for this library)."""
+    check(lib().tfpnp_release_cached_scratch(), "tfpnp_release_cached_scratch")

@@ -102,6 +102,39 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Scratch buffer out of a per-(device, stream) pool of cached cudaMalloc blocks (misc.cu).  The reverse-mode entry points
+// took ~15 cudaMalloc / cudaFree per call plus a stream synchronisation before freeing; a released block goes back to the
+// pool of ITS stream and is only ever handed to later work on that stream, so stream order alone makes the reuse safe and
+// no synchronisation is needed.  tfpnp_release_cached_scratch() frees the pools.
+void* scratch_pool_take(size_t bytes, cudaStream_t st, size_t* got);
+void scratch_pool_give(void* p, size_t bytes, cudaStream_t st);
+struct PoolBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaStream_t st = nullptr;
+  PoolBuf() {}
+  PoolBuf(const PoolBuf&) = delete;
+  PoolBuf& operator=(const PoolBuf&) = delete;
+  ~PoolBuf() { release(); }
+  int alloc(size_t n, cudaStream_t stream) {
+    release();
+    st = stream;
+    p = scratch_pool_take(n ? n : 1, st, &bytes);
+    if (!p) {
+      set_error("scratch allocation of %zu bytes failed", n);
+      return TFPNP_ERR_NOMEM;
+    }
+    return 0;
+  }
+  void release() {
+    if (p) scratch_pool_give(p, bytes, st);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 // kNumUnetConv3, kUnetParamCount, ConvSpec, unet_conv_specs(): grad_elem.cuh (plain C++, shared with the CPU emulation)
 
 // abstract denoiser: d -> clamp(UNet(cat[d, sigma]), 0, 1)

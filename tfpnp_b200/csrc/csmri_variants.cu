@@ -465,12 +465,12 @@ int admm_backward(Denoiser* den, const float* states, const float* y0, const uin
   constexpr int N = 32 * R;
   const int HW = N * N;
   const size_t n = (size_t)B * HW;
-  DevBuf gx, gz, gu, A, IN, Q, Rr, T, y0p, zero, gxt, v, gv, maskp, P;
+  PoolBuf gx, gz, gu, A, IN, Q, Rr, T, y0p, zero, gxt, v, gv, maskp, P;
   auto body = [&]() -> int {
-    for (DevBuf* b : {&gx, &gz, &gu, &A, &IN, &Q, &Rr, &T, &y0p, &zero}) TFPNP_TRY(b->alloc(n * sizeof(float2)));
-    for (DevBuf* b : {&gxt, &v, &gv}) TFPNP_TRY(b->alloc(n * sizeof(float)));
-    TFPNP_TRY(maskp.alloc(n));
-    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float)));
+    for (PoolBuf* b : {&gx, &gz, &gu, &A, &IN, &Q, &Rr, &T, &y0p, &zero}) TFPNP_TRY(b->alloc(n * sizeof(float2), st));
+    for (PoolBuf* b : {&gxt, &v, &gv}) TFPNP_TRY(b->alloc(n * sizeof(float), st));
+    TFPNP_TRY(maskp.alloc(n, st));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float), st));
     TFPNP_CUDA_OK(cudaMemsetAsync(zero.p, 0, n * sizeof(float2), st));
     gather_params3<<<cdiv(B * iters, 256), 256, 0, st>>>(sigma_d, mu, nullptr, rs, cs, P.as<float>(), B, iters);
     TFPNP_COUNT_LAUNCH();
@@ -482,11 +482,10 @@ int admm_backward(Denoiser* den, const float* states, const float* y0, const uin
                                                 reinterpret_cast<const float2*>(grad_out), g_sigma, g_mu,
                                                 reinterpret_cast<float2*>(g_state_in), w));
     TFPNP_CUDA_OK(cudaGetLastError());
-    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers are freed on return
     return 0;
   };
   const int rc = body();
-  for (DevBuf* b : {&gx, &gz, &gu, &A, &IN, &Q, &Rr, &T, &y0p, &zero, &gxt, &v, &gv, &maskp, &P}) b->release();
+  for (PoolBuf* b : {&gx, &gz, &gu, &A, &IN, &Q, &Rr, &T, &y0p, &zero, &gxt, &v, &gv, &maskp, &P}) b->release();
   return rc;
 }
 
@@ -598,12 +597,12 @@ int variant_backward(int algo, Denoiser* den, const float* states, const float* 
   constexpr int N = 32 * R;
   const int HW = N * N;
   const size_t n = (size_t)B * HW;
-  DevBuf cb[10], fb[5], maskp, P;
+  PoolBuf cb[10], fb[5], maskp, P;
   auto body = [&]() -> int {
-    for (DevBuf& b : cb) TFPNP_TRY(b.alloc(n * sizeof(float2)));
-    for (DevBuf& b : fb) TFPNP_TRY(b.alloc(n * sizeof(float)));
-    TFPNP_TRY(maskp.alloc(n));
-    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float)));
+    for (PoolBuf& b : cb) TFPNP_TRY(b.alloc(n * sizeof(float2), st));
+    for (PoolBuf& b : fb) TFPNP_TRY(b.alloc(n * sizeof(float), st));
+    TFPNP_TRY(maskp.alloc(n, st));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float), st));
     TFPNP_CUDA_OK(cudaMemsetAsync(cb[9].p, 0, n * sizeof(float2), st));                 // zero y0
     TFPNP_CUDA_OK(cudaMemsetAsync(P.p, 0, (size_t)B * iters * 3 * sizeof(float), st));
     gather_params3<<<cdiv(B * iters, 256), 256, 0, st>>>(p0, p1, p2, rs, cs, P.as<float>(), B, iters);
@@ -617,12 +616,11 @@ int variant_backward(int algo, Denoiser* den, const float* states, const float* 
                                                    reinterpret_cast<const float2*>(grad_out), g_p0, g_p1, g_p2,
                                                    reinterpret_cast<float2*>(g_state_in), w));
     TFPNP_CUDA_OK(cudaGetLastError());
-    TFPNP_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
   };
   const int rc = body();
-  for (DevBuf& b : cb) b.release();
-  for (DevBuf& b : fb) b.release();
+  for (PoolBuf& b : cb) b.release();
+  for (PoolBuf& b : fb) b.release();
   maskp.release(); P.release();
   return rc;
 }

@@ -1,4 +1,5 @@
 // Stand-alone entry points: the CT operators and the PSNR reward metric.
+#include <utility>
 #include "tasks.cuh"
 #include <map>
 #include <memory>
@@ -239,11 +240,11 @@ int tfpnp_ct_iadmm_backward(void* denoiser, const float* states, const float* y0
   CtGeom* g = geom_cache().get(N, views, cos_host, sin_host, st, B);
   if (!g) return TFPNP_ERR_CUDA;
   const size_t n = (size_t)B * N * N;
-  DevBuf bufs[11], sino, P;
+  PoolBuf bufs[11], sino, P;
   auto body = [&]() -> int {
-    for (DevBuf& b : bufs) TFPNP_TRY(b.alloc(n * sizeof(float)));
-    TFPNP_TRY(sino.alloc((size_t)B * g->views * g->det * sizeof(float)));
-    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float)));
+    for (PoolBuf& b : bufs) TFPNP_TRY(b.alloc(n * sizeof(float), st));
+    TFPNP_TRY(sino.alloc((size_t)B * g->views * g->det * sizeof(float), st));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float), st));
     gather_params_t3<<<cdiv(B * iters, 256), 256, 0, st>>>(sigma_d, mu, tau, row_stride, col_stride, P.as<float>(), B, iters);
     TFPNP_COUNT_LAUNCH();
     CtGradOps ops{static_cast<Denoiser*>(denoiser), g, y0, sino.as<float>(), 1.0f / (opnorm * opnorm), B, st};
@@ -253,13 +254,72 @@ int tfpnp_ct_iadmm_backward(void* denoiser, const float* states, const float* y0
     TFPNP_TRY(grad_elem::ct_backward_sequence(ops, states, P.as<float>(), B, N * N, iters, grad_out, grad_sigma_d, grad_mu,
                                               grad_tau, grad_state_in, w));
     TFPNP_CUDA_OK(cudaGetLastError());
-    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers are freed on return
     return 0;
   };
   const int rc = body();
-  for (DevBuf& b : bufs) b.release();
+  for (PoolBuf& b : bufs) b.release();
   sino.release(); P.release();
   return rc;
 }
 
 }  // extern "C"
+
+// ---- scratch pool (common.cuh: PoolBuf) ------------------------------------------------------------------------------------
+namespace tfpnp {
+namespace {
+struct ScratchPool {
+  std::mutex mu;
+  std::map<std::pair<int, cudaStream_t>, std::multimap<size_t, void*>> free_blocks;
+  void release_all() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& kv : free_blocks) {
+      cudaSetDevice(kv.first.first);
+      if (!kv.second.empty()) cudaStreamSynchronize(kv.first.second);   // (a destroyed stream reports an error: ignored)
+      for (auto& b : kv.second) cudaFree(b.second);
+    }
+    cudaGetLastError();
+    free_blocks.clear();
+  }
+};
+ScratchPool& scratch_pool() { static ScratchPool* p = new ScratchPool; return *p; }   // leaked on purpose: no teardown order issues
+}  // namespace
+
+void* scratch_pool_take(size_t bytes, cudaStream_t st, size_t* got) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t want = (bytes + 511) & ~(size_t)511;
+  ScratchPool& P = scratch_pool();
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto& m = P.free_blocks[{dev, st}];
+    auto it = m.lower_bound(want);
+    if (it != m.end() && it->first <= 2 * want + (1u << 20)) {   // best fit, but never park a huge block under a small request
+      void* p = it->second;
+      *got = it->first;
+      m.erase(it);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    P.release_all();                                             // cached blocks may be what is in the way
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  }
+  *got = want;
+  return p;
+}
+
+void scratch_pool_give(void* p, size_t bytes, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  ScratchPool& P = scratch_pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.free_blocks[{dev, st}].emplace(bytes, p);
+}
+}  // namespace tfpnp
+
+extern "C" int tfpnp_release_cached_scratch(void) {
+  tfpnp::scratch_pool().release_all();
+  return 0;
+}

@@ -521,12 +521,12 @@ extern "C" int tfpnp_pr_iadmm_backward(void* denoiser, const float* states, cons
   g_launch_count = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = (size_t)B * N * N, nm = n * n_masks;
-  DevBuf c1[7], cm[5], f1[5], P;
+  PoolBuf c1[7], cm[5], f1[5], P;
   auto body = [&]() -> int {
-    for (DevBuf& b : c1) TFPNP_TRY(b.alloc(n * sizeof(float2)));
-    for (DevBuf& b : cm) TFPNP_TRY(b.alloc(nm * sizeof(float2)));
-    for (DevBuf& b : f1) TFPNP_TRY(b.alloc(n * sizeof(float)));
-    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float)));
+    for (PoolBuf& b : c1) TFPNP_TRY(b.alloc(n * sizeof(float2), st));
+    for (PoolBuf& b : cm) TFPNP_TRY(b.alloc(nm * sizeof(float2), st));
+    for (PoolBuf& b : f1) TFPNP_TRY(b.alloc(n * sizeof(float), st));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 3 * sizeof(float), st));
     prg_gather_params<<<cdiv(B * iters, 256), 256, 0, st>>>(sigma_d, mu, tau, row_stride, col_stride, P.as<float>(), B, iters);
     TFPNP_COUNT_LAUNCH();
     PrGradOps ops{static_cast<Denoiser*>(denoiser), reinterpret_cast<const float2*>(mask), y0, cm[4].as<float2>(), B, n_masks, N, st};
@@ -538,13 +538,12 @@ extern "C" int tfpnp_pr_iadmm_backward(void* denoiser, const float* states, cons
                                               reinterpret_cast<const float2*>(grad_out), grad_sigma_d, grad_mu, grad_tau,
                                               reinterpret_cast<float2*>(grad_state_in), w));
     TFPNP_CUDA_OK(cudaGetLastError());
-    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers are freed on return
     return 0;
   };
   const int rc = body();
-  for (DevBuf& b : c1) b.release();
-  for (DevBuf& b : cm) b.release();
-  for (DevBuf& b : f1) b.release();
+  for (PoolBuf& b : c1) b.release();
+  for (PoolBuf& b : cm) b.release();
+  for (PoolBuf& b : f1) b.release();
   P.release();
   return rc;
 }

@@ -167,10 +167,10 @@ int spi_backward(Denoiser* den, const float* states, const float* x0, const floa
                  const float* mu, int64_t rs, int64_t cs, int B, int H, int W, int iters, const float* grad_out, float* g_sigma,
                  float* g_mu, float* g_state_in, cudaStream_t st) {
   const size_t n = (size_t)B * H * W;
-  DevBuf bufs[6], P;
+  PoolBuf bufs[6], P;
   auto body = [&]() -> int {
-    for (DevBuf& b : bufs) TFPNP_TRY(b.alloc(n * sizeof(float)));
-    TFPNP_TRY(P.alloc((size_t)B * iters * 2 * sizeof(float)));
+    for (PoolBuf& b : bufs) TFPNP_TRY(b.alloc(n * sizeof(float), st));
+    TFPNP_TRY(P.alloc((size_t)B * iters * 2 * sizeof(float), st));
     spi_gather_params<<<cdiv(B * iters, 256), 256, 0, st>>>(sigma_d, mu, rs, cs, P.as<float>(), B, iters);
     TFPNP_COUNT_LAUNCH();
     SpiGradOps ops{den, B, H, W, st, x0, K, K_stride};
@@ -178,11 +178,10 @@ int spi_backward(Denoiser* den, const float* states, const float* x0, const floa
                              bufs[4].as<float>(), bufs[5].as<float>()};
     TFPNP_TRY(grad_elem::spi_backward_sequence(ops, states, P.as<float>(), B, H * W, iters, grad_out, g_sigma, g_mu, g_state_in, w));
     TFPNP_CUDA_OK(cudaGetLastError());
-    TFPNP_CUDA_OK(cudaStreamSynchronize(st));    // the scratch buffers are freed on return
     return 0;
   };
   const int rc = body();
-  for (DevBuf& b : bufs) b.release();
+  for (PoolBuf& b : bufs) b.release();
   P.release();
   return rc;
 }
