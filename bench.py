@@ -322,6 +322,25 @@ def main():
             ms = t.item()
         return ms
 
+    def timed_pipelined(fn, finish, steps):
+        """K pipelined steps inside ONE event bracket (the copies of neighbouring steps overlap the solves, so per-step brackets
+        would not add up); `finish` drains the copy stream before the closing event.  The L2 flushes sit inside the bracket."""
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            flush.fill_(1)
+            fn()
+        finish()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
     def measure(task, precision, d_host, aux, par, opnorm, steps, sampler=None):
         """value / e2e / in-graph segment split of one task in one arithmetic mode."""
         cfg = TASKS[task]
@@ -377,18 +396,20 @@ def main():
                 out.record_stream(copy_stream); p.record_stream(copy_stream)
                 out_host.copy_(out, non_blocking=True)
                 psnr_host.copy_(p, non_blocking=True)
-            cur.wait_stream(copy_stream)                    # the step ends when its result is on the host
             state["k"] += 1
+
+        def finish_e2e():
+            torch.cuda.current_stream().wait_stream(copy_stream)   # the region ends when the last result is on the host
 
         for _ in range(args.warmup):
             step_resident()
-        step_e2e(); step_e2e()
+        step_e2e(); step_e2e(); finish_e2e()
         torch.cuda.synchronize()
         if sampler is not None:
             sampler.start()
         ms_res = timed(step_resident, steps)
         launches = solver.last_launch_count + 1       # + the PSNR kernel
-        ms_e2e = timed(step_e2e, steps)
+        ms_e2e = timed_pipelined(step_e2e, finish_e2e, steps)
         clocks = sampler.stop() if sampler is not None else None
         torch.cuda.synchronize()
 
@@ -418,7 +439,7 @@ def main():
             "value": B_total * ITERS / (ms_res / 1e3), "ms_per_step": ms_res,
             "e2e": {"value": B_total * ITERS / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_b * world, "d2h_bytes_per_step": d2h_b,
-                    "overlap": "copy stream, double-buffered: H2D of step k+1 and D2H of step k-1 under the solve of step k"},
+                    "overlap": "copy stream, double-buffered, pipelined across the K steps of one event bracket: H2D of step k+1 and D2H of step k-1 under the solve of step k; the bracket closes after the last D2H"},
             "gpu_launches": int(launches * steps),
             "roofline": {"bound": "tensor", "kernel": "denoiser segment (tcgen05 implicit-GEMM convs: conv3x3_x3 / conv3x3_pair / "
                                                        "conv3x3_tc2 + first layer)",
