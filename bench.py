@@ -548,4 +548,18 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line (the JSON): anything a library prints there while the bench runs (NCCL's
+    # "NCCL version ..." banner under NCCL_DEBUG=VERSION/INFO goes to stdout) is sent to stderr instead
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):   # noqa: A001  (the two JSON prints above)
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        _print(*a, **k)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
     main()
