@@ -347,6 +347,41 @@ def test_radon_pair_vs_oracle(dev):
     assert abs(lhs - rhs) <= 1e-5 * (abs(lhs) + abs(rhs))       # <Ax,y> = <x,A^T y>
 
 
+@pytest.mark.parametrize("n,scale", [(40, 1.0), (64, 1.25), (48, 0.8), (128, 1.0)])
+def test_radon_pair_kernel_variants_vs_oracle(dev, n, scale):
+    """The three back-projection paths of ct.cu against the oracle's Radon pair: shared-memory windows per 16x16 tile (unit-norm
+    tables, N % 16 == 0), the clamped row gather (unit-norm tables, other sizes) and the guarded gather (tables that are NOT unit
+    vectors: bins can fall outside the detector); the forward projector's clipped ray walk must add exactly the same terms."""
+    from tfpnp_b200 import _lib
+    views = 20
+    cs, sn, det = O.ct_geometry(n, views)
+    cs, sn = (cs * scale).contiguous(), (sn * scale).contiguous()
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(2, 1, n, n, generator=g)
+    sino = torch.randn(2, 1, views, det, generator=g)
+    fw = torch.empty(2, 1, views, det, device=dev)
+    bw = torch.empty(2, 1, n, n, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().tfpnp_radon_forward(img.to(dev).data_ptr(), fw.data_ptr(), 2, n, views, cs.data_ptr(), sn.data_ptr(), st), "fwd")
+    _lib.check(_lib.lib().tfpnp_radon_backward(sino.to(dev).data_ptr(), bw.data_ptr(), 2, n, views, cs.data_ptr(), sn.data_ptr(), st), "bwd")
+    torch.cuda.synchronize()
+    assert_close(fw, O.radon_forward(img, cs, sn, det), 1e-5, f"radon fwd n={n} scale={scale}")
+    assert_close(bw, O.radon_backward(sino, cs, sn, n), 1e-5, f"radon bwd n={n} scale={scale}")
+
+
+@pytest.mark.parametrize("n_masks", [1, 3, 6])
+def test_pr_256_mask_counts_vs_oracle(dev, n_masks):
+    """pr256_rows_inv splits the masks over four half-warps per row: mask counts that are not a multiple of four."""
+    import tfpnp_b200 as T
+    d = synth.pr_batch(1, 256, 2, seed=11, n_masks=n_masks)
+    ref = O.iadmm_pr(weights("default"), d["state"], d["y0"], d["mask"], d["sigma_d"], d["mu"], d["tau"])
+    dd = cu(d, dev)
+    s = T.IADMMSolver_PR(denoiser("fp32_simt", "default"))
+    with torch.no_grad():
+        out = s((dd["state"], (dd["y0"], dd["mask"])), (dd["sigma_d"], dd["mu"], dd["tau"]))
+    assert_close(out, ref, 1e-4, f"pr 256 with {n_masks} masks")
+
+
 @pytest.mark.parametrize("prec", ["fp32_simt", "fp16x3"])
 def test_ct_vs_oracle(dev, prec):
     import tfpnp_b200 as T

@@ -242,15 +242,20 @@ pr256_rows_inv(const float2* __restrict__ T, const float2* __restrict__ mask, co
   float2 v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
-  for (int m = ml; m < M; m += 4) {
-    const size_t mrow = ((b * M + m) * 256 + r) * 256;
+  // the trip count is uniform over the CTA (fft256_run synchronises the whole warp and its two half-warps own different
+  // masks): a half-warp whose mask index runs past M transforms zeros -- with 1 or 3 masks the two halves of a warp would
+  // otherwise execute different numbers of __syncwarp and hang
+  for (int m0 = 0; m0 < M; m0 += 4) {
+    const int m = m0 + ml;
+    const bool live = m < M;
+    const size_t mrow = ((b * M + (live ? m : 0)) * 256 + r) * 256;
     float2 acc[16], mk[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = v[j];       // (M <= 4: zero, folded away by the first trip)
+    for (int j = 0; j < 16; ++j) acc[j] = v[j];       // (first trip: zero)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = T[mrow + t + 16 * j];
+    for (int j = 0; j < 16; ++j) v[j] = live ? T[mrow + t + 16 * j] : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) mk[j] = __ldcs(mask + mrow + t + 16 * j);
+    for (int j = 0; j < 16; ++j) mk[j] = live ? __ldcs(mask + mrow + t + 16 * j) : make_float2(0.f, 0.f);
     fft256_run<true, 1>(v, t, s_x[hw], s_tw);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
