@@ -1,2 +1,6 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "radon_pair_kernel_variants or pr_256_mask_counts" 2>&1 | tail -8
+mkdir -p gpurun_out
+for tool in memcheck racecheck; do
+timeout 400 compute-sanitizer --tool $tool --error-exitcode 9 --launch-timeout 120 python tools/sanitize_updates.py > gpurun_out/sanitize_updates_$tool.log 2>&1
+echo "$tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^pr|^ct|^radon|hazard|Invalid" gpurun_out/sanitize_updates_$tool.log | sort | uniq -c | head -12
+done
