@@ -15,6 +15,7 @@
 #include "tasks.cuh"
 #include "fft.cuh"
 #include "fft256.cuh"
+#include "sm100.cuh"
 
 namespace tfpnp {
 namespace {
@@ -291,6 +292,111 @@ pr256_rows_inv(const float2* __restrict__ T, const float2* __restrict__ mask, co
   }
 }
 
+
+// The column pass with its tile staged by TMA: ONE cp.async.bulk.tensor load brings the 256 x 16 float2 tile of an (image, mask)
+// spectrum into shared memory (128-byte rows, SWIZZLE_128B: element (r, w) sits in 16-byte chunk (w/2) ^ (r & 7) of row r, so
+// a column walk by 16 lanes touches all 32 banks twice), the half-warps transform their columns through separate exchange
+// slots, write the result back into the tile and ONE bulk tensor store returns it.  Replaces 2 x 16 (LDG/STG + STS/LDS +
+// index arithmetic) per thread of pr256_cols.
+// 2-D TMA tile moves (this file's only use of them): global -> shared completing on an mbarrier, shared -> global as a bulk group
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          sm100::smem_u32(smem_dst)),
+      "l"(map), "r"(sm100::smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(sm100::smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+constexpr int kColsTmaTile = 256 * 128;                                             // bytes
+constexpr int kColsTmaSmem = 1024 + kColsTmaTile + 16 * kF256Slots * 8 + 256 * 8 + 16;   // align slack, tile, slots, twiddles, barrier
+
+__global__ void __launch_bounds__(256, 2)
+pr256_cols_tma(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ y0p) {
+  extern __shared__ uint8_t cols_raw[];
+  uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(cols_raw) + 1023) & ~(uintptr_t)1023);
+  float2* s_x = reinterpret_cast<float2*>(tile + kColsTmaTile);
+  float2* s_tw = s_x + 16 * kF256Slots;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_tw + 256);
+  const int tid = threadIdx.x;
+  const size_t bm = blockIdx.y;
+  const int c0 = blockIdx.x * 16;
+  if (tid == 0) {
+    sm100::mbar_init(bar, 1);
+    sm100::fence_barrier_init();
+  }
+  s_tw[tid] = g_fft_tw256[tid];
+  __syncthreads();
+  if (tid == 0) {
+    sm100::mbar_arrive_expect_tx(bar, kColsTmaTile);
+    tma_load_2d(tile, &tmap, bar, 2 * c0, (int)(bm * 256));   // coordinates in fp32 elements (2 per float2), rows
+  }
+  const int w = tid >> 4, t = tid & 15;
+  const float* yc = y0p + (bm * 256 + c0 + w) * 256;
+  float yv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) yv[j] = __ldcs(yc + t + 16 * j);   // in flight during the tile load and the forward transform
+  sm100::mbar_wait(bar, 0);
+  // (r & 7) == (t & 7) for r = t + 16 j: the chunk of this lane's element is the same in every row it touches
+  uint8_t* lane_base = tile + t * 128 + ((((w >> 1) ^ (t & 7)) << 4) | ((w & 1) << 3));
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(lane_base + j * (16 * 128));
+  fft256_run<false, 1>(v, t, s_x + w * kF256Slots, s_tw);
+  const float inv_n = 1.0f / 256.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float2 a = make_float2(v[j].x * inv_n, v[j].y * inv_n);     // Az
+    float yh = sqrtf(a.x * a.x + a.y * a.y);                    // complex_abs, transforms.py:118
+    float ratio = (yh - yv[j]) / yh;                            // meas_err / y_hat, solver.py:66-67
+    v[j] = make_float2(ratio * a.x, ratio * a.y);
+  }
+  fft256_run<true, 1>(v, t, s_x + w * kF256Slots, s_tw);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) *reinterpret_cast<float2*>(lane_base + j * (16 * 128)) = v[j];
+  sm100::fence_proxy_async();        // generic-proxy writes to the tile -> visible to the bulk store
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_2d(&tmap, tile, 2 * c0, (int)(bm * 256));
+    tma_store_commit_and_wait();
+  }
+}
+
+// 2-D fp32 view of the spectra workspace T: [B*M*256 rows][512 floats], box 32 floats x 256 rows, 128-byte swizzle
+int pr256_encode_map(CUtensorMap* m, float2* T, int BM) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    TFPNP_CHECK(e == cudaSuccess && q == cudaDriverEntryPointSuccess && p, "cuTensorMapEncodeTiled entry point unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  const cuuint64_t dims[2] = {512, (cuuint64_t)BM * 256};
+  const cuuint64_t strides[1] = {2048};
+  const cuuint32_t box[2] = {32, 256}, estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, T, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TFPNP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (pr spectra, %d rows)", (int)r, BM * 256);
+  return 0;
+}
+
+int pr256_cols_use_tma() {
+  static const int v = getenv("TFPNP_PR_COLS_TMA") ? atoi(getenv("TFPNP_PR_COLS_TMA")) : 1;
+  return v;
+}
+
 // TFPNP_PR_FFT16=0 keeps the warp-wide transform at N = 256 (A/B switch; read once)
 bool pr_use_fft16() {
   static const int v = getenv("TFPNP_PR_FFT16") ? atoi(getenv("TFPNP_PR_FFT16")) : 1;
@@ -323,7 +429,18 @@ int launch_update256(const float* x, float2* z, float2* u, float* d, float2* T, 
     TFPNP_COUNT_LAUNCH();
     const int occ = pr256_occ();
     const dim3 g8(256 / 8, nb * M), g16(256 / 16, nb * M);
-    if (pr256_cols_width() == 8) {
+    if (pr256_cols_use_tma() && chunk >= B) {
+      static unsigned long long attr_set = 0;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!((attr_set >> (dev & 63)) & 1ull)) {
+        TFPNP_CUDA_OK(cudaFuncSetAttribute(pr256_cols_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kColsTmaSmem));
+        attr_set |= 1ull << (dev & 63);
+      }
+      CUtensorMap tmap;
+      TFPNP_TRY(pr256_encode_map(&tmap, T, B * M));
+      pr256_cols_tma<<<g16, 256, kColsTmaSmem, st>>>(tmap, y0p);
+    } else if (pr256_cols_width() == 8) {
       if (occ / 10 == 3) pr256_cols<8, 3><<<g8, 8 * 16, 0, st>>>(T + om, y0p + om);
       else pr256_cols<8, 2><<<g8, 8 * 16, 0, st>>>(T + om, y0p + om);
     } else {
