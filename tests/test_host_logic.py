@@ -219,3 +219,45 @@ def test_pdl_kernels_read_dependent_data_after_the_wait():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_pdl_sass.py")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "kernels execute griddepcontrol.wait" in r.stdout
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the arm that needs no GPU): stdout is ONE line of JSON with the contract's keys, whatever the
+    libraries print while it runs (bench.py sends everything else on fd 1 to stderr)."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_profile_traffic_tag_matches_the_hash_tool():
+    """profiles/r02_traffic_*.json carry tools/src_hash.py's hash of the sources they were captured from; bench.py prints
+    roofline.traffic only on a match, so a stale capture can never be reported as measured."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from src_hash import src_sha16, CSMRI_ITERATION
+    for f in CSMRI_ITERATION:
+        assert os.path.exists(os.path.join(ROOT, "tfpnp_b200", "csrc", f)), f
+    h = src_sha16(ROOT)
+    assert re.fullmatch(r"[0-9a-f]{16}", h) and h == src_sha16(ROOT)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    for prec in ("fp16x3", "fp16"):
+        p = os.path.join(ROOT, "profiles", f"r02_traffic_csmri_{prec}.json")
+        d = json.load(open(p))
+        got = bench.ncu_traffic("csmri", prec)
+        assert (got is not None) == (d.get("src_sha16") == h)      # printed only while the tree still hashes to the capture
