@@ -57,7 +57,7 @@ def _psnr_native(o: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
 
 class _PsnrFn(torch.autograd.Function):
     """torch_psnr under autograd (the reward enters the actor loss, tfpnp/trainer/mddpg/trainer.py:189): native forward,
-    tfpnp_psnr_backward.  Reverse mode is round-1 code that has not run on a GPU yet."""
+    tfpnp_psnr_backward (validated on the GPU in round 2 against autograd through the reference, tests/test_grad.py)."""
 
     @staticmethod
     def forward(ctx, o, g):
