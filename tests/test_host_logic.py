@@ -261,3 +261,19 @@ def test_profile_traffic_tag_matches_the_hash_tool():
         d = json.load(open(p))
         got = bench.ncu_traffic("csmri", prec)
         assert (got is not None) == (d.get("src_sha16") == h)      # printed only while the tree still hashes to the capture
+
+
+def test_fft256_half_warp_transform_on_the_host(tmp_path):
+    """fft256.cuh (radix-4^2 16-point DFT in registers, lane twiddle, one exchange, second DFT): its __host__ __device__ bodies run
+    lane by lane on the CPU against a double-precision DFT, forward and inverse (tests/fft256_host.cu)."""
+    import shutil
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not available")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "fft256_host")
+    r = subprocess.run([nvcc, "-O1", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "tfpnp_b200", "csrc"), "-o", exe,
+                        os.path.join(ROOT, "tests", "fft256_host.cu")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("max err") == 2
