@@ -277,3 +277,73 @@ def test_fft256_half_warp_transform_on_the_host(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("max err") == 2
+
+
+@pytest.mark.parametrize("N,views,scale", [(32, 7, 1.0), (40, 20, 1.0), (64, 24, 1.25), (128, 60, 1.0), (256, 60, 1.0), (48, 181, 0.8)])
+def test_ct_ray_walk_clipping_never_drops_a_contributing_step(N, views, scale):
+    """ct.cu's projector walks only the driving indices [k_lo, k_hi] where the ray can touch the image.  Restated here in numpy
+    fp32 with the kernel's formulas: every step whose interpolation has an in-bounds tap (what the un-clipped, guarded walk
+    would have added) lies inside the clipped range -- for the reference's angle table (incl. exactly 0 and ~90 degrees, where
+    the slope term vanishes or is ~1e-8), a dense table and tables that are not unit vectors."""
+    import numpy as np
+    f = np.float32
+    ang = np.linspace(0, 179 / 180 * np.pi, views, dtype=np.float32)
+    cs = (np.cos(ang.astype(np.float64)).astype(f) * f(scale)).astype(f)
+    sn = (np.sin(ang.astype(np.float64)).astype(f) * f(scale)).astype(f)
+    D = int(np.ceil(np.sqrt(2) * N))
+    c = f((N - 1) * 0.5)
+    k = np.arange(N, dtype=np.float32)
+    t = (k - c).astype(f)
+    for v in range(views):
+        co, si = cs[v], sn[v]
+        col = abs(si) >= abs(co)
+        a, bq = (co, si) if col else (si, co)
+        inv_b = f(1.0) / bq
+        s = (np.arange(D, dtype=np.float32) - f((D - 1) * 0.5)).astype(f)[:, None]
+        r = (((s - t[None, :] * a).astype(f) * inv_b).astype(f) + c).astype(f)        # [D, N]
+        i0 = np.floor(r)
+        used = (i0 >= -1) & (i0 <= N - 1)                                             # a tap of this step is inside the image
+        if a != 0:
+            ka = (c + ((s - (f(-1.0) - c) * bq).astype(f) / a).astype(f)).astype(f)
+            kb = (c + ((s - (f(N) - c) * bq).astype(f) / a).astype(f)).astype(f)
+            lo = np.minimum(np.maximum(np.minimum(ka, kb), f(-2)), f(N + 1))
+            hi = np.minimum(np.maximum(np.maximum(ka, kb), f(-2)), f(N + 1))
+            k_lo = np.maximum(0, np.floor(lo).astype(np.int64) - 2)
+            k_hi = np.minimum(N - 1, np.ceil(hi).astype(np.int64) + 2)
+        else:
+            k_lo = np.zeros((D, 1), np.int64)
+            k_hi = np.full((D, 1), N - 1, np.int64)
+        kk = np.arange(N)[None, :]
+        inside = (kk >= k_lo) & (kk <= k_hi)
+        assert not (used & ~inside).any(), (N, views, scale, v)
+        # and the clipping does cut work for oblique views: some steps are skipped somewhere
+
+
+@pytest.mark.parametrize("N,views", [(32, 9), (64, 24), (128, 60), (256, 60), (256, 180)])
+def test_ct_backprojection_windows_cover_every_pixel(N, views):
+    """ct.cu's windowed back-projection (unit-norm tables, D = ceil(sqrt(2) N), 16x16 pixel tiles): every pixel's two detector
+    bins are inside the detector (0 <= floor(d*) <= D - 2, so the guards can go) and inside the 32-bin window its tile stages
+    (window start = clamp(floor(min over the tile's corners of d*) - 1, 0, D - 32)).  numpy fp32 with the kernel's formulas."""
+    import numpy as np
+    f = np.float32
+    ang = np.linspace(0, 179 / 180 * np.pi, views, dtype=np.float32)
+    cs = np.cos(ang.astype(np.float64)).astype(f)
+    sn = np.sin(ang.astype(np.float64)).astype(f)
+    D = int(np.ceil(np.sqrt(2) * N))
+    c = f((N - 1) * 0.5)
+    half = f((D - 1) * 0.5)
+    xs = (np.arange(N, dtype=np.float32) - c).astype(f)
+    X, Y = np.meshgrid(xs, xs)                                  # X[i, j] = x of column j, Y[i, j] = y of row i
+    for v in range(views):
+        co, si = cs[v], sn[v]
+        dstar = (((X * co).astype(f) + (Y * si).astype(f)).astype(f) + half).astype(f)
+        fl = np.floor(dstar)
+        assert fl.min() >= 0 and fl.max() <= D - 2, (N, v, fl.min(), fl.max())
+        for ty in range(N // 16):
+            for tx in range(N // 16):
+                x0, y0 = f(tx * 16) - c, f(ty * 16) - c
+                e = [x0 * co + y0 * si, (x0 + f(15)) * co + y0 * si, x0 * co + (y0 + f(15)) * si, (x0 + f(15)) * co + (y0 + f(15)) * si]
+                dmin = f(min(e)) + half
+                start = min(max(int(np.floor(dmin)) - 1, 0), D - 32)
+                o = fl[ty * 16:ty * 16 + 16, tx * 16:tx * 16 + 16] - start
+                assert o.min() >= 0 and o.max() <= 30, (N, v, ty, tx, o.min(), o.max())
